@@ -1,0 +1,258 @@
+#!/usr/bin/env python
+"""Generate the golden fixtures in tests/golden/ by running the REAL reference.
+
+Run in the build container only (needs /root/reference):
+
+    PYTHONDONTWRITEBYTECODE=1 python tests/golden/make_golden.py
+
+Every fixture stores outputs of the unmodified reference (`bsi.bsi`, `bsi.models.*`,
+`bsi.nn.*` imported from /root/reference) on deterministic inputs that the tests can
+rebuild bit-identically from tests/helpers.py (numpy Philox), so only small tensors are
+committed.  Reference entry points exercised (file:line in the reference):
+  Discretization.bucketize / bin_boundaries      bsi/bsi.py:29-35
+  LogUniform.icdf/cdf, BSI._edm_preconditioning  bsi/bsi.py:76-84, 390-403
+  BSI.sample_history / sample                    bsi/bsi.py:312-373
+  BSI.train_loss / elbo / finite_elbo            bsi/bsi.py:152-310
+  DenoisingDiT.forward, DenoisingVDMUNet.forward bsi/models/dit.py:225-233, bsi/models/vdm_unet.py:92-100
+  NyquistPositionalEmbedding, FourierFeatures    bsi/models/pos_emb.py:77-84, bsi/nn/fourier_features.py:24-36
+"""
+
+import os
+import sys
+
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+import helpers as H  # noqa: E402
+
+O = H.O
+ref_bsi, ref_dit, ref_unet, ref_pos, ref_nn = H.import_reference()
+
+torch.set_num_threads(8)
+torch.manual_seed(0)
+
+HYPER = dict(lambda_0=1e-2, alpha_M=1e6, alpha_R=2e6, preconditioning="edm")
+
+
+def _compact(obj):
+    """Clone tensors so views do not drag their whole base storage into the file."""
+    if isinstance(obj, torch.Tensor):
+        return obj.detach().clone().contiguous()
+    if isinstance(obj, dict):
+        return {k: _compact(v) for k, v in obj.items()}
+    return obj
+
+
+def save(name, obj):
+    path = os.path.join(HERE, name)
+    torch.save(_compact(obj), path)
+    print(f"{name}: {os.path.getsize(path) / 1024:.1f} KiB")
+
+
+def load_into(module, sd):
+    missing, unexpected = module.load_state_dict(sd, strict=False)
+    assert not unexpected, unexpected
+    # only non-persistent buffers may be "missing" (they are not in state_dict at all)
+    assert not missing, missing
+    return module.eval()
+
+
+# ---------------------------------------------------------------- A. discretisation
+def gen_disc():
+    D8 = ref_bsi.Discretization.image_8bit()
+    u8 = torch.arange(256, dtype=torch.float32)
+    on_grid = u8 * (2 / 255) - 1
+    edges32 = D8.bin_boundaries(torch.device("cpu"), torch.float32)
+    off = H.det_uniform("disc.off", (4096,)) * 1.2
+    near = torch.cat([edges32, torch.nextafter(edges32, torch.tensor(2.0)), torch.nextafter(edges32, torch.tensor(-2.0))])
+    x = torch.cat([on_grid, off, near, torch.tensor([-5.0, 5.0, -1.0, 1.0, 0.0])])
+    out = {
+        "x": x,
+        "idx": D8.bucketize(x).to(torch.int16),
+        "edges32": edges32,
+        "edges64": D8.bin_boundaries(torch.device("cpu"), torch.float64),
+        "to_unit": D8.to_unit_interval(x),
+        "to_u8": D8.to_8bit_image(x),
+        # the reference's own unit tests (tests/test_bsi.py:7-34), evaluated in float64 as conftest sets
+        "t_rgb_x": torch.tensor([-0.1, 0.0, 1.0, 1.0 - 1 / 256], dtype=torch.float64),
+        "t_rgb_idx": ref_bsi.Discretization(0.0, 1.0, 256).bucketize(
+            torch.tensor([-0.1, 0.0, 1.0, 1.0 - 1 / 256], dtype=torch.float64)
+        ),
+        "t_edges5": ref_bsi.Discretization(-1.0, 1.0, 5).bin_boundaries(torch.device("cpu"), torch.float64),
+        "t_edges3": ref_bsi.Discretization(-1.0, 1.0, 3).bin_boundaries(torch.device("cpu"), torch.float32),
+    }
+    b5 = out["t_edges5"]
+    out["t_idx5_at"] = ref_bsi.Discretization(-1.0, 1.0, 5).bucketize(b5)
+    out["t_idx5_below"] = ref_bsi.Discretization(-1.0, 1.0, 5).bucketize(b5 - 1e-8)
+    save("disc.pt", out)
+
+
+# ---------------------------------------------------------------- B. schedule / coefficients
+def gen_schedule():
+    out = {}
+    for k in (50, 128, 256):
+        bsi = ref_bsi.BSI(torch.nn.Identity(), data_shape=(3, 32, 32), k=k, **HYPER)
+        t = bsi.default_schedule
+        lam = bsi.p_lambda.icdf(t)
+        cs, co, ci = bsi._edm_preconditioning(t)
+        out[f"k{k}"] = dict(t=t, lam=lam, alpha=lam.diff(), c_skip=cs, c_out=co, c_in=ci, t_back=bsi.p_lambda.cdf(lam), inv_pdf=bsi.p_lambda.reciprocal_pdf(lam))
+        out["ln_low"], out["ln_high"] = bsi.p_lambda.ln_low, bsi.p_lambda.ln_high
+    save("schedule.pt", out)
+
+
+# ---------------------------------------------------------------- C. config 1: README toy conv denoiser
+class ToyModel(torch.nn.Module):  # README.md:24-31 (user-side example model, restated)
+    def __init__(self):
+        super().__init__()
+        self.layer = torch.nn.Conv2d(in_channels=4, out_channels=3, kernel_size=3, padding=1)
+
+    def forward(self, mu, t):
+        t = torch.movedim(t.expand((1, *mu.shape[-2:], len(t))), -1, 0)
+        return self.layer(torch.cat((mu, t), dim=-3))
+
+
+def gen_toy():
+    model = load_into(ToyModel(), H.det_state_dict(H.TOY_SHAPES, seed=1, bf16_exact=False))
+    k = 128
+    bsi = ref_bsi.BSI(model, data_shape=(3, 32, 32), k=k, discretization=ref_bsi.Discretization.image_8bit(), **HYPER)
+    out = {"k": k}
+    with torch.inference_mode():
+        g = torch.Generator().manual_seed(7)
+        mus, xs, ys = bsi.sample_history(2, g)
+        g = torch.Generator().manual_seed(7)
+        final = bsi.sample(2, g)
+        assert torch.equal(final, xs[-1])
+        g = torch.Generator().manual_seed(7)
+        eps = O.draw_sample_noise(2, (3, 32, 32), k, g)
+        steps = [0, 1, 2, 64, 126, 127]
+        out["sample"] = dict(
+            seed=7, n=2, final=final, steps=torch.tensor(steps),
+            mu=mus[steps], x_hat=xs[steps], y=ys[steps], mu_next=mus[[s + 1 for s in steps]],
+            eps=eps[[s + 1 for s in steps]], eps0=eps[0], eps_sum=eps.double().sum(), eps_abs_sum=eps.double().abs().sum(),
+        )
+        # custom (cosine-like) schedule through the t= argument (scripts/generate_samples.py:120-152 style)
+        tt = torch.sin(torch.linspace(0, 1, 33) * torch.pi / 2) ** 2
+        g = torch.Generator().manual_seed(11)
+        out["sample_custom_t"] = dict(seed=11, n=2, t=tt, final=bsi.sample(2, g, t=tt))
+
+        x = H.det_images("toy.x", 8, (3, 32, 32), seed=2)
+        g = torch.Generator().manual_seed(3)
+        out["train_loss"] = dict(seed=3, loss=bsi.train_loss(x, g))
+        g = torch.Generator().manual_seed(4)
+        e, b, ex = bsi.elbo(x, 1, 10, g)
+        out["elbo_1_10"] = dict(seed=4, elbo=e, bpd=b, l_recon=ex["l_recon"], l_measure=ex["l_measure"])
+        g = torch.Generator().manual_seed(5)
+        e, b, ex = bsi.elbo(x, 2, 3, g, estimate_var=True)
+        out["elbo_2_3_var"] = dict(seed=5, elbo=e, bpd=b, l_recon=ex["l_recon"], l_measure=ex["l_measure"], bpd_var=ex["bpd_var"])
+        g = torch.Generator().manual_seed(6)
+        e, b, ex = bsi.finite_elbo(x, 2, 3, g)
+        out["finite_elbo_2_3"] = dict(seed=6, elbo=e, bpd=b, l_recon=ex["l_recon"], l_measure=ex["l_measure"])
+        # the raw loss terms on fixed x_hat so kernels can be pinned without any RNG
+        xh = (x[None] + 0.002 * H.det_uniform("toy.xh", (2, *x.shape))).contiguous()
+        p = torch.distributions.Normal(xh, torch.full_like(xh, torch.rsqrt(bsi.alpha_R)), validate_args=False)
+        D8 = bsi.discretization
+        edges = D8.bin_boundaries(x.device, x.dtype)
+        idx = D8.bucketize(x)
+        cl = torch.where(idx == 0, 0, p.cdf(edges[idx]))
+        cr = torch.where(idx == 255, 1, p.cdf(edges[idx + 1]))
+        out["recon_terms"] = dict(value=(-torch.log(torch.clamp(cr - cl, min=1e-20))).flatten(2).sum(2))
+    save("toy.pt", out)
+
+
+# ---------------------------------------------------------------- D. DiT
+def make_ref_dit(spec):
+    ff = None if spec.fourier is None else ref_nn.FourierFeatures(n_min=spec.fourier[0], n_max=spec.fourier[1])
+    m = ref_dit.DenoisingDiT(spec.data_shape, spec.patch, spec.dim, spec.depth, spec.heads, dropout=0.05, fourier_features=ff)
+    sd = H.det_state_dict(H.dit_shapes(spec), seed=1)
+    assert {k: tuple(v.shape) for k, v in m.state_dict().items()} == {k: tuple(v.shape) for k, v in sd.items()}
+    return load_into(m, sd), sd
+
+
+def gen_dit():
+    out = {}
+    specs = {
+        "small64": O.DiTSpec((3, 64, 64), 4, 128, 2, 2),
+        "small32": O.DiTSpec((3, 32, 32), 2, 128, 2, 2),
+        "L2x64": O.DiTSpec((3, 64, 64), 4, 1024, 2, 16),
+        "L2x32": O.DiTSpec((3, 32, 32), 2, 1024, 2, 16),
+        "nofourier": O.DiTSpec((3, 32, 32), 2, 128, 1, 2, fourier=None),
+    }
+    with torch.inference_mode():
+        for name, spec in specs.items():
+            m, _ = make_ref_dit(spec)
+            B = 2
+            mu = 1.5 * H.det_uniform(f"dit.{name}.mu", (B, *spec.data_shape))
+            t = torch.tensor([0.3, 0.9])
+            rec = dict(y=m(mu, t))
+            if name.startswith("small"):
+                x = mu if spec.fourier is None else torch.cat((mu, m.fourier_features(mu, dim=1)), dim=1)
+                emb = m.dit.patch_encoder(m.dit.patchify(x)) + m.dit.patch_pos_embedding
+                h = emb
+                c = m.dit.t_embedding(t)
+                for blk in m.dit.blocks:
+                    h = blk(h, c)
+                rec.update(embed=emb, blocks=h, cond=c, pos=m.dit.patch_pos_embedding)
+            out[name] = rec
+
+        # BSI on the small DiT: losses + one trajectory prefix
+        spec = specs["small64"]
+        m, _ = make_ref_dit(spec)
+        bsi = ref_bsi.BSI(m, data_shape=spec.data_shape, k=16, discretization=ref_bsi.Discretization.image_8bit(), **HYPER)
+        x = H.det_images("dit.x", 4, spec.data_shape, seed=2)
+        g = torch.Generator().manual_seed(21)
+        e, b, ex = bsi.elbo(x, 1, 2, g)
+        out["bsi_small64"] = dict(elbo_seed=21, elbo=e, bpd=b, l_recon=ex["l_recon"], l_measure=ex["l_measure"])
+        g = torch.Generator().manual_seed(22)
+        out["bsi_small64"]["train_seed"] = 22
+        out["bsi_small64"]["train_loss"] = bsi.train_loss(x, g)
+        g = torch.Generator().manual_seed(23)
+        mus, xs, ys = bsi.sample_history(2, g)
+        g = torch.Generator().manual_seed(23)
+        eps = O.draw_sample_noise(2, spec.data_shape, 16, g)
+        steps = [0, 1, 8, 15]
+        out["bsi_small64"]["traj"] = dict(
+            seed=23, steps=torch.tensor(steps), mu=mus[steps], x_hat=xs[steps], mu_next=mus[[s + 1 for s in steps]],
+            eps=eps[[s + 1 for s in steps]], last_mu=mus[-1], final=xs[-1],
+        )
+    save("dit.pt", out)
+
+
+# ---------------------------------------------------------------- E. U-Net
+def gen_unet():
+    spec = O.UNetSpec((3, 32, 32), dim=64, levels=2)
+    pe = ref_pos.NyquistPositionalEmbedding(spec.pos_size, spec.pos_rate)
+    ff = ref_nn.FourierFeatures(n_min=6, n_max=8)
+    m = ref_unet.DenoisingVDMUNet(spec.data_shape, pe, "silu", spec.dim, spec.levels, spec.pos_mult, n_attention_heads=1, dropout=0.1, fourier_features=ff)
+    sd = H.det_state_dict(H.unet_shapes(spec), seed=1)
+    assert {k: tuple(v.shape) for k, v in m.state_dict().items()} == {k: tuple(v.shape) for k, v in sd.items()}
+    load_into(m, sd)
+    with torch.inference_mode():
+        mu = 1.5 * H.det_uniform("unet.mu", (2, *spec.data_shape))
+        t = torch.tensor([0.2, 0.95])
+        save("unet.pt", dict(y=m(mu, t)))
+
+
+# ---------------------------------------------------------------- F. embeddings
+def gen_embed():
+    out = {}
+    with torch.inference_mode():
+        t = torch.tensor([0.0, 1 / 256, 0.5, 1.0])
+        out["nyq1024_1000"] = ref_pos.NyquistPositionalEmbedding(1024, 1000)(t)
+        out["nyq32_100"] = ref_pos.NyquistPositionalEmbedding(32, 100)(t)
+        x = 1.5 * H.det_uniform("ff.x", (2, 3, 4, 4))
+        out["fourier_6_8"] = ref_nn.FourierFeatures(n_min=6, n_max=8)(x, dim=1)
+        # reference unit test (tests/models/components/test_fourier_features.py:9-28), float64
+        xt = torch.tensor([1.333, -2.718281828459045 / 7], dtype=torch.float64)[None, :, None].expand(2, 2, 3)
+        ffm = ref_nn.FourierFeatures(n_min=5, n_max=6).double()
+        out["fourier_test_y"] = ffm(xt, dim=1)
+    save("embed.pt", out)
+
+
+if __name__ == "__main__":
+    gen_disc()
+    gen_schedule()
+    gen_toy()
+    gen_dit()
+    gen_unet()
+    gen_embed()
