@@ -1,0 +1,140 @@
+"""ctypes binding of libbsi_b200.so (the C ABI declared in include/bsi_b200.h).
+
+There is no CPU fallback: if the shared library is missing or a call fails, the caller
+gets an exception carrying bsi_last_error().
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "libbsi_b200.so")
+
+
+class RowRef(C.Structure):
+    _fields_ = [("base", C.c_void_p), ("sample_stride", C.c_int32), ("step_stride", C.c_int32)]
+
+
+class Noise(C.Structure):
+    _fields_ = [("eps", C.c_void_p), ("seed", C.c_uint64), ("sample_base", C.c_uint64), ("draw", C.c_int32)]
+
+
+class GemmArgs(C.Structure):
+    _fields_ = [
+        ("A", C.c_void_p), ("W", C.c_void_p), ("C", C.c_void_p), ("bias", C.c_void_p),
+        ("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32),
+        ("lda", C.c_int32), ("ldw", C.c_int32), ("ldc", C.c_int32),
+        ("batch", C.c_int32),
+        ("stride_a", C.c_int64), ("stride_w", C.c_int64), ("stride_c", C.c_int64), ("stride_bias", C.c_int64),
+        ("epilogue", C.c_int32),
+        ("gate", RowRef),
+        ("step_ptr", C.c_void_p),
+        ("rows_per_sample", C.c_int32),
+        ("pos", C.c_void_p),
+        ("patch", C.c_int32), ("grid_w", C.c_int32), ("channels", C.c_int32),
+    ]  # fmt: skip
+
+
+class DitConfig(C.Structure):
+    _fields_ = [
+        ("channels", C.c_int32), ("height", C.c_int32), ("width", C.c_int32),
+        ("patch", C.c_int32), ("dim", C.c_int32), ("depth", C.c_int32), ("heads", C.c_int32),
+        ("fourier_n_min", C.c_int32), ("fourier_n_max", C.c_int32),
+    ]  # fmt: skip
+
+
+EPI_BIAS_BF16, EPI_BIAS_GELU_BF16, EPI_BIAS_SILU_BF16, EPI_BIAS_F32, EPI_GATE_RESID_F32, EPI_POS_F32, EPI_UNPATCH_F32 = range(7)
+
+_vp, _i32, _i64, _f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
+
+# name -> (restype, argtypes); must list every symbol of include/bsi_b200.h (checked by tests/test_abi.py)
+SIGNATURES = {
+    "bsi_abi_version": (C.c_int, []),
+    "bsi_last_error": (C.c_char_p, []),
+    "bsi_device_arch": (C.c_int, []),
+    "bsi_sample_init": (C.c_int, [_vp, _vp, Noise, _i64, _i64, _vp]),
+    "bsi_step_fused": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, Noise, _vp, _vp, _i64, _i64, _vp]),
+    "bsi_step_advance": (C.c_int, [_vp, _vp]),
+    "bsi_edm_combine": (C.c_int, [_vp, _vp, _vp, RowRef, RowRef, _vp, _i64, _i64, _vp]),
+    "bsi_scale_rows": (C.c_int, [_vp, _vp, RowRef, _vp, _i64, _i64, _vp]),
+    "bsi_q_sample": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, Noise, _i64, _i64, _i64, _vp]),
+    "bsi_bucketize": (C.c_int, [_vp, _vp, _vp, _f32, _f32, _i32, _i64, _vp]),
+    "bsi_recon_reduce": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _f32, _f32, _f32, _i64, _i64, _i64, _vp]),
+    "bsi_sqerr_reduce": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _vp]),
+    "bsi_sqerr_backward": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _vp]),
+    "bsi_gemm_bf16": (C.c_int, [C.POINTER(GemmArgs), _vp]),
+    "bsi_cast_bf16": (C.c_int, [_vp, _vp, _i64, _i64, _i64, _vp]),
+    "bsi_layernorm_mod_bf16": (C.c_int, [_vp, _vp, RowRef, RowRef, _vp, _vp, _vp, _i32, _i64, _i32, _f32, _vp]),
+    "bsi_attention_bf16": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _vp]),
+    "bsi_dit_patch_operand": (C.c_int, [_vp, _vp, RowRef, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "bsi_time_embed": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp]),
+    "bsi_dit_create": (C.c_int, [C.POINTER(DitConfig), C.POINTER(_vp)]),
+    "bsi_dit_destroy": (None, [_vp]),
+    "bsi_dit_param_bytes": (_i64, [_vp]),
+    "bsi_dit_workspace_bytes": (_i64, [_vp, _i32]),
+    "bsi_dit_cond_bytes": (_i64, [_vp, _i32]),
+    "bsi_dit_bind_params": (C.c_int, [_vp, _vp, _i64]),
+    "bsi_dit_set_param": (C.c_int, [_vp, C.c_char_p, _vp, _i64, _vp]),
+    "bsi_dit_missing_params": (C.c_int, [_vp]),
+    "bsi_dit_cond_scratch_bytes": (_i64, [_vp, _i32]),
+    "bsi_dit_conditioning": (C.c_int, [_vp, _vp, _vp, _i32, _vp, _i64, _vp]),
+    "bsi_dit_forward": (C.c_int, [_vp, _vp, _vp, RowRef, _vp, _i32, _i32, _i32, _i32, _vp, _i32, _vp, _i64, _vp]),
+    "bsi_dit_peek": (C.c_int, [_vp, _i32, _vp, _i32, _vp, _vp]),
+}
+
+_lib = None
+
+
+class BsiNativeError(RuntimeError):
+    pass
+
+
+def load() -> C.CDLL:
+    """Load the shared library (building it is `python -m bsi_b200.build` / __graft_entry__.build())."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise BsiNativeError(
+                f"{LIB_PATH} is missing: build it with `python -m bsi_b200.build` — bsi_b200 has no CPU/PyTorch fallback"
+            )
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = lib
+    return _lib
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = load().bsi_last_error().decode(errors="replace")
+        raise BsiNativeError(f"{what or 'bsi_b200 call'} failed with status {rc}: {msg}")
+
+
+def ptr(t: torch.Tensor | None):
+    if t is None:
+        return None
+    assert t.is_cuda and t.is_contiguous(), "native kernels need contiguous CUDA tensors"
+    return t.data_ptr()
+
+
+def stream_ptr(device=None):
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def rowref(t: torch.Tensor | None, sample_stride: int = 0, step_stride: int = 0, offset: int = 0) -> RowRef:
+    """Reference into a float32 CUDA tensor (see bsi_rowref in include/bsi_b200.h)."""
+    if t is None:
+        return RowRef(None, 0, 0)
+    assert t.dtype == torch.float32
+    return RowRef(ptr(t) + 4 * offset, sample_stride, step_stride)
+
+
+def noise(eps: torch.Tensor | None = None, seed: int = 0, sample_base: int = 0, draw: int = 0) -> Noise:
+    if eps is not None:
+        assert eps.dtype == torch.float32
+    return Noise(ptr(eps), seed & 0xFFFFFFFFFFFFFFFF, sample_base, draw)

@@ -1,0 +1,94 @@
+// Shared host/device helpers for the bsi_b200 CUDA library.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/bsi_b200.h"
+
+namespace bsi {
+
+void set_error(const char* fmt, ...);
+
+#define BSI_CHECK_ARG(cond, ...)             \
+    do {                                     \
+        if (!(cond)) {                       \
+            ::bsi::set_error(__VA_ARGS__);   \
+            return BSI_ERR_INVALID_ARGUMENT; \
+        }                                    \
+    } while (0)
+
+#define BSI_CUDA_OK(expr)                                                                        \
+    do {                                                                                         \
+        cudaError_t _e = (expr);                                                                 \
+        if (_e != cudaSuccess) {                                                                 \
+            ::bsi::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+            return BSI_ERR_CUDA;                                                                 \
+        }                                                                                        \
+    } while (0)
+
+#define BSI_LAUNCH_OK(name)                                                                \
+    do {                                                                                   \
+        cudaError_t _e = cudaGetLastError();                                               \
+        if (_e != cudaSuccess) {                                                           \
+            ::bsi::set_error("launch of %s failed: %s", name, cudaGetErrorString(_e));     \
+            return BSI_ERR_CUDA;                                                           \
+        }                                                                                  \
+    } while (0)
+
+int sm_count();
+
+// Resolve a bsi_rowref for (sample, step).
+__device__ __forceinline__ float rowref_at(const bsi_rowref& r, int64_t sample, int step) {
+    return r.base[(int64_t)step * r.step_stride + sample * r.sample_stride];
+}
+__device__ __forceinline__ const float* rowref_ptr(const bsi_rowref& r, int64_t sample, int step) {
+    return r.base + (int64_t)step * r.step_stride + sample * r.sample_stride;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+
+// Philox4x32-10 (Salmon et al., SC'11), same constants as Random123.
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+        uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+        uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+        c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+        k.x += 0x9E3779B9u;
+        k.y += 0xBB67AE85u;
+    }
+    return c;
+}
+// Four N(0,1) values for (seed, global sample, draw, element-quad): Box-Muller on (r0,r1) and (r2,r3).
+__device__ __forceinline__ float4 philox_normal4(uint64_t seed, uint64_t sample, uint32_t draw, uint32_t quad) {
+    uint4 r = philox4x32_10(make_uint4(quad, draw, (uint32_t)sample, (uint32_t)(sample >> 32)),
+                            make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+    const float k2m32 = 2.3283064365386963e-10f;  // 2^-32
+    float u0 = ((float)r.x + 0.5f) * k2m32, u1 = ((float)r.y + 0.5f) * k2m32;
+    float u2 = ((float)r.z + 0.5f) * k2m32, u3 = ((float)r.w + 0.5f) * k2m32;
+    // (float)r can round up to 2^32 -> u = 1 -> log = 0: fine (radius 0).  u > 0 always.
+    float rad0 = sqrtf(-2.0f * logf(u0)), rad1 = sqrtf(-2.0f * logf(u2));
+    float s0, c0, s1, c1;
+    sincospif(2.0f * u1, &s0, &c0);
+    sincospif(2.0f * u3, &s1, &c1);
+    return make_float4(rad0 * c0, rad0 * s0, rad1 * c1, rad1 * s1);
+}
+
+}  // namespace bsi

@@ -1,0 +1,294 @@
+// DiT denoiser engine: host-side orchestration of the sm_100a kernels for
+// DenoisingDiT.forward (bsi/models/dit.py:174-181,225-233).  The engine owns no device memory:
+// weights live in a caller-provided arena (bf16 matrices + fp32 vectors, packed from the reference
+// state_dict by key), activations in a caller-provided workspace.  Every call only enqueues
+// kernels on the given stream, so a whole sampler step can be captured in a CUDA graph.
+#include <map>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+
+namespace bsi {
+
+static inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
+
+struct ParamSlot {
+    int64_t offset = 0;  // bytes into the arena
+    int64_t rows = 0, cols = 0, ld = 0;
+    bool bf16 = false;   // matrix packed to bf16 (ld = pitch) or fp32 vector copied verbatim
+    bool set = false;
+};
+
+}  // namespace bsi
+
+struct bsi_dit {
+    bsi_dit_config cfg;
+    int T, gh, gw, cin, P, ldp, nout, nfreq;
+    int64_t param_bytes = 0;
+    uint8_t* arena = nullptr;
+    std::map<std::string, bsi::ParamSlot> slots;
+
+    template <typename Tp>
+    Tp* ptr(const std::string& key) const {
+        return reinterpret_cast<Tp*>(arena + slots.at(key).offset);
+    }
+    std::string blk(int l, const char* s) const { return "dit.blocks." + std::to_string(l) + "." + s; }
+};
+
+namespace bsi {
+
+static void add_slot(bsi_dit* e, const std::string& key, int64_t rows, int64_t cols, bool bf16, int64_t ld = 0) {
+    ParamSlot s;
+    s.rows = rows, s.cols = cols, s.bf16 = bf16, s.ld = bf16 ? (ld ? ld : cols) : cols;
+    s.offset = e->param_bytes;
+    e->param_bytes = align_up(e->param_bytes + rows * s.ld * (bf16 ? 2 : 4), 256);
+    e->slots[key] = s;
+}
+
+struct Workspace {
+    __nv_bfloat16 *a_patch, *xm, *qkv, *att, *h;
+    float* x;
+    int64_t bytes;
+};
+static Workspace carve(const bsi_dit* e, int B, uint8_t* base) {
+    const int64_t M = (int64_t)B * e->T, d = e->cfg.dim;
+    Workspace w;
+    int64_t off = 0;
+    auto take = [&](int64_t bytes) {
+        uint8_t* p = base ? base + off : nullptr;
+        off = align_up(off + bytes, 1024);
+        return p;
+    };
+    w.x = reinterpret_cast<float*>(take(M * d * 4));
+    w.a_patch = reinterpret_cast<__nv_bfloat16*>(take(M * e->ldp * 2));
+    w.xm = reinterpret_cast<__nv_bfloat16*>(take(M * d * 2));
+    w.qkv = reinterpret_cast<__nv_bfloat16*>(take(M * 3 * d * 2));
+    w.att = reinterpret_cast<__nv_bfloat16*>(take(M * d * 2));
+    w.h = reinterpret_cast<__nv_bfloat16*>(take(M * 4 * d * 2));
+    w.bytes = off;
+    return w;
+}
+
+static int gemm(const void* A, int lda, const void* W, int ldw, void* C, int ldc, const float* bias, int M, int N, int K, int epi,
+                cudaStream_t st, const bsi_gemm_args* extra = nullptr) {
+    bsi_gemm_args a = extra ? *extra : bsi_gemm_args{};
+    a.A = A, a.W = W, a.C = C, a.bias = bias, a.M = M, a.N = N, a.K = K, a.lda = lda, a.ldw = ldw, a.ldc = ldc;
+    if (a.batch < 1) a.batch = 1;
+    a.epilogue = epi;
+    return bsi_gemm_bf16(&a, st);
+}
+
+}  // namespace bsi
+
+using namespace bsi;
+
+extern "C" {
+
+int bsi_dit_create(const bsi_dit_config* cfg, bsi_dit** out) {
+    BSI_CHECK_ARG(cfg && out, "bsi_dit_create: null argument");
+    BSI_CHECK_ARG(cfg->channels > 0 && cfg->patch > 0 && cfg->height % cfg->patch == 0 && cfg->width % cfg->patch == 0,
+                  "bsi_dit_create: data shape (%d,%d,%d) not divisible by patch %d", cfg->channels, cfg->height, cfg->width, cfg->patch);
+    BSI_CHECK_ARG(cfg->dim % 128 == 0 && cfg->dim <= 2048, "bsi_dit_create: dim=%d must be a multiple of 128 (<= 2048)", cfg->dim);
+    BSI_CHECK_ARG(cfg->heads > 0 && cfg->dim == cfg->heads * 64, "bsi_dit_create: only head_dim 64 is implemented (dim=%d heads=%d)",
+                  cfg->dim, cfg->heads);
+    BSI_CHECK_ARG(cfg->depth > 0, "bsi_dit_create: depth must be positive");
+    auto* e = new bsi_dit();
+    e->cfg = *cfg;
+    e->gh = cfg->height / cfg->patch, e->gw = cfg->width / cfg->patch, e->T = e->gh * e->gw;
+    e->nfreq = cfg->fourier_n_max >= cfg->fourier_n_min ? cfg->fourier_n_max - cfg->fourier_n_min + 1 : 0;
+    e->cin = cfg->channels * (1 + 2 * e->nfreq);
+    e->P = cfg->patch * cfg->patch * e->cin;
+    e->ldp = (int)align_up(e->P, 8);
+    e->nout = cfg->patch * cfg->patch * cfg->channels;
+    if (e->T % 128 != 0 || e->T > 512 || e->nout % 8 != 0) {
+        set_error("bsi_dit_create: tokens per sample T=%d must be 128/256/384/512 and patch*patch*channels=%d a multiple of 8", e->T, e->nout);
+        delete e;
+        return BSI_ERR_UNSUPPORTED;
+    }
+    const int d = cfg->dim, L = cfg->depth;
+    add_slot(e, "dit.patch_encoder.weight", d, e->P, true, e->ldp);
+    add_slot(e, "dit.patch_encoder.bias", 1, d, false);
+    add_slot(e, "dit.patch_pos_embedding", e->T, d, false);
+    add_slot(e, "dit.t_embedding.scale", 1, d, false);
+    add_slot(e, "dit.t_embedding.bias", 1, d, false);
+    // adaLN first/second Linear of all layers are stored contiguously so that conditioning is two GEMM launches
+    for (int l = 0; l < L; ++l) add_slot(e, e->blk(l, "adaLN_modulation.0.weight"), d, d, true);
+    for (int l = 0; l < L; ++l) add_slot(e, e->blk(l, "adaLN_modulation.0.bias"), 1, d, false);
+    for (int l = 0; l < L; ++l) add_slot(e, e->blk(l, "adaLN_modulation.2.weight"), 6 * d, d, true);
+    for (int l = 0; l < L; ++l) add_slot(e, e->blk(l, "adaLN_modulation.2.bias"), 1, 6 * d, false);
+    for (int l = 0; l < L; ++l) {
+        add_slot(e, e->blk(l, "attn.to_qkv.weight"), 3 * d, d, true);
+        add_slot(e, e->blk(l, "attn.to_qkv.bias"), 1, 3 * d, false);
+        add_slot(e, e->blk(l, "attn.to_out.weight"), d, d, true);
+        add_slot(e, e->blk(l, "attn.to_out.bias"), 1, d, false);
+        add_slot(e, e->blk(l, "mlp.0.weight"), 4 * d, d, true);
+        add_slot(e, e->blk(l, "mlp.0.bias"), 1, 4 * d, false);
+        add_slot(e, e->blk(l, "mlp.2.weight"), d, 4 * d, true);
+        add_slot(e, e->blk(l, "mlp.2.bias"), 1, d, false);
+    }
+    add_slot(e, "dit.patch_decoder.0.weight", 1, d, false);
+    add_slot(e, "dit.patch_decoder.0.bias", 1, d, false);
+    add_slot(e, "dit.patch_decoder.1.weight", e->nout, d, true);
+    add_slot(e, "dit.patch_decoder.1.bias", 1, e->nout, false);
+    *out = e;
+    return BSI_OK;
+}
+
+void bsi_dit_destroy(bsi_dit* e) { delete e; }
+
+int64_t bsi_dit_param_bytes(const bsi_dit* e) { return e ? e->param_bytes : 0; }
+int64_t bsi_dit_workspace_bytes(const bsi_dit* e, int32_t B) { return e && B > 0 ? carve(e, B, nullptr).bytes : 0; }
+int64_t bsi_dit_cond_bytes(const bsi_dit* e, int32_t rows) {
+    return e && rows > 0 ? (int64_t)e->cfg.depth * rows * 6 * e->cfg.dim * 4 : 0;
+}
+int64_t bsi_dit_cond_scratch_bytes(const bsi_dit* e, int32_t rows) {
+    if (!e || rows <= 0) return 0;
+    const int64_t d = e->cfg.dim, L = e->cfg.depth;
+    return align_up(rows * d * 2, 1024) + align_up(rows * L * d * 2, 1024);
+}
+
+int bsi_dit_bind_params(bsi_dit* e, void* arena, int64_t bytes) {
+    BSI_CHECK_ARG(e && arena, "bsi_dit_bind_params: null argument");
+    BSI_CHECK_ARG(bytes >= e->param_bytes, "parameter arena too small: %lld < %lld", (long long)bytes, (long long)e->param_bytes);
+    BSI_CHECK_ARG((reinterpret_cast<uintptr_t>(arena) & 255) == 0, "parameter arena must be 256-byte aligned");
+    e->arena = reinterpret_cast<uint8_t*>(arena);
+    for (auto& kv : e->slots) kv.second.set = false;
+    return BSI_OK;
+}
+
+int bsi_dit_set_param(bsi_dit* e, const char* key, const float* src, int64_t numel, void* stream) {
+    BSI_CHECK_ARG(e && key && src, "bsi_dit_set_param: null argument");
+    BSI_CHECK_ARG(e->arena, "bsi_dit_set_param: bind the parameter arena first");
+    auto it = e->slots.find(key);
+    BSI_CHECK_ARG(it != e->slots.end(), "bsi_dit_set_param: unknown state_dict key '%s'", key);
+    ParamSlot& s = it->second;
+    BSI_CHECK_ARG(numel == s.rows * s.cols, "bsi_dit_set_param: '%s' has %lld elements, expected %lld", key, (long long)numel,
+                  (long long)(s.rows * s.cols));
+    if (s.bf16) {
+        int rc = bsi_cast_bf16(e->arena + s.offset, src, s.rows, s.cols, s.ld, stream);
+        if (rc != BSI_OK) return rc;
+    } else {
+        BSI_CUDA_OK(cudaMemcpyAsync(e->arena + s.offset, src, numel * 4, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    }
+    s.set = true;
+    return BSI_OK;
+}
+
+int bsi_dit_missing_params(const bsi_dit* e) {
+    if (!e) return -1;
+    int n = 0;
+    for (auto& kv : e->slots) n += kv.second.set ? 0 : 1;
+    return n;
+}
+
+int bsi_dit_conditioning(const bsi_dit* e, float* cond, const float* t, int32_t rows, void* scratch, int64_t scratch_bytes,
+                         void* stream) {
+    BSI_CHECK_ARG(e && cond && t && scratch && rows > 0, "bsi_dit_conditioning: bad arguments");
+    if (bsi_dit_missing_params(e) != 0) {
+        set_error("bsi_dit_conditioning: %d parameters not set", bsi_dit_missing_params(e));
+        return BSI_ERR_NOT_READY;
+    }
+    if (scratch_bytes < bsi_dit_cond_scratch_bytes(e, rows)) {
+        set_error("conditioning scratch too small");
+        return BSI_ERR_WORKSPACE;
+    }
+    const int d = e->cfg.dim, L = e->cfg.depth;
+    cudaStream_t st = (cudaStream_t)stream;
+    auto* c16 = reinterpret_cast<__nv_bfloat16*>(scratch);
+    auto* h16 = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<uint8_t*>(scratch) + align_up((int64_t)rows * d * 2, 1024));
+    // c = t_embedding(t)                                                   (dit.py:177)
+    int rc = bsi_time_embed(c16, nullptr, t, e->ptr<float>("dit.t_embedding.scale"), e->ptr<float>("dit.t_embedding.bias"), rows, d, st);
+    if (rc != BSI_OK) return rc;
+    // h[:, l*d:(l+1)*d] = SiLU(c W0_l^T + b0_l) for all layers in one GEMM   (dit.py:79-80)
+    rc = gemm(c16, d, e->ptr<void>(e->blk(0, "adaLN_modulation.0.weight")), d, h16, L * d, e->ptr<float>(e->blk(0, "adaLN_modulation.0.bias")),
+              rows, L * d, d, BSI_EPI_BIAS_SILU_BF16, st);
+    if (rc != BSI_OK) return rc;
+    // cond[l] = h_l W2_l^T + b2_l, batched over layers                        (dit.py:81)
+    bsi_gemm_args x{};
+    x.batch = L;
+    x.stride_a = d, x.stride_w = (int64_t)6 * d * d, x.stride_c = (int64_t)rows * 6 * d, x.stride_bias = 6 * d;
+    return gemm(h16, L * d, e->ptr<void>(e->blk(0, "adaLN_modulation.2.weight")), d, cond, 6 * d,
+                e->ptr<float>(e->blk(0, "adaLN_modulation.2.bias")), rows, 6 * d, d, BSI_EPI_BIAS_F32, st, &x);
+}
+
+int bsi_dit_forward(const bsi_dit* e, float* out, const float* mu, bsi_rowref in_scale, const float* cond, int32_t cond_rows,
+                    int32_t cond_row0, int32_t cond_sample_rows, int32_t cond_step_rows, const int32_t* step_ptr, int32_t B,
+                    void* workspace, int64_t workspace_bytes, void* stream) {
+    BSI_CHECK_ARG(e && out && mu && in_scale.base && cond && workspace && B > 0 && cond_rows > 0, "bsi_dit_forward: bad arguments");
+    if (bsi_dit_missing_params(e) != 0) {
+        set_error("bsi_dit_forward: %d parameters not set", bsi_dit_missing_params(e));
+        return BSI_ERR_NOT_READY;
+    }
+    Workspace w = carve(e, B, reinterpret_cast<uint8_t*>(workspace));
+    if (workspace_bytes < w.bytes) {
+        set_error("workspace too small: %lld < %lld", (long long)workspace_bytes, (long long)w.bytes);
+        return BSI_ERR_WORKSPACE;
+    }
+    const bsi_dit_config& c = e->cfg;
+    const int d = c.dim, T = e->T, M = B * T;
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc;
+#define BSI_TRY(call) \
+    if ((rc = (call)) != BSI_OK) return rc
+
+    // patchify + Fourier features + c_in scaling -> bf16 operand; then patch_encoder + positional table
+    BSI_TRY(bsi_dit_patch_operand(w.a_patch, mu, in_scale, step_ptr, B, c.channels, c.height, c.width, c.patch, c.fourier_n_min,
+                                  c.fourier_n_max, e->ldp, st));
+    {
+        bsi_gemm_args x{};
+        x.rows_per_sample = T, x.pos = e->ptr<float>("dit.patch_pos_embedding");
+        BSI_TRY(gemm(w.a_patch, e->ldp, e->ptr<void>("dit.patch_encoder.weight"), e->ldp, w.x, d, e->ptr<float>("dit.patch_encoder.bias"),
+                     M, d, e->P, BSI_EPI_POS_F32, st, &x));
+    }
+    for (int l = 0; l < c.depth; ++l) {
+        const float* cl = cond + ((int64_t)l * cond_rows + cond_row0) * 6 * d;
+        auto part = [&](int p) {
+            bsi_rowref r;
+            r.base = cl + (int64_t)p * d, r.sample_stride = cond_sample_rows * 6 * d, r.step_stride = cond_step_rows * 6 * d;
+            return r;
+        };
+        bsi_gemm_args g{};
+        g.rows_per_sample = T, g.step_ptr = step_ptr;
+        // attention branch: x += gate_msa * to_out(attn(to_qkv(modulate(norm(x), shift_msa, scale_msa))))   (dit.py:93-97)
+        BSI_TRY(bsi_layernorm_mod_bf16(w.xm, w.x, part(0), part(1), step_ptr, nullptr, nullptr, T, M, d, 1e-5f, st));
+        BSI_TRY(gemm(w.xm, d, e->ptr<void>(e->blk(l, "attn.to_qkv.weight")), d, w.qkv, 3 * d, e->ptr<float>(e->blk(l, "attn.to_qkv.bias")), M,
+                     3 * d, d, BSI_EPI_BIAS_BF16, st));
+        BSI_TRY(bsi_attention_bf16(w.att, w.qkv, B, T, c.heads, d / c.heads, st));
+        g.gate = part(2);
+        BSI_TRY(gemm(w.att, d, e->ptr<void>(e->blk(l, "attn.to_out.weight")), d, w.x, d, e->ptr<float>(e->blk(l, "attn.to_out.bias")), M, d, d,
+                     BSI_EPI_GATE_RESID_F32, st, &g));
+        // MLP branch: x += gate_mlp * mlp(modulate(norm(x), shift_mlp, scale_mlp))                          (dit.py:98-102)
+        BSI_TRY(bsi_layernorm_mod_bf16(w.xm, w.x, part(3), part(4), step_ptr, nullptr, nullptr, T, M, d, 1e-5f, st));
+        BSI_TRY(gemm(w.xm, d, e->ptr<void>(e->blk(l, "mlp.0.weight")), d, w.h, 4 * d, e->ptr<float>(e->blk(l, "mlp.0.bias")), M, 4 * d, d,
+                     BSI_EPI_BIAS_GELU_BF16, st));
+        g.gate = part(5);
+        BSI_TRY(gemm(w.h, 4 * d, e->ptr<void>(e->blk(l, "mlp.2.weight")), 4 * d, w.x, d, e->ptr<float>(e->blk(l, "mlp.2.bias")), M, d, 4 * d,
+                     BSI_EPI_GATE_RESID_F32, st, &g));
+    }
+    // patch_decoder: affine LayerNorm -> Linear -> unpatchify                                               (dit.py:163-172,181)
+    bsi_rowref none{};
+    BSI_TRY(bsi_layernorm_mod_bf16(w.xm, w.x, none, none, nullptr, e->ptr<float>("dit.patch_decoder.0.weight"),
+                                   e->ptr<float>("dit.patch_decoder.0.bias"), T, M, d, 1e-5f, st));
+    {
+        bsi_gemm_args x{};
+        x.rows_per_sample = T, x.patch = c.patch, x.grid_w = e->gw, x.channels = c.channels;
+        BSI_TRY(gemm(w.xm, d, e->ptr<void>("dit.patch_decoder.1.weight"), d, out, e->nout, e->ptr<float>("dit.patch_decoder.1.bias"), M,
+                     e->nout, d, BSI_EPI_UNPATCH_F32, st, &x));
+    }
+#undef BSI_TRY
+    return BSI_OK;
+}
+
+int bsi_dit_peek(const bsi_dit* e, int32_t what, float* out, int32_t B, const void* workspace, void* stream) {
+    BSI_CHECK_ARG(e && out && workspace && B > 0, "bsi_dit_peek: bad arguments");
+    Workspace w = carve(e, B, const_cast<uint8_t*>(reinterpret_cast<const uint8_t*>(workspace)));
+    if (what == 0) {
+        BSI_CUDA_OK(cudaMemcpyAsync(out, w.x, (int64_t)B * e->T * e->cfg.dim * 4, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+        return BSI_OK;
+    }
+    set_error("bsi_dit_peek: unknown selector %d", what);
+    return BSI_ERR_INVALID_ARGUMENT;
+}
+
+}  // extern "C"

@@ -1,0 +1,352 @@
+// HBM-bound elementwise kernels of the BSI hot path: sampler init/step, q-sample, EDM combine,
+// bucketize, casts, time embedding and the patch-embed operand builder.
+// Each kernel states its algorithmic bytes per element; all use 128-bit accesses on the
+// contiguous axis and a grid of (SM count x resident CTAs) with a grid-stride loop.
+#include "common.cuh"
+
+namespace bsi {
+
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+int sm_count() {
+    static int cached[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    if (cached[dev] == 0) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        cached[dev] = n;
+    }
+    return cached[dev];
+}
+
+constexpr int kThreads = 256;
+static inline int grid_for(int64_t work_items, int ctas_per_sm = 8) {
+    int64_t need = (work_items + kThreads - 1) / kThreads;
+    int64_t cap = (int64_t)sm_count() * ctas_per_sm;
+    return (int)(need < 1 ? 1 : (need < cap ? need : cap));
+}
+
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ float4 ld4_stream(const float* p) { return __ldcs(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+
+// torch.addcmul(a, b, c) with value=1 rounds the product before the add (no FMA contraction), and the
+// reference's eager op chains round after every op; the explicit _rn intrinsics keep nvcc from fusing.
+__device__ __forceinline__ float mul_rn(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float addcmul_rn(float a, float b, float c) { return __fadd_rn(a, __fmul_rn(b, c)); }
+
+__device__ __forceinline__ float4 noise4(const bsi_noise& nz, int step, int64_t sample, int64_t quad, int64_t D) {
+    if (nz.eps) return ld4_stream(nz.eps + sample * D + quad * 4);
+    return philox_normal4(nz.seed, nz.sample_base + (uint64_t)sample, (uint32_t)(nz.draw + step), (uint32_t)quad);
+}
+
+// ------------------------------------------------------------------ sampler init (bsi/bsi.py:325-327)
+// bytes/elem: 4 written (+4 read when noise is injected)
+__global__ void __launch_bounds__(kThreads) k_sample_init(float* __restrict__ mu, const float* __restrict__ sigma0_ptr,
+                                                          bsi_noise nz, int64_t n, int64_t D) {
+    const float s0 = sigma0_ptr[0];
+    const int64_t qpr = D >> 2, total = n * qpr;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int64_t s = i / qpr, q = i - s * qpr;
+        float4 e = noise4(nz, 0, s, q, D);
+        st4(mu + s * D + q * 4, make_float4(s0 * e.x, s0 * e.y, s0 * e.z, s0 * e.w));
+    }
+}
+
+// ------------------------------------------------------------------ fused sampler step (bsi/bsi.py:331-335, 381-386)
+// bytes/elem: read mu 4 + read f 4 + write mu' 4 = 12 (+4 injected eps, +8 when history outputs are requested)
+template <bool kPrecond>
+__global__ void __launch_bounds__(kThreads)
+    k_step_fused(float* __restrict__ mu, const float* __restrict__ f, const float* __restrict__ coef,
+                 const int32_t* __restrict__ step_ptr, int32_t step_arg, bsi_noise nz, float* __restrict__ x_hat_out,
+                 float* __restrict__ y_out, int64_t n, int64_t D) {
+    const int step = step_ptr ? *step_ptr : step_arg;
+    const float* c = coef + (int64_t)step * 8;
+    const float c_skip = c[0], c_out = c[1], sigma = c[2], alpha = c[3], lam = c[4], lam_next = c[5];
+    const int64_t qpr = D >> 2, total = n * qpr;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int64_t s = i / qpr, q = i - s * qpr;
+        int64_t off = s * D + q * 4;
+        float4 m = ld4(mu + off);
+        float4 fo = ld4_stream(f + off);
+        float4 e = noise4(nz, step, s, q, D);
+        float mv[4] = {m.x, m.y, m.z, m.w}, fv[4] = {fo.x, fo.y, fo.z, fo.w}, ev[4] = {e.x, e.y, e.z, e.w};
+        float xh[4], yv[4], out[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            // x_hat = addcmul(c_skip*mu, c_out, f); y = x_hat + rsqrt(alpha)*eps; mu' = (alpha*y + lam*mu)/lam_next
+            xh[j] = kPrecond ? addcmul_rn(mul_rn(c_skip, mv[j]), c_out, fv[j]) : fv[j];
+            yv[j] = addcmul_rn(xh[j], sigma, ev[j]);
+            out[j] = __fdiv_rn(__fadd_rn(mul_rn(alpha, yv[j]), mul_rn(lam, mv[j])), lam_next);
+        }
+        st4(mu + off, make_float4(out[0], out[1], out[2], out[3]));
+        if (x_hat_out) st4(x_hat_out + off, make_float4(xh[0], xh[1], xh[2], xh[3]));
+        if (y_out) st4(y_out + off, make_float4(yv[0], yv[1], yv[2], yv[3]));
+    }
+}
+
+__global__ void k_step_advance(int32_t* step_ptr) { *step_ptr += 1; }
+
+// ------------------------------------------------------------------ EDM combine / row scaling (bsi/bsi.py:381-386)
+// combine: 12 B/elem; scale: 8 B/elem
+__global__ void __launch_bounds__(kThreads)
+    k_edm_combine(float* __restrict__ x_hat, const float* __restrict__ mu, const float* __restrict__ f, bsi_rowref c_skip,
+                  bsi_rowref c_out, const int32_t* __restrict__ step_ptr, int64_t n, int64_t D) {
+    const int step = step_ptr ? *step_ptr : 0;
+    const int64_t qpr = D >> 2, total = n * qpr;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int64_t s = i / qpr, q = i - s * qpr, off = s * D + q * 4;
+        float cs = rowref_at(c_skip, s, step), co = rowref_at(c_out, s, step);
+        float4 m = ld4_stream(mu + off), fo = ld4_stream(f + off);
+        st4(x_hat + off, make_float4(addcmul_rn(mul_rn(cs, m.x), co, fo.x), addcmul_rn(mul_rn(cs, m.y), co, fo.y),
+                                     addcmul_rn(mul_rn(cs, m.z), co, fo.z), addcmul_rn(mul_rn(cs, m.w), co, fo.w)));
+    }
+}
+__global__ void __launch_bounds__(kThreads) k_scale_rows(float* __restrict__ out, const float* __restrict__ in, bsi_rowref sc,
+                                                         const int32_t* __restrict__ step_ptr, int64_t n, int64_t D) {
+    const int step = step_ptr ? *step_ptr : 0;
+    const int64_t qpr = D >> 2, total = n * qpr;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int64_t s = i / qpr, q = i - s * qpr, off = s * D + q * 4;
+        float c = rowref_at(sc, s, step);
+        float4 m = ld4_stream(in + off);
+        st4(out + off, make_float4(c * m.x, c * m.y, c * m.z, c * m.w));
+    }
+}
+
+// ------------------------------------------------------------------ q(mu|x,lambda) (bsi/bsi.py:405-420)
+// bytes/elem: read x 4 (L2-resident across the n replicas) + write mu 4 (+4 model_in, +4 injected eps)
+__global__ void __launch_bounds__(kThreads)
+    k_q_sample(float* __restrict__ mu, float* __restrict__ model_in, const float* __restrict__ x, const float* __restrict__ gamma,
+               const float* __restrict__ sigma, const float* __restrict__ c_in, bsi_noise nz, int64_t R, int64_t B, int64_t D) {
+    const int64_t qpr = D >> 2, total = R * qpr;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int64_t r = i / qpr, q = i - r * qpr, off = r * D + q * 4;
+        int64_t b = r % B;
+        float g = gamma[r], sg = sigma[r];
+        float4 xv = ld4(x + b * D + q * 4);
+        float4 e = noise4(nz, 0, r, q, D);
+        // addcmul(gamma*x, sigma, eps)
+        float4 m = make_float4(addcmul_rn(mul_rn(g, xv.x), sg, e.x), addcmul_rn(mul_rn(g, xv.y), sg, e.y),
+                               addcmul_rn(mul_rn(g, xv.z), sg, e.z), addcmul_rn(mul_rn(g, xv.w), sg, e.w));
+        st4(mu + off, m);
+        if (model_in) {
+            float ci = c_in[r];
+            st4(model_in + off, make_float4(ci * m.x, ci * m.y, ci * m.z, ci * m.w));
+        }
+    }
+}
+
+// ------------------------------------------------------------------ bucketize (bsi/bsi.py:32-35)
+__device__ __forceinline__ int bucket_of(float x, float lo_edge, float dx, int k) {
+    // fp32 subtract, true division, truncation toward zero, clamp — same op order as the reference.
+    float q = __fdiv_rn(__fsub_rn(x, lo_edge), dx);
+    // float->int64 conversion of the reference saturates far out of range; clamp first to stay defined.
+    q = fminf(fmaxf(q, -1.0f), (float)k);
+    int i = (int)q;  // trunc toward zero
+    return min(max(i, 0), k - 1);
+}
+__global__ void __launch_bounds__(kThreads) k_bucketize(const float* __restrict__ x, int64_t* __restrict__ o64,
+                                                        uint8_t* __restrict__ o8, float lo_edge, float dx, int k, int64_t numel) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < numel; i += (int64_t)gridDim.x * blockDim.x) {
+        int b = bucket_of(x[i], lo_edge, dx, k);
+        if (o64) o64[i] = b;
+        if (o8) o8[i] = (uint8_t)b;
+    }
+}
+
+// ------------------------------------------------------------------ fp32 -> bf16 cast with pitch
+__global__ void __launch_bounds__(kThreads) k_cast_bf16(__nv_bfloat16* __restrict__ out, const float* __restrict__ in,
+                                                        int64_t rows, int64_t cols, int64_t ld) {
+    const int64_t total = rows * ld;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int64_t r = i / ld, c = i - r * ld;
+        out[i] = __float2bfloat16(c < cols ? in[r * cols + c] : 0.0f);
+    }
+}
+
+// ------------------------------------------------------------------ time embedding (bsi/models/pos_emb.py:77-84)
+__global__ void __launch_bounds__(kThreads)
+    k_time_embed(__nv_bfloat16* __restrict__ o16, float* __restrict__ o32, const float* __restrict__ t,
+                 const float* __restrict__ scale, const float* __restrict__ bias, int64_t rows, int size) {
+    const int64_t total = rows * size;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int64_t r = i / size;
+        int j = (int)(i - r * size);
+        float v = sinf(addcmul_rn(bias[j], scale[j], t[r]));  // addcmul(bias, scale, t).sin()
+        if (o16) o16[i] = __float2bfloat16(v);
+        if (o32) o32[i] = v;
+    }
+}
+
+// ------------------------------------------------------------------ patch-embed operand
+// (bsi/models/dit.py:149-153,228-231 + bsi/nn/fourier_features.py:24-36), fused with the c_in scaling.
+// One thread per (sample, pixel): reads C floats, writes Cin bf16 (contiguous in the operand row).
+// bytes/pixel: 4*C read + 2*Cin written.
+__global__ void __launch_bounds__(kThreads)
+    k_patch_operand(__nv_bfloat16* __restrict__ A, const float* __restrict__ mu, bsi_rowref scale,
+                    const int32_t* __restrict__ step_ptr, int B, int C, int H, int W, int p, int n_min, int n_max, int lda) {
+    const int step = step_ptr ? *step_ptr : 0;
+    const int nfreq = n_max >= n_min ? n_max - n_min + 1 : 0;
+    const int cin = C * (1 + 2 * nfreq);
+    const int gw = W / p;
+    const int64_t HW = (int64_t)H * W, total = (int64_t)B * HW;
+    const int T = (H / p) * gw;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int64_t b = i / HW;
+        int pix = (int)(i - b * HW);
+        int y = pix / W, x = pix - y * W;
+        int tok = (y / p) * gw + (x / p);
+        int within = (y % p) * p + (x % p);
+        __nv_bfloat16* dst = A + ((int64_t)b * T + tok) * lda + (int64_t)within * cin;
+        const float sc = rowref_at(scale, b, step);
+        for (int c = 0; c < C; ++c) {
+            float v = sc * mu[(b * C + c) * HW + pix];
+            dst[c] = __float2bfloat16(v);
+            for (int f = 0; f < nfreq; ++f) {
+                // coefs = 2*pi*2^n as an fp32 buffer; args = addcmul(offset, coef, x); sin
+                float coef = 6.283185307179586f * (float)(1 << (n_min + f));
+                float a0 = mul_rn(coef, v);                             // offset 0
+                float a1 = addcmul_rn(1.5707963267948966f, coef, v);    // offset fp32(pi/2)
+                dst[C + c * 2 * nfreq + 2 * f] = __float2bfloat16(sinf(a0));
+                dst[C + c * 2 * nfreq + 2 * f + 1] = __float2bfloat16(sinf(a1));
+            }
+        }
+    }
+}
+// zero the pitch padding of the operand (columns [cols, lda)) once per allocation
+__global__ void __launch_bounds__(kThreads) k_zero_pad(__nv_bfloat16* __restrict__ A, int64_t rows, int cols, int lda) {
+    const int pad = lda - cols;
+    const int64_t total = rows * pad;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int64_t r = i / pad;
+        A[r * lda + cols + (i - r * pad)] = __float2bfloat16(0.0f);
+    }
+}
+
+}  // namespace bsi
+
+using namespace bsi;
+
+extern "C" {
+
+int bsi_abi_version(void) { return 1; }
+const char* bsi_last_error(void) { return g_err; }
+int bsi_device_arch(void) {
+    int dev = 0, major = 0, minor = 0;
+    BSI_CUDA_OK(cudaGetDevice(&dev));
+    BSI_CUDA_OK(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+    BSI_CUDA_OK(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev));
+    return major * 10 + minor;
+}
+
+#define BSI_REQUIRE_VEC4(D) BSI_CHECK_ARG((D) > 0 && ((D) % 4) == 0, "data numel per sample (%lld) must be a positive multiple of 4", (long long)(D))
+
+int bsi_sample_init(float* mu, const float* sigma0_ptr, bsi_noise noise, int64_t n, int64_t D, void* stream) {
+    BSI_CHECK_ARG(mu && sigma0_ptr && n > 0, "bsi_sample_init: null pointer or empty batch");
+    BSI_REQUIRE_VEC4(D);
+    k_sample_init<<<grid_for(n * D / 4), kThreads, 0, (cudaStream_t)stream>>>(mu, sigma0_ptr, noise, n, D);
+    BSI_LAUNCH_OK("k_sample_init");
+    return BSI_OK;
+}
+
+int bsi_step_fused(float* mu, const float* f, const float* coef, const int32_t* step_ptr, int32_t step, int32_t precond,
+                   bsi_noise noise, float* x_hat_out, float* y_out, int64_t n, int64_t D, void* stream) {
+    BSI_CHECK_ARG(mu && f && coef && n > 0, "bsi_step_fused: null pointer or empty batch");
+    BSI_REQUIRE_VEC4(D);
+    int grid = grid_for(n * D / 4);
+    if (precond)
+        k_step_fused<true><<<grid, kThreads, 0, (cudaStream_t)stream>>>(mu, f, coef, step_ptr, step, noise, x_hat_out, y_out, n, D);
+    else
+        k_step_fused<false><<<grid, kThreads, 0, (cudaStream_t)stream>>>(mu, f, coef, step_ptr, step, noise, x_hat_out, y_out, n, D);
+    BSI_LAUNCH_OK("k_step_fused");
+    return BSI_OK;
+}
+
+int bsi_step_advance(int32_t* step_ptr, void* stream) {
+    BSI_CHECK_ARG(step_ptr, "bsi_step_advance: null step pointer");
+    k_step_advance<<<1, 1, 0, (cudaStream_t)stream>>>(step_ptr);
+    BSI_LAUNCH_OK("k_step_advance");
+    return BSI_OK;
+}
+
+int bsi_edm_combine(float* x_hat, const float* mu, const float* f, bsi_rowref c_skip, bsi_rowref c_out, const int32_t* step_ptr,
+                    int64_t n, int64_t D, void* stream) {
+    BSI_CHECK_ARG(x_hat && mu && f && c_skip.base && c_out.base && n > 0, "bsi_edm_combine: null pointer or empty batch");
+    BSI_REQUIRE_VEC4(D);
+    k_edm_combine<<<grid_for(n * D / 4), kThreads, 0, (cudaStream_t)stream>>>(x_hat, mu, f, c_skip, c_out, step_ptr, n, D);
+    BSI_LAUNCH_OK("k_edm_combine");
+    return BSI_OK;
+}
+
+int bsi_scale_rows(float* out, const float* in, bsi_rowref scale, const int32_t* step_ptr, int64_t n, int64_t D, void* stream) {
+    BSI_CHECK_ARG(out && in && scale.base && n > 0, "bsi_scale_rows: null pointer or empty batch");
+    BSI_REQUIRE_VEC4(D);
+    k_scale_rows<<<grid_for(n * D / 4), kThreads, 0, (cudaStream_t)stream>>>(out, in, scale, step_ptr, n, D);
+    BSI_LAUNCH_OK("k_scale_rows");
+    return BSI_OK;
+}
+
+int bsi_q_sample(float* mu, float* model_in, const float* x, const float* gamma, const float* sigma, const float* c_in,
+                 bsi_noise noise, int64_t R, int64_t B, int64_t D, void* stream) {
+    BSI_CHECK_ARG(mu && x && gamma && sigma && R > 0 && B > 0, "bsi_q_sample: null pointer or empty batch");
+    BSI_CHECK_ARG(!model_in || c_in, "bsi_q_sample: model_in requested without c_in");
+    BSI_REQUIRE_VEC4(D);
+    k_q_sample<<<grid_for(R * D / 4), kThreads, 0, (cudaStream_t)stream>>>(mu, model_in, x, gamma, sigma, c_in, noise, R, B, D);
+    BSI_LAUNCH_OK("k_q_sample");
+    return BSI_OK;
+}
+
+int bsi_bucketize(const float* x, int64_t* out_i64, uint8_t* out_u8, float lo_edge, float dx, int32_t k, int64_t numel,
+                  void* stream) {
+    BSI_CHECK_ARG(x && (out_i64 || out_u8) && numel >= 0 && k > 0, "bsi_bucketize: bad arguments");
+    BSI_CHECK_ARG(!out_u8 || k <= 256, "bsi_bucketize: uint8 output needs k <= 256");
+    if (numel == 0) return BSI_OK;
+    k_bucketize<<<grid_for(numel), kThreads, 0, (cudaStream_t)stream>>>(x, out_i64, out_u8, lo_edge, dx, k, numel);
+    BSI_LAUNCH_OK("k_bucketize");
+    return BSI_OK;
+}
+
+int bsi_cast_bf16(void* out_bf16, const float* in, int64_t rows, int64_t cols, int64_t ld_out, void* stream) {
+    BSI_CHECK_ARG(out_bf16 && in && rows > 0 && cols > 0 && ld_out >= cols, "bsi_cast_bf16: bad arguments");
+    k_cast_bf16<<<grid_for(rows * ld_out), kThreads, 0, (cudaStream_t)stream>>>((__nv_bfloat16*)out_bf16, in, rows, cols, ld_out);
+    BSI_LAUNCH_OK("k_cast_bf16");
+    return BSI_OK;
+}
+
+int bsi_time_embed(void* out_bf16, float* out_f32, const float* t, const float* scale, const float* bias, int64_t rows,
+                   int32_t size, void* stream) {
+    BSI_CHECK_ARG((out_bf16 || out_f32) && t && scale && bias && rows > 0 && size > 0, "bsi_time_embed: bad arguments");
+    k_time_embed<<<grid_for(rows * size), kThreads, 0, (cudaStream_t)stream>>>((__nv_bfloat16*)out_bf16, out_f32, t, scale, bias,
+                                                                               rows, size);
+    BSI_LAUNCH_OK("k_time_embed");
+    return BSI_OK;
+}
+
+int bsi_dit_patch_operand(void* A_bf16, const float* mu, bsi_rowref scale, const int32_t* step_ptr, int32_t B, int32_t C,
+                          int32_t H, int32_t Wd, int32_t patch, int32_t n_min, int32_t n_max, int32_t lda, void* stream) {
+    BSI_CHECK_ARG(A_bf16 && mu && scale.base && B > 0 && C > 0 && patch > 0, "bsi_dit_patch_operand: bad arguments");
+    BSI_CHECK_ARG(H % patch == 0 && Wd % patch == 0, "image %dx%d not divisible by patch %d", H, Wd, patch);
+    BSI_CHECK_ARG(n_max < n_min || (n_min >= 0 && n_max < 24), "Fourier exponents out of range");
+    int nfreq = n_max >= n_min ? n_max - n_min + 1 : 0;
+    int cols = patch * patch * C * (1 + 2 * nfreq);
+    BSI_CHECK_ARG(lda >= cols, "operand pitch %d < %d", lda, cols);
+    if (lda > cols) {
+        int64_t rows = (int64_t)B * (H / patch) * (Wd / patch);
+        k_zero_pad<<<grid_for(rows * (lda - cols)), kThreads, 0, (cudaStream_t)stream>>>((__nv_bfloat16*)A_bf16, rows, cols, lda);
+        BSI_LAUNCH_OK("k_zero_pad");
+    }
+    k_patch_operand<<<grid_for((int64_t)B * H * Wd), kThreads, 0, (cudaStream_t)stream>>>((__nv_bfloat16*)A_bf16, mu, scale,
+                                                                                           step_ptr, B, C, H, Wd, patch, n_min,
+                                                                                           n_max, lda);
+    BSI_LAUNCH_OK("k_patch_operand");
+    return BSI_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,88 @@
+// LayerNorm (no affine) fused with the adaLN modulation, emitting the bf16 A-operand of the next
+// GEMM (bsi/models/dit.py:55,66,96,101), plus the affine LayerNorm of the patch decoder
+// (bsi/models/dit.py:164).  HBM-bound: reads 4 B/elem (fp32 residual stream), writes 2 B/elem.
+// One warp per token row; the row lives in registers (two-pass mean / variance).
+#include "common.cuh"
+
+namespace bsi {
+
+constexpr int kLnThreads = 256;
+
+template <int NV>  // NV float4 per lane: dim = 128 * NV
+__global__ void __launch_bounds__(kLnThreads)
+    k_layernorm_mod(__nv_bfloat16* __restrict__ out, const float* __restrict__ x, bsi_rowref shift, bsi_rowref scale,
+                    const int32_t* __restrict__ step_ptr, const float* __restrict__ gamma, const float* __restrict__ beta,
+                    int rows_per_sample, int64_t M, float eps) {
+    constexpr int dim = 128 * NV;
+    const int lane = threadIdx.x & 31;
+    const int64_t warps_total = (int64_t)gridDim.x * (kLnThreads / 32);
+    const int step = step_ptr ? *step_ptr : 0;
+    for (int64_t row = (int64_t)blockIdx.x * (kLnThreads / 32) + (threadIdx.x >> 5); row < M; row += warps_total) {
+        const float4* xr = reinterpret_cast<const float4*>(x + row * dim);
+        float4 v[NV];
+        float s = 0.0f;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            v[i] = xr[lane + 32 * i];
+            s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+        }
+        const float mean = warp_sum(s) * (1.0f / dim);
+        float ss = 0.0f;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+            ss += (a * a + b * b) + (c * c + d * d);
+        }
+        const float rstd = rsqrtf(warp_sum(ss) * (1.0f / dim) + eps);
+        const float4 *p_mul, *p_add;
+        if (gamma) {
+            p_mul = reinterpret_cast<const float4*>(gamma);
+            p_add = reinterpret_cast<const float4*>(beta);
+        } else {
+            const int64_t sample = row / rows_per_sample;
+            p_mul = reinterpret_cast<const float4*>(rowref_ptr(scale, sample, step));
+            p_add = reinterpret_cast<const float4*>(rowref_ptr(shift, sample, step));
+        }
+        const float one = gamma ? 0.0f : 1.0f;  // modulate uses (1 + scale)
+        uint2* o = reinterpret_cast<uint2*>(out + row * dim);
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            float4 m = p_mul[lane + 32 * i], a = p_add[lane + 32 * i];
+            float y0 = fmaf((v[i].x - mean) * rstd, m.x + one, a.x);
+            float y1 = fmaf((v[i].y - mean) * rstd, m.y + one, a.y);
+            float y2 = fmaf((v[i].z - mean) * rstd, m.z + one, a.z);
+            float y3 = fmaf((v[i].w - mean) * rstd, m.w + one, a.w);
+            o[lane + 32 * i] = make_uint2(pack_bf16(y0, y1), pack_bf16(y2, y3));
+        }
+    }
+}
+
+}  // namespace bsi
+
+using namespace bsi;
+
+extern "C" int bsi_layernorm_mod_bf16(void* out_bf16, const float* x, bsi_rowref shift, bsi_rowref scale, const int32_t* step_ptr,
+                                      const float* gamma, const float* beta, int32_t rows_per_sample, int64_t M, int32_t dim,
+                                      float eps, void* stream) {
+    BSI_CHECK_ARG(out_bf16 && x && M > 0, "bsi_layernorm_mod_bf16: null pointer or empty input");
+    BSI_CHECK_ARG((gamma && beta) || (shift.base && scale.base && rows_per_sample > 0),
+                  "bsi_layernorm_mod_bf16: need either gamma/beta or shift/scale");
+    BSI_CHECK_ARG(dim % 128 == 0 && dim >= 128 && dim <= 2048, "bsi_layernorm_mod_bf16: dim=%d must be a multiple of 128 in [128,2048]", dim);
+    int64_t blocks = (M + (kLnThreads / 32) - 1) / (kLnThreads / 32);
+    int64_t cap = (int64_t)sm_count() * 8;
+    int grid = (int)(blocks < cap ? blocks : cap);
+    auto* o = reinterpret_cast<__nv_bfloat16*>(out_bf16);
+    cudaStream_t st = (cudaStream_t)stream;
+#define BSI_LN_CASE(NV)                                                                                                         \
+    case NV:                                                                                                                    \
+        k_layernorm_mod<NV><<<grid, kLnThreads, 0, st>>>(o, x, shift, scale, step_ptr, gamma, beta, rows_per_sample, M, eps); \
+        break;
+    switch (dim / 128) {
+        BSI_LN_CASE(1) BSI_LN_CASE(2) BSI_LN_CASE(3) BSI_LN_CASE(4) BSI_LN_CASE(5) BSI_LN_CASE(6) BSI_LN_CASE(7) BSI_LN_CASE(8)
+        BSI_LN_CASE(9) BSI_LN_CASE(10) BSI_LN_CASE(11) BSI_LN_CASE(12) BSI_LN_CASE(13) BSI_LN_CASE(14) BSI_LN_CASE(15) BSI_LN_CASE(16)
+        default: set_error("unsupported dim %d", dim); return BSI_ERR_UNSUPPORTED;
+    }
+#undef BSI_LN_CASE
+    BSI_LAUNCH_OK("k_layernorm_mod");
+    return BSI_OK;
+}

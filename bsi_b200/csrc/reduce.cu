@@ -1,0 +1,172 @@
+// Warp-shuffle reductions for the ELBO / loss terms (HBM-bound).
+//   recon:  out[r] = -sum_d log clamp(cdf(edge[idx+1]) - cdf(edge[idx]), 1e-20)   (bsi/bsi.py:230-247)
+//   sqerr:  out[r] =  sum_d (x - x_hat)^2                                          (bsi/bsi.py:273,288,309)
+// x_hat = c_skip[r]*mu + c_out[r]*f is formed in registers and never written to HBM
+// (bsi/bsi.py:381-386).  Algorithmic bytes per element: mu 4 + f 4 (+ x 4, which stays in L2
+// across the n Monte-Carlo replicas of the same batch row) -> one float per row out.
+// One CTA per row r keeps the summation order fixed (deterministic results).
+#include "common.cuh"
+
+namespace bsi {
+
+constexpr int kRThreads = 256;
+
+__device__ __forceinline__ float block_sum(float v, float* red) {
+    v = warp_sum(v);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    if (warp == 0) {
+        float t = lane < (kRThreads / 32) ? red[lane] : 0.0f;
+        t = warp_sum(t);
+        if (lane == 0) red[0] = t;
+    }
+    __syncthreads();
+    return red[0];
+}
+
+__device__ __forceinline__ float combine(bool has_mu, float cs, float co, float m, float f) {
+    // addcmul(c_skip*mu, c_out, f): product rounded, then added (no FMA)
+    return has_mu ? __fadd_rn(__fmul_rn(cs, m), __fmul_rn(co, f)) : f;
+}
+
+__device__ __forceinline__ int bucket_of_r(float x, float lo_edge, float dx, int k) {
+    float q = __fdiv_rn(__fsub_rn(x, lo_edge), dx);
+    q = fminf(fmaxf(q, -1.0f), (float)k);
+    int i = (int)q;
+    return min(max(i, 0), k - 1);
+}
+
+__device__ __forceinline__ float normal_cdf(float v, float loc, float inv_scale) {
+    // torch.distributions.Normal.cdf: 0.5 * (1 + erf((v - loc) * scale.reciprocal() / sqrt(2)))
+    float z = __fdiv_rn(__fmul_rn(__fsub_rn(v, loc), inv_scale), 1.4142135623730951f);
+    return __fmul_rn(0.5f, __fadd_rn(1.0f, erff(z)));
+}
+
+__global__ void __launch_bounds__(kRThreads)
+    k_recon_reduce(float* __restrict__ out, const float* __restrict__ x, const float* __restrict__ mu, const float* __restrict__ f,
+                   const float* __restrict__ c_skip, const float* __restrict__ c_out, const float* __restrict__ edges, int k,
+                   float lo_edge, float dx, float inv_scale, int64_t B, int64_t D) {
+    extern __shared__ float s_edges[];  // k+1 boundaries
+    __shared__ float red[kRThreads / 32];
+    for (int i = threadIdx.x; i <= k; i += blockDim.x) s_edges[i] = edges[i];
+    __syncthreads();
+    const int64_t r = blockIdx.x, b = r % B;
+    const bool has_mu = mu != nullptr;
+    const float cs = has_mu ? c_skip[r] : 0.0f, co = has_mu ? c_out[r] : 1.0f;
+    const float4* x4 = reinterpret_cast<const float4*>(x + b * D);
+    const float4* m4 = has_mu ? reinterpret_cast<const float4*>(mu + r * D) : nullptr;
+    const float4* f4 = reinterpret_cast<const float4*>(f + r * D);
+    float acc = 0.0f;
+    for (int64_t q = threadIdx.x; q < (D >> 2); q += blockDim.x) {
+        float4 xv = x4[q];
+        float4 fv = __ldcs(f4 + q);
+        float4 mv = has_mu ? __ldcs(m4 + q) : make_float4(0, 0, 0, 0);
+        float xs[4] = {xv.x, xv.y, xv.z, xv.w}, fs[4] = {fv.x, fv.y, fv.z, fv.w}, ms[4] = {mv.x, mv.y, mv.z, mv.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float xh = combine(has_mu, cs, co, ms[j], fs[j]);
+            int idx = bucket_of_r(xs[j], lo_edge, dx, k);
+            float left = idx == 0 ? 0.0f : normal_cdf(s_edges[idx], xh, inv_scale);
+            float right = idx == k - 1 ? 1.0f : normal_cdf(s_edges[idx + 1], xh, inv_scale);
+            acc -= logf(fmaxf(__fsub_rn(right, left), 1e-20f));
+        }
+    }
+    float total = block_sum(acc, red);
+    if (threadIdx.x == 0) out[r] = total;
+}
+
+__global__ void __launch_bounds__(kRThreads)
+    k_sqerr_reduce(float* __restrict__ out, const float* __restrict__ x, const float* __restrict__ mu, const float* __restrict__ f,
+                   const float* __restrict__ c_skip, const float* __restrict__ c_out, int64_t B, int64_t D) {
+    __shared__ float red[kRThreads / 32];
+    const int64_t r = blockIdx.x, b = r % B;
+    const bool has_mu = mu != nullptr;
+    const float cs = has_mu ? c_skip[r] : 0.0f, co = has_mu ? c_out[r] : 1.0f;
+    const float4* x4 = reinterpret_cast<const float4*>(x + b * D);
+    const float4* m4 = has_mu ? reinterpret_cast<const float4*>(mu + r * D) : nullptr;
+    const float4* f4 = reinterpret_cast<const float4*>(f + r * D);
+    float acc = 0.0f;
+    for (int64_t q = threadIdx.x; q < (D >> 2); q += blockDim.x) {
+        float4 xv = x4[q];
+        float4 fv = __ldcs(f4 + q);
+        float4 mv = has_mu ? __ldcs(m4 + q) : make_float4(0, 0, 0, 0);
+        float xs[4] = {xv.x, xv.y, xv.z, xv.w}, fs[4] = {fv.x, fv.y, fv.z, fv.w}, ms[4] = {mv.x, mv.y, mv.z, mv.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float d = __fsub_rn(xs[j], combine(has_mu, cs, co, ms[j], fs[j]));
+            acc = fmaf(d, d, acc);
+        }
+    }
+    float total = block_sum(acc, red);
+    if (threadIdx.x == 0) out[r] = total;
+}
+
+// d/df of  w[r] * sum_d (x - (c_skip*mu + c_out*f))^2  =  -2 * w[r] * c_out[r] * (x - x_hat)
+// (autograd of bsi/bsi.py:309-310 w.r.t. the denoiser output).  16 B/elem.
+__global__ void __launch_bounds__(kRThreads)
+    k_sqerr_backward(float* __restrict__ grad_f, const float* __restrict__ w, const float* __restrict__ x,
+                     const float* __restrict__ mu, const float* __restrict__ f, const float* __restrict__ c_skip,
+                     const float* __restrict__ c_out, int64_t R, int64_t B, int64_t D) {
+    const int64_t qpr = D >> 2, total = R * qpr;
+    const bool has_mu = mu != nullptr;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int64_t r = i / qpr, q = i - r * qpr, b = r % B;
+        const float cs = has_mu ? c_skip[r] : 0.0f, co = has_mu ? c_out[r] : 1.0f;
+        const float g = -2.0f * w[r] * co;
+        float4 xv = *reinterpret_cast<const float4*>(x + b * D + q * 4);
+        float4 fv = __ldcs(reinterpret_cast<const float4*>(f + r * D) + q);
+        float4 mv = has_mu ? __ldcs(reinterpret_cast<const float4*>(mu + r * D) + q) : make_float4(0, 0, 0, 0);
+        float4 o;
+        o.x = g * (xv.x - combine(has_mu, cs, co, mv.x, fv.x));
+        o.y = g * (xv.y - combine(has_mu, cs, co, mv.y, fv.y));
+        o.z = g * (xv.z - combine(has_mu, cs, co, mv.z, fv.z));
+        o.w = g * (xv.w - combine(has_mu, cs, co, mv.w, fv.w));
+        *reinterpret_cast<float4*>(grad_f + r * D + q * 4) = o;
+    }
+}
+
+}  // namespace bsi
+
+using namespace bsi;
+
+extern "C" {
+
+int bsi_recon_reduce(float* out, const float* x, const float* mu, const float* f, const float* c_skip, const float* c_out,
+                     const float* edges, int32_t k, float lo_edge, float dx, float inv_scale, int64_t R, int64_t B, int64_t D,
+                     void* stream) {
+    BSI_CHECK_ARG(out && x && f && edges && R > 0 && B > 0, "bsi_recon_reduce: null pointer or empty batch");
+    BSI_CHECK_ARG(!mu || (c_skip && c_out), "bsi_recon_reduce: mu given without c_skip/c_out");
+    BSI_CHECK_ARG(k >= 2 && k <= 1024, "bsi_recon_reduce: k=%d outside [2,1024]", k);
+    BSI_CHECK_ARG(D > 0 && D % 4 == 0, "data numel per sample (%lld) must be a positive multiple of 4", (long long)D);
+    BSI_CHECK_ARG(R <= 0x7fffffff, "too many rows");
+    k_recon_reduce<<<(unsigned)R, kRThreads, (k + 1) * sizeof(float), (cudaStream_t)stream>>>(out, x, mu, f, c_skip, c_out, edges,
+                                                                                             k, lo_edge, dx, inv_scale, B, D);
+    BSI_LAUNCH_OK("k_recon_reduce");
+    return BSI_OK;
+}
+
+int bsi_sqerr_reduce(float* out, const float* x, const float* mu, const float* f, const float* c_skip, const float* c_out,
+                     int64_t R, int64_t B, int64_t D, void* stream) {
+    BSI_CHECK_ARG(out && x && f && R > 0 && B > 0, "bsi_sqerr_reduce: null pointer or empty batch");
+    BSI_CHECK_ARG(!mu || (c_skip && c_out), "bsi_sqerr_reduce: mu given without c_skip/c_out");
+    BSI_CHECK_ARG(D > 0 && D % 4 == 0, "data numel per sample (%lld) must be a positive multiple of 4", (long long)D);
+    BSI_CHECK_ARG(R <= 0x7fffffff, "too many rows");
+    k_sqerr_reduce<<<(unsigned)R, kRThreads, 0, (cudaStream_t)stream>>>(out, x, mu, f, c_skip, c_out, B, D);
+    BSI_LAUNCH_OK("k_sqerr_reduce");
+    return BSI_OK;
+}
+
+int bsi_sqerr_backward(float* grad_f, const float* w, const float* x, const float* mu, const float* f, const float* c_skip,
+                       const float* c_out, int64_t R, int64_t B, int64_t D, void* stream) {
+    BSI_CHECK_ARG(grad_f && w && x && f && R > 0 && B > 0, "bsi_sqerr_backward: null pointer or empty batch");
+    BSI_CHECK_ARG(!mu || (c_skip && c_out), "bsi_sqerr_backward: mu given without c_skip/c_out");
+    BSI_CHECK_ARG(D > 0 && D % 4 == 0, "data numel per sample (%lld) must be a positive multiple of 4", (long long)D);
+    int64_t need = (R * D / 4 + kRThreads - 1) / kRThreads, cap = (int64_t)sm_count() * 8;
+    k_sqerr_backward<<<(unsigned)(need < cap ? need : cap), kRThreads, 0, (cudaStream_t)stream>>>(grad_f, w, x, mu, f, c_skip, c_out,
+                                                                                                R, B, D);
+    BSI_LAUNCH_OK("k_sqerr_backward");
+    return BSI_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,2 @@
+from .dit import DenoisingDiT  # noqa: F401
+from .pos_emb import NyquistPositionalEmbedding  # noqa: F401

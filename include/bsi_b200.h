@@ -1,0 +1,229 @@
+/*
+ * bsi_b200 — C ABI of the B200-native (sm_100a) BSI hot path.
+ *
+ * The reference (martenlienen/bsi) is pure Python/PyTorch and has no FFI of its own; every
+ * entry point below replaces a group of ATen call sites of the reference, cited as
+ * file:line relative to the reference repository.  The host-side mirror of the reference's
+ * Python API (bsi_b200/bsi.py, bsi_b200/models/dit.py) binds these symbols with ctypes —
+ * see INTEGRATION.md for the stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - all pointers are DEVICE pointers unless the name ends in _host; the library never
+ *     allocates, frees or retains caller memory beyond the lifetime documented per call;
+ *   - `stream` is a cudaStream_t passed as void*; calls only enqueue work (no device sync),
+ *     so they are legal inside CUDA-graph stream capture;
+ *   - return value: 0 = ok, negative = bsi_status; bsi_last_error() gives a message for the
+ *     calling thread;
+ *   - one host thread per device at a time (same as the reference: one process per GPU).
+ */
+#ifndef BSI_B200_H
+#define BSI_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum bsi_status {
+    BSI_OK = 0,
+    BSI_ERR_INVALID_ARGUMENT = -1,
+    BSI_ERR_CUDA = -2,
+    BSI_ERR_UNSUPPORTED = -3,
+    BSI_ERR_WORKSPACE = -4,
+    BSI_ERR_NOT_READY = -5
+} bsi_status;
+
+/* ABI version (bumped on any signature change) and last error text of the calling thread. */
+int bsi_abi_version(void);
+const char* bsi_last_error(void);
+/* Compute capability of the current device as major*10+minor, or negative status. */
+int bsi_device_arch(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Row-coefficient reference.  Per-sample scalars (c_skip, c_out, c_in, ...) are read as
+ *     base[ step * step_stride + sample * sample_stride ]
+ * where `step` is *step_ptr (a device int, so a captured CUDA graph can be replayed for every
+ * sampler step) or 0 when step_ptr is NULL.  sample_stride = 0 broadcasts one value to the
+ * whole batch (BSI.sample: same t for every sample, bsi/bsi.py:331).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct bsi_rowref {
+    const float* base;
+    int32_t sample_stride;
+    int32_t step_stride;
+} bsi_rowref;
+
+/* Counter-based noise: Philox4x32-10 keyed by `seed`; element e of global sample s at draw
+ * index d uses counter (e/4, d, s_lo, s_hi).  Replaces torch.randn (bsi/bsi.py:325,332,415). */
+typedef struct bsi_noise {
+    const float* eps;      /* injected N(0,1) noise [n, D] (parity mode), or NULL for in-kernel Philox */
+    uint64_t seed;         /* Philox key */
+    uint64_t sample_base;  /* global index of local sample 0 (multi-GPU sharding invariance) */
+    int32_t draw;          /* draw index; the kernel adds *step_ptr when step_ptr != NULL */
+} bsi_noise;
+
+/* mu0 = rsqrt(lambda_0) * eps  (bsi/bsi.py:325-327).  sigma0 = rsqrt(lambda[0]) read from sigma0_ptr[0]. */
+int bsi_sample_init(float* mu, const float* sigma0_ptr, bsi_noise noise, int64_t n, int64_t D, void* stream);
+
+/* One fused sampler step (bsi/bsi.py:331-335 + 381-386):
+ *     x_hat = c_skip*mu + c_out*f          (EDM combine; f = denoiser output)
+ *     y     = x_hat + sigma*eps            (sigma = rsqrt(alpha_i))
+ *     mu'   = (alpha*y + lam*mu) / lam_next
+ * coef points to a [steps][8] float table {c_skip, c_out, sigma, alpha, lam, lam_next, 0, 0};
+ * row = *step_ptr (or `step` if step_ptr NULL).  mu is updated in place.  Optional outputs
+ * x_hat_out / y_out (sample_history, bsi/bsi.py:338-373) may be NULL.  precond = 0 means
+ * x_hat = f (preconditioning=None, bsi/bsi.py:378-379). */
+int bsi_step_fused(float* mu, const float* f, const float* coef, const int32_t* step_ptr, int32_t step, int32_t precond,
+                   bsi_noise noise, float* x_hat_out, float* y_out, int64_t n, int64_t D, void* stream);
+
+/* *step_ptr += 1 (single thread; last node of the captured per-step graph). */
+int bsi_step_advance(int32_t* step_ptr, void* stream);
+
+/* x_hat = c_skip*mu + c_out*f with per-row coefficients (BSI._predict_x, bsi/bsi.py:381-386). */
+int bsi_edm_combine(float* x_hat, const float* mu, const float* f, bsi_rowref c_skip, bsi_rowref c_out,
+                    const int32_t* step_ptr, int64_t n, int64_t D, void* stream);
+
+/* out = scale[row] * in  (model input c_in*mu, bsi/bsi.py:385). */
+int bsi_scale_rows(float* out, const float* in, bsi_rowref scale, const int32_t* step_ptr, int64_t n, int64_t D, void* stream);
+
+/* q(mu | x, lambda): mu[r] = gamma[r]*x[r % B] + sigma[r]*eps[r]  for r in [0, R), R = n*B
+ * (BSI._sample_q_mu_lambda, bsi/bsi.py:405-420; gamma=(lam-lam0)/lam, sigma=rsqrt(lam)).
+ * If model_in != NULL also writes model_in[r] = c_in[r]*mu[r]. */
+int bsi_q_sample(float* mu, float* model_in, const float* x, const float* gamma, const float* sigma, const float* c_in,
+                 bsi_noise noise, int64_t R, int64_t B, int64_t D, void* stream);
+
+/* Discretization.bucketize (bsi/bsi.py:32-35): idx = clamp(trunc((x - lo_edge) / dx), 0, k-1).
+ * lo_edge and dx are the fp32-rounded python floats the reference feeds torch.  out_i64 and/or
+ * out_u8 may be NULL. */
+int bsi_bucketize(const float* x, int64_t* out_i64, uint8_t* out_u8, float lo_edge, float dx, int32_t k, int64_t numel,
+                  void* stream);
+
+/* Discretised-Gaussian reconstruction term (BSI.reconstruction_loss, bsi/bsi.py:230-247):
+ *   out[r] = - sum_d log clamp(cdf(edge[idx+1]) - cdf(edge[idx]), 1e-20),  r in [0,R), x row r % B,
+ *   x_hat = c_skip[r]*mu[r] + c_out[r]*f[r]   (mu == NULL: f already is x_hat),
+ *   cdf(v) = 0.5*(1+erf((v - x_hat)*inv_scale/sqrt2)), first/last bin open-ended.
+ * edges: k+1 fp32 bin boundaries (torch.linspace, bsi/bsi.py:29-30), k <= 1024. */
+int bsi_recon_reduce(float* out, const float* x, const float* mu, const float* f, const float* c_skip, const float* c_out,
+                     const float* edges, int32_t k, float lo_edge, float dx, float inv_scale, int64_t R, int64_t B, int64_t D,
+                     void* stream);
+
+/* Squared decoding error (bsi/bsi.py:273,288,309): out[r] = sum_d (x[r % B] - x_hat[r])^2. */
+int bsi_sqerr_reduce(float* out, const float* x, const float* mu, const float* f, const float* c_skip, const float* c_out,
+                     int64_t R, int64_t B, int64_t D, void* stream);
+
+/* Gradient of  sum_r w[r] * out[r]  (out from bsi_sqerr_reduce) w.r.t. the denoiser output f:
+ *   grad_f[r] = -2 * w[r] * c_out[r] * (x[r % B] - x_hat[r])    (autograd of bsi/bsi.py:309-310). */
+int bsi_sqerr_backward(float* grad_f, const float* w, const float* x, const float* mu, const float* f, const float* c_skip,
+                       const float* c_out, int64_t R, int64_t B, int64_t D, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Tensor-core GEMM (tcgen05 + TMEM + TMA), bf16 x bf16 -> fp32 accumulate:
+ *     C[b][m][n] = epilogue( sum_k A[b][m][k] * W[b][n][k] )      (nn.Linear: y = x W^T + bias)
+ * Replaces every nn.Linear of bsi/models/dit.py:33-34,71-76,79-81,154,163-165.
+ * ---------------------------------------------------------------------------------------- */
+typedef enum bsi_epilogue {
+    BSI_EPI_BIAS_BF16 = 0,       /* out_bf16 = acc + bias                                   */
+    BSI_EPI_BIAS_GELU_BF16 = 1,  /* out_bf16 = gelu_tanh(acc + bias)        (dit.py:71-76)  */
+    BSI_EPI_BIAS_SILU_BF16 = 2,  /* out_bf16 = silu(acc + bias)             (dit.py:79-81)  */
+    BSI_EPI_BIAS_F32 = 3,        /* out_f32  = acc + bias                                   */
+    BSI_EPI_GATE_RESID_F32 = 4,  /* out_f32 += gate[row] * (acc + bias)     (dit.py:93-102) */
+    BSI_EPI_POS_F32 = 5,         /* out_f32  = acc + bias + pos[m % T]      (dit.py:178)    */
+    BSI_EPI_UNPATCH_F32 = 6      /* out_f32[b,c,y,x] = acc + bias, unpatchified (dit.py:166-172) */
+} bsi_epilogue;
+
+typedef struct bsi_gemm_args {
+    const void* A;     /* bf16 [batch][M][lda] */
+    const void* W;     /* bf16 [batch][N][ldw] */
+    void* C;           /* bf16 or fp32 [batch][M][ldc] (layout per epilogue) */
+    const float* bias; /* [batch][N] or NULL */
+    int32_t M, N, K;
+    int32_t lda, ldw, ldc;                      /* row pitches in elements; lda, ldw multiples of 8 */
+    int32_t batch;                              /* >= 1 */
+    int64_t stride_a, stride_w, stride_c, stride_bias; /* elements between batches (stride_a may be 0) */
+    int32_t epilogue;                           /* bsi_epilogue */
+    /* GATE_RESID: gate for output row m is  gate.base[step*step_stride + (m / rows_per_sample)*sample_stride + n] */
+    bsi_rowref gate;
+    const int32_t* step_ptr;
+    int32_t rows_per_sample; /* tokens per sample T (GATE_RESID, POS, UNPATCH) */
+    const float* pos;        /* POS: [T][N] fp32 */
+    int32_t patch, grid_w, channels; /* UNPATCH: patch size p, patches per row, output channels; N = p*p*channels */
+} bsi_gemm_args;
+
+int bsi_gemm_bf16(const bsi_gemm_args* args, void* stream);
+
+/* fp32 -> bf16 cast of a [rows][cols] matrix into pitch `ld_out` (>= cols; padding zero-filled). */
+int bsi_cast_bf16(void* out_bf16, const float* in, int64_t rows, int64_t cols, int64_t ld_out, void* stream);
+
+/* LayerNorm (eps, no affine) + adaLN modulate -> bf16 (dit.py:55,66,96,101):
+ *   out[m] = LN(x[m]) * (1 + scale[row(m)]) + shift[row(m)],  row(m) = m / rows_per_sample.
+ * If gamma/beta != NULL (patch_decoder LayerNorm, dit.py:164) uses out = LN(x)*gamma + beta instead. */
+int bsi_layernorm_mod_bf16(void* out_bf16, const float* x, bsi_rowref shift, bsi_rowref scale, const int32_t* step_ptr,
+                           const float* gamma, const float* beta, int32_t rows_per_sample, int64_t M, int32_t dim, float eps,
+                           void* stream);
+
+/* Multi-head attention over packed QKV (dit.py:36-47): qkv bf16 [B*T][3*dim] with columns
+ * (qkv, head, channel); out bf16 [B*T][dim] with columns (head, channel).  head_dim = 64. */
+int bsi_attention_bf16(void* out_bf16, const void* qkv_bf16, int32_t B, int32_t T, int32_t heads, int32_t head_dim, void* stream);
+
+/* Patch-embed operand (dit.py:149-153,228-231; fourier_features.py:24-36):
+ *   A[b*T + tok][(py*p+px)*Cin + c] = bf16( feature_c( scale[b] * mu[b,:,y,x] ) )
+ * Cin = C*(1 + 2*(n_max-n_min+1)) when n_max >= n_min else C; feature order: raw channels, then
+ * for each channel (n, {sin,cos}).  Pitch lda >= p*p*Cin, padding zero-filled. */
+int bsi_dit_patch_operand(void* A_bf16, const float* mu, bsi_rowref scale, const int32_t* step_ptr, int32_t B, int32_t C,
+                          int32_t H, int32_t Wd, int32_t patch, int32_t n_min, int32_t n_max, int32_t lda, void* stream);
+
+/* NyquistPositionalEmbedding (pos_emb.py:77-84): out_bf16[r][j] = sin(bias[j] + scale[j]*t[r]); also fp32 copy if out_f32 != NULL. */
+int bsi_time_embed(void* out_bf16, float* out_f32, const float* t, const float* scale, const float* bias, int64_t rows,
+                   int32_t size, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * DiT denoiser engine (DenoisingDiT.forward, bsi/models/dit.py:174-181,225-233).
+ * All device memory is caller-owned: a parameter arena (packed bf16 weights + fp32 vectors)
+ * and a workspace; the engine object itself only holds offsets and shapes (host memory).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct bsi_dit_config {
+    int32_t channels, height, width; /* data_shape */
+    int32_t patch, dim, depth, heads;
+    int32_t fourier_n_min, fourier_n_max; /* n_max < n_min: no Fourier features */
+} bsi_dit_config;
+
+typedef struct bsi_dit bsi_dit;
+
+int bsi_dit_create(const bsi_dit_config* cfg, bsi_dit** out);
+void bsi_dit_destroy(bsi_dit* e);
+/* Bytes of the parameter arena / of the workspace for a forward at batch B (cond_rows = rows of the
+ * conditioning table: B for per-sample t, k+1 for a tabulated sampler schedule). */
+int64_t bsi_dit_param_bytes(const bsi_dit* e);
+int64_t bsi_dit_workspace_bytes(const bsi_dit* e, int32_t B);
+int64_t bsi_dit_cond_bytes(const bsi_dit* e, int32_t cond_rows);
+/* Bind the arena (256-byte aligned).  Must precede bsi_dit_set_param. */
+int bsi_dit_bind_params(bsi_dit* e, void* arena, int64_t bytes);
+/* Pack one tensor of the reference state_dict (fp32, device) by its reference key, e.g.
+ * "dit.blocks.3.attn.to_qkv.weight" (key layout: SURVEY §8 a15).  Also accepts the non-persistent
+ * buffers "dit.patch_pos_embedding", "dit.t_embedding.scale", "dit.t_embedding.bias". */
+int bsi_dit_set_param(bsi_dit* e, const char* key, const float* src, int64_t numel, void* stream);
+/* Number of state_dict tensors still missing (0 = ready). */
+int bsi_dit_missing_params(const bsi_dit* e);
+
+/* Conditioning table: cond[layer][row][6*dim] fp32 = adaLN_modulation(t_embedding(t[row])) for all
+ * layers (dit.py:79-81,90-92,177).  `scratch` >= bsi_dit_cond_scratch_bytes(rows). */
+int64_t bsi_dit_cond_scratch_bytes(const bsi_dit* e, int32_t rows);
+int bsi_dit_conditioning(const bsi_dit* e, float* cond, const float* t, int32_t rows, void* scratch, int64_t scratch_bytes,
+                         void* stream);
+
+/* out[B,C,H,W] = DiT(in_scale[b] * mu[b], cond rows).  Conditioning row of sample b is
+ *   cond_row0 + (*step_ptr or 0) * cond_step_rows + b * cond_sample_rows
+ * (per-sample t: cond_sample_rows = 1, cond_step_rows = 0;  sampler: 0 and 1). */
+int bsi_dit_forward(const bsi_dit* e, float* out, const float* mu, bsi_rowref in_scale, const float* cond, int32_t cond_rows,
+                    int32_t cond_row0, int32_t cond_sample_rows, int32_t cond_step_rows, const int32_t* step_ptr, int32_t B,
+                    void* workspace, int64_t workspace_bytes, void* stream);
+
+/* Debug/introspection for parity tests: copy an intermediate of the last forward out of the workspace.
+ * what: 0 = residual stream after embed+blocks [B*T][dim] fp32 (valid after forward). */
+int bsi_dit_peek(const bsi_dit* e, int32_t what, float* out, int32_t B, const void* workspace, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BSI_B200_H */

@@ -1,0 +1,132 @@
+"""BSI public API with a caller-owned PyTorch denoiser (config 1: README toy Conv2d) vs the CPU oracle and goldens."""
+
+import pytest
+import torch
+
+import helpers as H
+from gpu_util import dev, report, sync
+from bsi_b200 import BSI, Discretization
+
+O = H.O
+pytestmark = pytest.mark.gpu
+C32 = O.make_consts(1e-2, 1e6, 2e6)
+HYPER = dict(lambda_0=1e-2, alpha_M=1e6, alpha_R=2e6, preconditioning="edm")
+
+
+class ToyModel(torch.nn.Module):
+    """User-side denoiser of the reference README (README.md:24-31)."""
+
+    def __init__(self):
+        super().__init__()
+        self.layer = torch.nn.Conv2d(4, 3, 3, padding=1)
+
+    def forward(self, mu, t):
+        plane = t.reshape(-1, 1, 1, 1).expand(-1, 1, *mu.shape[-2:])
+        return self.layer(torch.cat((mu, plane), dim=1))
+
+
+def make(k=128, noise="torch"):
+    model = ToyModel()
+    sd = H.det_state_dict(H.TOY_SHAPES, seed=1, bf16_exact=False)
+    model.load_state_dict(sd)
+    torch.backends.cudnn.allow_tf32 = False
+    bsi = BSI(model.to(dev()), data_shape=(3, 32, 32), k=k, discretization=Discretization.image_8bit(), **HYPER).to(dev())
+    bsi.noise_source = noise
+    return bsi, sd
+
+
+def cuda_noise_like_reference(seed, n, k):
+    gen = torch.Generator(device=dev()).manual_seed(seed)
+    return torch.stack([torch.randn((n, 3, 32, 32), device=dev(), generator=gen) for _ in range(k + 1)]).cpu()
+
+
+def test_sample_free_running_vs_oracle_config1():
+    """Config 1 is not chaotic: the whole k=128 trajectory is compared free-running at the fp32 tier."""
+    bsi, sd = make()
+    with torch.inference_mode():
+        out = bsi.sample(16, torch.Generator(device=dev()).manual_seed(7))
+        eps = cuda_noise_like_reference(7, 16, 128)
+        ref = O.sample_with_noise(lambda mu, t: O.toy_conv_forward(sd, mu, t), C32, torch.linspace(0.0, 1.0, 129), eps)
+    assert out.shape == (16, 3, 32, 32)
+    report("config-1 sample (free running, fp32 tier 1e-5)", out, ref, 1e-5, 1e-5)
+
+
+def test_sample_history_vs_golden_teacher_forced():
+    bsi, sd = make()
+    g = H.load_golden("toy.pt")["sample"]
+    t = torch.linspace(0.0, 1.0, 129)
+    with torch.inference_mode():
+        for j, i in enumerate(g["steps"].tolist()):
+            x_hat = bsi._predict_x(g["mu"][j].to(dev()), t[i].expand(2).to(dev()))
+            report(f"_predict_x step {i} vs reference", x_hat, g["x_hat"][j], 1e-5, 1e-5)
+        mus, xs, ys = bsi.sample_history(2, torch.Generator(device=dev()).manual_seed(7))
+    assert mus.shape == (129, 2, 3, 32, 32) and ys.shape == (128, 2, 3, 32, 32)
+
+
+def test_losses_vs_oracle_config1():
+    bsi, sd = make()
+    f = lambda mu, t: O.toy_conv_forward(sd, mu, t)
+    x = H.det_images("toy.x", 32, (3, 32, 32), seed=2)
+    with torch.inference_mode():
+        e, b, ex = bsi.elbo(x.to(dev()), 1, 10, torch.Generator(device=dev()).manual_seed(4))
+        gen = torch.Generator(device=dev()).manual_seed(4)
+        eps_r = torch.randn((1, 32, 3, 32, 32), device=dev(), generator=gen).cpu()
+        off, perm = torch.rand((), device=dev(), generator=gen).cpu(), torch.randperm(320, device=dev(), generator=gen).cpu()
+        eps_m = torch.randn((10, 32, 3, 32, 32), device=dev(), generator=gen).cpu()
+        l_r = O.recon_loss(f, C32, x, 1, eps_r, O.GRID_8BIT)
+        l_m = O.inf_measure_loss(f, C32, x, O.lam_of_t(C32, O.ld_times(10, 32, off, perm)), eps_m)
+        e_ref, b_ref, _ = O.combine_elbo(l_r, l_m, 3072)
+    report("l_recon", ex["l_recon"], l_r, 1e-4, 1e-2)
+    report("l_measure", ex["l_measure"], l_m, 1e-4, 1e-3)
+    assert float((b.cpu() - b_ref).abs().max()) < 1e-3
+    # estimate_var and finite_elbo shapes / semantics
+    with torch.inference_mode():
+        e2, b2, ex2 = bsi.elbo(x.to(dev()), 2, 3, torch.Generator(device=dev()).manual_seed(5), estimate_var=True)
+        e3, b3, ex3 = bsi.finite_elbo(x.to(dev()), 2, 3, torch.Generator(device=dev()).manual_seed(6))
+    assert ex2["bpd_var"].shape == (32,) and bool((ex2["bpd_var"] >= 0).all())
+    assert ex3["l_measure"].shape == (3, 32) and torch.isfinite(b3).all()
+    bsi.preconditioning = "vp"
+    with pytest.raises(RuntimeError):
+        bsi.train_loss(x.to(dev()))
+
+
+def test_train_loss_backward_matches_oracle_autograd():
+    bsi, sd = make()
+    x = H.det_images("toy.x", 32, (3, 32, 32), seed=2)
+    loss = bsi.train_loss(x.to(dev()), torch.Generator(device=dev()).manual_seed(3))
+    assert loss.shape == (32,) and loss.requires_grad
+    loss.mean().backward()
+    gen = torch.Generator(device=dev()).manual_seed(3)
+    off, perm = torch.rand((), device=dev(), generator=gen).cpu(), torch.randperm(32, device=dev(), generator=gen).cpu()
+    eps = torch.randn((1, 32, 3, 32, 32), device=dev(), generator=gen).cpu()[0]
+    w = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    ref = O.train_loss_with(lambda mu, t: O.toy_conv_forward(w, mu, t), C32, x, O.lam_of_t(C32, O.ld_times(1, 32, off, perm))[0], eps)
+    ref.mean().backward()
+    report("train_loss values", loss, ref, 1e-4, 1e-6)
+    report("grad conv weight", bsi.model.layer.weight.grad, w["layer.weight"].grad, 1e-3, 1e-5)
+    report("grad conv bias", bsi.model.layer.bias.grad, w["layer.bias"].grad, 1e-3, 1e-5)
+
+
+def test_philox_mode_statistics_and_seed_control():
+    bsi, sd = make(k=16, noise="philox")
+    with torch.inference_mode():
+        a = bsi.sample(8, seed=5)
+        b = bsi.sample(8, seed=5)
+        c = bsi.sample(8, seed=6)
+        torch.manual_seed(0)
+        d = bsi.sample(8)
+        torch.manual_seed(0)
+        e = bsi.sample(8)
+    assert torch.equal(a, b) and not torch.equal(a, c) and torch.equal(d, e)
+    assert torch.isfinite(a).all()
+
+
+def test_cpu_tensors_are_rejected_loudly():
+    from bsi_b200._lib import BsiNativeError
+
+    model = ToyModel()
+    bsi = BSI(model, data_shape=(3, 32, 32), k=4, **HYPER)
+    with pytest.raises(BsiNativeError):
+        bsi.sample(2)
+    with pytest.raises(BsiNativeError):
+        Discretization.image_8bit().bucketize(torch.zeros(4))

