@@ -56,6 +56,9 @@ SIGNATURES = {
     "bsi_abi_version": (C.c_int, []),
     "bsi_last_error": (C.c_char_p, []),
     "bsi_device_arch": (C.c_int, []),
+    "bsi_launch_counter": (C.c_longlong, []),
+    "bsi_profile_gemm_begin": (C.c_int, []),
+    "bsi_profile_gemm_end": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(_i32)]),
     "bsi_sample_init": (C.c_int, [_vp, _vp, Noise, _i64, _i64, _vp]),
     "bsi_step_fused": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, Noise, _vp, _vp, _i64, _i64, _vp]),
     "bsi_step_advance": (C.c_int, [_vp, _vp]),

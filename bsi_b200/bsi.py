@@ -246,9 +246,10 @@ class BSI(nn.Module):
         if c_in is None:
             return self.model(mu, t)
         scaled = torch.empty_like(mu)
+        c_in = c_in.contiguous()  # held in a local until the launch is enqueued
         with torch.cuda.device(dev):
             L.check(
-                L.load().bsi_scale_rows(L.ptr(scaled), L.ptr(mu), L.rowref(c_in.contiguous(), 1), None, mu.shape[0], mu[0].numel(), L.stream_ptr(dev)),
+                L.load().bsi_scale_rows(L.ptr(scaled), L.ptr(mu), L.rowref(c_in, 1), None, mu.shape[0], mu[0].numel(), L.stream_ptr(dev)),
                 "bsi_scale_rows",
             )
         return self.model(scaled, t)
@@ -265,10 +266,11 @@ class BSI(nn.Module):
         if f.requires_grad:  # differentiable combine for callers that backprop through _predict_x
             return torch.addcmul(broadcast_right(c_skip, mu) * mu, broadcast_right(c_out, mu), f)
         x_hat = torch.empty_like(mu)
+        c_skip, c_out = c_skip.contiguous(), c_out.contiguous()
         with torch.cuda.device(mu.device):
             L.check(
                 L.load().bsi_edm_combine(
-                    L.ptr(x_hat), L.ptr(mu), L.ptr(f), L.rowref(c_skip.contiguous(), 1), L.rowref(c_out.contiguous(), 1), None,
+                    L.ptr(x_hat), L.ptr(mu), L.ptr(f), L.rowref(c_skip, 1), L.rowref(c_out, 1), None,
                     mu.shape[0], mu[0].numel(), L.stream_ptr(mu.device),
                 ),
                 "bsi_edm_combine",
@@ -290,10 +292,11 @@ class BSI(nn.Module):
         nz, _keep = self._noise((*lambda_.shape, *self.data_shape), generator, _draw, 0, _seed)
         mu = torch.empty((*lambda_.shape, *self.data_shape), **self.tensor_args)
         model_in = torch.empty_like(mu) if _c_in is not None else None
+        c_in = _c_in.contiguous() if _c_in is not None else None
         with torch.cuda.device(dev):
             L.check(
                 L.load().bsi_q_sample(
-                    L.ptr(mu), L.ptr(model_in), L.ptr(x), L.ptr(gamma), L.ptr(sigma), L.ptr(_c_in.contiguous()) if _c_in is not None else None,
+                    L.ptr(mu), L.ptr(model_in), L.ptr(x), L.ptr(gamma), L.ptr(sigma), L.ptr(c_in),
                     nz, R, B, D, L.stream_ptr(dev),
                 ),
                 "bsi_q_sample",
@@ -352,10 +355,11 @@ class BSI(nn.Module):
         edges = disc.bin_boundaries(dev, torch.float32)
         inv_scale = float(torch.rsqrt(self.alpha_R).reciprocal())
         out = torch.empty(n_samples * B, **self.tensor_args)
+        c_skip, c_out = c_skip.contiguous(), c_out.contiguous()
         with torch.cuda.device(dev):
             L.check(
                 L.load().bsi_recon_reduce(
-                    L.ptr(out), L.ptr(x), L.ptr(mu_f), L.ptr(f), L.ptr(c_skip.contiguous()), L.ptr(c_out.contiguous()), L.ptr(edges),
+                    L.ptr(out), L.ptr(x), L.ptr(mu_f), L.ptr(f), L.ptr(c_skip), L.ptr(c_out), L.ptr(edges),
                     disc.k, disc.range[0], disc.dx, inv_scale, n_samples * B, B, D, L.stream_ptr(dev),
                 ),
                 "bsi_recon_reduce",

@@ -11,6 +11,7 @@
 namespace bsi {
 
 void set_error(const char* fmt, ...);
+void count_launch();  // host-side counter of kernels launched by this library (bsi_launch_counter)
 
 #define BSI_CHECK_ARG(cond, ...)             \
     do {                                     \
@@ -36,6 +37,7 @@ void set_error(const char* fmt, ...);
             ::bsi::set_error("launch of %s failed: %s", name, cudaGetErrorString(_e));     \
             return BSI_ERR_CUDA;                                                           \
         }                                                                                  \
+        ::bsi::count_launch();                                                             \
     } while (0)
 
 int sm_count();

@@ -101,8 +101,8 @@ int bsi_dit_create(const bsi_dit_config* cfg, bsi_dit** out) {
     e->P = cfg->patch * cfg->patch * e->cin;
     e->ldp = (int)align_up(e->P, 8);
     e->nout = cfg->patch * cfg->patch * cfg->channels;
-    if (e->T % 128 != 0 || e->T > 512 || e->nout % 8 != 0) {
-        set_error("bsi_dit_create: tokens per sample T=%d must be 128/256/384/512 and patch*patch*channels=%d a multiple of 8", e->T, e->nout);
+    if (e->T % 128 != 0 || e->T > 512 || e->nout % 4 != 0) {
+        set_error("bsi_dit_create: tokens per sample T=%d must be 128/256/384/512 and patch*patch*channels=%d a multiple of 4", e->T, e->nout);
         delete e;
         return BSI_ERR_UNSUPPORTED;
     }

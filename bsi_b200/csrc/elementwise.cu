@@ -2,6 +2,8 @@
 // bucketize, casts, time embedding and the patch-embed operand builder.
 // Each kernel states its algorithmic bytes per element; all use 128-bit accesses on the
 // contiguous axis and a grid of (SM count x resident CTAs) with a grid-stride loop.
+#include <atomic>
+
 #include "common.cuh"
 
 namespace bsi {
@@ -13,6 +15,8 @@ void set_error(const char* fmt, ...) {
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
 }
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 int sm_count() {
     static int cached[64] = {0};
     int dev = 0;
@@ -237,6 +241,7 @@ using namespace bsi;
 extern "C" {
 
 int bsi_abi_version(void) { return 1; }
+long long bsi_launch_counter(void) { return g_launches.load(std::memory_order_relaxed); }
 const char* bsi_last_error(void) { return g_err; }
 int bsi_device_arch(void) {
     int dev = 0, major = 0, minor = 0;
@@ -305,9 +310,9 @@ int bsi_q_sample(float* mu, float* model_in, const float* x, const float* gamma,
 
 int bsi_bucketize(const float* x, int64_t* out_i64, uint8_t* out_u8, float lo_edge, float dx, int32_t k, int64_t numel,
                   void* stream) {
-    BSI_CHECK_ARG(x && (out_i64 || out_u8) && numel >= 0 && k > 0, "bsi_bucketize: bad arguments");
-    BSI_CHECK_ARG(!out_u8 || k <= 256, "bsi_bucketize: uint8 output needs k <= 256");
     if (numel == 0) return BSI_OK;
+    BSI_CHECK_ARG(x && (out_i64 || out_u8) && numel > 0 && k > 0, "bsi_bucketize: bad arguments");
+    BSI_CHECK_ARG(!out_u8 || k <= 256, "bsi_bucketize: uint8 output needs k <= 256");
     k_bucketize<<<grid_for(numel), kThreads, 0, (cudaStream_t)stream>>>(x, out_i64, out_u8, lo_edge, dx, k, numel);
     BSI_LAUNCH_OK("k_bucketize");
     return BSI_OK;

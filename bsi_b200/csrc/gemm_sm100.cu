@@ -14,6 +14,8 @@
 // Roofline: tensor-bound.  Algorithmic work 2*M*N*K flop per launch.
 #include <cuda.h>
 
+#include <vector>
+
 #include "common.cuh"
 #include "ptx_sm100.cuh"
 
@@ -56,7 +58,7 @@ __device__ __forceinline__ void epilogue_chunk(const EpiParams& ep, int batch, i
     float v[32];
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
-    const int ncols = min(32, ep.N - n0);  // multiple of 8 by contract
+    const int ncols = min(32, ep.N - n0);  // multiple of 8 by contract (4 for UNPATCH)
     if (bias) {
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
@@ -289,9 +291,17 @@ int make_operand_map(CUtensorMap* map, const void* base, int64_t rows, int64_t K
     return BSI_OK;
 }
 
+// Optional per-launch timing of the GEMM kernel (bench.py roofline): CUDA events on the launching stream.
+struct GemmRecord {
+    cudaEvent_t start, stop;
+    double flops;
+};
+static bool g_profile = false;
+static std::vector<GemmRecord> g_records;
+
 template <int EPI>
 static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mw, const EpiParams& ep, int m_tiles, int n_tiles, int k_blocks,
-                       int batch, int a_shared, cudaStream_t stream) {
+                       int batch, int a_shared, cudaStream_t stream, int k_dim) {
     static bool configured = false;
     if (!configured) {
         BSI_CUDA_OK(cudaFuncSetAttribute(k_gemm_bf16<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
@@ -299,8 +309,19 @@ static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mw, const EpiPa
     }
     int total = batch * m_tiles * n_tiles;
     int grid = total < sm_count() ? total : sm_count();
+    GemmRecord rec{};
+    if (g_profile) {
+        BSI_CUDA_OK(cudaEventCreate(&rec.start));
+        BSI_CUDA_OK(cudaEventCreate(&rec.stop));
+        rec.flops = 2.0 * batch * (double)ep.M * (double)ep.N * (double)k_dim;
+        BSI_CUDA_OK(cudaEventRecord(rec.start, stream));
+    }
     k_gemm_bf16<EPI><<<grid, kGemmThreads, kSmemBytes, stream>>>(ma, mw, ep, m_tiles, n_tiles, k_blocks, batch, a_shared);
     BSI_LAUNCH_OK("k_gemm_bf16");
+    if (g_profile) {
+        BSI_CUDA_OK(cudaEventRecord(rec.stop, stream));
+        g_records.push_back(rec);
+    }
     return BSI_OK;
 }
 
@@ -312,7 +333,7 @@ extern "C" int bsi_gemm_bf16(const bsi_gemm_args* a, void* stream) {
     BSI_CHECK_ARG(a && a->A && a->W && a->C, "bsi_gemm_bf16: null operand");
     BSI_CHECK_ARG(a->M > 0 && a->N > 0 && a->K > 0 && a->batch >= 1, "bsi_gemm_bf16: bad shape M=%d N=%d K=%d batch=%d", a->M,
                   a->N, a->K, a->batch);
-    BSI_CHECK_ARG(a->N % 8 == 0, "bsi_gemm_bf16: N=%d must be a multiple of 8", a->N);
+    BSI_CHECK_ARG(a->N % (a->epilogue == BSI_EPI_UNPATCH_F32 ? 4 : 8) == 0, "bsi_gemm_bf16: N=%d must be a multiple of 8 (4 for UNPATCH)", a->N);
     BSI_CHECK_ARG(a->lda >= a->K && a->ldw >= a->K, "bsi_gemm_bf16: pitch smaller than K");
     const bool f32_out = a->epilogue >= BSI_EPI_BIAS_F32;
     if (a->epilogue != BSI_EPI_UNPATCH_F32) {
@@ -344,13 +365,38 @@ extern "C" int bsi_gemm_bf16(const bsi_gemm_args* a, void* stream) {
     const int m_tiles = (a->M + BM - 1) / BM, n_tiles = (a->N + BN - 1) / BN, k_blocks = (a->K + BK - 1) / BK;
     cudaStream_t st = (cudaStream_t)stream;
     switch (a->epilogue) {
-        case BSI_EPI_BIAS_BF16: return launch_gemm<BSI_EPI_BIAS_BF16>(ma, mw, ep, m_tiles, n_tiles, k_blocks, a->batch, a_shared, st);
-        case BSI_EPI_BIAS_GELU_BF16: return launch_gemm<BSI_EPI_BIAS_GELU_BF16>(ma, mw, ep, m_tiles, n_tiles, k_blocks, a->batch, a_shared, st);
-        case BSI_EPI_BIAS_SILU_BF16: return launch_gemm<BSI_EPI_BIAS_SILU_BF16>(ma, mw, ep, m_tiles, n_tiles, k_blocks, a->batch, a_shared, st);
-        case BSI_EPI_BIAS_F32: return launch_gemm<BSI_EPI_BIAS_F32>(ma, mw, ep, m_tiles, n_tiles, k_blocks, a->batch, a_shared, st);
-        case BSI_EPI_GATE_RESID_F32: return launch_gemm<BSI_EPI_GATE_RESID_F32>(ma, mw, ep, m_tiles, n_tiles, k_blocks, a->batch, a_shared, st);
-        case BSI_EPI_POS_F32: return launch_gemm<BSI_EPI_POS_F32>(ma, mw, ep, m_tiles, n_tiles, k_blocks, a->batch, a_shared, st);
-        case BSI_EPI_UNPATCH_F32: return launch_gemm<BSI_EPI_UNPATCH_F32>(ma, mw, ep, m_tiles, n_tiles, k_blocks, a->batch, a_shared, st);
+        case BSI_EPI_BIAS_BF16: return launch_gemm<BSI_EPI_BIAS_BF16>(ma, mw, ep, m_tiles, n_tiles, k_blocks, a->batch, a_shared, st, a->K);
+        case BSI_EPI_BIAS_GELU_BF16: return launch_gemm<BSI_EPI_BIAS_GELU_BF16>(ma, mw, ep, m_tiles, n_tiles, k_blocks, a->batch, a_shared, st, a->K);
+        case BSI_EPI_BIAS_SILU_BF16: return launch_gemm<BSI_EPI_BIAS_SILU_BF16>(ma, mw, ep, m_tiles, n_tiles, k_blocks, a->batch, a_shared, st, a->K);
+        case BSI_EPI_BIAS_F32: return launch_gemm<BSI_EPI_BIAS_F32>(ma, mw, ep, m_tiles, n_tiles, k_blocks, a->batch, a_shared, st, a->K);
+        case BSI_EPI_GATE_RESID_F32: return launch_gemm<BSI_EPI_GATE_RESID_F32>(ma, mw, ep, m_tiles, n_tiles, k_blocks, a->batch, a_shared, st, a->K);
+        case BSI_EPI_POS_F32: return launch_gemm<BSI_EPI_POS_F32>(ma, mw, ep, m_tiles, n_tiles, k_blocks, a->batch, a_shared, st, a->K);
+        case BSI_EPI_UNPATCH_F32: return launch_gemm<BSI_EPI_UNPATCH_F32>(ma, mw, ep, m_tiles, n_tiles, k_blocks, a->batch, a_shared, st, a->K);
         default: set_error("bsi_gemm_bf16: unknown epilogue %d", a->epilogue); return BSI_ERR_INVALID_ARGUMENT;
     }
+}
+
+// Start / stop timing every bsi_gemm_bf16 launch with CUDA events (not legal during stream capture).
+extern "C" int bsi_profile_gemm_begin(void) {
+    g_records.clear();
+    g_profile = true;
+    return BSI_OK;
+}
+// Synchronises the recorded events and returns the summed device time [ms], algorithmic flops and launch count.
+extern "C" int bsi_profile_gemm_end(double* total_ms, double* total_flops, int32_t* launches) {
+    g_profile = false;
+    double ms = 0.0, fl = 0.0;
+    for (auto& r : g_records) {
+        float t = 0.0f;
+        BSI_CUDA_OK(cudaEventSynchronize(r.stop));
+        BSI_CUDA_OK(cudaEventElapsedTime(&t, r.start, r.stop));
+        ms += t, fl += r.flops;
+        cudaEventDestroy(r.start);
+        cudaEventDestroy(r.stop);
+    }
+    if (total_ms) *total_ms = ms;
+    if (total_flops) *total_flops = fl;
+    if (launches) *launches = (int32_t)g_records.size();
+    g_records.clear();
+    return BSI_OK;
 }

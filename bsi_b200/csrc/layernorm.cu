@@ -9,7 +9,7 @@ namespace bsi {
 constexpr int kLnThreads = 256;
 
 template <int NV>  // NV float4 per lane: dim = 128 * NV
-__global__ void __launch_bounds__(kLnThreads)
+__global__ void __launch_bounds__(kLnThreads, 2)
     k_layernorm_mod(__nv_bfloat16* __restrict__ out, const float* __restrict__ x, bsi_rowref shift, bsi_rowref scale,
                     const int32_t* __restrict__ step_ptr, const float* __restrict__ gamma, const float* __restrict__ beta,
                     int rows_per_sample, int64_t M, float eps) {

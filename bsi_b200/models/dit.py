@@ -84,7 +84,7 @@ class DenoisingDiT(nn.Module):
         self._engine = None
         self._arena = None
         self._packed_sig = None
-        self._buffers: dict = {}
+        self._scratch: dict = {}
 
     # ---- engine / parameter arena ---------------------------------------------------------------
     def __del__(self):
@@ -102,7 +102,18 @@ class DenoisingDiT(nn.Module):
         yield "dit.t_embedding.bias", self.dit.t_embedding.bias
 
     def _signature(self):
-        return tuple((p.data_ptr(), p._version) for _, p in self._named_tensors())
+        """(address, version) of every tensor the engine packs; a change triggers re-packing.
+
+        Tensors created under torch.inference_mode() carry no version counter: for those only a new
+        allocation is detected and in-place updates need an explicit `repack()`."""
+        sig = []
+        for _, p in self._named_tensors():
+            try:
+                version = p._version
+            except RuntimeError:
+                version = -1
+            sig.append((p.data_ptr(), version))
+        return tuple(sig)
 
     def _ensure_packed(self, device):
         lib = L.load()
@@ -136,10 +147,10 @@ class DenoisingDiT(nn.Module):
         self._packed_sig = None
 
     def _buffer(self, name: str, nbytes: int, device) -> Tensor:
-        buf = self._buffers.get(name)
+        buf = self._scratch.get(name)
         if buf is None or buf.device != device or buf.numel() < nbytes:
             buf = torch.empty(int(nbytes), dtype=torch.uint8, device=device)
-            self._buffers[name] = buf
+            self._scratch[name] = buf
         return buf
 
     def _conditioning(self, eng, t: Tensor, name: str = "cond") -> Tensor:
@@ -189,11 +200,11 @@ class DenoisingDiT(nn.Module):
 
     def residual_stream(self, B: int) -> Tensor:
         """Debug: fp32 token stream [B*T, dim] after the last block of the previous forward."""
-        dev = self._buffers["workspace"].device
+        dev = self._scratch["workspace"].device
         T = (self.data_shape[1] // self._cfg.patch) * (self.data_shape[2] // self._cfg.patch)
         out = torch.empty((B * T, self._cfg.dim), dtype=torch.float32, device=dev)
         with torch.cuda.device(dev):
-            L.check(L.load().bsi_dit_peek(self._engine, 0, out.data_ptr(), B, self._buffers["workspace"].data_ptr(), L.stream_ptr(dev)), "bsi_dit_peek")
+            L.check(L.load().bsi_dit_peek(self._engine, 0, out.data_ptr(), B, self._scratch["workspace"].data_ptr(), L.stream_ptr(dev)), "bsi_dit_peek")
         return out
 
     # ---- k-step sampler with a CUDA graph per step (reference bsi/bsi.py:328-336) -------------------

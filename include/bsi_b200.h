@@ -38,6 +38,8 @@ typedef enum bsi_status {
 /* ABI version (bumped on any signature change) and last error text of the calling thread. */
 int bsi_abi_version(void);
 const char* bsi_last_error(void);
+/* Number of CUDA kernels this library has launched in this process (host-side counter). */
+long long bsi_launch_counter(void);
 /* Compute capability of the current device as major*10+minor, or negative status. */
 int bsi_device_arch(void);
 
@@ -151,6 +153,12 @@ typedef struct bsi_gemm_args {
 } bsi_gemm_args;
 
 int bsi_gemm_bf16(const bsi_gemm_args* args, void* stream);
+
+/* Measurement aid (bench.py roofline): between begin and end every bsi_gemm_bf16 launch is bracketed by
+ * CUDA events on its stream; end synchronises them and returns the summed kernel time, the algorithmic
+ * flops (2*M*N*K*batch) and the number of launches.  Not legal while the stream is being captured. */
+int bsi_profile_gemm_begin(void);
+int bsi_profile_gemm_end(double* total_ms, double* total_flops, int32_t* launches);
 
 /* fp32 -> bf16 cast of a [rows][cols] matrix into pitch `ld_out` (>= cols; padding zero-filled). */
 int bsi_cast_bf16(void* out_bf16, const float* in, int64_t rows, int64_t cols, int64_t ld_out, void* stream);

@@ -22,3 +22,13 @@ def pytest_collection_modifyitems(config, items):
     for item in items:
         if "gpu" in item.keywords:
             item.add_marker(skip)
+
+
+@pytest.fixture(autouse=True)
+def _no_leaked_inference_mode():
+    """Each test must start and end outside torch.inference_mode (a leak would turn new tensors into inference tensors)."""
+    import torch
+
+    assert not torch.is_inference_mode_enabled(), "inference mode leaked from a previous test"
+    yield
+    assert not torch.is_inference_mode_enabled(), "this test leaked inference mode"

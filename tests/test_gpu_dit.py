@@ -105,7 +105,7 @@ def test_bsi_on_native_dit_teacher_forced_trajectory():
     t = torch.linspace(0.0, 1.0, 17)
     lam, alpha = O.schedule(C32, t)
     k, lam_d, coef, c_in, t_rows = bsi._step_table(bsi.default_schedule)
-    assert torch.equal(lam_d.cpu(), lam)
+    torch.testing.assert_close(lam_d.cpu(), lam, rtol=2e-6, atol=0)  # CUDA exp vs CPU exp: <= 1 ulp apart
     from bsi_b200 import _lib as L
 
     with torch.inference_mode():
@@ -116,7 +116,8 @@ def test_bsi_on_native_dit_teacher_forced_trajectory():
             assert err < 3e-2, f"x_hat at step {i}: max abs err {err}"
             f = m.forward_scaled(mu, t[i].expand(2).to(dev()), c_in[i].expand(2))
             mu_next = mu.clone()
-            L.check(L.load().bsi_step_fused(L.ptr(mu_next), L.ptr(f), L.ptr(coef), None, i, 1, L.noise(eps=tr["eps"][j].to(dev())), None, None, 2,
+            eps_d = tr["eps"][j].to(dev())
+            L.check(L.load().bsi_step_fused(L.ptr(mu_next), L.ptr(f), L.ptr(coef), None, i, 1, L.noise(eps=eps_d), None, None, 2,
                                             12288, L.stream_ptr()))
             sync()
             ref = tr["mu_next"][j]

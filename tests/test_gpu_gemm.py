@@ -176,7 +176,8 @@ def test_patch_operand_and_time_embed():
     # in32 geometry with pitch padding (84 -> 88)
     mu2 = rnd("po.mu2", (B, C, 32, 32), 1.5)
     A2 = torch.full((B * 256, 88), 7.0, dtype=torch.bfloat16, device=dev())
-    call("bsi_dit_patch_operand", L.ptr(A2), L.ptr(mu2), L.rowref(torch.ones(1, device=dev()), 0), None, B, C, 32, 32, 2, 6, 8, 88, L.stream_ptr())
+    one = torch.ones(1, device=dev())
+    call("bsi_dit_patch_operand", L.ptr(A2), L.ptr(mu2), L.rowref(one, 0), None, B, C, 32, 32, 2, 6, 8, 88, L.stream_ptr())
     sync()
     ref2 = H.O.patchify(H.O.with_fourier(mu2.cpu(), (6, 8)), 2).reshape(B * 256, 84)
     report("patch operand in32", A2[:, :84], ref2, 1e-2, 1e-2)
@@ -184,6 +185,7 @@ def test_patch_operand_and_time_embed():
     t = torch.tensor([0.0, 1 / 256, 0.5, 1.0], device=dev())
     sc, bi = H.O.nyquist_tables(1024, 1000)
     o32 = torch.empty(4, 1024, device=dev())
-    call("bsi_time_embed", None, L.ptr(o32), L.ptr(t), L.ptr(sc.to(dev())), L.ptr(bi.to(dev())), 4, 1024, L.stream_ptr())
+    sc_d, bi_d = sc.to(dev()), bi.to(dev())
+    call("bsi_time_embed", None, L.ptr(o32), L.ptr(t), L.ptr(sc_d), L.ptr(bi_d), 4, 1024, L.stream_ptr())
     sync()
     report("time embed", o32, H.load_golden("embed.pt")["nyq1024_1000"], 1e-5, 2e-4)
