@@ -70,6 +70,7 @@ SIGNATURES = {
     "bsi_sqerr_reduce": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _vp]),
     "bsi_sqerr_backward": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _vp]),
     "bsi_gemm_bf16": (C.c_int, [C.POINTER(GemmArgs), _vp]),
+    "bsi_gemm_force_cta_group": (C.c_int, [_i32]),
     "bsi_cast_bf16": (C.c_int, [_vp, _vp, _i64, _i64, _i64, _vp]),
     "bsi_layernorm_mod_bf16": (C.c_int, [_vp, _vp, RowRef, RowRef, _vp, _vp, _vp, _i32, _i64, _i32, _f32, _vp]),
     "bsi_attention_bf16": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _vp]),

@@ -40,10 +40,12 @@ __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast
 __device__ __forceinline__ float4 ld4_stream(const float* p) { return __ldcs(reinterpret_cast<const float4*>(p)); }
 __device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
 
-// torch.addcmul(a, b, c) with value=1 rounds the product before the add (no FMA contraction), and the
-// reference's eager op chains round after every op; the explicit _rn intrinsics keep nvcc from fusing.
+// Rounding points follow the reference's eager torch ops: torch.addcmul(a, b, c) is a single FMA (measured on both
+// the CPU and the CUDA backend), every other op of a chain rounds separately; the explicit _rn intrinsics pin this
+// down so nvcc cannot contract differently.
 __device__ __forceinline__ float mul_rn(float a, float b) { return __fmul_rn(a, b); }
-__device__ __forceinline__ float addcmul_rn(float a, float b, float c) { return __fadd_rn(a, __fmul_rn(b, c)); }
+__device__ __forceinline__ float addcmul_rn(float a, float b, float c) { return __fmaf_rn(b, c, a); }  // torch.addcmul: one FMA (CPU and CUDA)
+__device__ __forceinline__ float add_mul_sep(float a, float b, float c) { return __fadd_rn(a, __fmul_rn(b, c)); }  // a + b*c as two eager ops
 
 __device__ __forceinline__ float4 noise4(const bsi_noise& nz, int step, int64_t sample, int64_t quad, int64_t D) {
     if (nz.eps) return ld4_stream(nz.eps + sample * D + quad * 4);
@@ -86,7 +88,7 @@ __global__ void __launch_bounds__(kThreads)
         for (int j = 0; j < 4; ++j) {
             // x_hat = addcmul(c_skip*mu, c_out, f); y = x_hat + rsqrt(alpha)*eps; mu' = (alpha*y + lam*mu)/lam_next
             xh[j] = kPrecond ? addcmul_rn(mul_rn(c_skip, mv[j]), c_out, fv[j]) : fv[j];
-            yv[j] = addcmul_rn(xh[j], sigma, ev[j]);
+            yv[j] = add_mul_sep(xh[j], sigma, ev[j]);
             out[j] = __fdiv_rn(__fadd_rn(mul_rn(alpha, yv[j]), mul_rn(lam, mv[j])), lam_next);
         }
         st4(mu + off, make_float4(out[0], out[1], out[2], out[3]));

@@ -1,17 +1,21 @@
 // bf16 x bf16 -> fp32 GEMM on the 5th-generation tensor cores (tcgen05.mma, accumulators in TMEM),
 // operands staged by TMA into 128B-swizzled shared memory, persistent CTAs, warp-specialised:
-//   warp 0  : TMA producer (one elected lane)
-//   warp 1  : MMA issuer   (one elected lane, tcgen05.mma cta_group::1, UMMA 128 x 256 x 16)
+//   warp 0  : TMA producer (one lane)
+//   warp 1  : MMA issuer   (one lane of the pair's leader CTA)
 //   warp 2  : TMEM allocator
 //   warps 4-7: epilogue (tcgen05.ld 32x32b -> registers -> fused epilogue -> global)
-// The accumulator is double-buffered in TMEM (2 x 256 columns) so the epilogue of tile i overlaps
-// the main loop of tile i+1.
+// Two variants of the same kernel (template parameter CG):
+//   CG = 2  CTA pair (cluster of 2, cta_group::2): UMMA 256 x 256 x 16, each CTA holds 128 rows of A and half of
+//           the W tile, so every operand byte fetched from L2 feeds twice the math of the single-CTA tile.  The
+//           single-CTA kernel measured 0.98 PFLOP/s — exactly the L2->SM bandwidth bound of a 128x256 tile
+//           (94 B/clk/SM needed at full MMA rate vs ~40 delivered); the pair needs 64 B/clk/SM.
+//   CG = 1  single CTA, UMMA 128 x 256 x 16 (small problems, cross-check in the tests).
+// The accumulator is double-buffered in TMEM (2 x 256 columns): the epilogue of tile i overlaps the main loop of
+// tile i+1.
 //
-// C[b][m][n] = epi( sum_k A[b][m][k] * W[b][n][k] ): both operands K-major (row-major activations
-// and nn.Linear weights), which is what every Linear of the reference DiT needs
-// (bsi/models/dit.py:33-34,71-76,79-81,154,163-165).
-//
-// Roofline: tensor-bound.  Algorithmic work 2*M*N*K flop per launch.
+// C[b][m][n] = epi( sum_k A[b][m][k] * W[b][n][k] ): both operands K-major (row-major activations and nn.Linear
+// weights) — every Linear of the reference DiT (bsi/models/dit.py:33-34,71-76,79-81,154,163-165).
+// Roofline: tensor-bound, 2*M*N*K flop per launch.
 #include <cuda.h>
 
 #include <vector>
@@ -21,13 +25,20 @@
 
 namespace bsi {
 
-constexpr int BM = 128, BN = 256, BK = 64;
-constexpr int UMMA_K = 16;
-constexpr int kStages = 4;
-constexpr int kABytes = BM * BK * 2, kBBytes = BN * BK * 2, kStageBytes = kABytes + kBBytes;
+constexpr int BM = 128;  // rows of A per CTA
+constexpr int BN = 256, BK = 64, UMMA_K = 16;
 constexpr int kGemmThreads = 256;
 constexpr int kTmemCols = 512;
-constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int kABytes = BM * BK * 2;
+
+template <int CG>
+struct Cfg {
+    static constexpr int kBRows = BN / CG;           // rows of the W tile this CTA loads
+    static constexpr int kBBytes = kBRows * BK * 2;
+    static constexpr int kStageBytes = kABytes + kBBytes;
+    static constexpr int kStages = CG == 1 ? 4 : 6;  // 192 KB of operand staging either way
+    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+};
 
 struct EpiParams {
     void* C;
@@ -50,9 +61,9 @@ __device__ __forceinline__ float gelu_tanh(float x) {
 }
 __device__ __forceinline__ float silu(float x) { return x / (1.0f + __expf(-x)); }
 
-// Epilogue for one thread's row and a chunk of 32 consecutive columns starting at n0.
+// Epilogue for one thread's row and a chunk of 32 consecutive columns starting at n0 (all modes but GATE_RESID).
 template <int EPI>
-__device__ __forceinline__ void epilogue_chunk(const EpiParams& ep, int batch, int row, int n0, const uint32_t (&acc)[32], int step) {
+__device__ __forceinline__ void epilogue_chunk(const EpiParams& ep, int batch, int row, int n0, const uint32_t (&acc)[32]) {
     if (row >= ep.M || n0 >= ep.N) return;
     const float* bias = ep.bias ? ep.bias + (long long)batch * ep.stride_bias : nullptr;
     float v[32];
@@ -90,20 +101,6 @@ __device__ __forceinline__ void epilogue_chunk(const EpiParams& ep, int batch, i
 #pragma unroll
         for (int j = 0; j < 32; j += 4)
             if (j < ncols) *reinterpret_cast<float4*>(out + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-    } else if constexpr (EPI == BSI_EPI_GATE_RESID_F32) {
-        // x = addcmul(x, gate, branch)  (bsi/models/dit.py:93-102)
-        float* out = reinterpret_cast<float*>(ep.C) + (long long)batch * ep.stride_c + (long long)row * ep.ldc + n0;
-        const float* g = rowref_ptr(ep.gate, row / ep.rows_per_sample, step) + n0;
-#pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-            if (j < ncols) {
-                float4 x4 = *reinterpret_cast<const float4*>(out + j);
-                float4 g4 = *reinterpret_cast<const float4*>(g + j);
-                x4.x = fmaf(g4.x, v[j], x4.x), x4.y = fmaf(g4.y, v[j + 1], x4.y);
-                x4.z = fmaf(g4.z, v[j + 2], x4.z), x4.w = fmaf(g4.w, v[j + 3], x4.w);
-                *reinterpret_cast<float4*>(out + j) = x4;
-            }
-        }
     } else if constexpr (EPI == BSI_EPI_POS_F32) {
         float* out = reinterpret_cast<float*>(ep.C) + (long long)batch * ep.stride_c + (long long)row * ep.ldc + n0;
         const float* p = ep.pos + (long long)(row % ep.rows_per_sample) * ep.N + n0;
@@ -130,13 +127,79 @@ __device__ __forceinline__ void epilogue_chunk(const EpiParams& ep, int batch, i
     }
 }
 
-template <int EPI>
+// Whole-tile epilogue of one warp: 32 rows (one per lane) x BN columns of TMEM buffer `taddr`.
+// `release()` must be called once, after the last tcgen05.ld of the buffer has completed.
+template <int EPI, class Release>
+__device__ __forceinline__ void epilogue_tile(const EpiParams& ep, int batch, int row, int n_base, uint32_t taddr, int step, Release release) {
+    if constexpr (EPI == BSI_EPI_GATE_RESID_F32) {
+        // x = addcmul(x, gate, branch)  (bsi/models/dit.py:93-102): fp32 read-modify-write of the residual stream.
+        // The residual row is prefetched one 64-column group ahead of the TMEM reads (16 independent 16-byte loads
+        // per thread in flight) — with loads issued one at a time behind the stores this epilogue ran at 17 TFLOP/s.
+        const bool valid = row < ep.M;
+        float* out = reinterpret_cast<float*>(ep.C) + (long long)batch * ep.stride_c + (long long)row * ep.ldc + n_base;
+        const float* gate = rowref_ptr(ep.gate, row / ep.rows_per_sample, step) + n_base;
+        const float* bias = ep.bias ? ep.bias + (long long)batch * ep.stride_bias + n_base : nullptr;
+        float4 res[2][16];
+        auto load_group = [&](int g, float4(&r)[16]) {
+            if (valid && n_base + g * 64 < ep.N) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) r[j] = *reinterpret_cast<const float4*>(out + g * 64 + 4 * j);
+            }
+        };
+        load_group(0, res[0]);
+#pragma unroll
+        for (int g = 0; g < BN / 64; ++g) {
+            if (g + 1 < BN / 64) load_group(g + 1, res[(g + 1) & 1]);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int c0 = g * 64 + h * 32;
+                uint32_t acc[32];
+                ptx::tmem_ld_32x32b_x32(taddr + c0, acc);
+                const bool live = valid && n_base + c0 < ep.N;
+                float4 g4[8], b4[8];
+                if (live) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        g4[j] = *reinterpret_cast<const float4*>(gate + c0 + 4 * j);
+                        b4[j] = bias ? *reinterpret_cast<const float4*>(bias + c0 + 4 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                }
+                ptx::tmem_ld_wait();
+                if (g == BN / 64 - 1 && h == 1) release();
+                if (live) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        float4 x4 = res[g & 1][h * 8 + j];
+                        x4.x = fmaf(g4[j].x, __uint_as_float(acc[4 * j]) + b4[j].x, x4.x);
+                        x4.y = fmaf(g4[j].y, __uint_as_float(acc[4 * j + 1]) + b4[j].y, x4.y);
+                        x4.z = fmaf(g4[j].z, __uint_as_float(acc[4 * j + 2]) + b4[j].z, x4.z);
+                        x4.w = fmaf(g4[j].w, __uint_as_float(acc[4 * j + 3]) + b4[j].w, x4.w);
+                        *reinterpret_cast<float4*>(out + c0 + 4 * j) = x4;
+                    }
+                }
+            }
+        }
+    } else {
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+            uint32_t acc[32];
+            ptx::tmem_ld_32x32b_x32(taddr + c0, acc);
+            ptx::tmem_ld_wait();
+            if (c0 + 32 >= BN) release();
+            epilogue_chunk<EPI>(ep, batch, row, n_base + c0, acc);
+        }
+    }
+}
+
+template <int EPI, int CG>
 __global__ void __launch_bounds__(kGemmThreads, 1)
     k_gemm_bf16(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, const EpiParams ep,
                 const int m_tiles, const int n_tiles, const int k_blocks, const int batch, const int a_shared) {
+    using C = Cfg<CG>;
+    constexpr int kStages = C::kStages;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * C::kStageBytes);
     uint64_t* empty_bar = full_bar + kStages;
     uint64_t* tmem_full = empty_bar + kStages;
     uint64_t* tmem_empty = tmem_full + 2;
@@ -144,6 +207,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int total_tiles = batch * m_tiles * n_tiles;
+    const int cta_rank = CG == 2 ? (int)ptx::cluster_ctarank() : 0;  // rank inside the CTA pair; 0 issues the MMAs
+    const int worker = CG == 2 ? blockIdx.x / 2 : blockIdx.x;          // persistent worker = CTA or CTA pair
+    const int num_workers = CG == 2 ? gridDim.x / 2 : gridDim.x;
 
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tensormap(&map_a);
@@ -151,47 +217,57 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < kStages; ++s) {
-            ptx::mbar_init(&full_bar[s], 1);
-            ptx::mbar_init(&empty_bar[s], 1);
+            ptx::mbar_init(&full_bar[s], 1);   // leader's arrive.expect_tx; TMA bytes of both CTAs land on the leader's barrier
+            ptx::mbar_init(&empty_bar[s], 1);  // tcgen05.commit (multicast to both CTAs of a pair)
         }
         for (int b = 0; b < 2; ++b) {
-            ptx::mbar_init(&tmem_full[b], 1);
-            ptx::mbar_init(&tmem_empty[b], 4);
+            ptx::mbar_init(&tmem_full[b], 1);        // tcgen05.commit after the last k-block
+            ptx::mbar_init(&tmem_empty[b], 4 * CG);  // one arrive per epilogue warp of every CTA of the pair
         }
         ptx::fence_mbar_init();
     }
     if (warp == 2) {
-        ptx::tmem_alloc<1>(tmem_slot, kTmemCols);
-        ptx::tmem_relinquish<1>();
+        ptx::tmem_alloc<CG>(tmem_slot, kTmemCols);
+        ptx::tmem_relinquish<CG>();
     }
     ptx::tc_fence_before();
-    __syncthreads();
+    if constexpr (CG == 2) ptx::cluster_sync_all();  // peer barriers must be initialised before remote arrives / TMA signals
+    else __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
         if (lane == 0) {
+            // ---------------- TMA producer: this CTA's 128 rows of A and its 256/CG rows of W per k-block
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            for (int tile = worker; tile < total_tiles; tile += num_workers) {
                 const int n_t = tile % n_tiles, m_t = (tile / n_tiles) % m_tiles, b = tile / (n_tiles * m_tiles);
+                const int row_a = (m_t * CG + cta_rank) * BM, row_w = n_t * BN + cta_rank * C::kBRows;
                 for (int kb = 0; kb < k_blocks; ++kb) {
                     ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
-                    ptx::mbar_arrive_expect_tx(&full_bar[stage], kStageBytes);
-                    uint8_t* sa = smem + stage * kStageBytes;
-                    ptx::tma_load_3d(sa, &map_a, &full_bar[stage], kb * BK, m_t * BM, a_shared ? 0 : b);
-                    ptx::tma_load_3d(sa + kABytes, &map_w, &full_bar[stage], kb * BK, n_t * BN, b);
+                    uint8_t* sa = smem + stage * C::kStageBytes;
+                    if constexpr (CG == 1) {
+                        ptx::mbar_arrive_expect_tx(&full_bar[stage], C::kStageBytes);
+                        ptx::tma_load_3d(sa, &map_a, &full_bar[stage], kb * BK, row_a, a_shared ? 0 : b);
+                        ptx::tma_load_3d(sa + kABytes, &map_w, &full_bar[stage], kb * BK, row_w, b);
+                    } else {
+                        if (cta_rank == 0) ptx::mbar_arrive_expect_tx(&full_bar[stage], 2 * C::kStageBytes);
+                        ptx::tma_load_3d_2sm(sa, &map_a, &full_bar[stage], kb * BK, row_a, a_shared ? 0 : b);
+                        ptx::tma_load_3d_2sm(sa + kABytes, &map_w, &full_bar[stage], kb * BK, row_w, b);
+                    }
                     if (++stage == kStages) stage = 0, phase ^= 1;
                 }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            constexpr uint32_t idesc = ptx::umma_idesc_bf16(BM, BN);
+        if (lane == 0 && cta_rank == 0) {
+            // ---------------- MMA issuer (leader CTA): D[tmem] += A[smem] * W[smem]^T, UMMA (128*CG) x 256 x 16
+            constexpr uint32_t idesc = ptx::umma_idesc_bf16(BM * CG, BN);
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+            for (int tile = worker; tile < total_tiles; tile += num_workers, ++it) {
                 const int buf = it & 1;
                 ptx::mbar_wait(&tmem_empty[buf], ((it >> 1) & 1) ^ 1);
                 ptx::tc_fence_after();
@@ -199,51 +275,52 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
                 for (int kb = 0; kb < k_blocks; ++kb) {
                     ptx::mbar_wait(&full_bar[stage], phase);
                     ptx::tc_fence_after();
-                    const uint32_t sa = ptx::smem_u32(smem + stage * kStageBytes);
+                    const uint32_t sa = ptx::smem_u32(smem + stage * C::kStageBytes);
                     const uint64_t da = ptx::umma_desc_k_sw128(sa), db = ptx::umma_desc_k_sw128(sa + kABytes);
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; ++k) {
                         // advance 32 B (16 bf16) inside the 128 B swizzle row: +2 in 16-byte address units
-                        ptx::umma_bf16_ss<1>(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                        ptx::umma_bf16_ss<CG>(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
                     }
-                    ptx::umma_commit<1>(&empty_bar[stage]);  // frees the smem stage when these MMAs retire
+                    // free the smem stage (in both CTAs) once these MMAs have retired
+                    if constexpr (CG == 1) ptx::umma_commit<1>(&empty_bar[stage]);
+                    else ptx::umma_commit_mcast2(&empty_bar[stage], 0x3);
                     if (++stage == kStages) stage = 0, phase ^= 1;
                 }
-                ptx::umma_commit<1>(&tmem_full[buf]);  // accumulator complete
+                if constexpr (CG == 1) ptx::umma_commit<1>(&tmem_full[buf]);  // accumulator complete
+                else ptx::umma_commit_mcast2(&tmem_full[buf], 0x3);
             }
         }
     } else if (warp >= 4) {
-        const int q = warp - 4;  // TMEM lane quarter == warp_id % 4
+        // ---------------- epilogue: warp q owns TMEM lanes [32q, 32q+32) = rows of this CTA's half of the tile
+        const int q = warp - 4;
         const int step = ep.step_ptr ? *ep.step_ptr : 0;
         int it = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        for (int tile = worker; tile < total_tiles; tile += num_workers, ++it) {
             const int n_t = tile % n_tiles, m_t = (tile / n_tiles) % m_tiles, b = tile / (n_tiles * m_tiles);
             const int buf = it & 1;
             ptx::mbar_wait(&tmem_full[buf], (it >> 1) & 1);
             ptx::tc_fence_after();
-            const int row = m_t * BM + q * 32 + lane;
+            const int row = (m_t * CG + cta_rank) * BM + q * 32 + lane;
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * BN;
-#pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += 32) {
-                uint32_t acc[32];
-                ptx::tmem_ld_32x32b_x32(taddr + c0, acc);
-                ptx::tmem_ld_wait();
-                if (c0 + 32 >= BN) {
-                    // all TMEM reads of this buffer are done: hand it back to the MMA warp before the last stores
-                    ptx::tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) ptx::mbar_arrive(&tmem_empty[buf]);
+            epilogue_tile<EPI>(ep, b, row, n_t * BN, taddr, step, [&]() {
+                // all TMEM reads of this buffer are done: hand it back to the MMA warp before the remaining stores
+                ptx::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                    if (CG == 1 || cta_rank == 0) ptx::mbar_arrive(&tmem_empty[buf]);
+                    else ptx::mbar_arrive_cluster(&tmem_empty[buf], 0);
                 }
-                epilogue_chunk<EPI>(ep, b, row, n_t * BN + c0, acc, step);
-            }
+            });
         }
     }
 
     ptx::tc_fence_before();
-    __syncthreads();
+    if constexpr (CG == 2) ptx::cluster_sync_all();
+    else __syncthreads();
     if (warp == 2) {
         ptx::tc_fence_after();
-        ptx::tmem_dealloc<1>(tmem_base, kTmemCols);
+        ptx::tmem_dealloc<CG>(tmem_base, kTmemCols);
     }
 }
 
@@ -298,31 +375,54 @@ struct GemmRecord {
 };
 static bool g_profile = false;
 static std::vector<GemmRecord> g_records;
+static int g_force_cta_group = 0;  // 0 = automatic, 1 / 2 = forced (tests)
 
-template <int EPI>
-static int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mw, const EpiParams& ep, int m_tiles, int n_tiles, int k_blocks,
-                       int batch, int a_shared, cudaStream_t stream, int k_dim) {
+template <int EPI, int CG>
+static int launch_gemm(const bsi_gemm_args* a, const EpiParams& ep, int a_shared, cudaStream_t stream) {
+    using C = Cfg<CG>;
     static bool configured = false;
     if (!configured) {
-        BSI_CUDA_OK(cudaFuncSetAttribute(k_gemm_bf16<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+        BSI_CUDA_OK(cudaFuncSetAttribute(k_gemm_bf16<EPI, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
         configured = true;
     }
-    int total = batch * m_tiles * n_tiles;
-    int grid = total < sm_count() ? total : sm_count();
+    CUtensorMap ma, mw;
+    int rc = make_operand_map(&ma, a->A, a->M, a->K, a->lda, a_shared ? 1 : a->batch, a->stride_a, BM);
+    if (rc != BSI_OK) return rc;
+    rc = make_operand_map(&mw, a->W, a->N, a->K, a->ldw, a->batch, a->stride_w, C::kBRows);
+    if (rc != BSI_OK) return rc;
+    const int m_tiles = (a->M + BM * CG - 1) / (BM * CG), n_tiles = (a->N + BN - 1) / BN, k_blocks = (a->K + BK - 1) / BK;
+    const int total = a->batch * m_tiles * n_tiles;
+    const int max_workers = sm_count() / CG;
+    const int workers = total < max_workers ? total : max_workers;
+
     GemmRecord rec{};
     if (g_profile) {
         BSI_CUDA_OK(cudaEventCreate(&rec.start));
         BSI_CUDA_OK(cudaEventCreate(&rec.stop));
-        rec.flops = 2.0 * batch * (double)ep.M * (double)ep.N * (double)k_dim;
+        rec.flops = 2.0 * a->batch * (double)a->M * (double)a->N * (double)a->K;
         BSI_CUDA_OK(cudaEventRecord(rec.start, stream));
     }
-    k_gemm_bf16<EPI><<<grid, kGemmThreads, kSmemBytes, stream>>>(ma, mw, ep, m_tiles, n_tiles, k_blocks, batch, a_shared);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(workers * CG), cfg.blockDim = dim3(kGemmThreads);
+    cfg.dynamicSmemBytes = C::kSmemBytes, cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CG, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr, cfg.numAttrs = 1;
+    BSI_CUDA_OK(cudaLaunchKernelEx(&cfg, k_gemm_bf16<EPI, CG>, ma, mw, ep, m_tiles, n_tiles, k_blocks, (int)a->batch, a_shared));
     BSI_LAUNCH_OK("k_gemm_bf16");
     if (g_profile) {
         BSI_CUDA_OK(cudaEventRecord(rec.stop, stream));
         g_records.push_back(rec);
     }
     return BSI_OK;
+}
+
+template <int EPI>
+static int dispatch_cta_group(const bsi_gemm_args* a, const EpiParams& ep, int a_shared, cudaStream_t stream) {
+    // CTA pairs pay off as soon as there are at least two 128-row blocks; tiny problems keep the finer 128-row tiles
+    const bool pair = g_force_cta_group ? g_force_cta_group == 2 : a->M > BM;
+    return pair ? launch_gemm<EPI, 2>(a, ep, a_shared, stream) : launch_gemm<EPI, 1>(a, ep, a_shared, stream);
 }
 
 }  // namespace bsi
@@ -342,38 +442,39 @@ extern "C" int bsi_gemm_bf16(const bsi_gemm_args* a, void* stream) {
     }
     BSI_CHECK_ARG(!a->bias || (reinterpret_cast<uintptr_t>(a->bias) & 15) == 0, "bsi_gemm_bf16: bias must be 16-byte aligned");
     if (a->epilogue == BSI_EPI_GATE_RESID_F32)
-        BSI_CHECK_ARG(a->gate.base && a->rows_per_sample > 0, "bsi_gemm_bf16: GATE_RESID needs gate and rows_per_sample");
+        BSI_CHECK_ARG(a->gate.base && a->rows_per_sample > 0 && a->N % 64 == 0 && (reinterpret_cast<uintptr_t>(a->gate.base) & 15) == 0,
+                      "bsi_gemm_bf16: GATE_RESID needs a 16-byte aligned gate, rows_per_sample and N %% 64 == 0");
     if (a->epilogue == BSI_EPI_POS_F32) BSI_CHECK_ARG(a->pos && a->rows_per_sample > 0, "bsi_gemm_bf16: POS needs pos table");
     if (a->epilogue == BSI_EPI_UNPATCH_F32)
         BSI_CHECK_ARG(a->patch > 0 && a->grid_w > 0 && a->channels > 0 && a->rows_per_sample % a->grid_w == 0 &&
                           a->N == a->patch * a->patch * a->channels && a->batch == 1,
                       "bsi_gemm_bf16: UNPATCH geometry invalid");
 
-    CUtensorMap ma, mw;
     const int a_shared = (a->batch > 1 && a->stride_a == 0) ? 1 : 0;
-    int rc = make_operand_map(&ma, a->A, a->M, a->K, a->lda, a_shared ? 1 : a->batch, a->stride_a, BM);
-    if (rc != BSI_OK) return rc;
-    rc = make_operand_map(&mw, a->W, a->N, a->K, a->ldw, a->batch, a->stride_w, BN);
-    if (rc != BSI_OK) return rc;
-
     EpiParams ep;
     ep.C = a->C, ep.bias = a->bias, ep.M = a->M, ep.N = a->N, ep.ldc = a->ldc;
     ep.stride_c = a->stride_c, ep.stride_bias = a->stride_bias;
     ep.gate = a->gate, ep.step_ptr = a->step_ptr, ep.rows_per_sample = a->rows_per_sample > 0 ? a->rows_per_sample : 1;
     ep.pos = a->pos, ep.patch = a->patch, ep.grid_w = a->grid_w, ep.channels = a->channels;
 
-    const int m_tiles = (a->M + BM - 1) / BM, n_tiles = (a->N + BN - 1) / BN, k_blocks = (a->K + BK - 1) / BK;
     cudaStream_t st = (cudaStream_t)stream;
     switch (a->epilogue) {
-        case BSI_EPI_BIAS_BF16: return launch_gemm<BSI_EPI_BIAS_BF16>(ma, mw, ep, m_tiles, n_tiles, k_blocks, a->batch, a_shared, st, a->K);
-        case BSI_EPI_BIAS_GELU_BF16: return launch_gemm<BSI_EPI_BIAS_GELU_BF16>(ma, mw, ep, m_tiles, n_tiles, k_blocks, a->batch, a_shared, st, a->K);
-        case BSI_EPI_BIAS_SILU_BF16: return launch_gemm<BSI_EPI_BIAS_SILU_BF16>(ma, mw, ep, m_tiles, n_tiles, k_blocks, a->batch, a_shared, st, a->K);
-        case BSI_EPI_BIAS_F32: return launch_gemm<BSI_EPI_BIAS_F32>(ma, mw, ep, m_tiles, n_tiles, k_blocks, a->batch, a_shared, st, a->K);
-        case BSI_EPI_GATE_RESID_F32: return launch_gemm<BSI_EPI_GATE_RESID_F32>(ma, mw, ep, m_tiles, n_tiles, k_blocks, a->batch, a_shared, st, a->K);
-        case BSI_EPI_POS_F32: return launch_gemm<BSI_EPI_POS_F32>(ma, mw, ep, m_tiles, n_tiles, k_blocks, a->batch, a_shared, st, a->K);
-        case BSI_EPI_UNPATCH_F32: return launch_gemm<BSI_EPI_UNPATCH_F32>(ma, mw, ep, m_tiles, n_tiles, k_blocks, a->batch, a_shared, st, a->K);
+        case BSI_EPI_BIAS_BF16: return dispatch_cta_group<BSI_EPI_BIAS_BF16>(a, ep, a_shared, st);
+        case BSI_EPI_BIAS_GELU_BF16: return dispatch_cta_group<BSI_EPI_BIAS_GELU_BF16>(a, ep, a_shared, st);
+        case BSI_EPI_BIAS_SILU_BF16: return dispatch_cta_group<BSI_EPI_BIAS_SILU_BF16>(a, ep, a_shared, st);
+        case BSI_EPI_BIAS_F32: return dispatch_cta_group<BSI_EPI_BIAS_F32>(a, ep, a_shared, st);
+        case BSI_EPI_GATE_RESID_F32: return dispatch_cta_group<BSI_EPI_GATE_RESID_F32>(a, ep, a_shared, st);
+        case BSI_EPI_POS_F32: return dispatch_cta_group<BSI_EPI_POS_F32>(a, ep, a_shared, st);
+        case BSI_EPI_UNPATCH_F32: return dispatch_cta_group<BSI_EPI_UNPATCH_F32>(a, ep, a_shared, st);
         default: set_error("bsi_gemm_bf16: unknown epilogue %d", a->epilogue); return BSI_ERR_INVALID_ARGUMENT;
     }
+}
+
+// Test hook: force the single-CTA (1) or CTA-pair (2) kernel, 0 = automatic choice.
+extern "C" int bsi_gemm_force_cta_group(int32_t cg) {
+    BSI_CHECK_ARG(cg >= 0 && cg <= 2, "bsi_gemm_force_cta_group: expected 0, 1 or 2");
+    g_force_cta_group = cg;
+    return BSI_OK;
 }
 
 // Start / stop timing every bsi_gemm_bf16 launch with CUDA events (not legal during stream capture).

@@ -93,14 +93,15 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, u
         "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
         : "memory");
 }
-// 2-CTA pair variant: data lands in this CTA's smem, completion bytes are signalled on the
-// barrier at the same offset in the pair's leader CTA (peer bit cleared in the address).
+// 2-CTA pair variant: data lands in this CTA's smem, completion bytes are signalled on the barrier at the same
+// offset in the pair's leader CTA (cluster rank 0; `mapa` gives its shared::cluster address).
 __device__ __forceinline__ void tma_load_3d_2sm(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
-    uint32_t bar_addr = smem_u32(bar) & 0xFEFFFFFFu;
     asm volatile(
+        "{\n\t.reg .b32 rb;\n\t"
+        "mapa.shared::cluster.u32 rb, %2, 0;\n\t"
         "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], "
-        "[%2];" ::"r"(smem_u32(dst)),
-        "l"(map), "r"(bar_addr), "r"(c0), "r"(c1), "r"(c2)
+        "[rb];\n\t}\n" ::"r"(smem_u32(dst)),
+        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
         : "memory");
 }
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
@@ -125,7 +126,8 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
     return r;
 }
 __device__ __forceinline__ void cluster_sync_all() {
-    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+    // non-.aligned forms: role lanes of a warp may arrive here at different times
+    asm volatile("barrier.cluster.arrive.release;\n\tbarrier.cluster.wait.acquire;" ::: "memory");
 }
 
 // ------------------------------------------------------------------ TMEM

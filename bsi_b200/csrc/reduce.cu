@@ -26,8 +26,8 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
 }
 
 __device__ __forceinline__ float combine(bool has_mu, float cs, float co, float m, float f) {
-    // addcmul(c_skip*mu, c_out, f): product rounded, then added (no FMA)
-    return has_mu ? __fadd_rn(__fmul_rn(cs, m), __fmul_rn(co, f)) : f;
+    // addcmul(c_skip*mu, c_out, f): torch evaluates addcmul as one FMA on the rounded c_skip*mu
+    return has_mu ? __fmaf_rn(co, f, __fmul_rn(cs, m)) : f;
 }
 
 __device__ __forceinline__ int bucket_of_r(float x, float lo_edge, float dx, int k) {

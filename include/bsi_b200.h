@@ -154,6 +154,9 @@ typedef struct bsi_gemm_args {
 
 int bsi_gemm_bf16(const bsi_gemm_args* args, void* stream);
 
+/* Test hook: force the single-CTA kernel (1) or the CTA-pair / cta_group::2 kernel (2); 0 restores the automatic choice. */
+int bsi_gemm_force_cta_group(int32_t cta_group);
+
 /* Measurement aid (bench.py roofline): between begin and end every bsi_gemm_bf16 launch is bracketed by
  * CUDA events on its stream; end synchronises them and returns the summed kernel time, the algorithmic
  * flops (2*M*N*K*batch) and the number of launches.  Not legal while the stream is being captured. */

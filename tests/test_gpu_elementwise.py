@@ -34,10 +34,14 @@ def test_step_fused_bit_exact_vs_oracle_on_cuda():
     """The oracle's op sequence executed by torch on the SAME GPU (the reference as it runs in production) must be
     reproduced bit for bit by the fused kernel: same fp32 ops, same rounding points, injected noise."""
     k, n, shape = 128, 8, (3, 64, 64)
-    t, lam, alpha, coef = step_table(k)
     D = int(np.prod(shape))
-    coef_d = coef.to(dev())
-    lam_d, alpha_d, t_d = lam.to(dev()), alpha.to(dev()), t.to(dev())
+    # tabulate the schedule with torch ops on the device, exactly as bsi_b200.BSI._step_table (and the reference) would
+    t_d = torch.linspace(0.0, 1.0, k + 1, device=dev())
+    lam_d, alpha_d = O.schedule(C32, t_d)
+    cs_d, co_d, _ = O.edm_coeffs(C32, t_d)
+    coef_d = torch.zeros(k + 1, 8, device=dev())
+    coef_d[:, 0], coef_d[:, 1] = cs_d, co_d
+    coef_d[:k, 2], coef_d[:k, 3], coef_d[:k, 4], coef_d[:k, 5] = torch.rsqrt(alpha_d), alpha_d, lam_d[:k], lam_d[1:]
     exact = []
     for i in (0, 3, 64, 127):
         mu = (3.0 * H.det_uniform(f"sx.mu{i}", (n, *shape))).to(dev())

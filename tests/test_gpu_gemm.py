@@ -13,6 +13,14 @@ from bsi_b200 import _lib as L
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(autouse=True, params=[2, 1], ids=["cta_pair", "single_cta"])
+def cta_group(request):
+    """Every test of this file runs against both GEMM kernels: the cta_group::2 pair kernel and the single-CTA one."""
+    call("bsi_gemm_force_cta_group", request.param)
+    yield request.param
+    call("bsi_gemm_force_cta_group", 0)
+
+
 def rnd(tag, shape, scale=1.0):
     return (scale * H.det_uniform(tag, shape)).to(dev())
 

@@ -59,9 +59,13 @@ def main():
         gate = torch.randn(M // 256, N, device=dev)
         a = gemm_args(A, W, Cc, bias, epi, M, N, K, gate=L.rowref(gate, N, 0, 0))
         ms = timeit(lambda: L.check(lib.bsi_gemm_bf16(ctypes.byref(a), st)))
+        lib.bsi_gemm_force_cta_group(1)
+        ms1 = timeit(lambda: L.check(lib.bsi_gemm_bf16(ctypes.byref(a), st)))
+        lib.bsi_gemm_force_cta_group(0)
         ms_cublas = timeit(lambda: torch.matmul(A, W.t()))
         fl = 2.0 * M * N * K
-        out.append(dict(kernel=f"gemm_{name}", M=M, N=N, K=K, ms=ms, tflops=fl / ms / 1e9, cublas_ms=ms_cublas, cublas_tflops=fl / ms_cublas / 1e9))
+        out.append(dict(kernel=f"gemm_{name}", M=M, N=N, K=K, ms=ms, tflops=fl / ms / 1e9, single_cta_tflops=fl / ms1 / 1e9, cublas_ms=ms_cublas,
+                        cublas_tflops=fl / ms_cublas / 1e9))
         print(json.dumps(out[-1]), flush=True)
         del A, W, Cc
     B = M // 256
