@@ -161,9 +161,18 @@ __global__ void __launch_bounds__(kAttThreads, 2)
     }
 }
 
+int attention_tcgen05(void* out_bf16, const void* qkv_bf16, int B, int heads, cudaStream_t stream);  // attention_sm100.cu
+static int g_force_legacy_attention = 0;
+
 }  // namespace bsi
 
 using namespace bsi;
+
+// Test hook: 1 forces the warp-level mma.sync kernel even where the tcgen05 kernel applies, 0 restores the default.
+extern "C" int bsi_attention_force_legacy(int32_t on) {
+    g_force_legacy_attention = on ? 1 : 0;
+    return BSI_OK;
+}
 
 extern "C" int bsi_attention_bf16(void* out_bf16, const void* qkv_bf16, int32_t B, int32_t T, int32_t heads, int32_t head_dim,
                                   void* stream) {
@@ -172,6 +181,7 @@ extern "C" int bsi_attention_bf16(void* out_bf16, const void* qkv_bf16, int32_t 
         set_error("bsi_attention_bf16: only head_dim=64 and T in {128,256,384,512} are implemented (got head_dim=%d T=%d)", head_dim, T);
         return BSI_ERR_UNSUPPORTED;
     }
+    if (T == 256 && !g_force_legacy_attention) return attention_tcgen05(out_bf16, qkv_bf16, B, heads, (cudaStream_t)stream);
     const int dim = heads * head_dim;
     const int smem = (kQRows + 2 * T) * 128;
     static int configured_smem = 0;

@@ -1,0 +1,211 @@
+// Fused non-causal attention for the DiT block on tcgen05 (bsi/models/dit.py:36-47), T = 256 tokens, head dim 64.
+//   qkv [B*T][3*dim] bf16, columns (qkv, head, channel)  ->  out [B*T][dim] bf16, columns (head, channel)
+// One CTA per (128-query block, head, sample), two CTAs resident per SM (256 TMEM columns each) so one CTA's softmax
+// (SFU-bound: 256 exp2 per thread) overlaps the other's MMAs:
+//   control warp : TMA loads of Q (128x64), K and V (256x64) into 128B-swizzled tiles; issues
+//                  S = Q K^T   UMMA 128x256x16 (x4, both operands K-major from smem)  -> TMEM columns [0,256)
+//                  O = P V     UMMA 128x64x16 (x16, A = P from TMEM, B = V MN-major from smem) -> TMEM columns [128,192)
+//   4 softmax warps (thread = query row): row max, p = exp2((s - max) * scale*log2e), row sum, P as packed bf16
+//                  written back over the S columns it replaces (tcgen05.st), final O / sum -> bf16 -> TMA store.
+// The whole 128x256 score tile lives in TMEM: single-pass softmax statistics in fp32, no rescaling.
+// Tensor-bound work 4*T*T*64 flop per (head, sample); the kernel's own ceiling is the SFU (16 ex2/clk/SM).
+#include <cuda.h>
+
+#include "common.cuh"
+#include "ptx_sm100.cuh"
+
+namespace bsi {
+
+int make_tile_map(CUtensorMap* map, const void* base, int esize, int64_t rows, int64_t cols, int64_t ld, int64_t batch, int64_t batch_stride,
+                  int box_rows);
+
+namespace att {
+constexpr int T = 256, HD = 64, QB = 128;
+constexpr int kThreads = 160;  // 4 softmax warps + 1 control warp
+constexpr int kTileBytes = QB * 128;  // 128 rows x 64 bf16
+constexpr int kSmem = 5 * kTileBytes /*Q, K(2), V(2)*/ + 1024 /*align*/ + 128 /*barriers*/;
+constexpr int kTmemCols = 256;
+constexpr int kOCol = 128;  // O accumulator columns [128, 192): S columns that are dead once P is complete
+}  // namespace att
+
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+__global__ void __launch_bounds__(att::kThreads, 2)
+    k_attention_tc(const __grid_constant__ CUtensorMap map_qkv, const __grid_constant__ CUtensorMap map_out, const int dim, const float scale_log2) {
+    using namespace att;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sQ = smem;                   // 128 x 64, later reused as the output staging tile
+    uint8_t* sK = smem + kTileBytes;      // 256 x 64 (two 128-row TMA boxes)
+    uint8_t* sV = smem + 3 * kTileBytes;  // 256 x 64
+    uint64_t* bar_qk = reinterpret_cast<uint64_t*>(smem + 5 * kTileBytes);
+    uint64_t* bar_v = bar_qk + 1;
+    uint64_t* bar_s = bar_qk + 2;  // S complete (tcgen05.commit)
+    uint64_t* bar_p = bar_qk + 3;  // P written by the 4 softmax warps
+    uint64_t* bar_o = bar_qk + 4;  // O complete (tcgen05.commit)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_qk + 5);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int qblk = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+    const int row0 = b * T;  // first token row of this sample in the [B*T] matrices
+
+    if (warp == 4) {
+        if (lane == 0) {
+            ptx::prefetch_tensormap(&map_qkv);
+            ptx::prefetch_tensormap(&map_out);
+            ptx::mbar_init(bar_qk, 1);
+            ptx::mbar_init(bar_v, 1);
+            ptx::mbar_init(bar_s, 1);
+            ptx::mbar_init(bar_p, 4);
+            ptx::mbar_init(bar_o, 1);
+            ptx::fence_mbar_init();
+        }
+        __syncwarp();
+        ptx::tmem_alloc<1>(tmem_slot, kTmemCols);
+        ptx::tmem_relinquish<1>();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == 4) {
+        if (lane == 0) {
+            // ---- loads: Q and K gate the first MMA, V only the second
+            ptx::mbar_arrive_expect_tx(bar_qk, 3 * kTileBytes);
+            ptx::tma_load_3d(sQ, &map_qkv, bar_qk, h * HD, row0 + qblk * QB, 0);
+            ptx::tma_load_3d(sK, &map_qkv, bar_qk, dim + h * HD, row0, 0);
+            ptx::tma_load_3d(sK + kTileBytes, &map_qkv, bar_qk, dim + h * HD, row0 + QB, 0);
+            ptx::mbar_arrive_expect_tx(bar_v, 2 * kTileBytes);
+            ptx::tma_load_3d(sV, &map_qkv, bar_v, 2 * dim + h * HD, row0, 0);
+            ptx::tma_load_3d(sV + kTileBytes, &map_qkv, bar_v, 2 * dim + h * HD, row0 + QB, 0);
+
+            // ---- S = Q K^T : M = 128 queries, N = 256 keys, K = 64 channels
+            ptx::mbar_wait(bar_qk, 0);
+            ptx::tc_fence_after();
+            {
+                constexpr uint32_t idesc = ptx::umma_idesc_bf16(QB, T);
+                const uint64_t dq = ptx::umma_desc_k_sw128(ptx::smem_u32(sQ)), dk = ptx::umma_desc_k_sw128(ptx::smem_u32(sK));
+#pragma unroll
+                for (int k = 0; k < HD / 16; ++k) ptx::umma_bf16_ss<1>(tmem, dq + 2 * k, dk + 2 * k, idesc, k != 0 ? 1u : 0u);
+                ptx::umma_commit<1>(bar_s);
+            }
+            // ---- O = P V : M = 128 queries, N = 64 channels, K = 256 keys; A = P (bf16, 8 TMEM columns per 16 keys),
+            //      B = V as stored (key rows of 64 contiguous channels = MN-major, 16 keys = 2048 B per k-step)
+            ptx::mbar_wait(bar_p, 0);
+            ptx::mbar_wait(bar_v, 0);
+            ptx::tc_fence_after();
+            {
+                constexpr uint32_t idesc = ptx::umma_idesc_bf16(QB, HD, 0, 1);
+                const uint32_t v0 = ptx::smem_u32(sV);
+#pragma unroll
+                for (int k = 0; k < T / 16; ++k) {
+                    const uint64_t dv = ptx::umma_desc_mn_sw128(v0 + k * 2048, 8192, 1024);
+                    ptx::umma_bf16_ts(tmem + kOCol, tmem + 8 * k, dv, idesc, k != 0 ? 1u : 0u);
+                }
+                ptx::umma_commit<1>(bar_o);
+            }
+        }
+    } else {
+        // ---- softmax warps: thread = query row (TMEM lane), 256 scores in 8 chunks of 32 columns
+        const int r = warp * 32 + lane;
+        const uint32_t trow = tmem + (static_cast<uint32_t>(warp * 32) << 16);
+        ptx::mbar_wait(bar_s, 0);
+        ptx::tc_fence_after();
+        float mx = -INFINITY;
+#pragma unroll 1
+        for (int c = 0; c < T / 32; ++c) {
+            uint32_t s[32];
+            ptx::tmem_ld_32x32b_x32(trow + c * 32, s);
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(s[j]));
+        }
+        const float moff = mx * scale_log2;
+        float sum = 0.0f;
+#pragma unroll 1
+        for (int c = 0; c < T / 32; ++c) {
+            uint32_t s[32];
+            ptx::tmem_ld_32x32b_x32(trow + c * 32, s);
+            ptx::tmem_ld_wait();
+            uint32_t p[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const float p0 = ex2_approx(fmaf(__uint_as_float(s[2 * j]), scale_log2, -moff));
+                const float p1 = ex2_approx(fmaf(__uint_as_float(s[2 * j + 1]), scale_log2, -moff));
+                const uint32_t pk = pack_bf16(p0, p1);
+                // the row sum uses the bf16-rounded probabilities that the PV product will see
+                sum += __uint_as_float(pk << 16) + __uint_as_float(pk & 0xffff0000u);
+                p[j] = pk;
+            }
+            // P chunk c (32 keys = 16 packed columns) overwrites S columns [16c, 16c+16), which are already consumed
+            ptx::tmem_st_32x32b_x16(trow + c * 16, p);
+        }
+        ptx::tmem_st_wait();
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(bar_p);
+
+        // ---- O / sum -> bf16 -> staging tile (the Q tile is dead) -> TMA store
+        const float inv = 1.0f / sum;
+        ptx::mbar_wait(bar_o, 0);
+        ptx::tc_fence_after();
+        uint32_t o[2][32];
+        ptx::tmem_ld_32x32b_x32(trow + kOCol, o[0]);
+        ptx::tmem_ld_32x32b_x32(trow + kOCol + 32, o[1]);
+        ptx::tmem_ld_wait();
+        const uint32_t sq = ptx::smem_u32(sQ);
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                uint32_t w[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    w[i] = pack_bf16(__uint_as_float(o[hh][c * 8 + 2 * i]) * inv, __uint_as_float(o[hh][c * 8 + 2 * i + 1]) * inv);
+                const uint32_t addr = sq + (uint32_t)(r * 128 + (((hh * 4 + c) ^ (r & 7)) << 4));
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
+            }
+        }
+        ptx::fence_proxy_async();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (threadIdx.x == 0) {
+            ptx::tma_store_3d(&map_out, sQ, h * HD, row0 + qblk * QB, 0);
+            ptx::tma_store_commit();
+            ptx::tma_store_wait_all<0>();
+        }
+    }
+
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 4) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc<1>(tmem, kTmemCols);
+    }
+}
+
+int attention_tcgen05(void* out_bf16, const void* qkv_bf16, int B, int heads, cudaStream_t stream) {
+    using namespace att;
+    const int dim = heads * HD;
+    static bool configured = false;
+    if (!configured) {
+        BSI_CUDA_OK(cudaFuncSetAttribute(k_attention_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+        configured = true;
+    }
+    CUtensorMap mq, mo;
+    int rc = make_tile_map(&mq, qkv_bf16, 2, (int64_t)B * T, 3 * dim, 3 * dim, 1, 0, QB);
+    if (rc != BSI_OK) return rc;
+    rc = make_tile_map(&mo, out_bf16, 2, (int64_t)B * T, dim, dim, 1, 0, QB);
+    if (rc != BSI_OK) return rc;
+    const float scale_log2 = 1.4426950408889634f / sqrtf((float)HD);
+    dim3 grid(T / QB, heads, B);
+    k_attention_tc<<<grid, kThreads, kSmem, stream>>>(mq, mo, dim, scale_log2);
+    BSI_LAUNCH_OK("k_attention_tc");
+    return BSI_OK;
+}
+
+}  // namespace bsi

@@ -3,15 +3,16 @@
 //   warp 0  : TMA producer (one lane)
 //   warp 1  : MMA issuer   (one lane of the pair's leader CTA)
 //   warp 2  : TMEM allocator
-//   warps 4-7: epilogue (tcgen05.ld 32x32b -> registers -> fused epilogue -> global)
+//   warps 4-7: epilogue: tcgen05.ld (64 columns per wait, next batch in flight) -> fused epilogue in registers ->
+//              128B-swizzled staging tile in shared memory -> TMA store.  The fp32 residual update
+//              (x += gate * branch) also *loads* its tile by TMA, two chunks ahead of the math.
 // Two variants of the same kernel (template parameter CG):
 //   CG = 2  CTA pair (cluster of 2, cta_group::2): UMMA 256 x 256 x 16, each CTA holds 128 rows of A and half of
-//           the W tile, so every operand byte fetched from L2 feeds twice the math of the single-CTA tile.  The
-//           single-CTA kernel measured 0.98 PFLOP/s — exactly the L2->SM bandwidth bound of a 128x256 tile
-//           (94 B/clk/SM needed at full MMA rate vs ~40 delivered); the pair needs 64 B/clk/SM.
+//           the W tile, so every operand byte fetched from L2 feeds twice the math of the single-CTA tile.
 //   CG = 1  single CTA, UMMA 128 x 256 x 16 (small problems, cross-check in the tests).
 // The accumulator is double-buffered in TMEM (2 x 256 columns): the epilogue of tile i overlaps the main loop of
-// tile i+1.
+// tile i+1.  (First version: per-thread scattered 16-byte global stores straight from registers kept the tensor
+// pipe 51 % busy on the QKV shape and 30 % on the out-projection — profiles/ncu_gemm_full_r01_first.csv.)
 //
 // C[b][m][n] = epi( sum_k A[b][m][k] * W[b][n][k] ): both operands K-major (row-major activations and nn.Linear
 // weights) — every Linear of the reference DiT (bsi/models/dit.py:33-34,71-76,79-81,154,163-165).
@@ -30,14 +31,27 @@ constexpr int BN = 256, BK = 64, UMMA_K = 16;
 constexpr int kGemmThreads = 256;
 constexpr int kTmemCols = 512;
 constexpr int kABytes = BM * BK * 2;
+constexpr int kEpiBufBytes = BM * 128;  // staging tile: 128 rows x 128 B (64 bf16 or 32 fp32 columns)
 
-template <int CG>
+enum EpiKind { KIND_BF16 = 0, KIND_F32 = 1, KIND_RMW = 2, KIND_SCATTER = 3 };
+__host__ __device__ constexpr int epi_kind(int epi) {
+    return epi <= BSI_EPI_BIAS_SILU_BF16 ? KIND_BF16
+           : epi == BSI_EPI_GATE_RESID_F32 ? KIND_RMW
+           : epi == BSI_EPI_UNPATCH_F32  ? KIND_SCATTER
+                                         : KIND_F32;
+}
+
+template <int EPI, int CG>
 struct Cfg {
-    static constexpr int kBRows = BN / CG;           // rows of the W tile this CTA loads
+    static constexpr int kKind = epi_kind(EPI);
+    static constexpr int kBRows = BN / CG;  // rows of the W tile this CTA loads
     static constexpr int kBBytes = kBRows * BK * 2;
     static constexpr int kStageBytes = kABytes + kBBytes;
-    static constexpr int kStages = CG == 1 ? 4 : 6;  // 192 KB of operand staging either way
-    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+    static constexpr int kEpiBufs = kKind == KIND_RMW ? 4 : (kKind == KIND_SCATTER ? 0 : 2);
+    static constexpr int kStages = CG == 2 ? (kKind == KIND_RMW ? 4 : 5) : 3;
+    static constexpr int kVecBytes = 2 * 2 * BN * 4;  // bias and gate slices of the tile, double-buffered by tile parity
+    static constexpr int kSmemBytes = kStages * kStageBytes + kEpiBufs * kEpiBufBytes + kVecBytes + 1024 /*align*/ + 256 /*barriers*/;
+    static_assert(kSmemBytes <= 232448, "exceeds the 227 KB of shared memory per CTA");
 };
 
 struct EpiParams {
@@ -61,149 +75,35 @@ __device__ __forceinline__ float gelu_tanh(float x) {
 }
 __device__ __forceinline__ float silu(float x) { return x / (1.0f + __expf(-x)); }
 
-// Epilogue for one thread's row and a chunk of 32 consecutive columns starting at n0 (all modes but GATE_RESID).
-template <int EPI>
-__device__ __forceinline__ void epilogue_chunk(const EpiParams& ep, int batch, int row, int n0, const uint32_t (&acc)[32]) {
-    if (row >= ep.M || n0 >= ep.N) return;
-    const float* bias = ep.bias ? ep.bias + (long long)batch * ep.stride_bias : nullptr;
-    float v[32];
-#pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc[j]);
-    const int ncols = min(32, ep.N - n0);  // multiple of 8 by contract (4 for UNPATCH)
-    if (bias) {
-#pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-            if (j < ncols) {
-                float4 b4 = *reinterpret_cast<const float4*>(bias + n0 + j);
-                v[j] += b4.x, v[j + 1] += b4.y, v[j + 2] += b4.z, v[j + 3] += b4.w;
-            }
-        }
-    }
-    if constexpr (EPI == BSI_EPI_BIAS_BF16 || EPI == BSI_EPI_BIAS_GELU_BF16 || EPI == BSI_EPI_BIAS_SILU_BF16) {
-        __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(ep.C) + (long long)batch * ep.stride_c + (long long)row * ep.ldc + n0;
-#pragma unroll
-        for (int j = 0; j < 32; j += 8) {
-            if (j < ncols) {
-                float w[8];
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    float t = v[j + i];
-                    if constexpr (EPI == BSI_EPI_BIAS_GELU_BF16) t = gelu_tanh(t);
-                    if constexpr (EPI == BSI_EPI_BIAS_SILU_BF16) t = silu(t);
-                    w[i] = t;
-                }
-                uint4 pk = make_uint4(pack_bf16(w[0], w[1]), pack_bf16(w[2], w[3]), pack_bf16(w[4], w[5]), pack_bf16(w[6], w[7]));
-                *reinterpret_cast<uint4*>(out + j) = pk;
-            }
-        }
-    } else if constexpr (EPI == BSI_EPI_BIAS_F32) {
-        float* out = reinterpret_cast<float*>(ep.C) + (long long)batch * ep.stride_c + (long long)row * ep.ldc + n0;
-#pragma unroll
-        for (int j = 0; j < 32; j += 4)
-            if (j < ncols) *reinterpret_cast<float4*>(out + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-    } else if constexpr (EPI == BSI_EPI_POS_F32) {
-        float* out = reinterpret_cast<float*>(ep.C) + (long long)batch * ep.stride_c + (long long)row * ep.ldc + n0;
-        const float* p = ep.pos + (long long)(row % ep.rows_per_sample) * ep.N + n0;
-#pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-            if (j < ncols) {
-                float4 p4 = *reinterpret_cast<const float4*>(p + j);
-                *reinterpret_cast<float4*>(out + j) = make_float4(v[j] + p4.x, v[j + 1] + p4.y, v[j + 2] + p4.z, v[j + 3] + p4.w);
-            }
-        }
-    } else if constexpr (EPI == BSI_EPI_UNPATCH_F32) {
-        // b (nh nw) (ph pw c) -> b c (nh ph) (nw pw)   (bsi/models/dit.py:166-172)
-        float* out = reinterpret_cast<float*>(ep.C);
-        const int T = ep.rows_per_sample, p = ep.patch, gw = ep.grid_w, ch = ep.channels;
-        const int b = row / T, tok = row - b * T;
-        const int gy = tok / gw, gx = tok - gy * gw;
-        const int Wimg = gw * p, Himg = (T / gw) * p;
-        for (int j = 0; j < ncols; ++j) {
-            int n = n0 + j;
-            int c = n % ch, within = n / ch;
-            int py = within / p, px = within - py * p;
-            out[(((long long)b * ch + c) * Himg + gy * p + py) * Wimg + gx * p + px] = v[j];
-        }
-    }
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
-
-// Whole-tile epilogue of one warp: 32 rows (one per lane) x BN columns of TMEM buffer `taddr`.
-// `release()` must be called once, after the last tcgen05.ld of the buffer has completed.
-template <int EPI, class Release>
-__device__ __forceinline__ void epilogue_tile(const EpiParams& ep, int batch, int row, int n_base, uint32_t taddr, int step, Release release) {
-    if constexpr (EPI == BSI_EPI_GATE_RESID_F32) {
-        // x = addcmul(x, gate, branch)  (bsi/models/dit.py:93-102): fp32 read-modify-write of the residual stream.
-        // The residual row is prefetched one 64-column group ahead of the TMEM reads (16 independent 16-byte loads
-        // per thread in flight) — with loads issued one at a time behind the stores this epilogue ran at 17 TFLOP/s.
-        const bool valid = row < ep.M;
-        float* out = reinterpret_cast<float*>(ep.C) + (long long)batch * ep.stride_c + (long long)row * ep.ldc + n_base;
-        const float* gate = rowref_ptr(ep.gate, row / ep.rows_per_sample, step) + n_base;
-        const float* bias = ep.bias ? ep.bias + (long long)batch * ep.stride_bias + n_base : nullptr;
-        float4 res[2][16];
-        auto load_group = [&](int g, float4(&r)[16]) {
-            if (valid && n_base + g * 64 < ep.N) {
-#pragma unroll
-                for (int j = 0; j < 16; ++j) r[j] = *reinterpret_cast<const float4*>(out + g * 64 + 4 * j);
-            }
-        };
-        load_group(0, res[0]);
-#pragma unroll
-        for (int g = 0; g < BN / 64; ++g) {
-            if (g + 1 < BN / 64) load_group(g + 1, res[(g + 1) & 1]);
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int c0 = g * 64 + h * 32;
-                uint32_t acc[32];
-                ptx::tmem_ld_32x32b_x32(taddr + c0, acc);
-                const bool live = valid && n_base + c0 < ep.N;
-                float4 g4[8], b4[8];
-                if (live) {
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        g4[j] = *reinterpret_cast<const float4*>(gate + c0 + 4 * j);
-                        b4[j] = bias ? *reinterpret_cast<const float4*>(bias + c0 + 4 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    }
-                }
-                ptx::tmem_ld_wait();
-                if (g == BN / 64 - 1 && h == 1) release();
-                if (live) {
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        float4 x4 = res[g & 1][h * 8 + j];
-                        x4.x = fmaf(g4[j].x, __uint_as_float(acc[4 * j]) + b4[j].x, x4.x);
-                        x4.y = fmaf(g4[j].y, __uint_as_float(acc[4 * j + 1]) + b4[j].y, x4.y);
-                        x4.z = fmaf(g4[j].z, __uint_as_float(acc[4 * j + 2]) + b4[j].z, x4.z);
-                        x4.w = fmaf(g4[j].w, __uint_as_float(acc[4 * j + 3]) + b4[j].w, x4.w);
-                        *reinterpret_cast<float4*>(out + c0 + 4 * j) = x4;
-                    }
-                }
-            }
-        }
-    } else {
-#pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
-            uint32_t acc[32];
-            ptx::tmem_ld_32x32b_x32(taddr + c0, acc);
-            ptx::tmem_ld_wait();
-            if (c0 + 32 >= BN) release();
-            epilogue_chunk<EPI>(ep, batch, row, n_base + c0, acc);
-        }
-    }
+__device__ __forceinline__ float4 ld_shared_f4(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+    return v;
 }
+// byte offset of 16-byte chunk `c` of row `r` inside a 128B-swizzled staging tile (what TMA SWIZZLE_128B expects)
+__device__ __forceinline__ uint32_t swz(int r, int c) { return (uint32_t)(r * 128 + ((c ^ (r & 7)) << 4)); }
 
 template <int EPI, int CG>
 __global__ void __launch_bounds__(kGemmThreads, 1)
-    k_gemm_bf16(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, const EpiParams ep,
-                const int m_tiles, const int n_tiles, const int k_blocks, const int batch, const int a_shared) {
-    using C = Cfg<CG>;
-    constexpr int kStages = C::kStages;
+    k_gemm_bf16(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
+                const __grid_constant__ CUtensorMap map_c, const EpiParams ep, const int m_tiles, const int n_tiles, const int k_blocks,
+                const int batch, const int a_shared) {
+    using C = Cfg<EPI, CG>;
+    constexpr int kStages = C::kStages, kKind = C::kKind;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * C::kStageBytes);
+    uint8_t* epi_buf = smem + kStages * C::kStageBytes;                       // kEpiBufs x 16 KB, 1024-aligned
+    float* s_vec = reinterpret_cast<float*>(epi_buf + C::kEpiBufs * kEpiBufBytes);  // [parity][bias|gate][256]
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(s_vec) + C::kVecBytes);
     uint64_t* empty_bar = full_bar + kStages;
     uint64_t* tmem_full = empty_bar + kStages;
     uint64_t* tmem_empty = tmem_full + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+    uint64_t* c_full = tmem_empty + 2;  // residual chunk landed (KIND_RMW), one per staging buffer
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(c_full + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int total_tiles = batch * m_tiles * n_tiles;
@@ -214,6 +114,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tensormap(&map_a);
         ptx::prefetch_tensormap(&map_w);
+        if (kKind != KIND_SCATTER) ptx::prefetch_tensormap(&map_c);
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < kStages; ++s) {
@@ -224,6 +125,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
             ptx::mbar_init(&tmem_full[b], 1);        // tcgen05.commit after the last k-block
             ptx::mbar_init(&tmem_empty[b], 4 * CG);  // one arrive per epilogue warp of every CTA of the pair
         }
+        for (int b = 0; b < 4; ++b) ptx::mbar_init(&c_full[b], 1);
         ptx::fence_mbar_init();
     }
     if (warp == 2) {
@@ -293,26 +195,189 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
         }
     } else if (warp >= 4) {
         // ---------------- epilogue: warp q owns TMEM lanes [32q, 32q+32) = rows of this CTA's half of the tile
-        const int q = warp - 4;
+        const int q = warp - 4, et = threadIdx.x - 128;  // et: epilogue thread 0..127 == row inside the CTA tile
         const int step = ep.step_ptr ? *ep.step_ptr : 0;
+        const uint32_t buf0 = ptx::smem_u32(epi_buf);
+        const int my_tiles = worker < total_tiles ? (total_tiles - worker + num_workers - 1) / num_workers : 0;
+
+        // KIND_RMW: residual chunk g (8 per tile, 32 fp32 columns each) of this CTA's tile sequence -> staging buffer g & 3
+        auto issue_residual_load = [&](int g) {
+            if (g >= my_tiles * 8) return;
+            const int tile = worker + (g >> 3) * num_workers, c = g & 7;
+            const int n_t = tile % n_tiles, m_t = (tile / n_tiles) % m_tiles, b = tile / (n_tiles * m_tiles);
+            ptx::mbar_arrive_expect_tx(&c_full[g & 3], kEpiBufBytes);
+            ptx::tma_load_3d(epi_buf + (g & 3) * kEpiBufBytes, &map_c, &c_full[g & 3], n_t * BN + c * 32, (m_t * CG + cta_rank) * BM, b);
+        };
+        if constexpr (kKind == KIND_RMW) {
+            if (et == 0) {
+                issue_residual_load(0);
+                issue_residual_load(1);
+            }
+        }
+
         int it = 0;
         for (int tile = worker; tile < total_tiles; tile += num_workers, ++it) {
             const int n_t = tile % n_tiles, m_t = (tile / n_tiles) % m_tiles, b = tile / (n_tiles * m_tiles);
             const int buf = it & 1;
+            const int row_base = (m_t * CG + cta_rank) * BM, n_base = n_t * BN;
+            const int row = row_base + et;
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * BN;
+
+            // stage the bias (and gate) slice of this tile in shared memory: every thread needs all 256 columns
+            float* s_bias = s_vec + (it & 1) * 2 * BN;
+            float* s_gate = s_bias + BN;
+            {
+                const float* bias = ep.bias ? ep.bias + (long long)b * ep.stride_bias : nullptr;
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const int n = n_base + et * 2 + j;
+                    s_bias[et * 2 + j] = (bias && n < ep.N) ? bias[n] : 0.0f;
+                    if constexpr (kKind == KIND_RMW) {
+                        // all 128 rows of the CTA tile belong to one sample (rows_per_sample % 128 == 0, checked on the host)
+                        s_gate[et * 2 + j] = (n < ep.N && row_base < ep.M) ? rowref_ptr(ep.gate, row_base / ep.rows_per_sample, step)[n] : 0.0f;
+                    }
+                }
+            }
+            epi_bar();
             ptx::mbar_wait(&tmem_full[buf], (it >> 1) & 1);
             ptx::tc_fence_after();
-            const int row = (m_t * CG + cta_rank) * BM + q * 32 + lane;
-            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * BN;
-            epilogue_tile<EPI>(ep, b, row, n_t * BN, taddr, step, [&]() {
-                // all TMEM reads of this buffer are done: hand it back to the MMA warp before the remaining stores
-                ptx::tc_fence_before();
-                __syncwarp();
-                if (lane == 0) {
-                    if (CG == 1 || cta_rank == 0) ptx::mbar_arrive(&tmem_empty[buf]);
-                    else ptx::mbar_arrive_cluster(&tmem_empty[buf], 0);
+
+            uint32_t acc[2][2][32];  // [batch parity][half][32 columns]: 64 columns per tcgen05.wait::ld, next batch in flight
+            ptx::tmem_ld_32x32b_x32(taddr, acc[0][0]);
+            ptx::tmem_ld_32x32b_x32(taddr + 32, acc[0][1]);
+#pragma unroll
+            for (int jb = 0; jb < BN / 64; ++jb) {
+                ptx::tmem_ld_wait();
+                if (jb + 1 < BN / 64) {
+                    ptx::tmem_ld_32x32b_x32(taddr + (jb + 1) * 64, acc[(jb + 1) & 1][0]);
+                    ptx::tmem_ld_32x32b_x32(taddr + (jb + 1) * 64 + 32, acc[(jb + 1) & 1][1]);
+                } else {
+                    // all TMEM reads of this buffer are done: hand it back to the MMA warp before the remaining stores
+                    ptx::tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) {
+                        if (CG == 1 || cta_rank == 0) ptx::mbar_arrive(&tmem_empty[buf]);
+                        else ptx::mbar_arrive_cluster(&tmem_empty[buf], 0);
+                    }
                 }
-            });
+                const uint32_t(&a)[2][32] = acc[jb & 1];
+
+                if constexpr (kKind == KIND_BF16) {
+                    // ---- 64 bf16 columns -> one 128 x 128 B staging tile -> TMA store
+                    const uint32_t sb = buf0 + (jb & 1) * kEpiBufBytes;
+                    if (et == 0) ptx::tma_store_wait_read<1>();  // the store that last read this buffer has drained
+                    epi_bar();
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            float w[8];
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                float t = __uint_as_float(a[h][c * 8 + i]) + s_bias[jb * 64 + h * 32 + c * 8 + i];
+                                if constexpr (EPI == BSI_EPI_BIAS_GELU_BF16) t = gelu_tanh(t);
+                                if constexpr (EPI == BSI_EPI_BIAS_SILU_BF16) t = silu(t);
+                                w[i] = t;
+                            }
+                            st_shared_v4(sb + swz(et, h * 4 + c), pack_bf16(w[0], w[1]), pack_bf16(w[2], w[3]), pack_bf16(w[4], w[5]),
+                                         pack_bf16(w[6], w[7]));
+                        }
+                    }
+                    ptx::fence_proxy_async();
+                    epi_bar();
+                    if (et == 0) {
+                        ptx::tma_store_3d(&map_c, epi_buf + (jb & 1) * kEpiBufBytes, n_base + jb * 64, row_base, b);
+                        ptx::tma_store_commit();
+                    }
+                } else if constexpr (kKind == KIND_F32) {
+                    // ---- 2 x (32 fp32 columns -> staging tile -> TMA store)
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int cidx = jb * 2 + h;  // 32-column chunk of the tile
+                        const uint32_t sb = buf0 + (cidx & 1) * kEpiBufBytes;
+                        if (et == 0) ptx::tma_store_wait_read<1>();
+                        epi_bar();
+                        const float* pos = nullptr;
+                        if constexpr (EPI == BSI_EPI_POS_F32) pos = ep.pos + (long long)(row % ep.rows_per_sample) * ep.N + n_base + cidx * 32;
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) {
+                            float4 v;
+                            v.x = __uint_as_float(a[h][c * 4 + 0]) + s_bias[cidx * 32 + c * 4 + 0];
+                            v.y = __uint_as_float(a[h][c * 4 + 1]) + s_bias[cidx * 32 + c * 4 + 1];
+                            v.z = __uint_as_float(a[h][c * 4 + 2]) + s_bias[cidx * 32 + c * 4 + 2];
+                            v.w = __uint_as_float(a[h][c * 4 + 3]) + s_bias[cidx * 32 + c * 4 + 3];
+                            if constexpr (EPI == BSI_EPI_POS_F32) {
+                                if (n_base + cidx * 32 + c * 4 < ep.N) {
+                                    const float4 p4 = *reinterpret_cast<const float4*>(pos + c * 4);
+                                    v.x += p4.x, v.y += p4.y, v.z += p4.z, v.w += p4.w;
+                                }
+                            }
+                            st_shared_v4(sb + swz(et, c), __float_as_uint(v.x), __float_as_uint(v.y), __float_as_uint(v.z), __float_as_uint(v.w));
+                        }
+                        ptx::fence_proxy_async();
+                        epi_bar();
+                        if (et == 0) {
+                            ptx::tma_store_3d(&map_c, epi_buf + (cidx & 1) * kEpiBufBytes, n_base + cidx * 32, row_base, b);
+                            ptx::tma_store_commit();
+                        }
+                    }
+                } else if constexpr (kKind == KIND_RMW) {
+                    // ---- x = addcmul(x, gate, branch) (bsi/models/dit.py:93-102): residual chunk arrives by TMA (issued two chunks
+                    //      ahead), is updated in place in shared memory and goes back by TMA store
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int cidx = jb * 2 + h;
+                        const int g = it * 8 + cidx;  // running chunk index of this CTA
+                        if (et == 0) {
+                            ptx::tma_store_wait_read<1>();  // buffer (g+2)&3 was last read by the store of chunk g-2
+                            issue_residual_load(g + 2);
+                        }
+                        ptx::mbar_wait(&c_full[g & 3], (g >> 2) & 1);
+                        const uint32_t sb = buf0 + (g & 3) * kEpiBufBytes;
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) {
+                            const uint32_t addr = sb + swz(et, c);
+                            float4 x4 = ld_shared_f4(addr);
+                            const float* gt = s_gate + cidx * 32 + c * 4;
+                            const float* bs = s_bias + cidx * 32 + c * 4;
+                            x4.x = fmaf(gt[0], __uint_as_float(a[h][c * 4 + 0]) + bs[0], x4.x);
+                            x4.y = fmaf(gt[1], __uint_as_float(a[h][c * 4 + 1]) + bs[1], x4.y);
+                            x4.z = fmaf(gt[2], __uint_as_float(a[h][c * 4 + 2]) + bs[2], x4.z);
+                            x4.w = fmaf(gt[3], __uint_as_float(a[h][c * 4 + 3]) + bs[3], x4.w);
+                            st_shared_v4(addr, __float_as_uint(x4.x), __float_as_uint(x4.y), __float_as_uint(x4.z), __float_as_uint(x4.w));
+                        }
+                        ptx::fence_proxy_async();
+                        epi_bar();
+                        if (et == 0) {
+                            ptx::tma_store_3d(&map_c, epi_buf + (g & 3) * kEpiBufBytes, n_base + cidx * 32, row_base, b);
+                            ptx::tma_store_commit();
+                        }
+                    }
+                } else {
+                    // ---- KIND_SCATTER: b (nh nw) (ph pw c) -> b c (nh ph) (nw pw)   (bsi/models/dit.py:166-172); N = p*p*c is tiny
+                    if (row < ep.M) {
+                        float* out = reinterpret_cast<float*>(ep.C);
+                        const int T = ep.rows_per_sample, p = ep.patch, gw = ep.grid_w, ch = ep.channels;
+                        const int bb = row / T, tok = row - bb * T;
+                        const int gy = tok / gw, gx = tok - gy * gw;
+                        const int Wimg = gw * p, Himg = (T / gw) * p;
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) {
+                                const int nl = jb * 64 + h * 32 + j, n = n_base + nl;
+                                if (n < ep.N) {
+                                    const int cc = n % ch, within = n / ch;
+                                    const int py = within / p, px = within - py * p;
+                                    out[(((long long)bb * ch + cc) * Himg + gy * p + py) * Wimg + gx * p + px] = __uint_as_float(a[h][j]) + s_bias[nl];
+                                }
+                            }
+                        }
+                    }
+                }
+            }
         }
+        if (et == 0) ptx::tma_store_wait_all<0>();  // every staged tile has reached global memory
     }
 
     ptx::tc_fence_before();
@@ -341,28 +406,29 @@ static EncodeTiledFn get_encode_fn() {
     return fn;
 }
 
-// bf16 [batch][rows][ld] tensor, box {64 (K), box_rows, 1}, 128-byte swizzle, zero fill out of bounds.
-int make_operand_map(CUtensorMap* map, const void* base, int64_t rows, int64_t K, int64_t ld, int64_t batch, int64_t batch_stride,
-                     int box_rows) {
+// [batch][rows][ld] tensor of `esize`-byte elements, box {128 B of columns, box_rows, 1}, 128-byte swizzle, zero fill out of bounds.
+int make_tile_map(CUtensorMap* map, const void* base, int esize, int64_t rows, int64_t cols, int64_t ld, int64_t batch, int64_t batch_stride,
+                  int box_rows) {
     EncodeTiledFn enc = get_encode_fn();
     if (!enc) {
         set_error("cuTensorMapEncodeTiled entry point unavailable");
         return BSI_ERR_CUDA;
     }
-    if ((reinterpret_cast<uintptr_t>(base) & 15) || (ld % 8) != 0 || (batch > 1 && (batch_stride % 8) != 0)) {
-        set_error("GEMM operand must be 16-byte aligned with pitch multiple of 8 elements (ld=%lld)", (long long)ld);
+    const int per16 = 16 / esize;
+    if ((reinterpret_cast<uintptr_t>(base) & 15) || (ld % per16) != 0 || (batch > 1 && (batch_stride % per16) != 0)) {
+        set_error("GEMM operand must be 16-byte aligned with a pitch multiple of 16 bytes (ld=%lld)", (long long)ld);
         return BSI_ERR_INVALID_ARGUMENT;
     }
-    cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)rows, (cuuint64_t)(batch > 1 ? batch : 1)};
-    cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)(batch > 1 ? batch_stride : rows * ld) * 2};
-    cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)box_rows, 1};
+    cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)(batch > 1 ? batch : 1)};
+    cuuint64_t strides[2] = {(cuuint64_t)ld * esize, (cuuint64_t)(batch > 1 ? batch_stride : rows * ld) * esize};
+    cuuint32_t box[3] = {(cuuint32_t)(128 / esize), (cuuint32_t)box_rows, 1};
     cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+    CUresult r = enc(map, esize == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(base), dims,
+                     strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
-        set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows=%lld K=%lld ld=%lld batch=%lld)", (int)r, (long long)rows,
-                  (long long)K, (long long)ld, (long long)batch);
+        set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows=%lld cols=%lld ld=%lld batch=%lld esize=%d)", (int)r, (long long)rows,
+                  (long long)cols, (long long)ld, (long long)batch, esize);
         return BSI_ERR_CUDA;
     }
     return BSI_OK;
@@ -379,17 +445,23 @@ static int g_force_cta_group = 0;  // 0 = automatic, 1 / 2 = forced (tests)
 
 template <int EPI, int CG>
 static int launch_gemm(const bsi_gemm_args* a, const EpiParams& ep, int a_shared, cudaStream_t stream) {
-    using C = Cfg<CG>;
+    using C = Cfg<EPI, CG>;
     static bool configured = false;
     if (!configured) {
         BSI_CUDA_OK(cudaFuncSetAttribute(k_gemm_bf16<EPI, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
         configured = true;
     }
-    CUtensorMap ma, mw;
-    int rc = make_operand_map(&ma, a->A, a->M, a->K, a->lda, a_shared ? 1 : a->batch, a->stride_a, BM);
+    CUtensorMap ma, mw, mc;
+    int rc = make_tile_map(&ma, a->A, 2, a->M, a->K, a->lda, a_shared ? 1 : a->batch, a->stride_a, BM);
     if (rc != BSI_OK) return rc;
-    rc = make_operand_map(&mw, a->W, a->N, a->K, a->ldw, a->batch, a->stride_w, C::kBRows);
+    rc = make_tile_map(&mw, a->W, 2, a->N, a->K, a->ldw, a->batch, a->stride_w, C::kBRows);
     if (rc != BSI_OK) return rc;
+    if (C::kKind != KIND_SCATTER) {
+        rc = make_tile_map(&mc, a->C, C::kKind == KIND_BF16 ? 2 : 4, a->M, a->N, a->ldc, a->batch, a->stride_c, BM);
+        if (rc != BSI_OK) return rc;
+    } else {
+        mc = ma;  // unused by the scatter epilogue
+    }
     const int m_tiles = (a->M + BM * CG - 1) / (BM * CG), n_tiles = (a->N + BN - 1) / BN, k_blocks = (a->K + BK - 1) / BK;
     const int total = a->batch * m_tiles * n_tiles;
     const int max_workers = sm_count() / CG;
@@ -409,7 +481,7 @@ static int launch_gemm(const bsi_gemm_args* a, const EpiParams& ep, int a_shared
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = CG, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr, cfg.numAttrs = 1;
-    BSI_CUDA_OK(cudaLaunchKernelEx(&cfg, k_gemm_bf16<EPI, CG>, ma, mw, ep, m_tiles, n_tiles, k_blocks, (int)a->batch, a_shared));
+    BSI_CUDA_OK(cudaLaunchKernelEx(&cfg, k_gemm_bf16<EPI, CG>, ma, mw, mc, ep, m_tiles, n_tiles, k_blocks, (int)a->batch, a_shared));
     BSI_LAUNCH_OK("k_gemm_bf16");
     if (g_profile) {
         BSI_CUDA_OK(cudaEventRecord(rec.stop, stream));
@@ -440,11 +512,11 @@ extern "C" int bsi_gemm_bf16(const bsi_gemm_args* a, void* stream) {
         BSI_CHECK_ARG(a->ldc >= a->N && a->ldc % (f32_out ? 4 : 8) == 0, "bsi_gemm_bf16: ldc=%d invalid for N=%d", a->ldc, a->N);
         BSI_CHECK_ARG((reinterpret_cast<uintptr_t>(a->C) & 15) == 0, "bsi_gemm_bf16: C must be 16-byte aligned");
     }
-    BSI_CHECK_ARG(!a->bias || (reinterpret_cast<uintptr_t>(a->bias) & 15) == 0, "bsi_gemm_bf16: bias must be 16-byte aligned");
     if (a->epilogue == BSI_EPI_GATE_RESID_F32)
-        BSI_CHECK_ARG(a->gate.base && a->rows_per_sample > 0 && a->N % 64 == 0 && (reinterpret_cast<uintptr_t>(a->gate.base) & 15) == 0,
-                      "bsi_gemm_bf16: GATE_RESID needs a 16-byte aligned gate, rows_per_sample and N %% 64 == 0");
-    if (a->epilogue == BSI_EPI_POS_F32) BSI_CHECK_ARG(a->pos && a->rows_per_sample > 0, "bsi_gemm_bf16: POS needs pos table");
+        BSI_CHECK_ARG(a->gate.base && a->rows_per_sample > 0 && a->rows_per_sample % BM == 0,
+                      "bsi_gemm_bf16: GATE_RESID needs a gate and rows_per_sample %% 128 == 0 (got %d)", a->rows_per_sample);
+    if (a->epilogue == BSI_EPI_POS_F32)
+        BSI_CHECK_ARG(a->pos && a->rows_per_sample > 0 && (reinterpret_cast<uintptr_t>(a->pos) & 15) == 0, "bsi_gemm_bf16: POS needs a 16-byte aligned pos table");
     if (a->epilogue == BSI_EPI_UNPATCH_F32)
         BSI_CHECK_ARG(a->patch > 0 && a->grid_w > 0 && a->channels > 0 && a->rows_per_sample % a->grid_w == 0 &&
                           a->N == a->patch * a->patch * a->channels && a->batch == 1,

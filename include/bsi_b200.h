@@ -176,6 +176,8 @@ int bsi_layernorm_mod_bf16(void* out_bf16, const float* x, bsi_rowref shift, bsi
 /* Multi-head attention over packed QKV (dit.py:36-47): qkv bf16 [B*T][3*dim] with columns
  * (qkv, head, channel); out bf16 [B*T][dim] with columns (head, channel).  head_dim = 64. */
 int bsi_attention_bf16(void* out_bf16, const void* qkv_bf16, int32_t B, int32_t T, int32_t heads, int32_t head_dim, void* stream);
+/* Test hook: T = 256 runs the tcgen05 kernel (scores in TMEM); 1 forces the warp-level mma.sync kernel used for other T. */
+int bsi_attention_force_legacy(int32_t on);
 
 /* Patch-embed operand (dit.py:149-153,228-231; fourier_features.py:24-36):
  *   A[b*T + tok][(py*p+px)*Cin + c] = bf16( feature_c( scale[b] * mu[b,:,y,x] ) )

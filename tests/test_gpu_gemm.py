@@ -156,9 +156,11 @@ def test_layernorm_modulate(dim):
     report(f"layernorm affine {dim}", out, F.layer_norm(x, (dim,), gamma, beta, 1e-5), 1e-2, 1e-2)
 
 
+@pytest.mark.parametrize("legacy", [0, 1], ids=["tcgen05", "mma_sync"])
 @pytest.mark.parametrize("heads,B", [(2, 2), (16, 3)])
-def test_attention(heads, B):
+def test_attention(heads, B, legacy):
     T, hd = 256, 64
+    call("bsi_attention_force_legacy", legacy)
     dim = heads * hd
     qkv = rnd(f"at.{heads}", (B * T, 3 * dim), 2.0).bfloat16()
     out = torch.zeros((B * T, dim), dtype=torch.bfloat16, device=dev())
@@ -166,7 +168,8 @@ def test_attention(heads, B):
     sync()
     q, k, v = qkv.float().reshape(B, T, 3, heads, hd).permute(2, 0, 3, 1, 4)
     ref = F.scaled_dot_product_attention(q, k, v).permute(0, 2, 1, 3).reshape(B * T, dim)
-    report(f"attention h{heads}", out, ref, 2e-2, 1e-2)
+    call("bsi_attention_force_legacy", 0)
+    report(f"attention h{heads} legacy={legacy}", out, ref, 2e-2, 1e-2)
 
 
 def test_patch_operand_and_time_embed():

@@ -72,10 +72,13 @@ def main():
     qkv = torch.randn(M, 3072, device=dev).bfloat16()
     o = torch.empty(M, 1024, device=dev, dtype=torch.bfloat16)
     ms = timeit(lambda: L.check(lib.bsi_attention_bf16(o.data_ptr(), qkv.data_ptr(), B, 256, 16, 64, st)))
+    lib.bsi_attention_force_legacy(1)
+    ms_legacy = timeit(lambda: L.check(lib.bsi_attention_bf16(o.data_ptr(), qkv.data_ptr(), B, 256, 16, 64, st)))
+    lib.bsi_attention_force_legacy(0)
     q, k, v = qkv.reshape(B, 256, 3, 16, 64).permute(2, 0, 3, 1, 4).contiguous()
     ms_sdpa = timeit(lambda: torch.nn.functional.scaled_dot_product_attention(q, k, v))
     fl = 4.0 * B * 16 * 256 * 256 * 64
-    print(json.dumps(dict(kernel="attention", B=B, ms=ms, tflops=fl / ms / 1e9, sdpa_ms=ms_sdpa, sdpa_tflops=fl / ms_sdpa / 1e9)), flush=True)
+    print(json.dumps(dict(kernel="attention", B=B, ms=ms, tflops=fl / ms / 1e9, mma_sync_ms=ms_legacy, sdpa_ms=ms_sdpa, sdpa_tflops=fl / ms_sdpa / 1e9)), flush=True)
     x = torch.randn(M, 1024, device=dev)
     tab = torch.randn(B, 6144, device=dev)
     xm = torch.empty(M, 1024, device=dev, dtype=torch.bfloat16)
