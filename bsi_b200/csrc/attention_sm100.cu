@@ -1,10 +1,11 @@
 // Fused non-causal attention for the DiT block on tcgen05 (bsi/models/dit.py:36-47), T = 256 tokens, head dim 64.
 //   qkv [B*T][3*dim] bf16, columns (qkv, head, channel)  ->  out [B*T][dim] bf16, columns (head, channel)
-// One CTA per (128-query block, head, sample), two CTAs resident per SM (256 TMEM columns each) so one CTA's softmax
-// (SFU-bound: 256 exp2 per thread) overlaps the other's MMAs:
-//   control warp : TMA loads of Q (128x64), K and V (256x64) into 128B-swizzled tiles; issues
-//                  S = Q K^T   UMMA 128x256x16 (x4, both operands K-major from smem)  -> TMEM columns [0,256)
-//                  O = P V     UMMA 128x64x16 (x16, A = P from TMEM, B = V MN-major from smem) -> TMEM columns [128,192)
+// Persistent kernel, two CTAs resident per SM (256 TMEM columns each); a work item is one (128-query block, head,
+// sample).  While one CTA is in its softmax (SFU-bound: 256 exp2 per thread) the other one runs its MMAs.
+//   control warp : TMA loads of Q (128x64), K and V (256x64) into 128B-swizzled tiles, issued for item i+1 as soon as
+//                  the MMAs of item i have consumed the buffers (Q,K after S; V after O), so loads never stall; issues
+//                  S = Q K^T   UMMA 128x256x16 (x4, both operands K-major from smem)        -> TMEM columns [0,256)
+//                  O = P V     UMMA 128x64x16 (x16, A = P from TMEM, B = V MN-major smem)  -> TMEM columns [128,192)
 //   4 softmax warps (thread = query row): row max, p = exp2((s - max) * scale*log2e), row sum, P as packed bf16
 //                  written back over the S columns it replaces (tcgen05.st), final O / sum -> bf16 -> TMA store.
 // The whole 128x256 score tile lives in TMEM: single-pass softmax statistics in fp32, no rescaling.
@@ -21,9 +22,9 @@ int make_tile_map(CUtensorMap* map, const void* base, int esize, int64_t rows, i
 
 namespace att {
 constexpr int T = 256, HD = 64, QB = 128;
-constexpr int kThreads = 160;  // 4 softmax warps + 1 control warp
+constexpr int kThreads = 160;         // 4 softmax warps + 1 control warp
 constexpr int kTileBytes = QB * 128;  // 128 rows x 64 bf16
-constexpr int kSmem = 5 * kTileBytes /*Q, K(2), V(2)*/ + 1024 /*align*/ + 128 /*barriers*/;
+constexpr int kSmem = 6 * kTileBytes /*Q, K(2), V(2), out staging*/ + 1024 /*align*/ + 128 /*barriers*/;
 constexpr int kTmemCols = 256;
 constexpr int kOCol = 128;  // O accumulator columns [128, 192): S columns that are dead once P is complete
 }  // namespace att
@@ -35,23 +36,24 @@ __device__ __forceinline__ float ex2_approx(float x) {
 }
 
 __global__ void __launch_bounds__(att::kThreads, 2)
-    k_attention_tc(const __grid_constant__ CUtensorMap map_qkv, const __grid_constant__ CUtensorMap map_out, const int dim, const float scale_log2) {
+    k_attention_tc(const __grid_constant__ CUtensorMap map_qkv, const __grid_constant__ CUtensorMap map_out, const int dim, const int heads,
+                   const int total_items, const float scale_log2) {
     using namespace att;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* sQ = smem;                   // 128 x 64, later reused as the output staging tile
-    uint8_t* sK = smem + kTileBytes;      // 256 x 64 (two 128-row TMA boxes)
-    uint8_t* sV = smem + 3 * kTileBytes;  // 256 x 64
-    uint64_t* bar_qk = reinterpret_cast<uint64_t*>(smem + 5 * kTileBytes);
+    uint8_t* sQ = smem;                    // 128 x 64
+    uint8_t* sK = smem + kTileBytes;       // 256 x 64 (two 128-row TMA boxes)
+    uint8_t* sV = smem + 3 * kTileBytes;   // 256 x 64
+    uint8_t* sO = smem + 5 * kTileBytes;   // output staging tile
+    uint64_t* bar_qk = reinterpret_cast<uint64_t*>(smem + 6 * kTileBytes);
     uint64_t* bar_v = bar_qk + 1;
-    uint64_t* bar_s = bar_qk + 2;  // S complete (tcgen05.commit)
-    uint64_t* bar_p = bar_qk + 3;  // P written by the 4 softmax warps
-    uint64_t* bar_o = bar_qk + 4;  // O complete (tcgen05.commit)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_qk + 5);
+    uint64_t* bar_s = bar_qk + 2;      // S complete (tcgen05.commit): softmax may start, Q/K tiles may be refilled
+    uint64_t* bar_p = bar_qk + 3;      // P written by the 4 softmax warps
+    uint64_t* bar_o = bar_qk + 4;      // O complete (tcgen05.commit): epilogue may start, V tile may be refilled
+    uint64_t* bar_ofree = bar_qk + 5;  // O (and with it the whole TMEM tile) read out by the 4 softmax warps
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_qk + 6);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int qblk = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
-    const int row0 = b * T;  // first token row of this sample in the [B*T] matrices
 
     if (warp == 4) {
         if (lane == 0) {
@@ -62,6 +64,7 @@ __global__ void __launch_bounds__(att::kThreads, 2)
             ptx::mbar_init(bar_s, 1);
             ptx::mbar_init(bar_p, 4);
             ptx::mbar_init(bar_o, 1);
+            ptx::mbar_init(bar_ofree, 4);
             ptx::fence_mbar_init();
         }
         __syncwarp();
@@ -73,111 +76,162 @@ __global__ void __launch_bounds__(att::kThreads, 2)
     ptx::tc_fence_after();
     const uint32_t tmem = *tmem_slot;
 
+    // work item -> (query block, head, sample); consecutive items share K/V in L2
+    auto coords = [&](int item, int& qblk, int& h, int& row0) {
+        qblk = item & 1;
+        const int bh = item >> 1;
+        h = bh % heads;
+        row0 = (bh / heads) * T;
+    };
+
     if (warp == 4) {
         if (lane == 0) {
-            // ---- loads: Q and K gate the first MMA, V only the second
-            ptx::mbar_arrive_expect_tx(bar_qk, 3 * kTileBytes);
-            ptx::tma_load_3d(sQ, &map_qkv, bar_qk, h * HD, row0 + qblk * QB, 0);
-            ptx::tma_load_3d(sK, &map_qkv, bar_qk, dim + h * HD, row0, 0);
-            ptx::tma_load_3d(sK + kTileBytes, &map_qkv, bar_qk, dim + h * HD, row0 + QB, 0);
-            ptx::mbar_arrive_expect_tx(bar_v, 2 * kTileBytes);
-            ptx::tma_load_3d(sV, &map_qkv, bar_v, 2 * dim + h * HD, row0, 0);
-            ptx::tma_load_3d(sV + kTileBytes, &map_qkv, bar_v, 2 * dim + h * HD, row0 + QB, 0);
+            auto load_qk = [&](int item) {
+                int qblk, h, row0;
+                coords(item, qblk, h, row0);
+                ptx::mbar_arrive_expect_tx(bar_qk, 3 * kTileBytes);
+                ptx::tma_load_3d(sQ, &map_qkv, bar_qk, h * HD, row0 + qblk * QB, 0);
+                ptx::tma_load_3d(sK, &map_qkv, bar_qk, dim + h * HD, row0, 0);
+                ptx::tma_load_3d(sK + kTileBytes, &map_qkv, bar_qk, dim + h * HD, row0 + QB, 0);
+            };
+            auto load_v = [&](int item) {
+                int qblk, h, row0;
+                coords(item, qblk, h, row0);
+                ptx::mbar_arrive_expect_tx(bar_v, 2 * kTileBytes);
+                ptx::tma_load_3d(sV, &map_qkv, bar_v, 2 * dim + h * HD, row0, 0);
+                ptx::tma_load_3d(sV + kTileBytes, &map_qkv, bar_v, 2 * dim + h * HD, row0 + QB, 0);
+            };
+            constexpr uint32_t idesc_s = ptx::umma_idesc_bf16(QB, T);
+            constexpr uint32_t idesc_o = ptx::umma_idesc_bf16(QB, HD, 0, 1);
+            const uint64_t dq = ptx::umma_desc_k_sw128(ptx::smem_u32(sQ)), dk = ptx::umma_desc_k_sw128(ptx::smem_u32(sK));
+            const uint32_t v0 = ptx::smem_u32(sV);
 
-            // ---- S = Q K^T : M = 128 queries, N = 256 keys, K = 64 channels
-            ptx::mbar_wait(bar_qk, 0);
-            ptx::tc_fence_after();
-            {
-                constexpr uint32_t idesc = ptx::umma_idesc_bf16(QB, T);
-                const uint64_t dq = ptx::umma_desc_k_sw128(ptx::smem_u32(sQ)), dk = ptx::umma_desc_k_sw128(ptx::smem_u32(sK));
-#pragma unroll
-                for (int k = 0; k < HD / 16; ++k) ptx::umma_bf16_ss<1>(tmem, dq + 2 * k, dk + 2 * k, idesc, k != 0 ? 1u : 0u);
-                ptx::umma_commit<1>(bar_s);
+            if ((int)blockIdx.x < total_items) {
+                load_qk(blockIdx.x);
+                load_v(blockIdx.x);
             }
-            // ---- O = P V : M = 128 queries, N = 64 channels, K = 256 keys; A = P (bf16, 8 TMEM columns per 16 keys),
-            //      B = V as stored (key rows of 64 contiguous channels = MN-major, 16 keys = 2048 B per k-step)
-            ptx::mbar_wait(bar_p, 0);
-            ptx::mbar_wait(bar_v, 0);
-            ptx::tc_fence_after();
-            {
-                constexpr uint32_t idesc = ptx::umma_idesc_bf16(QB, HD, 0, 1);
-                const uint32_t v0 = ptx::smem_u32(sV);
+            int it = 0;
+            for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++it) {
+                const uint32_t ph = it & 1;
+                const int next = item + gridDim.x;
+                // ---- S = Q K^T : M = 128 queries, N = 256 keys, K = 64 channels (needs the previous item's O read out)
+                ptx::mbar_wait(bar_qk, ph);
+                ptx::mbar_wait(bar_ofree, ph ^ 1);
+                ptx::tc_fence_after();
+#pragma unroll
+                for (int k = 0; k < HD / 16; ++k) ptx::umma_bf16_ss<1>(tmem, dq + 2 * k, dk + 2 * k, idesc_s, k != 0 ? 1u : 0u);
+                ptx::umma_commit<1>(bar_s);
+                // Q and K are free once S has been computed: prefetch the next item behind this item's softmax
+                ptx::mbar_wait(bar_s, ph);
+                if (next < total_items) load_qk(next);
+                // ---- O = P V : M = 128 queries, N = 64 channels, K = 256 keys; A = P (bf16, 8 TMEM columns per 16 keys),
+                //      B = V as stored (key rows of 64 contiguous channels = MN-major, 16 keys = 2048 B per k-step)
+                ptx::mbar_wait(bar_p, ph);
+                ptx::mbar_wait(bar_v, ph);
+                ptx::tc_fence_after();
 #pragma unroll
                 for (int k = 0; k < T / 16; ++k) {
                     const uint64_t dv = ptx::umma_desc_mn_sw128(v0 + k * 2048, 8192, 1024);
-                    ptx::umma_bf16_ts(tmem + kOCol, tmem + 8 * k, dv, idesc, k != 0 ? 1u : 0u);
+                    ptx::umma_bf16_ts(tmem + kOCol, tmem + 8 * k, dv, idesc_o, k != 0 ? 1u : 0u);
                 }
                 ptx::umma_commit<1>(bar_o);
+                ptx::mbar_wait(bar_o, ph);
+                if (next < total_items) load_v(next);
             }
         }
     } else {
-        // ---- softmax warps: thread = query row (TMEM lane), 256 scores in 8 chunks of 32 columns
+        // ---- softmax warps: thread = query row (TMEM lane); 256 scores read in batches of 64 columns, next batch in flight
         const int r = warp * 32 + lane;
         const uint32_t trow = tmem + (static_cast<uint32_t>(warp * 32) << 16);
-        ptx::mbar_wait(bar_s, 0);
-        ptx::tc_fence_after();
-        float mx = -INFINITY;
-#pragma unroll 1
-        for (int c = 0; c < T / 32; ++c) {
-            uint32_t s[32];
-            ptx::tmem_ld_32x32b_x32(trow + c * 32, s);
-            ptx::tmem_ld_wait();
-#pragma unroll
-            for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(s[j]));
-        }
-        const float moff = mx * scale_log2;
-        float sum = 0.0f;
-#pragma unroll 1
-        for (int c = 0; c < T / 32; ++c) {
-            uint32_t s[32];
-            ptx::tmem_ld_32x32b_x32(trow + c * 32, s);
-            ptx::tmem_ld_wait();
-            uint32_t p[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const float p0 = ex2_approx(fmaf(__uint_as_float(s[2 * j]), scale_log2, -moff));
-                const float p1 = ex2_approx(fmaf(__uint_as_float(s[2 * j + 1]), scale_log2, -moff));
-                const uint32_t pk = pack_bf16(p0, p1);
-                // the row sum uses the bf16-rounded probabilities that the PV product will see
-                sum += __uint_as_float(pk << 16) + __uint_as_float(pk & 0xffff0000u);
-                p[j] = pk;
-            }
-            // P chunk c (32 keys = 16 packed columns) overwrites S columns [16c, 16c+16), which are already consumed
-            ptx::tmem_st_32x32b_x16(trow + c * 16, p);
-        }
-        ptx::tmem_st_wait();
-        ptx::tc_fence_before();
-        __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(bar_p);
+        const uint32_t so = ptx::smem_u32(sO);
+        int it = 0;
+        for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++it) {
+            const uint32_t ph = it & 1;
+            int qblk, h, row0;
+            coords(item, qblk, h, row0);
+            ptx::mbar_wait(bar_s, ph);
+            ptx::tc_fence_after();
 
-        // ---- O / sum -> bf16 -> staging tile (the Q tile is dead) -> TMA store
-        const float inv = 1.0f / sum;
-        ptx::mbar_wait(bar_o, 0);
-        ptx::tc_fence_after();
-        uint32_t o[2][32];
-        ptx::tmem_ld_32x32b_x32(trow + kOCol, o[0]);
-        ptx::tmem_ld_32x32b_x32(trow + kOCol + 32, o[1]);
-        ptx::tmem_ld_wait();
-        const uint32_t sq = ptx::smem_u32(sQ);
+            uint32_t s[2][2][32];
+            float mx = -INFINITY;
+            ptx::tmem_ld_32x32b_x32(trow, s[0][0]);
+            ptx::tmem_ld_32x32b_x32(trow + 32, s[0][1]);
 #pragma unroll
-        for (int hh = 0; hh < 2; ++hh) {
+            for (int bt = 0; bt < T / 64; ++bt) {
+                ptx::tmem_ld_wait();
+                // after the last max batch, start re-reading batch 0 for the exponent pass
+                const int nb = (bt + 1) & 3;
+                ptx::tmem_ld_32x32b_x32(trow + nb * 64, s[(bt + 1) & 1][0]);
+                ptx::tmem_ld_32x32b_x32(trow + nb * 64 + 32, s[(bt + 1) & 1][1]);
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                uint32_t w[4];
+                for (int hh = 0; hh < 2; ++hh)
 #pragma unroll
-                for (int i = 0; i < 4; ++i)
-                    w[i] = pack_bf16(__uint_as_float(o[hh][c * 8 + 2 * i]) * inv, __uint_as_float(o[hh][c * 8 + 2 * i + 1]) * inv);
-                const uint32_t addr = sq + (uint32_t)(r * 128 + (((hh * 4 + c) ^ (r & 7)) << 4));
-                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
+                    for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(s[bt & 1][hh][j]));
+            }
+            const float moff = mx * scale_log2;
+            float sum = 0.0f;
+#pragma unroll
+            for (int bt = 0; bt < T / 64; ++bt) {
+                ptx::tmem_ld_wait();  // batch bt sits in s[bt & 1] (T/64 is even, so the parity carries over from the max pass)
+                if (bt + 1 < T / 64) {
+                    ptx::tmem_ld_32x32b_x32(trow + (bt + 1) * 64, s[(bt + 1) & 1][0]);
+                    ptx::tmem_ld_32x32b_x32(trow + (bt + 1) * 64 + 32, s[(bt + 1) & 1][1]);
+                }
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh) {
+                    uint32_t p[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const float p0 = ex2_approx(fmaf(__uint_as_float(s[bt & 1][hh][2 * j]), scale_log2, -moff));
+                        const float p1 = ex2_approx(fmaf(__uint_as_float(s[bt & 1][hh][2 * j + 1]), scale_log2, -moff));
+                        const uint32_t pk = pack_bf16(p0, p1);
+                        // the row sum uses the bf16-rounded probabilities that the PV product will see
+                        sum += __uint_as_float(pk << 16) + __uint_as_float(pk & 0xffff0000u);
+                        p[j] = pk;
+                    }
+                    // P for keys [64bt+32hh, +32) = 16 packed columns at [32bt+16hh, +16): S columns that were read before
+                    // (the in-flight load of batch bt+1 covers columns >= 64(bt+1) > 32bt+32)
+                    ptx::tmem_st_32x32b_x16(trow + bt * 32 + hh * 16, p);
+                }
+            }
+            ptx::tmem_st_wait();
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(bar_p);
+
+            // ---- O / sum -> bf16 -> staging tile -> TMA store
+            const float inv = 1.0f / sum;
+            ptx::mbar_wait(bar_o, ph);
+            ptx::tc_fence_after();
+            uint32_t o[2][32];
+            ptx::tmem_ld_32x32b_x32(trow + kOCol, o[0]);
+            ptx::tmem_ld_32x32b_x32(trow + kOCol + 32, o[1]);
+            ptx::tmem_ld_wait();
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(bar_ofree);  // the TMEM tile may be overwritten by the next item's S
+            if (threadIdx.x == 0) ptx::tma_store_wait_read<0>();  // previous item's store has drained the staging tile
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    uint32_t w[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        w[i] = pack_bf16(__uint_as_float(o[hh][c * 8 + 2 * i]) * inv, __uint_as_float(o[hh][c * 8 + 2 * i + 1]) * inv);
+                    const uint32_t addr = so + (uint32_t)(r * 128 + (((hh * 4 + c) ^ (r & 7)) << 4));
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
+                }
+            }
+            ptx::fence_proxy_async();
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (threadIdx.x == 0) {
+                ptx::tma_store_3d(&map_out, sO, h * HD, row0 + qblk * QB, 0);
+                ptx::tma_store_commit();
             }
         }
-        ptx::fence_proxy_async();
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (threadIdx.x == 0) {
-            ptx::tma_store_3d(&map_out, sQ, h * HD, row0 + qblk * QB, 0);
-            ptx::tma_store_commit();
-            ptx::tma_store_wait_all<0>();
-        }
+        if (threadIdx.x == 0) ptx::tma_store_wait_all<0>();
     }
 
     ptx::tc_fence_before();
@@ -202,8 +256,9 @@ int attention_tcgen05(void* out_bf16, const void* qkv_bf16, int B, int heads, cu
     rc = make_tile_map(&mo, out_bf16, 2, (int64_t)B * T, dim, dim, 1, 0, QB);
     if (rc != BSI_OK) return rc;
     const float scale_log2 = 1.4426950408889634f / sqrtf((float)HD);
-    dim3 grid(T / QB, heads, B);
-    k_attention_tc<<<grid, kThreads, kSmem, stream>>>(mq, mo, dim, scale_log2);
+    const int total = B * heads * (T / QB);
+    const int resident = 2 * sm_count();
+    k_attention_tc<<<total < resident ? total : resident, kThreads, kSmem, stream>>>(mq, mo, dim, heads, total, scale_log2);
     BSI_LAUNCH_OK("k_attention_tc");
     return BSI_OK;
 }
