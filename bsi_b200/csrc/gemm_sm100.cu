@@ -35,7 +35,7 @@ constexpr int kEpiBufBytes = BM * 128;  // staging tile: 128 rows x 128 B (64 bf
 
 enum EpiKind { KIND_BF16 = 0, KIND_F32 = 1, KIND_RMW = 2, KIND_SCATTER = 3 };
 __host__ __device__ constexpr int epi_kind(int epi) {
-    return epi <= BSI_EPI_BIAS_SILU_BF16 ? KIND_BF16
+    return (epi <= BSI_EPI_BIAS_SILU_BF16 || epi == BSI_EPI_MOD_SILU_BF16) ? KIND_BF16
            : epi == BSI_EPI_GATE_RESID_F32 ? KIND_RMW
            : epi == BSI_EPI_UNPATCH_F32  ? KIND_SCATTER
                                          : KIND_F32;
@@ -49,7 +49,7 @@ struct Cfg {
     static constexpr int kStageBytes = kABytes + kBBytes;
     static constexpr int kEpiBufs = kKind == KIND_RMW ? 4 : (kKind == KIND_SCATTER ? 0 : 2);
     static constexpr int kStages = CG == 2 ? (kKind == KIND_RMW ? 4 : 5) : 3;
-    static constexpr int kVecBytes = 2 * 2 * BN * 4;  // bias and gate slices of the tile, double-buffered by tile parity
+    static constexpr int kVecBytes = 2 * 3 * BN * 4;  // bias, gate/scale and shift slices of the tile, double-buffered by tile parity
     static constexpr int kSmemBytes = kStages * kStageBytes + kEpiBufs * kEpiBufBytes + kVecBytes + 1024 /*align*/ + 256 /*barriers*/;
     static_assert(kSmemBytes <= 232448, "exceeds the 227 KB of shared memory per CTA");
 };
@@ -59,11 +59,21 @@ struct EpiParams {
     const float* bias;
     int M, N, ldc;
     long long stride_c, stride_bias;
-    bsi_rowref gate;
+    bsi_rowref gate;   // GATE_RESID: gate (base NULL = 1); MOD_SILU: scale
+    bsi_rowref shift;  // MOD_SILU: shift
     const int* step_ptr;
     int rows_per_sample;
     const float* pos;
     int patch, grid_w, channels;
+};
+
+// Implicit-GEMM 3x3 / 1x1 convolution over NHWC activations: the A tile of k-block (tap, channel block) is a 4-D TMA box
+// {64 channels, W, 128/W rows, 1 image} shifted by the tap offset; out-of-image elements are zero-filled by TMA, which is
+// exactly the zero padding of nn.Conv2d(padding=1).  Two sources implement the channel concat of the U-Net up path.
+struct ConvGeom {
+    int taps;      // 1 or 9
+    int cb1, cbt;  // 64-channel blocks of source 1, and of both sources together
+    int img_w, img_hw;
 };
 
 __device__ __forceinline__ float gelu_tanh(float x) {
@@ -87,11 +97,12 @@ __device__ __forceinline__ float4 ld_shared_f4(uint32_t addr) {
 // byte offset of 16-byte chunk `c` of row `r` inside a 128B-swizzled staging tile (what TMA SWIZZLE_128B expects)
 __device__ __forceinline__ uint32_t swz(int r, int c) { return (uint32_t)(r * 128 + ((c ^ (r & 7)) << 4)); }
 
-template <int EPI, int CG>
+template <int EPI, int CG, bool CONV>
 __global__ void __launch_bounds__(kGemmThreads, 1)
-    k_gemm_bf16(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
-                const __grid_constant__ CUtensorMap map_c, const EpiParams ep, const int m_tiles, const int n_tiles, const int k_blocks,
-                const int batch, const int a_shared) {
+    k_gemm_bf16(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_a2,
+                const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_c,
+                const __grid_constant__ CUtensorMap map_r, const EpiParams ep, const ConvGeom geo, const int m_tiles, const int n_tiles,
+                const int k_blocks, const int batch, const int a_shared) {
     using C = Cfg<EPI, CG>;
     constexpr int kStages = C::kStages, kKind = C::kKind;
     extern __shared__ uint8_t smem_raw[];
@@ -149,7 +160,22 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
                 for (int kb = 0; kb < k_blocks; ++kb) {
                     ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
                     uint8_t* sa = smem + stage * C::kStageBytes;
-                    if constexpr (CG == 1) {
+                    if constexpr (CONV) {
+                        const int tap = kb / geo.cbt, cb = kb - tap * geo.cbt;
+                        const int dy = geo.taps == 9 ? tap / 3 - 1 : 0, dx = geo.taps == 9 ? tap % 3 - 1 : 0;
+                        const int img = row_a / geo.img_hw, y0 = (row_a - img * geo.img_hw) / geo.img_w;
+                        const CUtensorMap* src = cb < geo.cb1 ? &map_a : &map_a2;
+                        const int c0 = (cb < geo.cb1 ? cb : cb - geo.cb1) * BK;
+                        if constexpr (CG == 1) {
+                            ptx::mbar_arrive_expect_tx(&full_bar[stage], C::kStageBytes);
+                            ptx::tma_load_4d(sa, src, &full_bar[stage], c0, dx, y0 + dy, img);
+                            ptx::tma_load_3d(sa + kABytes, &map_w, &full_bar[stage], kb * BK, row_w, b);
+                        } else {
+                            if (cta_rank == 0) ptx::mbar_arrive_expect_tx(&full_bar[stage], 2 * C::kStageBytes);
+                            ptx::tma_load_4d_2sm(sa, src, &full_bar[stage], c0, dx, y0 + dy, img);
+                            ptx::tma_load_3d_2sm(sa + kABytes, &map_w, &full_bar[stage], kb * BK, row_w, b);
+                        }
+                    } else if constexpr (CG == 1) {
                         ptx::mbar_arrive_expect_tx(&full_bar[stage], C::kStageBytes);
                         ptx::tma_load_3d(sa, &map_a, &full_bar[stage], kb * BK, row_a, a_shared ? 0 : b);
                         ptx::tma_load_3d(sa + kABytes, &map_w, &full_bar[stage], kb * BK, row_w, b);
@@ -206,7 +232,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
             const int tile = worker + (g >> 3) * num_workers, c = g & 7;
             const int n_t = tile % n_tiles, m_t = (tile / n_tiles) % m_tiles, b = tile / (n_tiles * m_tiles);
             ptx::mbar_arrive_expect_tx(&c_full[g & 3], kEpiBufBytes);
-            ptx::tma_load_3d(epi_buf + (g & 3) * kEpiBufBytes, &map_c, &c_full[g & 3], n_t * BN + c * 32, (m_t * CG + cta_rank) * BM, b);
+            ptx::tma_load_3d(epi_buf + (g & 3) * kEpiBufBytes, &map_r, &c_full[g & 3], n_t * BN + c * 32, (m_t * CG + cta_rank) * BM, b);
         };
         if constexpr (kKind == KIND_RMW) {
             if (et == 0) {
@@ -224,17 +250,22 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * BN;
 
             // stage the bias (and gate) slice of this tile in shared memory: every thread needs all 256 columns
-            float* s_bias = s_vec + (it & 1) * 2 * BN;
+            float* s_bias = s_vec + (it & 1) * 3 * BN;
             float* s_gate = s_bias + BN;
+            float* s_shift = s_gate + BN;
             {
                 const float* bias = ep.bias ? ep.bias + (long long)b * ep.stride_bias : nullptr;
 #pragma unroll
                 for (int j = 0; j < 2; ++j) {
                     const int n = n_base + et * 2 + j;
                     s_bias[et * 2 + j] = (bias && n < ep.N) ? bias[n] : 0.0f;
-                    if constexpr (kKind == KIND_RMW) {
-                        // all 128 rows of the CTA tile belong to one sample (rows_per_sample % 128 == 0, checked on the host)
-                        s_gate[et * 2 + j] = (n < ep.N && row_base < ep.M) ? rowref_ptr(ep.gate, row_base / ep.rows_per_sample, step)[n] : 0.0f;
+                    // all 128 rows of the CTA tile belong to one sample (rows_per_sample % 128 == 0, checked on the host)
+                    const bool in_range = n < ep.N && row_base < ep.M;
+                    if constexpr (kKind == KIND_RMW)
+                        s_gate[et * 2 + j] = !in_range ? 0.0f : (ep.gate.base ? rowref_ptr(ep.gate, row_base / ep.rows_per_sample, step)[n] : 1.0f);
+                    if constexpr (EPI == BSI_EPI_MOD_SILU_BF16) {
+                        s_gate[et * 2 + j] = in_range ? rowref_ptr(ep.gate, row_base / ep.rows_per_sample, step)[n] : 0.0f;
+                        s_shift[et * 2 + j] = in_range ? rowref_ptr(ep.shift, row_base / ep.rows_per_sample, step)[n] : 0.0f;
                     }
                 }
             }
@@ -274,9 +305,12 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
                             float w[8];
 #pragma unroll
                             for (int i = 0; i < 8; ++i) {
-                                float t = __uint_as_float(a[h][c * 8 + i]) + s_bias[jb * 64 + h * 32 + c * 8 + i];
+                                const int col = jb * 64 + h * 32 + c * 8 + i;
+                                float t = __uint_as_float(a[h][c * 8 + i]) + s_bias[col];
                                 if constexpr (EPI == BSI_EPI_BIAS_GELU_BF16) t = gelu_tanh(t);
                                 if constexpr (EPI == BSI_EPI_BIAS_SILU_BF16) t = silu(t);
+                                // FeatureModulation + SiLU: silu(shift + (1 + scale) * h)   (bsi/nn/residual_block.py:19-21,45-46)
+                                if constexpr (EPI == BSI_EPI_MOD_SILU_BF16) t = silu(fmaf(s_gate[col] + 1.0f, t, s_shift[col]));
                                 w[i] = t;
                             }
                             st_shared_v4(sb + swz(et, h * 4 + c), pack_bf16(w[0], w[1]), pack_bf16(w[2], w[3]), pack_bf16(w[4], w[5]),
