@@ -39,6 +39,15 @@ class GemmArgs(C.Structure):
     ]  # fmt: skip
 
 
+class ConvArgs(C.Structure):
+    _fields_ = [
+        ("X1", C.c_void_p), ("X2", C.c_void_p), ("W", C.c_void_p), ("Y", C.c_void_p), ("bias", C.c_void_p), ("resid", C.c_void_p),
+        ("B", C.c_int32), ("H", C.c_int32), ("Wd", C.c_int32), ("C1", C.c_int32), ("C2", C.c_int32), ("N", C.c_int32),
+        ("taps", C.c_int32), ("ldc", C.c_int32), ("epilogue", C.c_int32),
+        ("scale", RowRef), ("shift", RowRef), ("step_ptr", C.c_void_p),
+    ]  # fmt: skip
+
+
 class DitConfig(C.Structure):
     _fields_ = [
         ("channels", C.c_int32), ("height", C.c_int32), ("width", C.c_int32),
@@ -47,7 +56,14 @@ class DitConfig(C.Structure):
     ]  # fmt: skip
 
 
-EPI_BIAS_BF16, EPI_BIAS_GELU_BF16, EPI_BIAS_SILU_BF16, EPI_BIAS_F32, EPI_GATE_RESID_F32, EPI_POS_F32, EPI_UNPATCH_F32 = range(7)
+class UnetConfig(C.Structure):
+    _fields_ = [
+        ("channels", C.c_int32), ("height", C.c_int32), ("width", C.c_int32), ("dim", C.c_int32), ("levels", C.c_int32), ("heads", C.c_int32),
+        ("pos_size", C.c_int32), ("pos_mult", C.c_int32), ("fourier_n_min", C.c_int32), ("fourier_n_max", C.c_int32),
+    ]  # fmt: skip
+
+
+EPI_BIAS_BF16, EPI_BIAS_GELU_BF16, EPI_BIAS_SILU_BF16, EPI_BIAS_F32, EPI_GATE_RESID_F32, EPI_POS_F32, EPI_UNPATCH_F32, EPI_MOD_SILU_BF16 = range(8)
 
 _vp, _i32, _i64, _f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
 
@@ -70,6 +86,7 @@ SIGNATURES = {
     "bsi_sqerr_reduce": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _vp]),
     "bsi_sqerr_backward": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _vp]),
     "bsi_gemm_bf16": (C.c_int, [C.POINTER(GemmArgs), _vp]),
+    "bsi_conv_bf16": (C.c_int, [C.POINTER(ConvArgs), _vp]),
     "bsi_gemm_force_cta_group": (C.c_int, [_i32]),
     "bsi_cast_bf16": (C.c_int, [_vp, _vp, _i64, _i64, _i64, _vp]),
     "bsi_layernorm_mod_bf16": (C.c_int, [_vp, _vp, RowRef, RowRef, _vp, _vp, _vp, _i32, _i64, _i32, _f32, _vp]),
@@ -89,6 +106,22 @@ SIGNATURES = {
     "bsi_dit_conditioning": (C.c_int, [_vp, _vp, _vp, _i32, _vp, _i64, _vp]),
     "bsi_dit_forward": (C.c_int, [_vp, _vp, _vp, RowRef, _vp, _i32, _i32, _i32, _i32, _vp, _i32, _vp, _i64, _vp]),
     "bsi_dit_peek": (C.c_int, [_vp, _i32, _vp, _i32, _vp, _vp]),
+    "bsi_groupnorm_act_bf16": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _f32, _i32, _vp]),
+    "bsi_unet_input_bf16": (C.c_int, [_vp, _vp, RowRef, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "bsi_unet_decode": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp]),
+    "bsi_pack_conv_weight": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "bsi_attention_d128_bf16": (C.c_int, [_vp, _vp, _i32, _i32, _vp]),
+    "bsi_unet_create": (C.c_int, [C.POINTER(UnetConfig), C.POINTER(_vp)]),
+    "bsi_unet_destroy": (None, [_vp]),
+    "bsi_unet_param_bytes": (_i64, [_vp]),
+    "bsi_unet_workspace_bytes": (_i64, [_vp, _i32]),
+    "bsi_unet_cond_bytes": (_i64, [_vp, _i32]),
+    "bsi_unet_cond_scratch_bytes": (_i64, [_vp, _i32]),
+    "bsi_unet_bind_params": (C.c_int, [_vp, _vp, _i64]),
+    "bsi_unet_set_param": (C.c_int, [_vp, C.c_char_p, _vp, _i64, _vp]),
+    "bsi_unet_missing_params": (C.c_int, [_vp]),
+    "bsi_unet_conditioning": (C.c_int, [_vp, _vp, _vp, _i32, _vp, _i64, _vp]),
+    "bsi_unet_forward": (C.c_int, [_vp, _vp, _vp, RowRef, _vp, _i32, _i32, _i32, _i32, _vp, _i32, _vp, _i64, _vp]),
 }
 
 _lib = None

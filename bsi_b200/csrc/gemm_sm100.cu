@@ -468,6 +468,31 @@ int make_tile_map(CUtensorMap* map, const void* base, int esize, int64_t rows, i
     return BSI_OK;
 }
 
+// bf16 NHWC [B][H][W][C] activation tensor, box {64 channels, W, 128/W rows, 1 image}, 128-byte swizzle, zero fill outside.
+static int make_nhwc_map(CUtensorMap* map, const void* base, int64_t B, int64_t H, int64_t W, int64_t C) {
+    EncodeTiledFn enc = get_encode_fn();
+    if (!enc) {
+        set_error("cuTensorMapEncodeTiled entry point unavailable");
+        return BSI_ERR_CUDA;
+    }
+    if ((reinterpret_cast<uintptr_t>(base) & 15) || C % 64 != 0 || BM % W != 0 || H % (BM / W) != 0) {
+        set_error("conv operand needs 16-byte alignment, C %% 64 == 0, W | 128 and H %% (128/W) == 0 (H=%lld W=%lld C=%lld)", (long long)H,
+                  (long long)W, (long long)C);
+        return BSI_ERR_INVALID_ARGUMENT;
+    }
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+    cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)W, (cuuint32_t)(BM / W), 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled (NHWC) failed with CUresult %d", (int)r);
+        return BSI_ERR_CUDA;
+    }
+    return BSI_OK;
+}
+
 // Optional per-launch timing of the GEMM kernel (bench.py roofline): CUDA events on the launching stream.
 struct GemmRecord {
     cudaEvent_t start, stop;
@@ -477,27 +502,60 @@ static bool g_profile = false;
 static std::vector<GemmRecord> g_records;
 static int g_force_cta_group = 0;  // 0 = automatic, 1 / 2 = forced (tests)
 
-template <int EPI, int CG>
-static int launch_gemm(const bsi_gemm_args* a, const EpiParams& ep, int a_shared, cudaStream_t stream) {
+// One GEMM / implicit-GEMM convolution problem, common to bsi_gemm_bf16 and bsi_conv_bf16.
+struct Problem {
+    const void *A = nullptr, *A2 = nullptr, *W = nullptr;
+    void* C = nullptr;
+    const float* resid = nullptr;  // RMW residual source (fp32, same geometry as C); nullptr = C itself
+    int M = 0, N = 0, K = 0, lda = 0, ldw = 0, ldc = 0, batch = 1, a_shared = 0;
+    int64_t stride_a = 0, stride_w = 0, stride_c = 0;
+    // convolution geometry (conv == true): A/A2 are NHWC [B][H][W][C1|C2]
+    bool conv = false;
+    int img_b = 0, img_h = 0, img_w = 0, c1 = 0, c2 = 0, taps = 1;
+    EpiParams ep{};
+};
+
+template <int EPI, int CG, bool CONV>
+static int launch_gemm(const Problem& p, cudaStream_t stream) {
     using C = Cfg<EPI, CG>;
     static bool configured = false;
     if (!configured) {
-        BSI_CUDA_OK(cudaFuncSetAttribute(k_gemm_bf16<EPI, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
+        BSI_CUDA_OK(cudaFuncSetAttribute(k_gemm_bf16<EPI, CG, CONV>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
         configured = true;
     }
-    CUtensorMap ma, mw, mc;
-    int rc = make_tile_map(&ma, a->A, 2, a->M, a->K, a->lda, a_shared ? 1 : a->batch, a->stride_a, BM);
-    if (rc != BSI_OK) return rc;
-    rc = make_tile_map(&mw, a->W, 2, a->N, a->K, a->ldw, a->batch, a->stride_w, C::kBRows);
+    CUtensorMap ma, ma2, mw, mc, mr;
+    int rc;
+    ConvGeom geo{};
+    if (CONV) {
+        rc = make_nhwc_map(&ma, p.A, p.img_b, p.img_h, p.img_w, p.c1);
+        if (rc != BSI_OK) return rc;
+        ma2 = ma;
+        if (p.A2) {
+            rc = make_nhwc_map(&ma2, p.A2, p.img_b, p.img_h, p.img_w, p.c2);
+            if (rc != BSI_OK) return rc;
+        }
+        geo.taps = p.taps, geo.cb1 = p.c1 / BK, geo.cbt = (p.c1 + (p.A2 ? p.c2 : 0)) / BK;
+        geo.img_w = p.img_w, geo.img_hw = p.img_h * p.img_w;
+    } else {
+        rc = make_tile_map(&ma, p.A, 2, p.M, p.K, p.lda, p.a_shared ? 1 : p.batch, p.stride_a, BM);
+        if (rc != BSI_OK) return rc;
+        ma2 = ma;
+    }
+    rc = make_tile_map(&mw, p.W, 2, p.N, p.K, p.ldw, p.batch, p.stride_w, C::kBRows);
     if (rc != BSI_OK) return rc;
     if (C::kKind != KIND_SCATTER) {
-        rc = make_tile_map(&mc, a->C, C::kKind == KIND_BF16 ? 2 : 4, a->M, a->N, a->ldc, a->batch, a->stride_c, BM);
+        rc = make_tile_map(&mc, p.C, C::kKind == KIND_BF16 ? 2 : 4, p.M, p.N, p.ldc, p.batch, p.stride_c, BM);
         if (rc != BSI_OK) return rc;
     } else {
         mc = ma;  // unused by the scatter epilogue
     }
-    const int m_tiles = (a->M + BM * CG - 1) / (BM * CG), n_tiles = (a->N + BN - 1) / BN, k_blocks = (a->K + BK - 1) / BK;
-    const int total = a->batch * m_tiles * n_tiles;
+    mr = mc;
+    if (C::kKind == KIND_RMW && p.resid && p.resid != p.C) {
+        rc = make_tile_map(&mr, p.resid, 4, p.M, p.N, p.ldc, p.batch, p.stride_c, BM);
+        if (rc != BSI_OK) return rc;
+    }
+    const int m_tiles = (p.M + BM * CG - 1) / (BM * CG), n_tiles = (p.N + BN - 1) / BN, k_blocks = (p.K + BK - 1) / BK;
+    const int total = p.batch * m_tiles * n_tiles;
     const int max_workers = sm_count() / CG;
     const int workers = total < max_workers ? total : max_workers;
 
@@ -505,7 +563,7 @@ static int launch_gemm(const bsi_gemm_args* a, const EpiParams& ep, int a_shared
     if (g_profile) {
         BSI_CUDA_OK(cudaEventCreate(&rec.start));
         BSI_CUDA_OK(cudaEventCreate(&rec.stop));
-        rec.flops = 2.0 * a->batch * (double)a->M * (double)a->N * (double)a->K;
+        rec.flops = 2.0 * p.batch * (double)p.M * (double)p.N * (double)p.K;
         BSI_CUDA_OK(cudaEventRecord(rec.start, stream));
     }
     cudaLaunchConfig_t cfg{};
@@ -515,7 +573,7 @@ static int launch_gemm(const bsi_gemm_args* a, const EpiParams& ep, int a_shared
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = CG, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr, cfg.numAttrs = 1;
-    BSI_CUDA_OK(cudaLaunchKernelEx(&cfg, k_gemm_bf16<EPI, CG>, ma, mw, mc, ep, m_tiles, n_tiles, k_blocks, (int)a->batch, a_shared));
+    BSI_CUDA_OK(cudaLaunchKernelEx(&cfg, k_gemm_bf16<EPI, CG, CONV>, ma, ma2, mw, mc, mr, p.ep, geo, m_tiles, n_tiles, k_blocks, p.batch, p.a_shared));
     BSI_LAUNCH_OK("k_gemm_bf16");
     if (g_profile) {
         BSI_CUDA_OK(cudaEventRecord(rec.stop, stream));
@@ -524,11 +582,25 @@ static int launch_gemm(const bsi_gemm_args* a, const EpiParams& ep, int a_shared
     return BSI_OK;
 }
 
-template <int EPI>
-static int dispatch_cta_group(const bsi_gemm_args* a, const EpiParams& ep, int a_shared, cudaStream_t stream) {
+template <int EPI, bool CONV>
+static int dispatch_cta_group(const Problem& p, cudaStream_t stream) {
     // CTA pairs pay off as soon as there are at least two 128-row blocks; tiny problems keep the finer 128-row tiles
-    const bool pair = g_force_cta_group ? g_force_cta_group == 2 : a->M > BM;
-    return pair ? launch_gemm<EPI, 2>(a, ep, a_shared, stream) : launch_gemm<EPI, 1>(a, ep, a_shared, stream);
+    const bool pair = g_force_cta_group ? g_force_cta_group == 2 : p.M > BM;
+    return pair ? launch_gemm<EPI, 2, CONV>(p, stream) : launch_gemm<EPI, 1, CONV>(p, stream);
+}
+
+static int check_common(const Problem& p, int epilogue) {
+    BSI_CHECK_ARG(p.M > 0 && p.N > 0 && p.K > 0 && p.batch >= 1, "gemm: bad shape M=%d N=%d K=%d batch=%d", p.M, p.N, p.K, p.batch);
+    BSI_CHECK_ARG(p.N % (epilogue == BSI_EPI_UNPATCH_F32 ? 4 : 8) == 0, "gemm: N=%d must be a multiple of 8 (4 for UNPATCH)", p.N);
+    const bool f32_out = epi_kind(epilogue) != KIND_BF16;
+    if (epilogue != BSI_EPI_UNPATCH_F32) {
+        BSI_CHECK_ARG(p.ldc >= p.N && p.ldc % (f32_out ? 4 : 8) == 0, "gemm: ldc=%d invalid for N=%d", p.ldc, p.N);
+        BSI_CHECK_ARG((reinterpret_cast<uintptr_t>(p.C) & 15) == 0, "gemm: C must be 16-byte aligned");
+    }
+    if (epilogue == BSI_EPI_GATE_RESID_F32 || epilogue == BSI_EPI_MOD_SILU_BF16)
+        BSI_CHECK_ARG(p.ep.rows_per_sample > 0 && p.ep.rows_per_sample % BM == 0, "gemm: epilogue %d needs rows_per_sample %% 128 == 0 (got %d)", epilogue,
+                      p.ep.rows_per_sample);
+    return BSI_OK;
 }
 
 }  // namespace bsi
@@ -537,18 +609,21 @@ using namespace bsi;
 
 extern "C" int bsi_gemm_bf16(const bsi_gemm_args* a, void* stream) {
     BSI_CHECK_ARG(a && a->A && a->W && a->C, "bsi_gemm_bf16: null operand");
-    BSI_CHECK_ARG(a->M > 0 && a->N > 0 && a->K > 0 && a->batch >= 1, "bsi_gemm_bf16: bad shape M=%d N=%d K=%d batch=%d", a->M,
-                  a->N, a->K, a->batch);
-    BSI_CHECK_ARG(a->N % (a->epilogue == BSI_EPI_UNPATCH_F32 ? 4 : 8) == 0, "bsi_gemm_bf16: N=%d must be a multiple of 8 (4 for UNPATCH)", a->N);
     BSI_CHECK_ARG(a->lda >= a->K && a->ldw >= a->K, "bsi_gemm_bf16: pitch smaller than K");
-    const bool f32_out = a->epilogue >= BSI_EPI_BIAS_F32;
-    if (a->epilogue != BSI_EPI_UNPATCH_F32) {
-        BSI_CHECK_ARG(a->ldc >= a->N && a->ldc % (f32_out ? 4 : 8) == 0, "bsi_gemm_bf16: ldc=%d invalid for N=%d", a->ldc, a->N);
-        BSI_CHECK_ARG((reinterpret_cast<uintptr_t>(a->C) & 15) == 0, "bsi_gemm_bf16: C must be 16-byte aligned");
-    }
-    if (a->epilogue == BSI_EPI_GATE_RESID_F32)
-        BSI_CHECK_ARG(a->gate.base && a->rows_per_sample > 0 && a->rows_per_sample % BM == 0,
-                      "bsi_gemm_bf16: GATE_RESID needs a gate and rows_per_sample %% 128 == 0 (got %d)", a->rows_per_sample);
+    BSI_CHECK_ARG(a->epilogue >= BSI_EPI_BIAS_BF16 && a->epilogue <= BSI_EPI_UNPATCH_F32, "bsi_gemm_bf16: unknown epilogue %d", a->epilogue);
+    Problem p;
+    p.A = a->A, p.W = a->W, p.C = a->C;
+    p.M = a->M, p.N = a->N, p.K = a->K, p.lda = a->lda, p.ldw = a->ldw, p.ldc = a->ldc, p.batch = a->batch;
+    p.stride_a = a->stride_a, p.stride_w = a->stride_w, p.stride_c = a->stride_c;
+    p.a_shared = (a->batch > 1 && a->stride_a == 0) ? 1 : 0;
+    EpiParams& ep = p.ep;
+    ep.C = a->C, ep.bias = a->bias, ep.M = a->M, ep.N = a->N, ep.ldc = a->ldc;
+    ep.stride_c = a->stride_c, ep.stride_bias = a->stride_bias;
+    ep.gate = a->gate, ep.shift = bsi_rowref{}, ep.step_ptr = a->step_ptr, ep.rows_per_sample = a->rows_per_sample > 0 ? a->rows_per_sample : 1;
+    ep.pos = a->pos, ep.patch = a->patch, ep.grid_w = a->grid_w, ep.channels = a->channels;
+    int rc = check_common(p, a->epilogue);
+    if (rc != BSI_OK) return rc;
+    if (a->epilogue == BSI_EPI_GATE_RESID_F32) BSI_CHECK_ARG(a->gate.base, "bsi_gemm_bf16: GATE_RESID needs a gate");
     if (a->epilogue == BSI_EPI_POS_F32)
         BSI_CHECK_ARG(a->pos && a->rows_per_sample > 0 && (reinterpret_cast<uintptr_t>(a->pos) & 15) == 0, "bsi_gemm_bf16: POS needs a 16-byte aligned pos table");
     if (a->epilogue == BSI_EPI_UNPATCH_F32)
@@ -556,23 +631,43 @@ extern "C" int bsi_gemm_bf16(const bsi_gemm_args* a, void* stream) {
                           a->N == a->patch * a->patch * a->channels && a->batch == 1,
                       "bsi_gemm_bf16: UNPATCH geometry invalid");
 
-    const int a_shared = (a->batch > 1 && a->stride_a == 0) ? 1 : 0;
-    EpiParams ep;
-    ep.C = a->C, ep.bias = a->bias, ep.M = a->M, ep.N = a->N, ep.ldc = a->ldc;
-    ep.stride_c = a->stride_c, ep.stride_bias = a->stride_bias;
-    ep.gate = a->gate, ep.step_ptr = a->step_ptr, ep.rows_per_sample = a->rows_per_sample > 0 ? a->rows_per_sample : 1;
-    ep.pos = a->pos, ep.patch = a->patch, ep.grid_w = a->grid_w, ep.channels = a->channels;
-
     cudaStream_t st = (cudaStream_t)stream;
     switch (a->epilogue) {
-        case BSI_EPI_BIAS_BF16: return dispatch_cta_group<BSI_EPI_BIAS_BF16>(a, ep, a_shared, st);
-        case BSI_EPI_BIAS_GELU_BF16: return dispatch_cta_group<BSI_EPI_BIAS_GELU_BF16>(a, ep, a_shared, st);
-        case BSI_EPI_BIAS_SILU_BF16: return dispatch_cta_group<BSI_EPI_BIAS_SILU_BF16>(a, ep, a_shared, st);
-        case BSI_EPI_BIAS_F32: return dispatch_cta_group<BSI_EPI_BIAS_F32>(a, ep, a_shared, st);
-        case BSI_EPI_GATE_RESID_F32: return dispatch_cta_group<BSI_EPI_GATE_RESID_F32>(a, ep, a_shared, st);
-        case BSI_EPI_POS_F32: return dispatch_cta_group<BSI_EPI_POS_F32>(a, ep, a_shared, st);
-        case BSI_EPI_UNPATCH_F32: return dispatch_cta_group<BSI_EPI_UNPATCH_F32>(a, ep, a_shared, st);
-        default: set_error("bsi_gemm_bf16: unknown epilogue %d", a->epilogue); return BSI_ERR_INVALID_ARGUMENT;
+        case BSI_EPI_BIAS_BF16: return dispatch_cta_group<BSI_EPI_BIAS_BF16, false>(p, st);
+        case BSI_EPI_BIAS_GELU_BF16: return dispatch_cta_group<BSI_EPI_BIAS_GELU_BF16, false>(p, st);
+        case BSI_EPI_BIAS_SILU_BF16: return dispatch_cta_group<BSI_EPI_BIAS_SILU_BF16, false>(p, st);
+        case BSI_EPI_BIAS_F32: return dispatch_cta_group<BSI_EPI_BIAS_F32, false>(p, st);
+        case BSI_EPI_GATE_RESID_F32: return dispatch_cta_group<BSI_EPI_GATE_RESID_F32, false>(p, st);
+        case BSI_EPI_POS_F32: return dispatch_cta_group<BSI_EPI_POS_F32, false>(p, st);
+        default: return dispatch_cta_group<BSI_EPI_UNPATCH_F32, false>(p, st);
+    }
+}
+
+extern "C" int bsi_conv_bf16(const bsi_conv_args* a, void* stream) {
+    BSI_CHECK_ARG(a && a->X1 && a->W && a->Y, "bsi_conv_bf16: null operand");
+    BSI_CHECK_ARG(a->taps == 1 || a->taps == 9, "bsi_conv_bf16: taps must be 1 (1x1) or 9 (3x3), got %d", a->taps);
+    BSI_CHECK_ARG(a->B > 0 && a->H > 0 && a->Wd > 0 && a->C1 > 0 && a->C1 % 64 == 0 && (!a->X2 || (a->C2 > 0 && a->C2 % 64 == 0)),
+                  "bsi_conv_bf16: bad geometry B=%d H=%d W=%d C1=%d C2=%d", a->B, a->H, a->Wd, a->C1, a->C2);
+    Problem p;
+    p.conv = true;
+    p.A = a->X1, p.A2 = a->X2, p.W = a->W, p.C = a->Y, p.resid = a->resid;
+    p.img_b = a->B, p.img_h = a->H, p.img_w = a->Wd, p.c1 = a->C1, p.c2 = a->X2 ? a->C2 : 0, p.taps = a->taps;
+    p.M = a->B * a->H * a->Wd, p.N = a->N, p.K = a->taps * (p.c1 + p.c2);
+    p.ldw = p.K, p.ldc = a->ldc, p.batch = 1;
+    EpiParams& ep = p.ep;
+    ep.C = a->Y, ep.bias = a->bias, ep.M = p.M, ep.N = p.N, ep.ldc = a->ldc, ep.stride_c = 0, ep.stride_bias = 0;
+    ep.gate = a->scale, ep.shift = a->shift, ep.step_ptr = a->step_ptr, ep.rows_per_sample = a->H * a->Wd;
+    ep.pos = nullptr, ep.patch = ep.grid_w = ep.channels = 0;
+    int rc = check_common(p, a->epilogue);
+    if (rc != BSI_OK) return rc;
+    if (a->epilogue == BSI_EPI_MOD_SILU_BF16) BSI_CHECK_ARG(a->scale.base && a->shift.base, "bsi_conv_bf16: MOD_SILU needs scale and shift");
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (a->epilogue) {
+        case BSI_EPI_BIAS_BF16: return dispatch_cta_group<BSI_EPI_BIAS_BF16, true>(p, st);
+        case BSI_EPI_BIAS_F32: return dispatch_cta_group<BSI_EPI_BIAS_F32, true>(p, st);
+        case BSI_EPI_GATE_RESID_F32: return dispatch_cta_group<BSI_EPI_GATE_RESID_F32, true>(p, st);
+        case BSI_EPI_MOD_SILU_BF16: return dispatch_cta_group<BSI_EPI_MOD_SILU_BF16, true>(p, st);
+        default: set_error("bsi_conv_bf16: epilogue %d is not available for convolutions", a->epilogue); return BSI_ERR_UNSUPPORTED;
     }
 }
 

@@ -1,0 +1,310 @@
+// VDM U-Net denoiser engine: host-side orchestration of the sm_100a kernels for DenoisingVDMUNet.forward
+// (bsi/models/vdm_unet.py:92-100, bsi/nn/simplified_unet.py:33-48, bsi/nn/residual_block.py:26-64, bsi/nn/attention.py:21-41).
+// Activations are NHWC; every 3x3 / 1x1 convolution is an implicit GEMM on tcgen05 (bsi_conv_bf16), the channel concat of the
+// up path is a two-source K loop, the residual adds are the GEMM's fp32 read-modify-write epilogue (gate = 1), and the skip
+// tensors are simply the outputs of the down blocks (no copies).  Like the DiT engine it owns no device memory.
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+
+namespace bsi {
+static inline int64_t up_to(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
+
+enum SlotKind { SLOT_VEC = 0, SLOT_MAT = 1, SLOT_CONV = 2 };
+struct USlot {
+    int64_t offset = 0, bytes = 0;
+    int kind = SLOT_VEC;
+    int64_t rows = 0, cols = 0;           // MAT: [rows][cols] -> bf16 ; VEC: cols floats
+    int n = 0, cin = 0, taps = 1, cpad = 0;  // CONV: fp32 [n][cin][taps] -> bf16 [n][taps][cpad]
+    bool set = false;
+};
+}  // namespace bsi
+
+struct bsi_unet {
+    bsi_unet_config cfg;
+    int HW, d, cdim, L, nb, cin_img, cin_pad;
+    int64_t param_bytes = 0;
+    uint8_t* arena = nullptr;
+    std::map<std::string, bsi::USlot> slots;
+    std::vector<std::string> block_prefix;  // down 0..L-1, center 0, center 2, up 0..L-1
+
+    template <typename Tp>
+    Tp* ptr(const std::string& key) const {
+        return reinterpret_cast<Tp*>(arena + slots.at(key).offset);
+    }
+};
+
+namespace bsi {
+
+static void add(bsi_unet* e, const std::string& key, USlot s) {
+    s.offset = e->param_bytes;
+    e->param_bytes = up_to(e->param_bytes + s.bytes, 256);
+    e->slots[key] = s;
+}
+static void add_vec(bsi_unet* e, const std::string& key, int64_t n) {
+    USlot s;
+    s.kind = SLOT_VEC, s.cols = n, s.bytes = n * 4;
+    add(e, key, s);
+}
+static void add_mat(bsi_unet* e, const std::string& key, int64_t rows, int64_t cols) {
+    USlot s;
+    s.kind = SLOT_MAT, s.rows = rows, s.cols = cols, s.bytes = rows * cols * 2;
+    add(e, key, s);
+}
+static void add_conv(bsi_unet* e, const std::string& key, int n, int cin, int taps, int cpad) {
+    USlot s;
+    s.kind = SLOT_CONV, s.n = n, s.cin = cin, s.taps = taps, s.cpad = cpad, s.bytes = (int64_t)n * taps * cpad * 2;
+    add(e, key, s);
+}
+
+struct UWork {
+    __nv_bfloat16 *in_op, *act1, *act2, *raw1, *raw2, *h, *qkv, *att;
+    float *stream, *bufA, *bufB;  // stream: (L+1) x [P][d]
+    int64_t bytes;
+};
+static UWork carve_unet(const bsi_unet* e, int B, uint8_t* base) {
+    const int64_t P = (int64_t)B * e->HW, d = e->d;
+    UWork w;
+    int64_t off = 0;
+    auto take = [&](int64_t bytes) {
+        uint8_t* p = base ? base + off : nullptr;
+        off = up_to(off + bytes, 1024);
+        return p;
+    };
+    w.in_op = (__nv_bfloat16*)take(P * e->cin_pad * 2);
+    w.act1 = (__nv_bfloat16*)take(P * d * 2), w.act2 = (__nv_bfloat16*)take(P * d * 2);
+    w.raw1 = (__nv_bfloat16*)take(P * d * 2), w.raw2 = (__nv_bfloat16*)take(P * d * 2);
+    w.h = (__nv_bfloat16*)take(P * d * 2);
+    w.qkv = (__nv_bfloat16*)take(P * 3 * d * 2), w.att = (__nv_bfloat16*)take(P * d * 2);
+    w.stream = (float*)take((int64_t)(e->L + 1) * P * d * 4);
+    w.bufA = (float*)take(P * d * 4), w.bufB = (float*)take(P * d * 4);
+    w.bytes = off;
+    return w;
+}
+
+}  // namespace bsi
+
+using namespace bsi;
+
+extern "C" {
+
+int bsi_unet_create(const bsi_unet_config* cfg, bsi_unet** out) {
+    BSI_CHECK_ARG(cfg && out, "bsi_unet_create: null argument");
+    BSI_CHECK_ARG(cfg->channels > 0 && cfg->height > 0 && cfg->width > 0 && 128 % cfg->width == 0 && cfg->height % (128 / cfg->width) == 0,
+                  "bsi_unet_create: image %dx%d unsupported (width must divide 128, height a multiple of 128/width)", cfg->height, cfg->width);
+    BSI_CHECK_ARG(cfg->dim == 128, "bsi_unet_create: only dim=128 (the cifar10-vdm configuration, 1 attention head of 128) is implemented, got %d", cfg->dim);
+    BSI_CHECK_ARG(cfg->levels > 0 && cfg->heads == 1 && cfg->pos_size > 0 && cfg->pos_size % 8 == 0 && cfg->pos_mult > 0 && (cfg->pos_size * cfg->pos_mult) % 64 == 0,
+                  "bsi_unet_create: unsupported levels/heads/pos_emb configuration");
+    auto* e = new bsi_unet();
+    e->cfg = *cfg;
+    e->HW = cfg->height * cfg->width, e->d = cfg->dim, e->L = cfg->levels, e->nb = 2 * cfg->levels + 2;
+    e->cdim = cfg->pos_size * cfg->pos_mult;
+    const int nfreq = cfg->fourier_n_max >= cfg->fourier_n_min ? cfg->fourier_n_max - cfg->fourier_n_min + 1 : 0;
+    e->cin_img = cfg->channels * (1 + 2 * nfreq);
+    e->cin_pad = (int)up_to(e->cin_img, 64);
+    if ((e->HW % 128) != 0) {
+        set_error("bsi_unet_create: H*W must be a multiple of 128");
+        delete e;
+        return BSI_ERR_UNSUPPORTED;
+    }
+    const int d = e->d, L = e->L;
+    for (int i = 0; i < L; ++i) e->block_prefix.push_back("u_net.downsampling_blocks." + std::to_string(i) + ".0");
+    e->block_prefix.push_back("u_net.center_block.0");
+    e->block_prefix.push_back("u_net.center_block.2");
+    for (int i = 0; i < L; ++i) e->block_prefix.push_back("u_net.upsampling_blocks." + std::to_string(i) + ".0");
+
+    add_vec(e, "pos_emb.scale", cfg->pos_size), add_vec(e, "pos_emb.bias", cfg->pos_size);
+    add_mat(e, "pos_map.1.weight", e->cdim, cfg->pos_size), add_vec(e, "pos_map.1.bias", e->cdim);
+    add_mat(e, "pos_map.3.weight", e->cdim, e->cdim), add_vec(e, "pos_map.3.bias", e->cdim);
+    // scale/shift projections of all blocks stacked: conditioning is one batched GEMM
+    for (auto& p : e->block_prefix) add_mat(e, p + ".project_onto_scale_shift.weight", 2 * d, e->cdim);
+    for (auto& p : e->block_prefix) add_vec(e, p + ".project_onto_scale_shift.bias", 2 * d);
+    add_conv(e, "encode.weight", d, e->cin_img, 9, e->cin_pad), add_vec(e, "encode.bias", d);
+    add_vec(e, "decode.weight", (int64_t)cfg->channels * d), add_vec(e, "decode.bias", cfg->channels);
+    for (size_t b = 0; b < e->block_prefix.size(); ++b) {
+        const std::string& p = e->block_prefix[b];
+        const bool up = (int)b >= L + 2;
+        const int cin = up ? 2 * d : d;
+        add_vec(e, p + ".layers.0.weight", cin), add_vec(e, p + ".layers.0.bias", cin);
+        add_conv(e, p + ".layers.2.weight", d, cin, 9, cin), add_vec(e, p + ".layers.2.bias", d);
+        add_conv(e, p + ".conv2.weight", d, d, 9, d), add_vec(e, p + ".conv2.bias", d);  // layers.6 (dropout configured) or layers.5
+        if (up) add_conv(e, p + ".skip.weight", d, cin, 1, cin), add_vec(e, p + ".skip.bias", d);
+    }
+    const std::string a = "u_net.center_block.1.fn";
+    add_vec(e, a + ".0.weight", d), add_vec(e, a + ".0.bias", d);
+    add_conv(e, a + ".1.to_qkv.weight", 3 * d, d, 9, d), add_vec(e, a + ".1.to_qkv.bias", 3 * d);
+    add_conv(e, a + ".1.to_out.weight", d, d, 9, d), add_vec(e, a + ".1.to_out.bias", d);
+    *out = e;
+    return BSI_OK;
+}
+
+void bsi_unet_destroy(bsi_unet* e) { delete e; }
+int64_t bsi_unet_param_bytes(const bsi_unet* e) { return e ? e->param_bytes : 0; }
+int64_t bsi_unet_workspace_bytes(const bsi_unet* e, int32_t B) { return e && B > 0 ? carve_unet(e, B, nullptr).bytes : 0; }
+int64_t bsi_unet_cond_bytes(const bsi_unet* e, int32_t rows) { return e && rows > 0 ? (int64_t)e->nb * rows * 2 * e->d * 4 : 0; }
+int64_t bsi_unet_cond_scratch_bytes(const bsi_unet* e, int32_t rows) {
+    if (!e || rows <= 0) return 0;
+    return up_to((int64_t)rows * e->cfg.pos_size * 2, 1024) + 2 * up_to((int64_t)rows * e->cdim * 2, 1024);
+}
+
+int bsi_unet_bind_params(bsi_unet* e, void* arena, int64_t bytes) {
+    BSI_CHECK_ARG(e && arena && bytes >= e->param_bytes && (reinterpret_cast<uintptr_t>(arena) & 255) == 0,
+                  "bsi_unet_bind_params: arena missing, too small or not 256-byte aligned");
+    e->arena = reinterpret_cast<uint8_t*>(arena);
+    for (auto& kv : e->slots) kv.second.set = false;
+    return BSI_OK;
+}
+
+int bsi_unet_set_param(bsi_unet* e, const char* key_c, const float* src, int64_t numel, void* stream) {
+    BSI_CHECK_ARG(e && key_c && src && e->arena, "bsi_unet_set_param: null argument or arena not bound");
+    std::string key = key_c;
+    // the second convolution of a residual block sits at layers.6 when a Dropout is configured, else at layers.5
+    for (const char* alt : {".layers.6.", ".layers.5."}) {
+        size_t pos = key.find(alt);
+        if (pos != std::string::npos && e->slots.find(key) == e->slots.end()) key.replace(pos, strlen(alt), ".conv2.");
+    }
+    auto it = e->slots.find(key);
+    BSI_CHECK_ARG(it != e->slots.end(), "bsi_unet_set_param: unknown state_dict key '%s'", key_c);
+    USlot& s = it->second;
+    if (s.kind == SLOT_VEC) {
+        BSI_CHECK_ARG(numel == s.cols, "bsi_unet_set_param: '%s' has %lld elements, expected %lld", key_c, (long long)numel, (long long)s.cols);
+        BSI_CUDA_OK(cudaMemcpyAsync(e->arena + s.offset, src, numel * 4, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    } else if (s.kind == SLOT_MAT) {
+        BSI_CHECK_ARG(numel == s.rows * s.cols, "bsi_unet_set_param: '%s' has %lld elements, expected %lld", key_c, (long long)numel,
+                      (long long)(s.rows * s.cols));
+        int rc = bsi_cast_bf16(e->arena + s.offset, src, s.rows, s.cols, s.cols, stream);
+        if (rc != BSI_OK) return rc;
+    } else {
+        BSI_CHECK_ARG(numel == (int64_t)s.n * s.cin * s.taps, "bsi_unet_set_param: '%s' has %lld elements, expected %lld", key_c, (long long)numel,
+                      (long long)s.n * s.cin * s.taps);
+        int rc = bsi_pack_conv_weight(e->arena + s.offset, src, s.n, s.cin, s.taps, s.cpad, 0, s.cpad, stream);
+        if (rc != BSI_OK) return rc;
+    }
+    s.set = true;
+    return BSI_OK;
+}
+
+int bsi_unet_missing_params(const bsi_unet* e) {
+    if (!e) return -1;
+    int n = 0;
+    for (auto& kv : e->slots) n += kv.second.set ? 0 : 1;
+    return n;
+}
+
+// cond[block][row][2*dim] = project_onto_scale_shift_block( pos_map(t[row]) )   (vdm_unet.py:62-69, residual_block.py:39,62)
+int bsi_unet_conditioning(const bsi_unet* e, float* cond, const float* t, int32_t rows, void* scratch, int64_t scratch_bytes, void* stream) {
+    BSI_CHECK_ARG(e && cond && t && scratch && rows > 0, "bsi_unet_conditioning: bad arguments");
+    if (bsi_unet_missing_params(e) != 0) {
+        set_error("bsi_unet_conditioning: %d parameters not set", bsi_unet_missing_params(e));
+        return BSI_ERR_NOT_READY;
+    }
+    if (scratch_bytes < bsi_unet_cond_scratch_bytes(e, rows)) {
+        set_error("conditioning scratch too small");
+        return BSI_ERR_WORKSPACE;
+    }
+    const int ps = e->cfg.pos_size, cd = e->cdim, d = e->d;
+    uint8_t* sp = reinterpret_cast<uint8_t*>(scratch);
+    auto* emb = reinterpret_cast<__nv_bfloat16*>(sp);
+    auto* h1 = reinterpret_cast<__nv_bfloat16*>(sp + up_to((int64_t)rows * ps * 2, 1024));
+    auto* h2 = reinterpret_cast<__nv_bfloat16*>(sp + up_to((int64_t)rows * ps * 2, 1024) + up_to((int64_t)rows * cd * 2, 1024));
+    int rc = bsi_time_embed(emb, nullptr, t, e->ptr<float>("pos_emb.scale"), e->ptr<float>("pos_emb.bias"), rows, ps, stream);
+    if (rc != BSI_OK) return rc;
+    bsi_gemm_args g{};
+    g.batch = 1;
+    g.A = emb, g.lda = ps, g.W = e->ptr<void>("pos_map.1.weight"), g.ldw = ps, g.C = h1, g.ldc = cd, g.bias = e->ptr<float>("pos_map.1.bias");
+    g.M = rows, g.N = cd, g.K = ps, g.epilogue = BSI_EPI_BIAS_SILU_BF16;
+    if ((rc = bsi_gemm_bf16(&g, stream)) != BSI_OK) return rc;
+    g.A = h1, g.lda = cd, g.W = e->ptr<void>("pos_map.3.weight"), g.ldw = cd, g.C = h2, g.bias = e->ptr<float>("pos_map.3.bias"), g.K = cd;
+    if ((rc = bsi_gemm_bf16(&g, stream)) != BSI_OK) return rc;
+    bsi_gemm_args p{};
+    p.A = h2, p.lda = cd, p.stride_a = 0, p.batch = e->nb;
+    p.W = e->ptr<void>(e->block_prefix[0] + ".project_onto_scale_shift.weight"), p.ldw = cd, p.stride_w = (int64_t)2 * d * cd;
+    p.bias = e->ptr<float>(e->block_prefix[0] + ".project_onto_scale_shift.bias"), p.stride_bias = 2 * d;
+    p.C = cond, p.ldc = 2 * d, p.stride_c = (int64_t)rows * 2 * d;
+    p.M = rows, p.N = 2 * d, p.K = cd, p.epilogue = BSI_EPI_BIAS_F32;
+    return bsi_gemm_bf16(&p, stream);
+}
+
+int bsi_unet_forward(const bsi_unet* e, float* out, const float* mu, bsi_rowref in_scale, const float* cond, int32_t cond_rows, int32_t cond_row0,
+                     int32_t cond_sample_rows, int32_t cond_step_rows, const int32_t* step_ptr, int32_t B, void* workspace, int64_t workspace_bytes,
+                     void* stream) {
+    BSI_CHECK_ARG(e && out && mu && in_scale.base && cond && workspace && B > 0 && cond_rows > 0, "bsi_unet_forward: bad arguments");
+    if (bsi_unet_missing_params(e) != 0) {
+        set_error("bsi_unet_forward: %d parameters not set", bsi_unet_missing_params(e));
+        return BSI_ERR_NOT_READY;
+    }
+    UWork w = carve_unet(e, B, reinterpret_cast<uint8_t*>(workspace));
+    if (workspace_bytes < w.bytes) {
+        set_error("workspace too small: %lld < %lld", (long long)workspace_bytes, (long long)w.bytes);
+        return BSI_ERR_WORKSPACE;
+    }
+    const bsi_unet_config& c = e->cfg;
+    const int d = e->d, L = e->L, HW = e->HW;
+    const int64_t P = (int64_t)B * HW;
+    int rc;
+#define U_TRY(call) \
+    if ((rc = (call)) != BSI_OK) return rc
+
+    auto conv = [&](const void* x1, int c1, const void* x2, int c2, const std::string& wkey, const std::string& bkey, int taps, int N, void* y, int ldc,
+                    int epi, const float* resid, bsi_rowref scale, bsi_rowref shift) {
+        bsi_conv_args a{};
+        a.X1 = x1, a.X2 = x2, a.W = e->ptr<void>(wkey), a.Y = y, a.bias = e->ptr<float>(bkey), a.resid = resid;
+        a.B = B, a.H = c.height, a.Wd = c.width, a.C1 = c1, a.C2 = c2, a.N = N, a.taps = taps, a.ldc = ldc, a.epilogue = epi;
+        a.scale = scale, a.shift = shift, a.step_ptr = step_ptr;
+        return bsi_conv_bf16(&a, stream);
+    };
+    auto modref = [&](int blk, int part) {
+        bsi_rowref r;
+        r.base = cond + ((int64_t)blk * cond_rows + cond_row0) * 2 * d + (int64_t)part * d;
+        r.sample_stride = cond_sample_rows * 2 * d, r.step_stride = cond_step_rows * 2 * d;
+        return r;
+    };
+    const bsi_rowref none{};
+    // ResidualBlock: y = skip(x) + conv2(silu(mod(conv1(silu(GN(x))))))   (residual_block.py:26-64)
+    auto resblock = [&](int blk, const float* x, const float* skip, float* y) -> int {
+        const std::string& p = e->block_prefix[blk];
+        const float* gam = e->ptr<float>(p + ".layers.0.weight");
+        const float* bet = e->ptr<float>(p + ".layers.0.bias");
+        if (!skip) {
+            U_TRY(bsi_groupnorm_act_bf16(w.act1, nullptr, x, gam, bet, B, HW, d, d / 32, 1e-5f, 1, stream));
+            U_TRY(conv(w.act1, d, nullptr, 0, p + ".layers.2.weight", p + ".layers.2.bias", 9, d, w.h, d, BSI_EPI_MOD_SILU_BF16, nullptr, modref(blk, 0),
+                       modref(blk, 1)));
+            return conv(w.h, d, nullptr, 0, p + ".conv2.weight", p + ".conv2.bias", 9, d, y, d, BSI_EPI_GATE_RESID_F32, x, none, none);
+        }
+        // up path: the input is cat(x, skip) (simplified_unet.py:46); GroupNorm(32, 2d) splits into 16 groups per source
+        U_TRY(bsi_groupnorm_act_bf16(w.act1, w.raw1, x, gam, bet, B, HW, d, 2 * d / 32, 1e-5f, 1, stream));
+        U_TRY(bsi_groupnorm_act_bf16(w.act2, w.raw2, skip, gam + d, bet + d, B, HW, d, 2 * d / 32, 1e-5f, 1, stream));
+        U_TRY(conv(w.act1, d, w.act2, d, p + ".layers.2.weight", p + ".layers.2.bias", 9, d, w.h, d, BSI_EPI_MOD_SILU_BF16, nullptr, modref(blk, 0),
+                   modref(blk, 1)));
+        U_TRY(conv(w.raw1, d, w.raw2, d, p + ".skip.weight", p + ".skip.bias", 1, d, y, d, BSI_EPI_BIAS_F32, nullptr, none, none));
+        return conv(w.h, d, nullptr, 0, p + ".conv2.weight", p + ".conv2.bias", 9, d, y, d, BSI_EPI_GATE_RESID_F32, y, none, none);
+    };
+
+    U_TRY(bsi_unet_input_bf16(w.in_op, mu, in_scale, step_ptr, B, c.channels, HW, c.fourier_n_min, c.fourier_n_max, e->cin_pad, stream));
+    U_TRY(conv(w.in_op, e->cin_pad, nullptr, 0, "encode.weight", "encode.bias", 9, d, w.stream, d, BSI_EPI_BIAS_F32, nullptr, none, none));
+    for (int i = 0; i < L; ++i) U_TRY(resblock(i, w.stream + (int64_t)i * P * d, nullptr, w.stream + (int64_t)(i + 1) * P * d));
+    // centre: ResidualBlock, Residual(GroupNorm -> Attention2D), ResidualBlock   (vdm_unet.py:79-89)
+    U_TRY(resblock(L, w.stream + (int64_t)L * P * d, nullptr, w.bufA));
+    {
+        const std::string a = "u_net.center_block.1.fn";
+        U_TRY(bsi_groupnorm_act_bf16(w.act1, nullptr, w.bufA, e->ptr<float>(a + ".0.weight"), e->ptr<float>(a + ".0.bias"), B, HW, d, d / 32, 1e-5f, 0, stream));
+        U_TRY(conv(w.act1, d, nullptr, 0, a + ".1.to_qkv.weight", a + ".1.to_qkv.bias", 9, 3 * d, w.qkv, 3 * d, BSI_EPI_BIAS_BF16, nullptr, none, none));
+        U_TRY(bsi_attention_d128_bf16(w.att, w.qkv, B, HW, stream));
+        U_TRY(conv(w.att, d, nullptr, 0, a + ".1.to_out.weight", a + ".1.to_out.bias", 9, d, w.bufB, d, BSI_EPI_GATE_RESID_F32, w.bufA, none, none));
+    }
+    U_TRY(resblock(L + 1, w.bufB, nullptr, w.bufA));
+    float* cur = w.bufA;
+    for (int j = 0; j < L; ++j) {
+        float* nxt = cur == w.bufA ? w.bufB : w.bufA;
+        U_TRY(resblock(L + 2 + j, cur, w.stream + (int64_t)(L - j) * P * d, nxt));  // skips.pop(): last pushed first
+        cur = nxt;
+    }
+    U_TRY(bsi_unet_decode(out, cur, e->ptr<float>("decode.weight"), e->ptr<float>("decode.bias"), B, HW, d, c.channels, stream));
+#undef U_TRY
+    return BSI_OK;
+}
+
+}  // extern "C"

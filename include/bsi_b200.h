@@ -131,7 +131,8 @@ typedef enum bsi_epilogue {
     BSI_EPI_BIAS_F32 = 3,        /* out_f32  = acc + bias                                   */
     BSI_EPI_GATE_RESID_F32 = 4,  /* out_f32 += gate[row] * (acc + bias)     (dit.py:93-102) */
     BSI_EPI_POS_F32 = 5,         /* out_f32  = acc + bias + pos[m % T]      (dit.py:178)    */
-    BSI_EPI_UNPATCH_F32 = 6      /* out_f32[b,c,y,x] = acc + bias, unpatchified (dit.py:166-172) */
+    BSI_EPI_UNPATCH_F32 = 6,     /* out_f32[b,c,y,x] = acc + bias, unpatchified (dit.py:166-172) */
+    BSI_EPI_MOD_SILU_BF16 = 7    /* out_bf16 = silu(shift[b] + (1+scale[b])*(acc+bias))  (residual_block.py:19-21,45-46); conv only */
 } bsi_epilogue;
 
 typedef struct bsi_gemm_args {
@@ -153,6 +154,31 @@ typedef struct bsi_gemm_args {
 } bsi_gemm_args;
 
 int bsi_gemm_bf16(const bsi_gemm_args* args, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Implicit-GEMM convolution (same tcgen05 kernel, A operand gathered by shifted 4-D TMA boxes):
+ *     Y[b,y,x,:] = epi( sum_{tap,c} X[b, y+dy(tap), x+dx(tap), c] * W[n][tap*(C1+C2) + c] )
+ * 3x3 (taps = 9, zero padding 1) or 1x1 (taps = 1) over NHWC bf16 activations; an optional second source X2
+ * supplies channels [C1, C1+C2) — the torch.cat((x, x_skip)) of the U-Net up path without the concat copy.
+ * Replaces nn.Conv2d at bsi/nn/residual_block.py:40,44,48, bsi/nn/attention.py:29-30, bsi/models/vdm_unet.py:71.
+ * Epilogues: BIAS_BF16, BIAS_F32, MOD_SILU_BF16 (scale/shift per image), GATE_RESID_F32 (Y = resid + gate*(acc+bias),
+ * gate.base NULL = 1, resid NULL = Y in place).  C1, C2 multiples of 64; W | 128; H % (128/W) == 0.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct bsi_conv_args {
+    const void* X1;      /* bf16 [B][H][W][C1] */
+    const void* X2;      /* bf16 [B][H][W][C2] or NULL */
+    const void* W;       /* bf16 [N][taps*(C1+C2)], K index = tap*(C1+C2) + channel, tap = (dy+1)*3 + (dx+1) */
+    void* Y;             /* [B*H*W][ldc] bf16 or fp32 (per epilogue) */
+    const float* bias;   /* [N] or NULL */
+    const float* resid;  /* GATE_RESID: fp32 residual source [B*H*W][ldc], NULL = Y */
+    int32_t B, H, Wd, C1, C2, N, taps, ldc;
+    int32_t epilogue;
+    bsi_rowref scale;    /* MOD_SILU: scale; GATE_RESID: gate (per image) */
+    bsi_rowref shift;    /* MOD_SILU: shift */
+    const int32_t* step_ptr;
+} bsi_conv_args;
+
+int bsi_conv_bf16(const bsi_conv_args* args, void* stream);
 
 /* Test hook: force the single-CTA kernel (1) or the CTA-pair / cta_group::2 kernel (2); 0 restores the automatic choice. */
 int bsi_gemm_force_cta_group(int32_t cta_group);
@@ -235,6 +261,50 @@ int bsi_dit_forward(const bsi_dit* e, float* out, const float* mu, bsi_rowref in
 /* Debug/introspection for parity tests: copy an intermediate of the last forward out of the workspace.
  * what: 0 = residual stream after embed+blocks [B*T][dim] fp32 (valid after forward). */
 int bsi_dit_peek(const bsi_dit* e, int32_t what, float* out, int32_t B, const void* workspace, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * VDM U-Net denoiser (DenoisingVDMUNet.forward, bsi/models/vdm_unet.py:92-100): building blocks and engine.
+ * Activations are NHWC; convolutions go through bsi_conv_bf16.
+ * ---------------------------------------------------------------------------------------- */
+/* act_bf16[b,p,c] = f(GroupNorm(x)[b,p,c]*gamma[c] + beta[c]), f = SiLU if apply_silu (vdm_unet.py:52, residual_block.py:42-43);
+ * x fp32 [B][HW][C]; groups of `channels_per_group` consecutive channels; raw_bf16 (optional) receives bf16(x). */
+int bsi_groupnorm_act_bf16(void* act_bf16, void* raw_bf16, const float* x, const float* gamma, const float* beta, int32_t B, int32_t HW, int32_t C,
+                           int32_t channels_per_group, float eps, int32_t apply_silu, void* stream);
+/* bf16 NHWC [B][HW][cpad] = cat(scale*mu, fourier(scale*mu)) zero-padded to cpad channels (vdm_unet.py:95-98); mu fp32 NCHW. */
+int bsi_unet_input_bf16(void* out_bf16, const float* mu, bsi_rowref scale, const int32_t* step_ptr, int32_t B, int32_t C, int32_t HW, int32_t n_min,
+                        int32_t n_max, int32_t cpad, void* stream);
+/* out fp32 NCHW [B][cout][HW] = 1x1 conv of x fp32 NHWC [B][HW][C] with w fp32 [cout][C] (vdm_unet.py:72,100). */
+int bsi_unet_decode(float* out, const float* x, const float* w, const float* bias, int32_t B, int32_t HW, int32_t C, int32_t cout, void* stream);
+/* fp32 conv weight [N][cin][kh][kw] -> bf16 [N][taps][ctotal], channels written at [c_offset, c_offset+cpad), zero padded beyond cin. */
+int bsi_pack_conv_weight(void* out_bf16, const float* w, int32_t N, int32_t cin, int32_t taps, int32_t cpad, int32_t c_offset, int32_t ctotal,
+                         void* stream);
+/* Single-head attention, head dim 128 (bsi/nn/attention.py:32-41): qkv bf16 [B*T][384] (q|k|v) -> out bf16 [B*T][128]. */
+int bsi_attention_d128_bf16(void* out_bf16, const void* qkv_bf16, int32_t B, int32_t T, void* stream);
+
+typedef struct bsi_unet_config {
+    int32_t channels, height, width; /* data_shape */
+    int32_t dim, levels, heads;      /* dim = 128, heads = 1 implemented */
+    int32_t pos_size, pos_mult;      /* NyquistPositionalEmbedding size and pos_emb_mult */
+    int32_t fourier_n_min, fourier_n_max;
+} bsi_unet_config;
+typedef struct bsi_unet bsi_unet;
+
+int bsi_unet_create(const bsi_unet_config* cfg, bsi_unet** out);
+void bsi_unet_destroy(bsi_unet* e);
+int64_t bsi_unet_param_bytes(const bsi_unet* e);
+int64_t bsi_unet_workspace_bytes(const bsi_unet* e, int32_t B);
+int64_t bsi_unet_cond_bytes(const bsi_unet* e, int32_t cond_rows);
+int64_t bsi_unet_cond_scratch_bytes(const bsi_unet* e, int32_t rows);
+int bsi_unet_bind_params(bsi_unet* e, void* arena, int64_t bytes);
+/* Keys of the reference state_dict, plus the buffers "pos_emb.scale" / "pos_emb.bias". */
+int bsi_unet_set_param(bsi_unet* e, const char* key, const float* src, int64_t numel, void* stream);
+int bsi_unet_missing_params(const bsi_unet* e);
+/* cond[block][row][2*dim] fp32 = project_onto_scale_shift_block(pos_map(t[row])); blocks ordered down 0..L-1, centre 0, centre 2, up 0..L-1. */
+int bsi_unet_conditioning(const bsi_unet* e, float* cond, const float* t, int32_t rows, void* scratch, int64_t scratch_bytes, void* stream);
+/* out[B,C,H,W] = UNet(in_scale[b]*mu[b]); conditioning rows addressed like bsi_dit_forward. */
+int bsi_unet_forward(const bsi_unet* e, float* out, const float* mu, bsi_rowref in_scale, const float* cond, int32_t cond_rows, int32_t cond_row0,
+                     int32_t cond_sample_rows, int32_t cond_step_rows, const int32_t* step_ptr, int32_t B, void* workspace, int64_t workspace_bytes,
+                     void* stream);
 
 #ifdef __cplusplus
 }

@@ -220,17 +220,25 @@ def gen_dit():
 
 # ---------------------------------------------------------------- E. U-Net
 def gen_unet():
-    spec = O.UNetSpec((3, 32, 32), dim=64, levels=2)
-    pe = ref_pos.NyquistPositionalEmbedding(spec.pos_size, spec.pos_rate)
-    ff = ref_nn.FourierFeatures(n_min=6, n_max=8)
-    m = ref_unet.DenoisingVDMUNet(spec.data_shape, pe, "silu", spec.dim, spec.levels, spec.pos_mult, n_attention_heads=1, dropout=0.1, fourier_features=ff)
-    sd = H.det_state_dict(H.unet_shapes(spec), seed=1)
-    assert {k: tuple(v.shape) for k, v in m.state_dict().items()} == {k: tuple(v.shape) for k, v in sd.items()}
-    load_into(m, sd)
-    with torch.inference_mode():
-        mu = 1.5 * H.det_uniform("unet.mu", (2, *spec.data_shape))
-        t = torch.tensor([0.2, 0.95])
-        save("unet.pt", dict(y=m(mu, t)))
+    out = {}
+    for name, spec in {"dim64": O.UNetSpec((3, 32, 32), dim=64, levels=2), "dim128": O.UNetSpec((3, 32, 32), dim=128, levels=2)}.items():
+        pe = ref_pos.NyquistPositionalEmbedding(spec.pos_size, spec.pos_rate)
+        ff = ref_nn.FourierFeatures(n_min=6, n_max=8)
+        m = ref_unet.DenoisingVDMUNet(spec.data_shape, pe, "silu", spec.dim, spec.levels, spec.pos_mult, n_attention_heads=1, dropout=0.1, fourier_features=ff)
+        sd = H.det_state_dict(H.unet_shapes(spec), seed=1)
+        assert {k: tuple(v.shape) for k, v in m.state_dict().items()} == {k: tuple(v.shape) for k, v in sd.items()}
+        load_into(m, sd)
+        with torch.inference_mode():
+            mu = 1.5 * H.det_uniform("unet.mu", (2, *spec.data_shape))
+            t = torch.tensor([0.2, 0.95])
+            out[name] = dict(y=m(mu, t))
+            if name == "dim128":
+                bsi = ref_bsi.BSI(m, data_shape=spec.data_shape, k=8, discretization=ref_bsi.Discretization.image_8bit(), **HYPER)
+                x = H.det_images("unet.x", 4, spec.data_shape, seed=2)
+                e, b, ex = bsi.elbo(x, 1, 2, torch.Generator().manual_seed(31))
+                out["bsi_dim128"] = dict(elbo_seed=31, bpd=b, l_recon=ex["l_recon"], l_measure=ex["l_measure"])
+    out["y"] = out["dim64"]["y"]
+    save("unet.pt", out)
 
 
 # ---------------------------------------------------------------- F. embeddings
@@ -250,6 +258,10 @@ def gen_embed():
 
 
 if __name__ == "__main__":
+    if len(sys.argv) > 1:
+        for name in sys.argv[1:]:
+            globals()["gen_" + name]()
+        sys.exit(0)
     gen_disc()
     gen_schedule()
     gen_toy()
