@@ -28,7 +28,6 @@ namespace bsi {
 
 constexpr int BM = 128;  // rows of A per CTA
 constexpr int BN = 256, BK = 64, UMMA_K = 16;
-constexpr int kGemmThreads = 256;
 constexpr int kTmemCols = 512;
 constexpr int kABytes = BM * BK * 2;
 constexpr int kEpiBufBytes = BM * 128;  // staging tile: 128 rows x 128 B (64 bf16 or 32 fp32 columns)
@@ -47,8 +46,14 @@ struct Cfg {
     static constexpr int kBRows = BN / CG;  // rows of the W tile this CTA loads
     static constexpr int kBBytes = kBRows * BK * 2;
     static constexpr int kStageBytes = kABytes + kBBytes;
-    static constexpr int kEpiBufs = kKind == KIND_RMW ? 4 : (kKind == KIND_SCATTER ? 0 : 2);
-    static constexpr int kStages = CG == 2 ? (kKind == KIND_RMW ? 4 : 5) : 3;
+    // bf16 epilogues (bias / GELU / SiLU / modulation) are ALU-bound with one warp per scheduler (ncu: 25 % issue utilisation,
+    // tensor pipe 63 % on the GELU shape): they get 8 epilogue warps, two per TMEM lane quarter, each pair splitting the columns
+    // (the plain bias epilogue keeps 4 warps and the fifth pipeline stage: it already holds the tensor pipe at 87 %)
+    static constexpr bool kHeavy = EPI == BSI_EPI_BIAS_GELU_BF16 || EPI == BSI_EPI_BIAS_SILU_BF16 || EPI == BSI_EPI_MOD_SILU_BF16;
+    static constexpr int kEpiWarps = kHeavy ? 8 : 4;
+    static constexpr int kThreads = 128 + 32 * kEpiWarps;
+    static constexpr int kEpiBufs = (kKind == KIND_RMW || kHeavy) ? 4 : (kKind == KIND_SCATTER ? 0 : 2);
+    static constexpr int kStages = CG == 2 ? ((kKind == KIND_RMW || kHeavy) ? 4 : 5) : 3;
     static constexpr int kVecBytes = 2 * 3 * BN * 4;  // bias, gate/scale and shift slices of the tile, double-buffered by tile parity
     static constexpr int kSmemBytes = kStages * kStageBytes + kEpiBufs * kEpiBufBytes + kVecBytes + 1024 /*align*/ + 256 /*barriers*/;
     static_assert(kSmemBytes <= 232448, "exceeds the 227 KB of shared memory per CTA");
@@ -85,7 +90,8 @@ __device__ __forceinline__ float gelu_tanh(float x) {
 }
 __device__ __forceinline__ float silu(float x) { return x / (1.0f + __expf(-x)); }
 
-__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+// named barrier of one group of 4 epilogue warps (group 0 or 1)
+__device__ __forceinline__ void epi_bar(int group = 0) { asm volatile("bar.sync %0, 128;" ::"r"(group + 1) : "memory"); }
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
@@ -98,7 +104,7 @@ __device__ __forceinline__ float4 ld_shared_f4(uint32_t addr) {
 __device__ __forceinline__ uint32_t swz(int r, int c) { return (uint32_t)(r * 128 + ((c ^ (r & 7)) << 4)); }
 
 template <int EPI, int CG, bool CONV>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+__global__ void __launch_bounds__(Cfg<EPI, CG>::kThreads, 1)
     k_gemm_bf16(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_a2,
                 const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_c,
                 const __grid_constant__ CUtensorMap map_r, const EpiParams ep, const ConvGeom geo, const int m_tiles, const int n_tiles,
@@ -134,7 +140,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
         }
         for (int b = 0; b < 2; ++b) {
             ptx::mbar_init(&tmem_full[b], 1);        // tcgen05.commit after the last k-block
-            ptx::mbar_init(&tmem_empty[b], 4 * CG);  // one arrive per epilogue warp of every CTA of the pair
+            ptx::mbar_init(&tmem_empty[b], C::kEpiWarps * CG);  // one arrive per epilogue warp of every CTA of the pair
         }
         for (int b = 0; b < 4; ++b) ptx::mbar_init(&c_full[b], 1);
         ptx::fence_mbar_init();
@@ -221,7 +227,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
         }
     } else if (warp >= 4) {
         // ---------------- epilogue: warp q owns TMEM lanes [32q, 32q+32) = rows of this CTA's half of the tile
-        const int q = warp - 4, et = threadIdx.x - 128;  // et: epilogue thread 0..127 == row inside the CTA tile
+        // et: epilogue thread; er = row inside the CTA tile (TMEM lane); hf = column half handled by this warp (8-warp epilogues)
+        const int q = warp & 3, et = threadIdx.x - 128, er = et & 127, hf = et >> 7;
+        constexpr int kBatches = (BN / 64) / (C::kEpiWarps / 4);  // 64-column batches per warp
+        constexpr int kColsPerThread = BN / (32 * C::kEpiWarps);  // bias / gate staging
         const int step = ep.step_ptr ? *ep.step_ptr : 0;
         const uint32_t buf0 = ptx::smem_u32(epi_buf);
         const int my_tiles = worker < total_tiles ? (total_tiles - worker + num_workers - 1) / num_workers : 0;
@@ -246,7 +255,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
             const int n_t = tile % n_tiles, m_t = (tile / n_tiles) % m_tiles, b = tile / (n_tiles * m_tiles);
             const int buf = it & 1;
             const int row_base = (m_t * CG + cta_rank) * BM, n_base = n_t * BN;
-            const int row = row_base + et;
+            const int row = row_base + er;
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * BN;
 
             // stage the bias (and gate) slice of this tile in shared memory: every thread needs all 256 columns
@@ -256,32 +265,34 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
             {
                 const float* bias = ep.bias ? ep.bias + (long long)b * ep.stride_bias : nullptr;
 #pragma unroll
-                for (int j = 0; j < 2; ++j) {
-                    const int n = n_base + et * 2 + j;
-                    s_bias[et * 2 + j] = (bias && n < ep.N) ? bias[n] : 0.0f;
+                for (int j = 0; j < kColsPerThread; ++j) {
+                    const int sc = et * kColsPerThread + j, n = n_base + sc;  // 8-warp epilogues: each half stages the columns it reads
+                    s_bias[sc] = (bias && n < ep.N) ? bias[n] : 0.0f;
                     // all 128 rows of the CTA tile belong to one sample (rows_per_sample % 128 == 0, checked on the host)
                     const bool in_range = n < ep.N && row_base < ep.M;
                     if constexpr (kKind == KIND_RMW)
-                        s_gate[et * 2 + j] = !in_range ? 0.0f : (ep.gate.base ? rowref_ptr(ep.gate, row_base / ep.rows_per_sample, step)[n] : 1.0f);
+                        s_gate[sc] = !in_range ? 0.0f : (ep.gate.base ? rowref_ptr(ep.gate, row_base / ep.rows_per_sample, step)[n] : 1.0f);
                     if constexpr (EPI == BSI_EPI_MOD_SILU_BF16) {
-                        s_gate[et * 2 + j] = in_range ? rowref_ptr(ep.gate, row_base / ep.rows_per_sample, step)[n] : 0.0f;
-                        s_shift[et * 2 + j] = in_range ? rowref_ptr(ep.shift, row_base / ep.rows_per_sample, step)[n] : 0.0f;
+                        s_gate[sc] = in_range ? rowref_ptr(ep.gate, row_base / ep.rows_per_sample, step)[n] : 0.0f;
+                        s_shift[sc] = in_range ? rowref_ptr(ep.shift, row_base / ep.rows_per_sample, step)[n] : 0.0f;
                     }
                 }
             }
-            epi_bar();
+            epi_bar(hf);
             ptx::mbar_wait(&tmem_full[buf], (it >> 1) & 1);
             ptx::tc_fence_after();
 
             uint32_t acc[2][2][32];  // [batch parity][half][32 columns]: 64 columns per tcgen05.wait::ld, next batch in flight
-            ptx::tmem_ld_32x32b_x32(taddr, acc[0][0]);
-            ptx::tmem_ld_32x32b_x32(taddr + 32, acc[0][1]);
+            const int jb0 = hf * kBatches;
+            ptx::tmem_ld_32x32b_x32(taddr + jb0 * 64, acc[0][0]);
+            ptx::tmem_ld_32x32b_x32(taddr + jb0 * 64 + 32, acc[0][1]);
 #pragma unroll
-            for (int jb = 0; jb < BN / 64; ++jb) {
+            for (int jl = 0; jl < kBatches; ++jl) {
+                const int jb = jb0 + jl;
                 ptx::tmem_ld_wait();
-                if (jb + 1 < BN / 64) {
-                    ptx::tmem_ld_32x32b_x32(taddr + (jb + 1) * 64, acc[(jb + 1) & 1][0]);
-                    ptx::tmem_ld_32x32b_x32(taddr + (jb + 1) * 64 + 32, acc[(jb + 1) & 1][1]);
+                if (jl + 1 < kBatches) {
+                    ptx::tmem_ld_32x32b_x32(taddr + (jb + 1) * 64, acc[(jl + 1) & 1][0]);
+                    ptx::tmem_ld_32x32b_x32(taddr + (jb + 1) * 64 + 32, acc[(jl + 1) & 1][1]);
                 } else {
                     // all TMEM reads of this buffer are done: hand it back to the MMA warp before the remaining stores
                     ptx::tc_fence_before();
@@ -291,13 +302,14 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
                         else ptx::mbar_arrive_cluster(&tmem_empty[buf], 0);
                     }
                 }
-                const uint32_t(&a)[2][32] = acc[jb & 1];
+                const uint32_t(&a)[2][32] = acc[jl & 1];
 
                 if constexpr (kKind == KIND_BF16) {
                     // ---- 64 bf16 columns -> one 128 x 128 B staging tile -> TMA store
-                    const uint32_t sb = buf0 + (jb & 1) * kEpiBufBytes;
-                    if (et == 0) ptx::tma_store_wait_read<1>();  // the store that last read this buffer has drained
-                    epi_bar();
+                    const int sbuf = hf * 2 + (jl & 1);  // two staging tiles per column half
+                    const uint32_t sb = buf0 + sbuf * kEpiBufBytes;
+                    if (er == 0) ptx::tma_store_wait_read<1>();  // the store that last read this buffer has drained
+                    epi_bar(hf);
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
 #pragma unroll
@@ -313,14 +325,14 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
                                 if constexpr (EPI == BSI_EPI_MOD_SILU_BF16) t = silu(fmaf(s_gate[col] + 1.0f, t, s_shift[col]));
                                 w[i] = t;
                             }
-                            st_shared_v4(sb + swz(et, h * 4 + c), pack_bf16(w[0], w[1]), pack_bf16(w[2], w[3]), pack_bf16(w[4], w[5]),
+                            st_shared_v4(sb + swz(er, h * 4 + c), pack_bf16(w[0], w[1]), pack_bf16(w[2], w[3]), pack_bf16(w[4], w[5]),
                                          pack_bf16(w[6], w[7]));
                         }
                     }
                     ptx::fence_proxy_async();
-                    epi_bar();
-                    if (et == 0) {
-                        ptx::tma_store_3d(&map_c, epi_buf + (jb & 1) * kEpiBufBytes, n_base + jb * 64, row_base, b);
+                    epi_bar(hf);
+                    if (er == 0) {
+                        ptx::tma_store_3d(&map_c, epi_buf + sbuf * kEpiBufBytes, n_base + jb * 64, row_base, b);
                         ptx::tma_store_commit();
                     }
                 } else if constexpr (kKind == KIND_F32) {
@@ -411,7 +423,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
                 }
             }
         }
-        if (et == 0) ptx::tma_store_wait_all<0>();  // every staged tile has reached global memory
+        if (er == 0) ptx::tma_store_wait_all<0>();  // every staged tile has reached global memory
     }
 
     ptx::tc_fence_before();
@@ -567,7 +579,7 @@ static int launch_gemm(const Problem& p, cudaStream_t stream) {
         BSI_CUDA_OK(cudaEventRecord(rec.start, stream));
     }
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(workers * CG), cfg.blockDim = dim3(kGemmThreads);
+    cfg.gridDim = dim3(workers * CG), cfg.blockDim = dim3(C::kThreads);
     cfg.dynamicSmemBytes = C::kSmemBytes, cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
