@@ -27,7 +27,7 @@
 namespace bsi {
 
 constexpr int BM = 128;  // rows of A per CTA
-constexpr int BN = 256, BK = 64, UMMA_K = 16;
+constexpr int BK = 64, UMMA_K = 16;  // the N tile (256, or 128 for narrow convolutions) is the template parameter BN
 constexpr int kTmemCols = 512;
 constexpr int kABytes = BM * BK * 2;
 constexpr int kEpiBufBytes = BM * 128;  // staging tile: 128 rows x 128 B (64 bf16 or 32 fp32 columns)
@@ -40,7 +40,7 @@ __host__ __device__ constexpr int epi_kind(int epi) {
                                          : KIND_F32;
 }
 
-template <int EPI, int CG>
+template <int EPI, int CG, int BN>
 struct Cfg {
     static constexpr int kKind = epi_kind(EPI);
     static constexpr int kBRows = BN / CG;  // rows of the W tile this CTA loads
@@ -53,7 +53,7 @@ struct Cfg {
     static constexpr int kEpiWarps = kHeavy ? 8 : 4;
     static constexpr int kThreads = 128 + 32 * kEpiWarps;
     static constexpr int kEpiBufs = (kKind == KIND_RMW || kHeavy) ? 4 : (kKind == KIND_SCATTER ? 0 : 2);
-    static constexpr int kStages = CG == 2 ? ((kKind == KIND_RMW || kHeavy) ? 4 : 5) : 3;
+    static constexpr int kStages = BN == 128 ? (CG == 2 ? 6 : 4) : (CG == 2 ? ((kKind == KIND_RMW || kHeavy) ? 4 : 5) : 3);
     static constexpr int kVecBytes = 2 * 3 * BN * 4;  // bias, gate/scale and shift slices of the tile, double-buffered by tile parity
     static constexpr int kSmemBytes = kStages * kStageBytes + kEpiBufs * kEpiBufBytes + kVecBytes + 1024 /*align*/ + 256 /*barriers*/;
     static_assert(kSmemBytes <= 232448, "exceeds the 227 KB of shared memory per CTA");
@@ -103,13 +103,13 @@ __device__ __forceinline__ float4 ld_shared_f4(uint32_t addr) {
 // byte offset of 16-byte chunk `c` of row `r` inside a 128B-swizzled staging tile (what TMA SWIZZLE_128B expects)
 __device__ __forceinline__ uint32_t swz(int r, int c) { return (uint32_t)(r * 128 + ((c ^ (r & 7)) << 4)); }
 
-template <int EPI, int CG, bool CONV>
-__global__ void __launch_bounds__(Cfg<EPI, CG>::kThreads, 1)
+template <int EPI, int CG, bool CONV, int BN>
+__global__ void __launch_bounds__(Cfg<EPI, CG, BN>::kThreads, 1)
     k_gemm_bf16(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_a2,
                 const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_c,
                 const __grid_constant__ CUtensorMap map_r, const EpiParams ep, const ConvGeom geo, const int m_tiles, const int n_tiles,
                 const int k_blocks, const int batch, const int a_shared) {
-    using C = Cfg<EPI, CG>;
+    using C = Cfg<EPI, CG, BN>;
     constexpr int kStages = C::kStages, kKind = C::kKind;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -230,15 +230,15 @@ __global__ void __launch_bounds__(Cfg<EPI, CG>::kThreads, 1)
         // et: epilogue thread; er = row inside the CTA tile (TMEM lane); hf = column half handled by this warp (8-warp epilogues)
         const int q = warp & 3, et = threadIdx.x - 128, er = et & 127, hf = et >> 7;
         constexpr int kBatches = (BN / 64) / (C::kEpiWarps / 4);  // 64-column batches per warp
-        constexpr int kColsPerThread = BN / (32 * C::kEpiWarps);  // bias / gate staging
+        constexpr int kChunks = BN / 32;  // 32-column chunks of a tile (KIND_RMW / KIND_F32)
         const int step = ep.step_ptr ? *ep.step_ptr : 0;
         const uint32_t buf0 = ptx::smem_u32(epi_buf);
         const int my_tiles = worker < total_tiles ? (total_tiles - worker + num_workers - 1) / num_workers : 0;
 
         // KIND_RMW: residual chunk g (8 per tile, 32 fp32 columns each) of this CTA's tile sequence -> staging buffer g & 3
         auto issue_residual_load = [&](int g) {
-            if (g >= my_tiles * 8) return;
-            const int tile = worker + (g >> 3) * num_workers, c = g & 7;
+            if (g >= my_tiles * kChunks) return;
+            const int tile = worker + (g / kChunks) * num_workers, c = g % kChunks;
             const int n_t = tile % n_tiles, m_t = (tile / n_tiles) % m_tiles, b = tile / (n_tiles * m_tiles);
             ptx::mbar_arrive_expect_tx(&c_full[g & 3], kEpiBufBytes);
             ptx::tma_load_3d(epi_buf + (g & 3) * kEpiBufBytes, &map_r, &c_full[g & 3], n_t * BN + c * 32, (m_t * CG + cta_rank) * BM, b);
@@ -264,9 +264,9 @@ __global__ void __launch_bounds__(Cfg<EPI, CG>::kThreads, 1)
             float* s_shift = s_gate + BN;
             {
                 const float* bias = ep.bias ? ep.bias + (long long)b * ep.stride_bias : nullptr;
-#pragma unroll
-                for (int j = 0; j < kColsPerThread; ++j) {
-                    const int sc = et * kColsPerThread + j, n = n_base + sc;  // 8-warp epilogues: each half stages the columns it reads
+                // 8-warp epilogues: thread group hf stages exactly the columns [hf*BN/2, (hf+1)*BN/2) it reads later
+                for (int sc = (C::kEpiWarps == 8 ? hf * (BN / 2) + er : et); sc < (C::kEpiWarps == 8 ? (hf + 1) * (BN / 2) : BN); sc += 128) {
+                    const int n = n_base + sc;
                     s_bias[sc] = (bias && n < ep.N) ? bias[n] : 0.0f;
                     // all 128 rows of the CTA tile belong to one sample (rows_per_sample % 128 == 0, checked on the host)
                     const bool in_range = n < ep.N && row_base < ep.M;
@@ -373,7 +373,7 @@ __global__ void __launch_bounds__(Cfg<EPI, CG>::kThreads, 1)
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
                         const int cidx = jb * 2 + h;
-                        const int g = it * 8 + cidx;  // running chunk index of this CTA
+                        const int g = it * kChunks + cidx;  // running chunk index of this CTA
                         if (et == 0) {
                             ptx::tma_store_wait_read<1>();  // buffer (g+2)&3 was last read by the store of chunk g-2
                             issue_residual_load(g + 2);
@@ -527,12 +527,12 @@ struct Problem {
     EpiParams ep{};
 };
 
-template <int EPI, int CG, bool CONV>
+template <int EPI, int CG, bool CONV, int BN>
 static int launch_gemm(const Problem& p, cudaStream_t stream) {
-    using C = Cfg<EPI, CG>;
+    using C = Cfg<EPI, CG, BN>;
     static bool configured = false;
     if (!configured) {
-        BSI_CUDA_OK(cudaFuncSetAttribute(k_gemm_bf16<EPI, CG, CONV>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
+        BSI_CUDA_OK(cudaFuncSetAttribute(k_gemm_bf16<EPI, CG, CONV, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
         configured = true;
     }
     CUtensorMap ma, ma2, mw, mc, mr;
@@ -585,7 +585,7 @@ static int launch_gemm(const Problem& p, cudaStream_t stream) {
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = CG, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr, cfg.numAttrs = 1;
-    BSI_CUDA_OK(cudaLaunchKernelEx(&cfg, k_gemm_bf16<EPI, CG, CONV>, ma, ma2, mw, mc, mr, p.ep, geo, m_tiles, n_tiles, k_blocks, p.batch, p.a_shared));
+    BSI_CUDA_OK(cudaLaunchKernelEx(&cfg, k_gemm_bf16<EPI, CG, CONV, BN>, ma, ma2, mw, mc, mr, p.ep, geo, m_tiles, n_tiles, k_blocks, p.batch, p.a_shared));
     BSI_LAUNCH_OK("k_gemm_bf16");
     if (g_profile) {
         BSI_CUDA_OK(cudaEventRecord(rec.stop, stream));
@@ -598,7 +598,11 @@ template <int EPI, bool CONV>
 static int dispatch_cta_group(const Problem& p, cudaStream_t stream) {
     // CTA pairs pay off as soon as there are at least two 128-row blocks; tiny problems keep the finer 128-row tiles
     const bool pair = g_force_cta_group ? g_force_cta_group == 2 : p.M > BM;
-    return pair ? launch_gemm<EPI, 2, CONV>(p, stream) : launch_gemm<EPI, 1, CONV>(p, stream);
+    if constexpr (CONV) {
+        // the U-Net's convolutions have N = 128 outputs: a 128-wide tile halves the wasted MMA columns and epilogue work
+        if (p.N <= 128) return pair ? launch_gemm<EPI, 2, CONV, 128>(p, stream) : launch_gemm<EPI, 1, CONV, 128>(p, stream);
+    }
+    return pair ? launch_gemm<EPI, 2, CONV, 256>(p, stream) : launch_gemm<EPI, 1, CONV, 256>(p, stream);
 }
 
 static int check_common(const Problem& p, int epilogue) {
