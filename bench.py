@@ -26,7 +26,12 @@ import torch
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-DIT_FLOPS_SAMPLE = 161.26e9  # algorithmic forward flops / sample / denoiser call, adaLN excluded
+# BASELINE.json configs that fit one GPU; flops = algorithmic forward flops / sample / denoiser call
+CONFIGS = {
+    "imagenet64-dit": dict(kind="dit", shape=(3, 64, 64), patch=4, batch=256, depth=24, flops=161.26e9, label="DiT-L/4"),  # headline (configs[3])
+    "imagenet32-dit": dict(kind="dit", shape=(3, 32, 32), patch=2, batch=512, depth=24, flops=161.11e9, label="DiT-L/2"),
+    "cifar10-vdm": dict(kind="unet", shape=(3, 32, 32), patch=0, batch=256, depth=32, flops=53.47e9, label="VDM U-Net dim 128"),
+}
 
 
 def parse_args():
@@ -36,23 +41,33 @@ def parse_args():
     p.add_argument("--warmup", type=int, default=3)
     p.add_argument("--impl", default="native", choices=["native", "reference"])
     # development overrides (the judged configuration is the default)
-    p.add_argument("--batch", type=int, default=256, help="samples per GPU")
+    p.add_argument("--config", default="imagenet64-dit", choices=sorted(CONFIGS))
+    p.add_argument("--batch", type=int, default=None, help="samples per GPU (default: the configuration's batch)")
     p.add_argument("--k", type=int, default=256)
-    p.add_argument("--depth", type=int, default=24)
+    p.add_argument("--depth", type=int, default=None, help="DiT depth / U-Net levels (default: the configuration's)")
     p.add_argument("--no-cpu-baseline", action="store_true")
-    return p.parse_args()
+    a = p.parse_args()
+    a.cfg = CONFIGS[a.config]
+    a.batch = a.batch or a.cfg["batch"]
+    a.depth = a.depth or a.cfg["depth"]
+    return a
 
 
 # ------------------------------------------------------------------------------------------ workload
-def build_model(depth: int):
-    """DiT-L/4 for 3x64x64 (reference config/experiment/imagenet64.yaml:33-39), random init as SURVEY §8(d):
-    torch.manual_seed(0) construction, adaLN output layers re-randomised N(0, 0.02^2) with seed 1 (adaLN-Zero
-    would make every block the identity)."""
-    from bsi_b200.models import DenoisingDiT
+def build_model(a):
+    """Denoiser of the configuration (reference config/experiment/{imagenet64,imagenet32,cifar10-vdm}.yaml), random init as
+    SURVEY §8(d): torch.manual_seed(0) construction; the DiT's adaLN output layers are re-randomised N(0, 0.02^2) with seed 1
+    (adaLN-Zero would make every block the identity)."""
+    from bsi_b200.models import DenoisingDiT, DenoisingVDMUNet, NyquistPositionalEmbedding
     from bsi_b200.nn import FourierFeatures
 
     torch.manual_seed(0)
-    m = DenoisingDiT((3, 64, 64), 4, 1024, depth, 16, dropout=0.05, fourier_features=FourierFeatures(n_min=6, n_max=8))
+    cfg = a.cfg
+    if cfg["kind"] == "unet":
+        m = DenoisingVDMUNet(cfg["shape"], NyquistPositionalEmbedding(32, 100), "silu", 128, a.depth, 4, n_attention_heads=1, dropout=0.1,
+                             fourier_features=FourierFeatures(n_min=6, n_max=8))
+        return m.eval().requires_grad_(False)
+    m = DenoisingDiT(cfg["shape"], cfg["patch"], 1024, a.depth, 16, dropout=0.05, fourier_features=FourierFeatures(n_min=6, n_max=8))
     g = torch.Generator().manual_seed(1)
     with torch.no_grad():
         for blk in m.dit.blocks:
@@ -62,8 +77,10 @@ def build_model(depth: int):
 
 
 def workload_name(a):
-    tag = "" if (a.batch, a.k, a.depth) == (256, 256, 24) else " [REDUCED development run]"
-    return f"imagenet64-dit DiT-L/4 depth {a.depth} (random init) BSI.sample k={a.k}, batch {a.batch} of 3x64x64 per GPU{tag}"
+    c = a.cfg
+    tag = "" if (a.batch, a.k, a.depth) == (c["batch"], 256, c["depth"]) else " [REDUCED development run]"
+    shape = "x".join(str(v) for v in c["shape"])
+    return f"{a.config} {c['label']} depth/levels {a.depth} (random init) BSI.sample k={a.k}, batch {a.batch} of {shape} per GPU{tag}"
 
 
 class ClockSampler:
@@ -121,15 +138,21 @@ def cpu_sample_rate(a, model_cpu_sd=None, batch=8, k_cpu=2):
     from oracle import bsi_oracle as O
 
     torch.set_num_threads(os.cpu_count() or 1)
-    spec = O.DiTSpec((3, 64, 64), 4, 1024, a.depth, 16)
+    shape = a.cfg["shape"]
+    if a.cfg["kind"] == "unet":
+        spec = O.UNetSpec(shape, dim=128, levels=a.depth)
+        forward = lambda mu, tt: O.unet_forward(model_cpu_sd, spec, mu, tt)
+    else:
+        spec = O.DiTSpec(shape, a.cfg["patch"], 1024, a.depth, 16)
+        forward = lambda mu, tt: O.dit_forward(model_cpu_sd, spec, mu, tt)
     if model_cpu_sd is None:
-        model_cpu_sd = {k_: v.detach().float().cpu() for k_, v in build_model(a.depth).state_dict().items()}
+        model_cpu_sd = {k_: v.detach().float().cpu() for k_, v in build_model(a).state_dict().items()}
     consts = O.make_consts(1e-2, 1e6, 2e6)
     t = torch.linspace(0.0, 1.0, a.k + 1)[: k_cpu + 1].clone()
-    eps = torch.randn((k_cpu + 1, batch, 3, 64, 64), generator=torch.Generator().manual_seed(3))
+    eps = torch.randn((k_cpu + 1, batch, *shape), generator=torch.Generator().manual_seed(3))
     with torch.inference_mode():
         t0 = time.perf_counter()
-        O.sample_with_noise(lambda mu, tt: O.dit_forward(model_cpu_sd, spec, mu, tt), consts, t, eps)
+        O.sample_with_noise(forward, consts, t, eps)
         dt = time.perf_counter() - t0
     per_sample_call = dt / (batch * (k_cpu + 1))
     return 1.0 / (per_sample_call * (a.k + 1)), dt, torch.get_num_threads(), f"k={k_cpu} steps ({k_cpu + 1} denoiser calls) at batch {batch}, fp32 eager PyTorch CPU, extrapolated linearly to k={a.k}"
@@ -139,7 +162,7 @@ def run_reference(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sd = {k_: v.detach().float().cpu() for k_, v in build_model(a.depth).state_dict().items()}
+    sd = {k_: v.detach().float().cpu() for k_, v in build_model(a).state_dict().items()}
     for _ in range(a.warmup):
         cpu_sample_rate(a, sd)
     t0 = time.perf_counter()
@@ -174,10 +197,11 @@ def run_native(a):
     if lib.bsi_device_arch() != 100:
         raise RuntimeError(f"bsi_b200 kernels are built for sm_100a; device reports sm_{lib.bsi_device_arch()}")
 
-    model = build_model(a.depth).to(dev)
-    bsi = BSI(model, data_shape=(3, 64, 64), lambda_0=1e-2, alpha_M=1e6, alpha_R=2e6, k=a.k, preconditioning="edm",
+    model = build_model(a).to(dev)
+    shape = a.cfg["shape"]
+    bsi = BSI(model, data_shape=shape, lambda_0=1e-2, alpha_M=1e6, alpha_R=2e6, k=a.k, preconditioning="edm",
               discretization=Discretization.image_8bit()).to(dev)
-    n, D = a.batch, 3 * 64 * 64
+    n, D = a.batch, shape[0] * shape[1] * shape[2]
 
     def barrier():
         if world > 1:
@@ -205,7 +229,7 @@ def run_native(a):
         clock_info = clocks.stop()
         # ---- end-to-end: schedule from pinned host memory in, samples to pinned host memory out ----------------------
         t_host = torch.linspace(0.0, 1.0, a.k + 1).pin_memory()
-        out_host = torch.empty((n, 3, 64, 64), dtype=torch.float32).pin_memory()
+        out_host = torch.empty((n, *shape), dtype=torch.float32).pin_memory()
         barrier()
         f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         f0.record()
@@ -223,7 +247,8 @@ def run_native(a):
         kk, lam, coef, c_in, t_rows = bsi._step_table(torch.linspace(0.0, 1.0, k_prof + 1, device=dev))
         c1 = lib.bsi_launch_counter()
         model(out, torch.ones(n, device=dev))
-        fwd_launches = lib.bsi_launch_counter() - c1 - 3  # minus the 3 conditioning launches of a stand-alone forward
+        # minus the conditioning launches of a stand-alone forward (time embedding + 2 GEMMs for the DiT, + 3 for the U-Net)
+        fwd_launches = lib.bsi_launch_counter() - c1 - (4 if a.cfg["kind"] == "unet" else 3)
         torch.cuda.synchronize()
         L.check(lib.bsi_profile_gemm_begin())
         model.sample_loop(n, torch.rsqrt(lam[:1]).contiguous(), coef, c_in, t_rows, kk, 7, rank * n, 1, use_graph=False)
@@ -239,20 +264,20 @@ def run_native(a):
         value = world * n * a.steps / (ms / 1e3)
         e2e = world * n * a.steps / (ms_e2e / 1e3)
         gemm_tf = g_fl.value / g_ms.value / 1e9 if g_ms.value > 0 else 0.0
-        step_flops = n * (a.k + 1) * DIT_FLOPS_SAMPLE * a.depth / 24
+        step_flops = n * (a.k + 1) * a.cfg["flops"] * a.depth / a.cfg["depth"]
         # kernels executed per sample() call: init + 3 conditioning + eager warm-up forward + k x (forward + step + advance) + final forward + combine
-        per_call = 1 + 3 + fwd_launches + a.k * (fwd_launches + 2) + fwd_launches + 1
+        per_call = 1 + (4 if a.cfg["kind"] == "unet" else 3) + fwd_launches + a.k * (fwd_launches + 2) + fwd_launches + 1
         line = {
             "metric": "BSI.sample samples/sec", "value": value, "unit": "samples/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {
                 "workload": workload_name(a), "parallelism": f"sample-sharded x{world}, no data-path collective",
-                "l2": "working set per step (0.96 GB bf16 weights + 1.5 GB activations) exceeds the 126 MB L2; no explicit flush",
+                "l2": "working set per step (bf16 weights + GBs of activations per denoiser forward) exceeds the 126 MB L2; no explicit flush",
                 "precision": "bf16 tensor-core operands, fp32 accumulation, fp32 belief state / residual stream / losses",
                 "whole_step_tflops_per_gpu": step_flops / (ms / a.steps) / 1e9, "outputs_finite": finite,
             },
             "roofline": {
-                "bound": "tensor", "kernel": "k_gemm_bf16 (tcgen05)", "achieved": gemm_tf, "peak": peak_tf, "unit": "TFLOP/s",
+                "bound": "tensor", "kernel": "k_gemm_bf16 (tcgen05; implicit-GEMM convolutions for the U-Net)", "achieved": gemm_tf, "peak": peak_tf, "unit": "TFLOP/s",
                 "frac": gemm_tf / peak_tf if peak_tf else None, "traffic": None, "peak_source": peak_src,
                 "how": f"CUDA events around each of {g_n.value} GEMM launches of a {k_prof}-step eager sampler pass at the benchmark batch (sum flops / sum time)",
                 "gemm_share_of_step": (g_ms.value / (k_prof + 1)) * (a.k + 1) / (ms / a.steps),
