@@ -157,3 +157,51 @@ def test_gather_rows_gloo_world2():
     res = dict(q.get(timeout=120) for _ in procs)
     [p.join(60) for p in procs]
     assert res[0] == res[1] == [float(i) for i in range(7)]
+
+
+def test_reference_checkpoint_ingestion():
+    """A Lightning checkpoint of the reference (state_dict keys model.* / ema_model.ema_model.*, config under "config") loads unchanged."""
+    from bsi_b200.checkpoint import build_denoiser, denoiser_state_dict, from_reference_checkpoint
+
+    spec = O.DiTSpec((3, 32, 32), 2, 128, 1, 2)
+    sd = H.det_state_dict(H.dit_shapes(spec), seed=3)
+    ema = {k: v + 1 for k, v in sd.items()}
+    ckpt = {
+        "state_dict": {**{"model." + k: v for k, v in sd.items()}, **{"ema_model.ema_model." + k: v for k, v in ema.items()}, "ema_model.step": torch.tensor(5)},
+        "config": {
+            "data": {"name": "imagenet32"},
+            "task": {
+                "bsi": {"_target_": "bsi.bsi.BSI", "lambda_0": 1e-2, "alpha_M": 1e6, "alpha_R": 2e6, "k": 50, "preconditioning": "edm", "low_discrepancy_sampling": True},
+                "model": {"_target_": "bsi.models.dit.DenoisingDiT", "name": "DiT", "patch_size": 2, "dim": 128, "depth": 1, "heads": 2, "dropout": None,
+                          "fourier_features": {"_target_": "bsi.nn.FourierFeatures", "name": "fourier", "n_min": 6, "n_max": 8}},
+            },
+        },
+    }
+    assert set(denoiser_state_dict(ckpt, "online")) == set(sd)
+    assert torch.equal(denoiser_state_dict(ckpt, "ema")["dit.patch_encoder.bias"], ema["dit.patch_encoder.bias"])
+    bsi, model = from_reference_checkpoint(ckpt, which="ema", device="cpu")
+    assert bsi.k == 50 and bsi.data_shape == (3, 32, 32) and torch.equal(model.state_dict()["dit.patch_encoder.bias"], ema["dit.patch_encoder.bias"])
+    unet = build_denoiser({"_target_": "bsi.models.vdm_unet.DenoisingVDMUNet", "name": "unet", "actfn": "silu", "dim": 128, "levels": 1, "dropout": 0.1,
+                           "pos_emb_mult": 4, "downsampling_attention": False, "n_attention_heads": 1, "padding_mode": "zeros",
+                           "pos_emb": {"name": "nyquist", "size": 32, "expected_rate": 100}, "fourier_features": {"n_min": 6, "n_max": 8}}, (3, 32, 32))
+    assert {k: tuple(v.shape) for k, v in unet.state_dict().items()} == H.unet_shapes(O.UNetSpec((3, 32, 32), dim=128, levels=1))
+
+
+def test_unet_state_dict_layout_matches_reference():
+    from bsi_b200.models import DenoisingVDMUNet
+
+    spec = O.UNetSpec((3, 32, 32), dim=128, levels=2)
+    mk = lambda: DenoisingVDMUNet(spec.data_shape, NyquistPositionalEmbedding(32, 100), "silu", 128, 2, 4, n_attention_heads=1, dropout=0.1,
+                                  fourier_features=FourierFeatures(n_min=6, n_max=8), name="unet")
+    m = mk()
+    assert {k: tuple(v.shape) for k, v in m.state_dict().items()} == H.unet_shapes(spec)
+    if H.have_reference():
+        _, _, ref_unet, ref_pos, ref_nn = H.import_reference()
+        torch.manual_seed(0)
+        r = ref_unet.DenoisingVDMUNet(spec.data_shape, ref_pos.NyquistPositionalEmbedding(32, 100), "silu", 128, 2, 4, n_attention_heads=1, dropout=0.1,
+                                      fourier_features=ref_nn.FourierFeatures(n_min=6, n_max=8))
+        torch.manual_seed(0)
+        rs, ms = r.state_dict(), mk().state_dict()
+        assert list(rs) == list(ms) and all(torch.equal(rs[k], ms[k]) for k in rs)
+    with pytest.raises(NotImplementedError):
+        DenoisingVDMUNet(spec.data_shape, NyquistPositionalEmbedding(32, 100), "gelu", 128, 2, 4)
