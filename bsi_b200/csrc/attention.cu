@@ -184,11 +184,7 @@ extern "C" int bsi_attention_bf16(void* out_bf16, const void* qkv_bf16, int32_t 
     if (T == 256 && !g_force_legacy_attention) return attention_tcgen05(out_bf16, qkv_bf16, B, heads, (cudaStream_t)stream);
     const int dim = heads * head_dim;
     const int smem = (kQRows + 2 * T) * 128;
-    static int configured_smem = 0;
-    if (smem > configured_smem) {
-        BSI_CUDA_OK(cudaFuncSetAttribute(k_attention_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        configured_smem = smem;
-    }
+    BSI_ENSURE_SMEM(k_attention_mma, smem);
     const float scale_log2 = 1.4426950408889634f / sqrtf((float)head_dim);
     dim3 grid(T / kQRows, heads, B);
     k_attention_mma<<<grid, kAttThreads, smem, (cudaStream_t)stream>>>((__nv_bfloat16*)out_bf16, (const __nv_bfloat16*)qkv_bf16, T, dim,

@@ -1,13 +1,16 @@
 // Fused non-causal attention for the DiT block on tcgen05 (bsi/models/dit.py:36-47), T = 256 tokens, head dim 64.
 //   qkv [B*T][3*dim] bf16, columns (qkv, head, channel)  ->  out [B*T][dim] bf16, columns (head, channel)
 // Persistent kernel, two CTAs resident per SM (256 TMEM columns each); a work item is one (128-query block, head,
-// sample).  While one CTA is in its softmax (SFU-bound: 256 exp2 per thread) the other one runs its MMAs.
+// sample).  While one CTA is in its softmax (SFU-bound: exp2 per score) the other one runs its MMAs.
 //   control warp : TMA loads of Q (128x64), K and V (256x64) into 128B-swizzled tiles, issued for item i+1 as soon as
 //                  the MMAs of item i have consumed the buffers (Q,K after S; V after O), so loads never stall; issues
 //                  S = Q K^T   UMMA 128x256x16 (x4, both operands K-major from smem)        -> TMEM columns [0,256)
-//                  O = P V     UMMA 128x64x16 (x16, A = P from TMEM, B = V MN-major smem)  -> TMEM columns [128,192)
-//   4 softmax warps (thread = query row): row max, p = exp2((s - max) * scale*log2e), row sum, P as packed bf16
-//                  written back over the S columns it replaces (tcgen05.st), final O / sum -> bf16 -> TMA store.
+//                  O = P V     UMMA 128x64x16 (x16, A = P from TMEM, B = V MN-major smem)  -> TMEM columns [64,128)
+//   8 softmax warps: warp w owns query rows [32(w&3), +32) (its TMEM lane quarter) and keys [128(w>>2), +128); row
+//                  max and row sum are combined between the two key halves through shared memory.  p = exp2((s - max) *
+//                  scale*log2e) is written back as packed bf16 over S columns the same warp has already consumed:
+//                  keys [0,128) -> columns [0,64), keys [128,256) -> columns [128,192); O lands in [64,128).
+//                  Finally O / sum -> bf16 -> swizzled staging tile -> TMA store.
 // The whole 128x256 score tile lives in TMEM: single-pass softmax statistics in fp32, no rescaling.
 // Tensor-bound work 4*T*T*64 flop per (head, sample); the kernel's own ceiling is the SFU (16 ex2/clk/SM).
 #include <cuda.h>
@@ -22,11 +25,11 @@ int make_tile_map(CUtensorMap* map, const void* base, int esize, int64_t rows, i
 
 namespace att {
 constexpr int T = 256, HD = 64, QB = 128;
-constexpr int kThreads = 160;         // 4 softmax warps + 1 control warp
-constexpr int kTileBytes = QB * 128;  // 128 rows x 64 bf16
-constexpr int kSmem = 6 * kTileBytes /*Q, K(2), V(2), out staging*/ + 1024 /*align*/ + 128 /*barriers*/;
+constexpr int kSoftmaxWarps = 8, kThreads = 32 * (kSoftmaxWarps + 1);  // + 1 control warp
+constexpr int kTileBytes = QB * 128;                                   // 128 rows x 64 bf16
+constexpr int kSmem = 6 * kTileBytes /*Q, K(2), V(2), out staging*/ + 4 * QB * 4 /*max, sum exchange*/ + 1024 /*align*/ + 128 /*barriers*/;
 constexpr int kTmemCols = 256;
-constexpr int kOCol = 128;  // O accumulator columns [128, 192): S columns that are dead once P is complete
+constexpr int kOCol = 64;  // O accumulator columns [64, 128)
 }  // namespace att
 
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -34,6 +37,7 @@ __device__ __forceinline__ float ex2_approx(float x) {
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
+__device__ __forceinline__ void softmax_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 __global__ void __launch_bounds__(att::kThreads, 2)
     k_attention_tc(const __grid_constant__ CUtensorMap map_qkv, const __grid_constant__ CUtensorMap map_out, const int dim, const int heads,
@@ -41,30 +45,32 @@ __global__ void __launch_bounds__(att::kThreads, 2)
     using namespace att;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* sQ = smem;                    // 128 x 64
-    uint8_t* sK = smem + kTileBytes;       // 256 x 64 (two 128-row TMA boxes)
-    uint8_t* sV = smem + 3 * kTileBytes;   // 256 x 64
-    uint8_t* sO = smem + 5 * kTileBytes;   // output staging tile
-    uint64_t* bar_qk = reinterpret_cast<uint64_t*>(smem + 6 * kTileBytes);
+    uint8_t* sQ = smem;                   // 128 x 64
+    uint8_t* sK = smem + kTileBytes;      // 256 x 64 (two 128-row TMA boxes)
+    uint8_t* sV = smem + 3 * kTileBytes;  // 256 x 64
+    uint8_t* sO = smem + 5 * kTileBytes;  // output staging tile
+    float* s_max = reinterpret_cast<float*>(smem + 6 * kTileBytes);  // [2 halves][128 rows]
+    float* s_sum = s_max + 2 * QB;
+    uint64_t* bar_qk = reinterpret_cast<uint64_t*>(s_sum + 2 * QB);
     uint64_t* bar_v = bar_qk + 1;
     uint64_t* bar_s = bar_qk + 2;      // S complete (tcgen05.commit): softmax may start, Q/K tiles may be refilled
-    uint64_t* bar_p = bar_qk + 3;      // P written by the 4 softmax warps
+    uint64_t* bar_p = bar_qk + 3;      // P written by the softmax warps
     uint64_t* bar_o = bar_qk + 4;      // O complete (tcgen05.commit): epilogue may start, V tile may be refilled
-    uint64_t* bar_ofree = bar_qk + 5;  // O (and with it the whole TMEM tile) read out by the 4 softmax warps
+    uint64_t* bar_ofree = bar_qk + 5;  // O (and with it the whole TMEM tile) read out by the softmax warps
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_qk + 6);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-    if (warp == 4) {
+    if (warp == kSoftmaxWarps) {
         if (lane == 0) {
             ptx::prefetch_tensormap(&map_qkv);
             ptx::prefetch_tensormap(&map_out);
             ptx::mbar_init(bar_qk, 1);
             ptx::mbar_init(bar_v, 1);
             ptx::mbar_init(bar_s, 1);
-            ptx::mbar_init(bar_p, 4);
+            ptx::mbar_init(bar_p, kSoftmaxWarps);
             ptx::mbar_init(bar_o, 1);
-            ptx::mbar_init(bar_ofree, 4);
+            ptx::mbar_init(bar_ofree, kSoftmaxWarps);
             ptx::fence_mbar_init();
         }
         __syncwarp();
@@ -84,7 +90,7 @@ __global__ void __launch_bounds__(att::kThreads, 2)
         row0 = (bh / heads) * T;
     };
 
-    if (warp == 4) {
+    if (warp == kSoftmaxWarps) {
         if (lane == 0) {
             auto load_qk = [&](int item) {
                 int qblk, h, row0;
@@ -124,15 +130,17 @@ __global__ void __launch_bounds__(att::kThreads, 2)
                 // Q and K are free once S has been computed: prefetch the next item behind this item's softmax
                 ptx::mbar_wait(bar_s, ph);
                 if (next < total_items) load_qk(next);
-                // ---- O = P V : M = 128 queries, N = 64 channels, K = 256 keys; A = P (bf16, 8 TMEM columns per 16 keys),
-                //      B = V as stored (key rows of 64 contiguous channels = MN-major, 16 keys = 2048 B per k-step)
+                // ---- O = P V : M = 128 queries, N = 64 channels, K = 256 keys; A = P (bf16, 8 TMEM columns per 16 keys: keys
+                //      [0,128) at columns [0,64), keys [128,256) at columns [128,192)), B = V as stored (key rows of 64
+                //      contiguous channels = MN-major, 16 keys = 2048 B per k-step)
                 ptx::mbar_wait(bar_p, ph);
                 ptx::mbar_wait(bar_v, ph);
                 ptx::tc_fence_after();
 #pragma unroll
                 for (int k = 0; k < T / 16; ++k) {
                     const uint64_t dv = ptx::umma_desc_mn_sw128(v0 + k * 2048, 8192, 1024);
-                    ptx::umma_bf16_ts(tmem + kOCol, tmem + 8 * k, dv, idesc_o, k != 0 ? 1u : 0u);
+                    const uint32_t pa = tmem + (k < 8 ? 8 * k : 128 + 8 * (k - 8));
+                    ptx::umma_bf16_ts(tmem + kOCol, pa, dv, idesc_o, k != 0 ? 1u : 0u);
                 }
                 ptx::umma_commit<1>(bar_o);
                 ptx::mbar_wait(bar_o, ph);
@@ -140,9 +148,10 @@ __global__ void __launch_bounds__(att::kThreads, 2)
             }
         }
     } else {
-        // ---- softmax warps: thread = query row (TMEM lane); 256 scores read in batches of 64 columns, next batch in flight
-        const int r = warp * 32 + lane;
-        const uint32_t trow = tmem + (static_cast<uint32_t>(warp * 32) << 16);
+        const int q = warp & 3, hf = warp >> 2;
+        const int r = q * 32 + lane;  // query row inside the block == TMEM lane
+        const uint32_t trow = tmem + (static_cast<uint32_t>(q * 32) << 16);
+        const uint32_t scol = trow + hf * 128;  // this warp's 128 score columns (and, in their first half, its P columns)
         const uint32_t so = ptx::smem_u32(sO);
         int it = 0;
         for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++it) {
@@ -152,80 +161,68 @@ __global__ void __launch_bounds__(att::kThreads, 2)
             ptx::mbar_wait(bar_s, ph);
             ptx::tc_fence_after();
 
-            uint32_t s[2][2][32];
+            // ---- pass 1: partial row max over this warp's 128 keys (32 columns per load, next load in flight)
+            uint32_t s[2][32];
             float mx = -INFINITY;
-            ptx::tmem_ld_32x32b_x32(trow, s[0][0]);
-            ptx::tmem_ld_32x32b_x32(trow + 32, s[0][1]);
+            ptx::tmem_ld_32x32b_x32(scol, s[0]);
 #pragma unroll
-            for (int bt = 0; bt < T / 64; ++bt) {
+            for (int c = 0; c < 4; ++c) {
                 ptx::tmem_ld_wait();
-                // after the last max batch, start re-reading batch 0 for the exponent pass
-                const int nb = (bt + 1) & 3;
-                ptx::tmem_ld_32x32b_x32(trow + nb * 64, s[(bt + 1) & 1][0]);
-                ptx::tmem_ld_32x32b_x32(trow + nb * 64 + 32, s[(bt + 1) & 1][1]);
+                ptx::tmem_ld_32x32b_x32(scol + ((c + 1) & 3) * 32, s[(c + 1) & 1]);  // after the last chunk: chunk 0 again for pass 2
 #pragma unroll
-                for (int hh = 0; hh < 2; ++hh)
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(s[bt & 1][hh][j]));
+                for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(s[c & 1][j]));
             }
-            const float moff = mx * scale_log2;
+            s_max[hf * QB + r] = mx;
+            softmax_bar();
+            const float moff = fmaxf(mx, s_max[(hf ^ 1) * QB + r]) * scale_log2;
+
+            // ---- pass 2: p = exp2(s*scale - max*scale), partial row sum, P -> TMEM as packed bf16
             float sum = 0.0f;
 #pragma unroll
-            for (int bt = 0; bt < T / 64; ++bt) {
-                ptx::tmem_ld_wait();  // batch bt sits in s[bt & 1] (T/64 is even, so the parity carries over from the max pass)
-                if (bt + 1 < T / 64) {
-                    ptx::tmem_ld_32x32b_x32(trow + (bt + 1) * 64, s[(bt + 1) & 1][0]);
-                    ptx::tmem_ld_32x32b_x32(trow + (bt + 1) * 64 + 32, s[(bt + 1) & 1][1]);
-                }
+            for (int c = 0; c < 4; ++c) {
+                ptx::tmem_ld_wait();  // chunk c sits in s[c & 1]
+                if (c + 1 < 4) ptx::tmem_ld_32x32b_x32(scol + (c + 1) * 32, s[(c + 1) & 1]);
+                uint32_t p[16];
 #pragma unroll
-                for (int hh = 0; hh < 2; ++hh) {
-                    uint32_t p[16];
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const float p0 = ex2_approx(fmaf(__uint_as_float(s[bt & 1][hh][2 * j]), scale_log2, -moff));
-                        const float p1 = ex2_approx(fmaf(__uint_as_float(s[bt & 1][hh][2 * j + 1]), scale_log2, -moff));
-                        const uint32_t pk = pack_bf16(p0, p1);
-                        // the row sum uses the bf16-rounded probabilities that the PV product will see
-                        sum += __uint_as_float(pk << 16) + __uint_as_float(pk & 0xffff0000u);
-                        p[j] = pk;
-                    }
-                    // P for keys [64bt+32hh, +32) = 16 packed columns at [32bt+16hh, +16): S columns that were read before
-                    // (the in-flight load of batch bt+1 covers columns >= 64(bt+1) > 32bt+32)
-                    ptx::tmem_st_32x32b_x16(trow + bt * 32 + hh * 16, p);
+                for (int j = 0; j < 16; ++j) {
+                    const float p0 = ex2_approx(fmaf(__uint_as_float(s[c & 1][2 * j]), scale_log2, -moff));
+                    const float p1 = ex2_approx(fmaf(__uint_as_float(s[c & 1][2 * j + 1]), scale_log2, -moff));
+                    const uint32_t pk = pack_bf16(p0, p1);
+                    // the row sum uses the bf16-rounded probabilities that the PV product will see
+                    sum += __uint_as_float(pk << 16) + __uint_as_float(pk & 0xffff0000u);
+                    p[j] = pk;
                 }
+                // P chunk c (32 keys = 16 packed columns) at [16c, 16c+16) of this warp's range: score columns it has already read
+                ptx::tmem_st_32x32b_x16(scol + c * 16, p);
             }
+            s_sum[hf * QB + r] = sum;
             ptx::tmem_st_wait();
             ptx::tc_fence_before();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(bar_p);
 
-            // ---- O / sum -> bf16 -> staging tile -> TMA store
-            const float inv = 1.0f / sum;
+            // ---- O / sum -> bf16 -> staging tile -> TMA store; this warp normalises channels [32hf, 32hf+32)
             ptx::mbar_wait(bar_o, ph);
             ptx::tc_fence_after();
-            uint32_t o[2][32];
-            ptx::tmem_ld_32x32b_x32(trow + kOCol, o[0]);
-            ptx::tmem_ld_32x32b_x32(trow + kOCol + 32, o[1]);
+            uint32_t o[32];
+            ptx::tmem_ld_32x32b_x32(trow + kOCol + hf * 32, o);
             ptx::tmem_ld_wait();
             ptx::tc_fence_before();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(bar_ofree);  // the TMEM tile may be overwritten by the next item's S
             if (threadIdx.x == 0) ptx::tma_store_wait_read<0>();  // previous item's store has drained the staging tile
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            softmax_bar();  // also orders the s_sum exchange (written before bar_p above)
+            const float inv = 1.0f / (sum + s_sum[(hf ^ 1) * QB + r]);
 #pragma unroll
-            for (int hh = 0; hh < 2; ++hh) {
+            for (int c = 0; c < 4; ++c) {
+                uint32_t w[4];
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    uint32_t w[4];
-#pragma unroll
-                    for (int i = 0; i < 4; ++i)
-                        w[i] = pack_bf16(__uint_as_float(o[hh][c * 8 + 2 * i]) * inv, __uint_as_float(o[hh][c * 8 + 2 * i + 1]) * inv);
-                    const uint32_t addr = so + (uint32_t)(r * 128 + (((hh * 4 + c) ^ (r & 7)) << 4));
-                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
-                }
+                for (int i = 0; i < 4; ++i) w[i] = pack_bf16(__uint_as_float(o[c * 8 + 2 * i]) * inv, __uint_as_float(o[c * 8 + 2 * i + 1]) * inv);
+                const uint32_t addr = so + (uint32_t)(r * 128 + (((hf * 4 + c) ^ (r & 7)) << 4));
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
             }
             ptx::fence_proxy_async();
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            softmax_bar();
             if (threadIdx.x == 0) {
                 ptx::tma_store_3d(&map_out, sO, h * HD, row0 + qblk * QB, 0);
                 ptx::tma_store_commit();
@@ -236,7 +233,7 @@ __global__ void __launch_bounds__(att::kThreads, 2)
 
     ptx::tc_fence_before();
     __syncthreads();
-    if (warp == 4) {
+    if (warp == kSoftmaxWarps) {
         ptx::tc_fence_after();
         ptx::tmem_dealloc<1>(tmem, kTmemCols);
     }
@@ -245,11 +242,7 @@ __global__ void __launch_bounds__(att::kThreads, 2)
 int attention_tcgen05(void* out_bf16, const void* qkv_bf16, int B, int heads, cudaStream_t stream) {
     using namespace att;
     const int dim = heads * HD;
-    static bool configured = false;
-    if (!configured) {
-        BSI_CUDA_OK(cudaFuncSetAttribute(k_attention_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
-        configured = true;
-    }
+    BSI_ENSURE_SMEM(k_attention_tc, kSmem);
     CUtensorMap mq, mo;
     int rc = make_tile_map(&mq, qkv_bf16, 2, (int64_t)B * T, 3 * dim, 3 * dim, 1, 0, QB);
     if (rc != BSI_OK) return rc;

@@ -42,6 +42,18 @@ void count_launch();  // host-side counter of kernels launched by this library (
 
 int sm_count();
 
+// Opt a kernel into `bytes` of dynamic shared memory, once per (call site, device).
+#define BSI_ENSURE_SMEM(kernel, bytes)                                                                            \
+    do {                                                                                                          \
+        static int _done[64] = {0};                                                                               \
+        int _dev = 0;                                                                                             \
+        BSI_CUDA_OK(cudaGetDevice(&_dev));                                                                        \
+        if (_dev >= 0 && _dev < 64 && _done[_dev] < (bytes)) {                                                    \
+            BSI_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (bytes)));      \
+            _done[_dev] = (bytes);                                                                                \
+        }                                                                                                         \
+    } while (0)
+
 // Resolve a bsi_rowref for (sample, step).
 __device__ __forceinline__ float rowref_at(const bsi_rowref& r, int64_t sample, int step) {
     return r.base[(int64_t)step * r.step_stride + sample * r.sample_stride];

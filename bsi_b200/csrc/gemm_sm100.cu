@@ -530,11 +530,7 @@ struct Problem {
 template <int EPI, int CG, bool CONV, int BN>
 static int launch_gemm(const Problem& p, cudaStream_t stream) {
     using C = Cfg<EPI, CG, BN>;
-    static bool configured = false;
-    if (!configured) {
-        BSI_CUDA_OK(cudaFuncSetAttribute(k_gemm_bf16<EPI, CG, CONV, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
-        configured = true;
-    }
+    BSI_ENSURE_SMEM((k_gemm_bf16<EPI, CG, CONV, BN>), C::kSmemBytes);
     CUtensorMap ma, ma2, mw, mc, mr;
     int rc;
     ConvGeom geo{};

@@ -278,11 +278,7 @@ int bsi_groupnorm_act_bf16(void* act_bf16, void* raw_bf16, const float* x, const
                   "bsi_groupnorm_act_bf16: unsupported channel count %d / group size %d", C, channels_per_group);
     const int stripes = kGnThreads / (C / 4);
     const int smem = (stripes * C * 2 + 2 * C) * (int)sizeof(float);
-    static int configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
-        BSI_CUDA_OK(cudaFuncSetAttribute(k_groupnorm_act, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        configured = smem;
-    }
+    if (smem > 48 * 1024) BSI_ENSURE_SMEM(k_groupnorm_act, smem);
     k_groupnorm_act<<<B, kGnThreads, smem, (cudaStream_t)stream>>>((__nv_bfloat16*)act_bf16, (__nv_bfloat16*)raw_bf16, x, gamma, beta, HW, C,
                                                                   channels_per_group, eps, apply_silu);
     BSI_LAUNCH_OK("k_groupnorm_act");
@@ -330,11 +326,7 @@ int bsi_attention_d128_bf16(void* out_bf16, const void* qkv_bf16, int32_t B, int
         return BSI_ERR_UNSUPPORTED;
     }
     const int smem = (kA2Q + 4 * kA2KB) * 256;
-    static bool configured = false;
-    if (!configured) {
-        BSI_CUDA_OK(cudaFuncSetAttribute(k_attention_d128, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        configured = true;
-    }
+    BSI_ENSURE_SMEM(k_attention_d128, smem);
     const float scale_log2 = 1.4426950408889634f / sqrtf((float)kA2D);
     k_attention_d128<<<dim3(T / kA2Q, B), kA2Threads, smem, (cudaStream_t)stream>>>((__nv_bfloat16*)out_bf16, (const __nv_bfloat16*)qkv_bf16, T, scale_log2);
     BSI_LAUNCH_OK("k_attention_d128");
