@@ -82,6 +82,7 @@ SIGNATURES = {
     "bsi_scale_rows": (C.c_int, [_vp, _vp, RowRef, _vp, _i64, _i64, _vp]),
     "bsi_q_sample": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, Noise, _i64, _i64, _i64, _vp]),
     "bsi_bucketize": (C.c_int, [_vp, _vp, _vp, _f32, _f32, _i32, _i64, _vp]),
+    "bsi_to_uint8": (C.c_int, [_vp, _vp, _f32, _f32, _i64, _vp]),
     "bsi_recon_reduce": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _f32, _f32, _f32, _i64, _i64, _i64, _vp]),
     "bsi_sqerr_reduce": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _vp]),
     "bsi_sqerr_backward": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _vp]),

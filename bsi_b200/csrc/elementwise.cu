@@ -167,6 +167,15 @@ __global__ void __launch_bounds__(kThreads) k_bucketize(const float* __restrict_
     }
 }
 
+// ------------------------------------------------------------------ to_8bit_image (bsi/bsi.py:41-48): 4 B read, 1 B written per element
+__global__ void __launch_bounds__(kThreads) k_to_u8(uint8_t* __restrict__ out, const float* __restrict__ x, float lo, float span, int64_t numel) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < numel; i += (int64_t)gridDim.x * blockDim.x) {
+        // ((x - min) / (max - min) * 255).clamp(0, 255).to(uint8): same op order, truncation toward zero
+        float v = __fmul_rn(__fdiv_rn(__fsub_rn(x[i], lo), span), 255.0f);
+        out[i] = (uint8_t)(int)fminf(fmaxf(v, 0.0f), 255.0f);
+    }
+}
+
 // ------------------------------------------------------------------ fp32 -> bf16 cast with pitch
 __global__ void __launch_bounds__(kThreads) k_cast_bf16(__nv_bfloat16* __restrict__ out, const float* __restrict__ in,
                                                         int64_t rows, int64_t cols, int64_t ld) {
@@ -317,6 +326,14 @@ int bsi_bucketize(const float* x, int64_t* out_i64, uint8_t* out_u8, float lo_ed
     BSI_CHECK_ARG(!out_u8 || k <= 256, "bsi_bucketize: uint8 output needs k <= 256");
     k_bucketize<<<grid_for(numel), kThreads, 0, (cudaStream_t)stream>>>(x, out_i64, out_u8, lo_edge, dx, k, numel);
     BSI_LAUNCH_OK("k_bucketize");
+    return BSI_OK;
+}
+
+int bsi_to_uint8(uint8_t* out, const float* x, float lo, float hi, int64_t numel, void* stream) {
+    if (numel == 0) return BSI_OK;
+    BSI_CHECK_ARG(out && x && numel > 0 && hi > lo, "bsi_to_uint8: bad arguments");
+    k_to_u8<<<grid_for(numel), kThreads, 0, (cudaStream_t)stream>>>(out, x, lo, hi - lo, numel);
+    BSI_LAUNCH_OK("k_to_u8");
     return BSI_OK;
 }
 

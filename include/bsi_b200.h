@@ -101,6 +101,9 @@ int bsi_q_sample(float* mu, float* model_in, const float* x, const float* gamma,
 int bsi_bucketize(const float* x, int64_t* out_i64, uint8_t* out_u8, float lo_edge, float dx, int32_t k, int64_t numel,
                   void* stream);
 
+/* Discretization.to_8bit_image (bsi/bsi.py:41-48): out = uint8(clamp((x - lo)/(hi - lo)*255, 0, 255)), truncating. */
+int bsi_to_uint8(uint8_t* out, const float* x, float lo, float hi, int64_t numel, void* stream);
+
 /* Discretised-Gaussian reconstruction term (BSI.reconstruction_loss, bsi/bsi.py:230-247):
  *   out[r] = - sum_d log clamp(cdf(edge[idx+1]) - cdf(edge[idx]), 1e-20),  r in [0,R), x row r % B,
  *   x_hat = c_skip[r]*mu[r] + c_out[r]*f[r]   (mu == NULL: f already is x_hat),

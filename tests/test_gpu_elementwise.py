@@ -207,6 +207,14 @@ def test_bucketize_bit_exact_golden():
     assert torch.equal(d5.bucketize(torch.empty(0, device=dev())), torch.empty(0, dtype=torch.int64, device=dev()))
 
 
+def test_to_8bit_image_bit_exact():
+    g = H.load_golden("disc.pt")
+    disc = Discretization.image_8bit()
+    assert torch.equal(disc.to_8bit_image(g["x"].to(dev())).cpu(), g["to_u8"])
+    x = 1.3 * H.det_uniform("u8.x", (4, 3, 64, 64))
+    assert torch.equal(disc.to_8bit_image(x.to(dev())).cpu(), O.to_uint8(x, O.GRID_8BIT))
+
+
 def test_recon_and_sqerr_reduce_vs_oracle_and_golden():
     g = H.load_golden("toy.pt")["recon_terms"]
     B, shape, D = 8, (3, 32, 32), 3072
