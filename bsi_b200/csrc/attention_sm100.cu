@@ -81,6 +81,7 @@ __global__ void __launch_bounds__(att::kThreads, 2)
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem = *tmem_slot;
+    pdl_prologue_done();
 
     // work item -> (query block, head, sample); consecutive items share K/V in L2
     auto coords = [&](int item, int& qblk, int& h, int& row0) {
@@ -251,7 +252,12 @@ int attention_tcgen05(void* out_bf16, const void* qkv_bf16, int B, int heads, cu
     const float scale_log2 = 1.4426950408889634f / sqrtf((float)HD);
     const int total = B * heads * (T / QB);
     const int resident = 2 * sm_count();
-    k_attention_tc<<<total < resident ? total : resident, kThreads, kSmem, stream>>>(mq, mo, dim, heads, total, scale_log2);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(total < resident ? total : resident), cfg.blockDim = dim3(kThreads), cfg.dynamicSmemBytes = kSmem, cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    fill_pdl_attr(&attr[0]);
+    cfg.attrs = attr, cfg.numAttrs = use_pdl() ? 1 : 0;
+    BSI_CUDA_OK(cudaLaunchKernelEx(&cfg, k_attention_tc, mq, mo, dim, heads, total, scale_log2));
     BSI_LAUNCH_OK("k_attention_tc");
     return BSI_OK;
 }

@@ -41,6 +41,12 @@ void count_launch();  // host-side counter of kernels launched by this library (
     } while (0)
 
 int sm_count();
+// Programmatic dependent launch (PDL): kernels that start with pdl_prologue_done() may be launched with the
+// programmatic-stream-serialization attribute, so their prologue (barrier init, TMEM allocation, descriptor prefetch, launch
+// latency) overlaps the tail of the previous kernel in the stream / graph.  Off by default (measured slower inside the
+// captured sampler graph); BSI_PDL=1 in the environment enables it.
+bool use_pdl();
+void fill_pdl_attr(cudaLaunchAttribute* attr);
 
 // Opt a kernel into `bytes` of dynamic shared memory, once per (call site, device).
 #define BSI_ENSURE_SMEM(kernel, bytes)                                                                            \
@@ -60,6 +66,12 @@ __device__ __forceinline__ float rowref_at(const bsi_rowref& r, int64_t sample, 
 }
 __device__ __forceinline__ const float* rowref_ptr(const bsi_rowref& r, int64_t sample, int step) {
     return r.base + (int64_t)step * r.step_stride + sample * r.sample_stride;
+}
+
+// Let the next kernel of the stream begin its prologue, then wait until every kernel this one depends on has completed and
+// its memory is visible.  Must precede the first access to global memory written by earlier kernels.  No-op without PDL.
+__device__ __forceinline__ void pdl_prologue_done() {
+    asm volatile("griddepcontrol.launch_dependents;\n\tgriddepcontrol.wait;" ::: "memory");
 }
 
 __device__ __forceinline__ float warp_sum(float v) {

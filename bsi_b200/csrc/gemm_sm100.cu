@@ -154,6 +154,7 @@ __global__ void __launch_bounds__(Cfg<EPI, CG, BN>::kThreads, 1)
     else __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_prologue_done();  // everything above overlapped the previous kernel's tail; operands / residual / step counter are read below
 
     if (warp == 0) {
         if (lane == 0) {
@@ -577,10 +578,11 @@ static int launch_gemm(const Problem& p, cudaStream_t stream) {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(workers * CG), cfg.blockDim = dim3(C::kThreads);
     cfg.dynamicSmemBytes = C::kSmemBytes, cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = CG, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr, cfg.numAttrs = 1;
+    fill_pdl_attr(&attr[1]);
+    cfg.attrs = attr, cfg.numAttrs = use_pdl() ? 2 : 1;
     BSI_CUDA_OK(cudaLaunchKernelEx(&cfg, k_gemm_bf16<EPI, CG, CONV, BN>, ma, ma2, mw, mc, mr, p.ep, geo, m_tiles, n_tiles, k_blocks, p.batch, p.a_shared));
     BSI_LAUNCH_OK("k_gemm_bf16");
     if (g_profile) {

@@ -16,6 +16,7 @@ __global__ void __launch_bounds__(kLnThreads, 2)
     constexpr int dim = 128 * NV;
     const int lane = threadIdx.x & 31;
     const int64_t warps_total = (int64_t)gridDim.x * (kLnThreads / 32);
+    pdl_prologue_done();
     const int step = step_ptr ? *step_ptr : 0;
     for (int64_t row = (int64_t)blockIdx.x * (kLnThreads / 32) + (threadIdx.x >> 5); row < M; row += warps_total) {
         const float4* xr = reinterpret_cast<const float4*>(x + row * dim);
@@ -72,10 +73,14 @@ extern "C" int bsi_layernorm_mod_bf16(void* out_bf16, const float* x, bsi_rowref
     int64_t cap = (int64_t)sm_count() * 8;
     int grid = (int)(blocks < cap ? blocks : cap);
     auto* o = reinterpret_cast<__nv_bfloat16*>(out_bf16);
-    cudaStream_t st = (cudaStream_t)stream;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid), cfg.blockDim = dim3(kLnThreads), cfg.dynamicSmemBytes = 0, cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr[1];
+    fill_pdl_attr(&attr[0]);
+    cfg.attrs = attr, cfg.numAttrs = use_pdl() ? 1 : 0;
 #define BSI_LN_CASE(NV)                                                                                                         \
     case NV:                                                                                                                    \
-        k_layernorm_mod<NV><<<grid, kLnThreads, 0, st>>>(o, x, shift, scale, step_ptr, gamma, beta, rows_per_sample, M, eps); \
+        BSI_CUDA_OK(cudaLaunchKernelEx(&cfg, k_layernorm_mod<NV>, o, x, shift, scale, step_ptr, gamma, beta, rows_per_sample, M, eps)); \
         break;
     switch (dim / 128) {
         BSI_LN_CASE(1) BSI_LN_CASE(2) BSI_LN_CASE(3) BSI_LN_CASE(4) BSI_LN_CASE(5) BSI_LN_CASE(6) BSI_LN_CASE(7) BSI_LN_CASE(8)

@@ -206,3 +206,35 @@ def test_sample_history_and_custom_schedule_native():
     for i in range(4):
         ref = (alpha[i] * ys[i].cpu() + lam[i] * mus[i].cpu()) / lam[i + 1]
         report(f"history step {i}", mus[i + 1], ref, 1e-6, 1e-6)
+
+
+def test_full_width_dit_l_properties():
+    """Size-independent properties on the real DiT-L/4 width and depth (BASELINE configs[3] shapes, small n and k so it runs
+    in seconds): graph replay == eager loop bit for bit, results are invariant to how samples are sharded over ranks,
+    runs are deterministic, and a sample's denoiser output does not depend on its batch neighbours."""
+    import bench
+
+    a = type("A", (), {})()
+    a.config, a.cfg, a.depth, a.batch, a.k = "imagenet64-dit", bench.CONFIGS["imagenet64-dit"], 24, 8, 4
+    m = bench.build_model(a).to(dev())
+    bsi = BSI(m, data_shape=(3, 64, 64), k=4, discretization=Discretization.image_8bit(), **HYPER).to(dev())
+    with torch.inference_mode():
+        full = bsi.sample(8, seed=42)
+        again = bsi.sample(8, seed=42)
+        lo, hi = bsi.sample(4, seed=42, sample_offset=0), bsi.sample(4, seed=42, sample_offset=4)
+        k, lam, coef, c_in, t_rows = bsi._step_table(bsi.default_schedule)
+        eager = m.sample_loop(8, torch.rsqrt(lam[:1]).contiguous(), coef, c_in, t_rows, k, 42, 0, 1, use_graph=False)
+        sync()
+        assert torch.isfinite(full).all() and float(full.abs().max()) < 1e3
+        assert torch.equal(full, again), "sampling is not deterministic for a fixed seed"
+        assert torch.equal(full, eager), "CUDA-graph replay differs from the eager loop"
+        assert torch.equal(full, torch.cat((lo, hi))), "sharded sampling differs from the single-batch result"
+        x = H.det_images("full.x", 4, (3, 64, 64), seed=5).to(dev())
+        t1 = torch.full((4,), 0.7, device=dev())
+        mu = x + 0.05 * H.det_uniform("full.mu", (4, 3, 64, 64)).to(dev())
+        xa = bsi._predict_x(mu, t1)
+        xb = torch.cat((bsi._predict_x(mu[:2], t1[:2]), bsi._predict_x(mu[2:], t1[2:])))
+        sync()
+        assert torch.equal(xa, xb), "denoiser output of a sample depends on its batch neighbours"
+        idx = Discretization.image_8bit().bucketize(x)
+        assert torch.equal(idx, ((x + 1) * 127.5).round().long()), "8-bit bin indices of grid data must be exact"
