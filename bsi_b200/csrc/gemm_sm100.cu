@@ -50,7 +50,10 @@ struct Cfg {
     // tensor pipe 63 % on the GELU shape): they get 8 epilogue warps, two per TMEM lane quarter, each pair splitting the columns
     // (the plain bias epilogue keeps 4 warps and the fifth pipeline stage: it already holds the tensor pipe at 87 %)
     static constexpr bool kHeavy = EPI == BSI_EPI_BIAS_GELU_BF16 || EPI == BSI_EPI_BIAS_SILU_BF16 || EPI == BSI_EPI_MOD_SILU_BF16;
+    // (16 warps, one 64-column block each, measured no faster than 8: the GELU epilogue is bound by the fp32 pipe, not by latency)
     static constexpr int kEpiWarps = kHeavy ? 8 : 4;
+    static constexpr int kGroups = kEpiWarps / 4;                                   // groups of 4 warps, each owning BN / kGroups columns
+    static constexpr int kBufsPerGroup = kHeavy ? (kGroups == 4 ? 1 : 2) : 2;      // staging tiles per group (KIND_BF16)
     static constexpr int kThreads = 128 + 32 * kEpiWarps;
     static constexpr int kEpiBufs = (kKind == KIND_RMW || kHeavy) ? 4 : (kKind == KIND_SCATTER ? 0 : 2);
     static constexpr int kStages = BN == 128 ? (CG == 2 ? 6 : 4) : (CG == 2 ? ((kKind == KIND_RMW || kHeavy) ? 4 : 5) : 3);
@@ -82,13 +85,16 @@ struct ConvGeom {
 };
 
 __device__ __forceinline__ float gelu_tanh(float x) {
-    // 0.5*x*(1+tanh(sqrt(2/pi)*(x+0.044715x^3)))  (nn.GELU(approximate="tanh"), bsi/models/dit.py:75)
-    float u = 0.7978845608028654f * fmaf(0.044715f * x * x, x, x);
+    // 0.5*x*(1+tanh(sqrt(2/pi)*(x+0.044715x^3)))  (nn.GELU(approximate="tanh"), bsi/models/dit.py:75) in 5 fp32 ops + 1 MUFU:
+    // the epilogue of the MLP GEMM is bound by the fp32 pipe (2 clk per warp instruction), so every op counts
+    const float x2 = x * x;
+    const float u = x * fmaf(x2, 0.7978845608028654f * 0.044715f, 0.7978845608028654f);
     float t;
     asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(u));
-    return 0.5f * x * (1.0f + t);
+    const float hx = 0.5f * x;
+    return fmaf(hx, t, hx);
 }
-__device__ __forceinline__ float silu(float x) { return x / (1.0f + __expf(-x)); }
+__device__ __forceinline__ float silu(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 
 // named barrier of one group of 4 epilogue warps (group 0 or 1)
 __device__ __forceinline__ void epi_bar(int group = 0) { asm volatile("bar.sync %0, 128;" ::"r"(group + 1) : "memory"); }
@@ -230,7 +236,7 @@ __global__ void __launch_bounds__(Cfg<EPI, CG, BN>::kThreads, 1)
         // ---------------- epilogue: warp q owns TMEM lanes [32q, 32q+32) = rows of this CTA's half of the tile
         // et: epilogue thread; er = row inside the CTA tile (TMEM lane); hf = column half handled by this warp (8-warp epilogues)
         const int q = warp & 3, et = threadIdx.x - 128, er = et & 127, hf = et >> 7;
-        constexpr int kBatches = (BN / 64) / (C::kEpiWarps / 4);  // 64-column batches per warp
+        constexpr int kBatches = (BN / 64) / C::kGroups;  // 64-column batches per warp
         constexpr int kChunks = BN / 32;  // 32-column chunks of a tile (KIND_RMW / KIND_F32)
         const int step = ep.step_ptr ? *ep.step_ptr : 0;
         const uint32_t buf0 = ptx::smem_u32(epi_buf);
@@ -265,8 +271,8 @@ __global__ void __launch_bounds__(Cfg<EPI, CG, BN>::kThreads, 1)
             float* s_shift = s_gate + BN;
             {
                 const float* bias = ep.bias ? ep.bias + (long long)b * ep.stride_bias : nullptr;
-                // 8-warp epilogues: thread group hf stages exactly the columns [hf*BN/2, (hf+1)*BN/2) it reads later
-                for (int sc = (C::kEpiWarps == 8 ? hf * (BN / 2) + er : et); sc < (C::kEpiWarps == 8 ? (hf + 1) * (BN / 2) : BN); sc += 128) {
+                // warp group hf stages exactly the columns [hf*BN/kGroups, (hf+1)*BN/kGroups) it reads later
+                for (int sc = hf * (BN / C::kGroups) + er; sc < (hf + 1) * (BN / C::kGroups); sc += 128) {
                     const int n = n_base + sc;
                     s_bias[sc] = (bias && n < ep.N) ? bias[n] : 0.0f;
                     // all 128 rows of the CTA tile belong to one sample (rows_per_sample % 128 == 0, checked on the host)
@@ -307,9 +313,9 @@ __global__ void __launch_bounds__(Cfg<EPI, CG, BN>::kThreads, 1)
 
                 if constexpr (kKind == KIND_BF16) {
                     // ---- 64 bf16 columns -> one 128 x 128 B staging tile -> TMA store
-                    const int sbuf = hf * 2 + (jl & 1);  // two staging tiles per column half
+                    const int sbuf = hf * C::kBufsPerGroup + (jl % C::kBufsPerGroup);  // staging tiles of this warp group
                     const uint32_t sb = buf0 + sbuf * kEpiBufBytes;
-                    if (er == 0) ptx::tma_store_wait_read<1>();  // the store that last read this buffer has drained
+                    if (er == 0) ptx::tma_store_wait_read<C::kBufsPerGroup - 1>();  // the store that last read this buffer has drained
                     epi_bar(hf);
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
