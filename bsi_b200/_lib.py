@@ -63,12 +63,25 @@ class UnetConfig(C.Structure):
     ]  # fmt: skip
 
 
+class AdamWArgs(C.Structure):
+    _fields_ = [
+        ("param", C.c_void_p), ("grad", C.c_void_p), ("exp_avg", C.c_void_p), ("exp_avg_sq", C.c_void_p), ("ema", C.c_void_p),
+        ("param_bf16", C.c_void_p), ("grad_sumsq", C.c_void_p), ("numel", C.c_int64), ("step", C.c_int64),
+        ("lr", C.c_double), ("beta1", C.c_double), ("beta2", C.c_double), ("eps", C.c_double), ("weight_decay", C.c_double),
+        ("max_norm", C.c_float), ("ema_weight", C.c_float), ("ema_mode", C.c_int32), ("zero_grad", C.c_int32),
+    ]  # fmt: skip
+
+
 EPI_BIAS_BF16, EPI_BIAS_GELU_BF16, EPI_BIAS_SILU_BF16, EPI_BIAS_F32, EPI_GATE_RESID_F32, EPI_POS_F32, EPI_UNPATCH_F32, EPI_MOD_SILU_BF16 = range(8)
 
 _vp, _i32, _i64, _f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
 
 # name -> (restype, argtypes); must list every symbol of include/bsi_b200.h (checked by tests/test_abi.py)
 SIGNATURES = {
+    "bsi_grad_sumsq": (C.c_int, [_vp, _vp, _vp, _i64, _vp]),
+    "bsi_grad_sumsq_workspace_floats": (_i32, []),
+    "bsi_adamw_ema_step": (C.c_int, [C.POINTER(AdamWArgs), _vp]),
+    "bsi_ema_update": (C.c_int, [_vp, _vp, _i64, _f32, _i32, _vp]),
     "bsi_abi_version": (C.c_int, []),
     "bsi_last_error": (C.c_char_p, []),
     "bsi_device_arch": (C.c_int, []),

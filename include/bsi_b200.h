@@ -309,6 +309,42 @@ int bsi_unet_forward(const bsi_unet* e, float* out, const float* mu, bsi_rowref 
                      int32_t cond_sample_rows, int32_t cond_step_rows, const int32_t* step_ptr, int32_t B, void* workspace, int64_t workspace_bytes,
                      void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Optimizer side of the training step over flat fp32 arenas of `numel` elements
+ * (numel % 4 == 0).  Replaces, in two launches, Lightning's clip_grad_norm_ (config/train.yaml:40),
+ * torch.optim.AdamW(fused=True) (config/task/optimizer/adamw.yaml) and the EMA copy / _foreach_lerp_
+ * (bsi/tasks/ema_pytorch.py:316-341,425-434; bsi/tasks/bsi.py:196-198). */
+
+/* out[0] = sum_i grad[i]^2, deterministic (fixed grid, fp64 final pass).
+ * workspace: bsi_grad_sumsq_workspace_floats() floats of device scratch. */
+int bsi_grad_sumsq(float* out, float* workspace, const float* grad, int64_t numel, void* stream);
+int32_t bsi_grad_sumsq_workspace_floats(void);
+
+typedef struct bsi_adamw_args {
+    float* param;            /* fp32 weights, updated in place */
+    float* grad;             /* fp32 gradients (read; zeroed afterwards if zero_grad) */
+    float* exp_avg;          /* AdamW first moment */
+    float* exp_avg_sq;       /* AdamW second moment */
+    float* ema;              /* EMA weights (ema_mode != 0) */
+    void* param_bf16;        /* optional bf16 copy of the updated weights (GEMM operand), or NULL */
+    const float* grad_sumsq; /* device scalar from bsi_grad_sumsq (max_norm > 0) */
+    int64_t numel;
+    int64_t step;            /* optimizer step, counted from 1 (bias correction) */
+    double lr, beta1, beta2, eps, weight_decay;
+    float max_norm;          /* clip_grad_norm_(max_norm, 2): g *= min(max_norm / (||g|| + 1e-6), 1); <= 0 disables */
+    float ema_weight;        /* 1 - current_decay (EMA.get_current_decay, ema_pytorch.py:308-314) */
+    int32_t ema_mode;        /* 0 none, 1 ema = param (copy_params_from_model_to_ema), 2 ema.lerp_(param, ema_weight) */
+    int32_t zero_grad;       /* 1: leave the gradient arena zeroed (optimizer.zero_grad(set_to_none=False)) */
+} bsi_adamw_args;
+
+/* p *= 1 - lr*wd;  m = lerp(m, g, 1-b1);  v = v*b2 + (1-b2)*g*g;
+ * p -= lr/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps);  then the EMA action;  each op rounded to fp32 like
+ * torch.optim.adamw._single_tensor_adamw. */
+int bsi_adamw_ema_step(const bsi_adamw_args* args, void* stream);
+
+/* EMA on its own: mode 1 ema = param, mode 2 ema.lerp_(param, weight). */
+int bsi_ema_update(float* ema, const float* param, int64_t numel, float weight, int32_t mode, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -15,6 +15,7 @@ committed.  Reference entry points exercised (file:line in the reference):
   BSI.train_loss / elbo / finite_elbo            bsi/bsi.py:152-310
   DenoisingDiT.forward, DenoisingVDMUNet.forward bsi/models/dit.py:225-233, bsi/models/vdm_unet.py:92-100
   NyquistPositionalEmbedding, FourierFeatures    bsi/models/pos_emb.py:77-84, bsi/nn/fourier_features.py:24-36
+  EMA.update (+ clip_grad_norm_, torch AdamW)     bsi/tasks/ema_pytorch.py:316-341, config/train.yaml:40, config/task/optimizer/adamw.yaml
 """
 
 import os
@@ -255,6 +256,36 @@ def gen_embed():
         ffm = ref_nn.FourierFeatures(n_min=5, n_max=6).double()
         out["fourier_test_y"] = ffm(xt, dim=1)
     save("embed.pt", out)
+
+
+def gen_optim():
+    """Optimizer side of the training step: clip_grad_norm_(1.0) -> torch.optim.AdamW -> the reference's EMA.update()."""
+    from bsi.tasks.ema_pytorch import EMA  # the reference's own class (create_ema's arguments, bsi/tasks/bsi.py:73-81)
+
+    class Holder(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.ps = torch.nn.ParameterList([torch.nn.Parameter(H.det_uniform(f"optim.p{i}", shp)) for i, shp in enumerate(H.OPTIM_SHAPES)])
+
+    model = Holder()
+    sched = H.OPTIM_EMA
+    ema = EMA(model, beta=sched["beta"], update_after_step=sched["update_after_step"], update_every=sched["update_every"],
+              include_online_model=False, use_foreach=True)
+    opt = torch.optim.AdamW(model.parameters(), foreach=False, fused=False, **H.OPTIM_HYPER)
+    out = {"params": [], "ema": [], "decay": [], "coef": []}
+    for step in range(H.OPTIM_STEPS):
+        for i, p in enumerate(model.ps):
+            p.grad = H.optim_grad(i, step)
+        total = torch.nn.utils.clip_grad_norm_(model.parameters(), H.OPTIM_MAX_NORM)
+        out["coef"].append(torch.clamp(H.OPTIM_MAX_NORM / (total + 1e-6), max=1.0))
+        opt.step()
+        ema.update()
+        out["decay"].append(ema.get_current_decay())
+        out["params"].append([p.detach().clone() for p in model.ps])
+        out["ema"].append([p.detach().clone() for p in ema.ema_model.ps])
+    out["exp_avg"] = [opt.state[p]["exp_avg"].clone() for p in model.ps]
+    out["exp_avg_sq"] = [opt.state[p]["exp_avg_sq"].clone() for p in model.ps]
+    save("optim.pt", out)
 
 
 if __name__ == "__main__":

@@ -158,6 +158,20 @@ def have_reference() -> bool:
     return os.path.isdir(os.path.join(REFERENCE_DIR, "bsi"))
 
 
+# optimizer-side fixture (tests/golden/optim.pt): odd sizes so the flat arena needs padding, gradients scaled so that the
+# global-norm clip is active on some steps only, EMA schedule short enough to pass through init / copy / lerp / skipped steps
+OPTIM_SHAPES = [(7, 5), (33,), (4, 4, 3), (1,)]
+OPTIM_HYPER = dict(lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01)
+OPTIM_MAX_NORM = 1.0
+OPTIM_EMA = dict(beta=0.9999, update_after_step=4, update_every=2)
+OPTIM_STEPS = 14
+
+
+def optim_grad(i: int, step: int) -> torch.Tensor:
+    scale = (0.02, 0.3, 1.5)[step % 3]
+    return det_uniform(f"optim.g{i}.{step}", OPTIM_SHAPES[i]) * scale
+
+
 def import_reference():
     """Import the real reference package (build container only)."""
     if REFERENCE_DIR not in sys.path:

@@ -205,3 +205,37 @@ def test_unet_state_dict_layout_matches_reference():
         assert list(rs) == list(ms) and all(torch.equal(rs[k], ms[k]) for k in rs)
     with pytest.raises(NotImplementedError):
         DenoisingVDMUNet(spec.data_shape, NyquistPositionalEmbedding(32, 100), "gelu", 128, 2, 4)
+
+
+# ----- optimizer side: host logic of bsi_b200.optim (no GPU needed) -----
+def test_ema_schedule_host_logic_matches_oracle_and_reference_fixture():
+    from bsi_b200 import optim as NO
+    from oracle import optim_oracle as OO
+
+    g = H.load_golden("optim.pt")
+    ema = NO.EMA(torch.nn.Linear(3, 2), include_online_model=False, **H.OPTIM_EMA)
+    sched = OO.EMASchedule(**H.OPTIM_EMA)
+    step, initted = 0, False
+    names = {0: "none", 1: "copy", 2: "lerp"}
+    for i in range(H.OPTIM_STEPS):
+        mode, w = ema._next_action()
+        action, w_ref, step, initted = OO.ema_action(step, initted, sched)
+        assert names[mode] == action and w == w_ref
+        ema.step += 1  # what update() does to the counters (the kernel call itself needs a GPU)
+        ema.initted = True
+        assert ema.get_current_decay() == g["decay"][i] == OO.ema_current_decay(step, sched)
+    assert ema.get_extra_state() == {"initted": True, "step": H.OPTIM_STEPS}
+    created = NO.create_ema(torch.nn.Linear(3, 2), beta=0.9999, update_after_step=1000, update_every=1, power=0.5, inv_gamma=7.0, name="ema")
+    assert (created.power, created.inv_gamma, created.include_online_model) == (2 / 3, 1.0, False)  # yaml extras are swallowed (bsi/tasks/bsi.py:73-81)
+
+
+def test_flat_arena_layout_and_cpu_rejection():
+    from bsi_b200 import optim as NO
+
+    arena = NO.FlatArena([torch.Size(s) for s in H.OPTIM_SHAPES], torch.device("cpu"))
+    assert arena.offsets == [0, 36, 72, 120] and arena.numel == 124 and arena.numel % 4 == 0
+    v = arena.view(2)
+    v.fill_(3.0)
+    assert v.shape == (4, 4, 3) and float(arena.flat[72:120].sum()) == 144.0 and float(arena.flat.sum()) == 144.0
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        NO.FlatArena.adopt([torch.nn.Parameter(torch.zeros(4))])

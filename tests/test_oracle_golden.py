@@ -223,3 +223,37 @@ def test_philox_known_answer():
     # sharding invariance: rows depend only on the global sample index
     z2 = O.philox_normal(seed=3, sample0=32, n=32, numel=3072, draw=1)
     assert np.array_equal(z[32:], z2)
+
+
+# ----- optimizer side (clip_grad_norm_ -> AdamW -> reference EMA.update), fixture from the real classes -----
+def test_optimizer_side_oracle_matches_reference():
+    from oracle import optim_oracle as OO
+
+    g = H.load_golden("optim.pt")
+    params = [H.det_uniform(f"optim.p{i}", shp) for i, shp in enumerate(H.OPTIM_SHAPES)]
+    side = OO.OptimizerSide(params, max_norm=H.OPTIM_MAX_NORM, ema=OO.EMASchedule(**H.OPTIM_EMA), **H.OPTIM_HYPER)
+    for step in range(H.OPTIM_STEPS):
+        grads = [H.optim_grad(i, step) for i in range(len(params))]
+        assert torch.equal(OO.clip_coef(grads, H.OPTIM_MAX_NORM), g["coef"][step])
+        side.step(grads)
+        assert OO.ema_current_decay(side.ema_step, side.ema_schedule) == g["decay"][step]
+        for i in range(len(params)):
+            assert torch.equal(side.params[i], g["params"][step][i]), (step, i)  # bit-exact: same torch CPU ops in the same order
+            assert torch.equal(side.ema[i], g["ema"][step][i]), (step, i)
+    for i in range(len(params)):
+        assert torch.equal(side.m[i], g["exp_avg"][i]) and torch.equal(side.v[i], g["exp_avg_sq"][i])
+
+
+def test_ema_schedule_matches_create_ema_defaults():
+    from oracle import optim_oracle as OO
+
+    # create_ema (bsi/tasks/bsi.py:73-81) with config/task/ema/ema.yaml: beta 0.9999, update_after_step 1000, update_every 1
+    s = OO.EMASchedule(beta=0.9999, update_after_step=1000, update_every=1)
+    assert OO.ema_current_decay(1001, s) == 0.0
+    assert OO.ema_current_decay(1002, s) == 1 - 2 ** (-2 / 3)
+    assert OO.ema_current_decay(10**9, s) == 0.9999
+    step, initted, actions = 0, False, []
+    for _ in range(1004):
+        a, w, step, initted = OO.ema_action(step, initted, s)
+        actions.append(a)
+    assert actions[:1001] == ["copy"] * 1001 and actions[1001:] == ["lerp"] * 3
