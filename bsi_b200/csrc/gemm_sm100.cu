@@ -40,12 +40,20 @@ __host__ __device__ constexpr int epi_kind(int epi) {
                                          : KIND_F32;
 }
 
-template <int EPI, int CG, int BN>
+constexpr int kReuseMaxW = 32;  // widest image row for which a convolution's A box (128 + 2W pixels) fits the stage
+
+template <int EPI, int CG, int BN, bool CONV = false>
 struct Cfg {
     static constexpr int kKind = epi_kind(EPI);
     static constexpr int kBRows = BN / CG;  // rows of the W tile this CTA loads
     static constexpr int kBBytes = kBRows * BK * 2;
-    static constexpr int kStageBytes = kABytes + kBBytes;
+    // Narrow (N <= 128) 3x3 convolutions are bound by L2 -> SM traffic, most of it the A tile re-fetched for every tap.  Their
+    // stage therefore holds one A box with a one-row halo above and below ((128 + 2W) pixels) that serves the three taps
+    // dy = -1, 0, +1 of one dx through three smem descriptors W pixels apart, plus those three taps' weight tiles.
+    static constexpr bool kRowReuse = CONV && BN == 128;
+    static constexpr int kAStage = kRowReuse ? (BM + 2 * kReuseMaxW) * 128 : kABytes;
+    static constexpr int kBTiles = kRowReuse ? 3 : 1;
+    static constexpr int kStageBytes = kAStage + kBTiles * kBBytes;
     // bf16 epilogues (bias / GELU / SiLU / modulation) are ALU-bound with one warp per scheduler (ncu: 25 % issue utilisation,
     // tensor pipe 63 % on the GELU shape): they get 8 epilogue warps, two per TMEM lane quarter, each pair splitting the columns
     // (the plain bias epilogue keeps 4 warps and the fifth pipeline stage: it already holds the tensor pipe at 87 %)
@@ -56,8 +64,11 @@ struct Cfg {
     static constexpr int kBufsPerGroup = kHeavy ? (kGroups == 4 ? 1 : 2) : 2;      // staging tiles per group (KIND_BF16)
     static constexpr int kThreads = 128 + 32 * kEpiWarps;
     static constexpr int kEpiBufs = (kKind == KIND_RMW || kHeavy) ? 4 : (kKind == KIND_SCATTER ? 0 : 2);
-    static constexpr int kStages = BN == 128 ? (CG == 2 ? 6 : 4) : (CG == 2 ? ((kKind == KIND_RMW || kHeavy) ? 4 : 5) : 3);
     static constexpr int kVecBytes = 2 * 3 * BN * 4;  // bias, gate/scale and shift slices of the tile, double-buffered by tile parity
+    static constexpr int kStages = kRowReuse ? (232448 - 1280 - kVecBytes - kEpiBufs * kEpiBufBytes) / kStageBytes
+                                   : BN == 128 ? (CG == 2 ? 6 : 4)
+                                               : (CG == 2 ? ((kKind == KIND_RMW || kHeavy) ? 4 : 5) : 3);
+    static_assert(kStages >= 2, "pipeline needs two stages");
     static constexpr int kSmemBytes = kStages * kStageBytes + kEpiBufs * kEpiBufBytes + kVecBytes + 1024 /*align*/ + 256 /*barriers*/;
     static_assert(kSmemBytes <= 232448, "exceeds the 227 KB of shared memory per CTA");
 };
@@ -82,6 +93,7 @@ struct ConvGeom {
     int taps;      // 1 or 9
     int cb1, cbt;  // 64-channel blocks of source 1, and of both sources together
     int img_w, img_hw;
+    int reuse;  // 1: k-groups (dx, channel block), one haloed A box + three weight tiles per stage (Cfg::kRowReuse)
 };
 
 __device__ __forceinline__ float gelu_tanh(float x) {
@@ -110,12 +122,12 @@ __device__ __forceinline__ float4 ld_shared_f4(uint32_t addr) {
 __device__ __forceinline__ uint32_t swz(int r, int c) { return (uint32_t)(r * 128 + ((c ^ (r & 7)) << 4)); }
 
 template <int EPI, int CG, bool CONV, int BN>
-__global__ void __launch_bounds__(Cfg<EPI, CG, BN>::kThreads, 1)
+__global__ void __launch_bounds__(Cfg<EPI, CG, BN, CONV>::kThreads, 1)
     k_gemm_bf16(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_a2,
                 const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_c,
                 const __grid_constant__ CUtensorMap map_r, const EpiParams ep, const ConvGeom geo, const int m_tiles, const int n_tiles,
                 const int k_blocks, const int batch, const int a_shared) {
-    using C = Cfg<EPI, CG, BN>;
+    using C = Cfg<EPI, CG, BN, CONV>;
     constexpr int kStages = C::kStages, kKind = C::kKind;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -174,28 +186,48 @@ __global__ void __launch_bounds__(Cfg<EPI, CG, BN>::kThreads, 1)
                     ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
                     uint8_t* sa = smem + stage * C::kStageBytes;
                     if constexpr (CONV) {
-                        const int tap = kb / geo.cbt, cb = kb - tap * geo.cbt;
-                        const int dy = geo.taps == 9 ? tap / 3 - 1 : 0, dx = geo.taps == 9 ? tap % 3 - 1 : 0;
                         const int img = row_a / geo.img_hw, y0 = (row_a - img * geo.img_hw) / geo.img_w;
-                        const CUtensorMap* src = cb < geo.cb1 ? &map_a : &map_a2;
-                        const int c0 = (cb < geo.cb1 ? cb : cb - geo.cb1) * BK;
-                        if constexpr (CG == 1) {
-                            ptx::mbar_arrive_expect_tx(&full_bar[stage], C::kStageBytes);
-                            ptx::tma_load_4d(sa, src, &full_bar[stage], c0, dx, y0 + dy, img);
-                            ptx::tma_load_3d(sa + kABytes, &map_w, &full_bar[stage], kb * BK, row_w, b);
+                        if (C::kRowReuse && geo.reuse) {
+                            // k-group (dx, channel block): rows y0-1 .. y0+128/W of the image shifted by dx, and the weights of taps
+                            // (dy, dx), dy = -1, 0, +1 (tap-major K layout of bsi_pack_conv_weight)
+                            const int dxi = kb / geo.cbt, cb = kb - dxi * geo.cbt;
+                            const CUtensorMap* src = cb < geo.cb1 ? &map_a : &map_a2;
+                            const int c0 = (cb < geo.cb1 ? cb : cb - geo.cb1) * BK;
+                            const uint32_t bytes = (uint32_t)(BM + 2 * geo.img_w) * 128u + 3u * C::kBBytes;
+                            if constexpr (CG == 1) {
+                                ptx::mbar_arrive_expect_tx(&full_bar[stage], bytes);
+                                ptx::tma_load_4d(sa, src, &full_bar[stage], c0, dxi - 1, y0 - 1, img);
+                                for (int dyi = 0; dyi < 3; ++dyi)
+                                    ptx::tma_load_3d(sa + C::kAStage + dyi * C::kBBytes, &map_w, &full_bar[stage], ((dyi * 3 + dxi) * geo.cbt + cb) * BK, row_w, b);
+                            } else {
+                                if (cta_rank == 0) ptx::mbar_arrive_expect_tx(&full_bar[stage], 2 * bytes);
+                                ptx::tma_load_4d_2sm(sa, src, &full_bar[stage], c0, dxi - 1, y0 - 1, img);
+                                for (int dyi = 0; dyi < 3; ++dyi)
+                                    ptx::tma_load_3d_2sm(sa + C::kAStage + dyi * C::kBBytes, &map_w, &full_bar[stage], ((dyi * 3 + dxi) * geo.cbt + cb) * BK, row_w, b);
+                            }
                         } else {
-                            if (cta_rank == 0) ptx::mbar_arrive_expect_tx(&full_bar[stage], 2 * C::kStageBytes);
-                            ptx::tma_load_4d_2sm(sa, src, &full_bar[stage], c0, dx, y0 + dy, img);
-                            ptx::tma_load_3d_2sm(sa + kABytes, &map_w, &full_bar[stage], kb * BK, row_w, b);
+                            const int tap = kb / geo.cbt, cb = kb - tap * geo.cbt;
+                            const int dy = geo.taps == 9 ? tap / 3 - 1 : 0, dx = geo.taps == 9 ? tap % 3 - 1 : 0;
+                            const CUtensorMap* src = cb < geo.cb1 ? &map_a : &map_a2;
+                            const int c0 = (cb < geo.cb1 ? cb : cb - geo.cb1) * BK;
+                            if constexpr (CG == 1) {
+                                ptx::mbar_arrive_expect_tx(&full_bar[stage], kABytes + C::kBBytes);
+                                ptx::tma_load_4d(sa, src, &full_bar[stage], c0, dx, y0 + dy, img);
+                                ptx::tma_load_3d(sa + C::kAStage, &map_w, &full_bar[stage], kb * BK, row_w, b);
+                            } else {
+                                if (cta_rank == 0) ptx::mbar_arrive_expect_tx(&full_bar[stage], 2 * (kABytes + C::kBBytes));
+                                ptx::tma_load_4d_2sm(sa, src, &full_bar[stage], c0, dx, y0 + dy, img);
+                                ptx::tma_load_3d_2sm(sa + C::kAStage, &map_w, &full_bar[stage], kb * BK, row_w, b);
+                            }
                         }
                     } else if constexpr (CG == 1) {
                         ptx::mbar_arrive_expect_tx(&full_bar[stage], C::kStageBytes);
                         ptx::tma_load_3d(sa, &map_a, &full_bar[stage], kb * BK, row_a, a_shared ? 0 : b);
-                        ptx::tma_load_3d(sa + kABytes, &map_w, &full_bar[stage], kb * BK, row_w, b);
+                        ptx::tma_load_3d(sa + C::kAStage, &map_w, &full_bar[stage], kb * BK, row_w, b);
                     } else {
                         if (cta_rank == 0) ptx::mbar_arrive_expect_tx(&full_bar[stage], 2 * C::kStageBytes);
                         ptx::tma_load_3d_2sm(sa, &map_a, &full_bar[stage], kb * BK, row_a, a_shared ? 0 : b);
-                        ptx::tma_load_3d_2sm(sa + kABytes, &map_w, &full_bar[stage], kb * BK, row_w, b);
+                        ptx::tma_load_3d_2sm(sa + C::kAStage, &map_w, &full_bar[stage], kb * BK, row_w, b);
                     }
                     if (++stage == kStages) stage = 0, phase ^= 1;
                 }
@@ -217,11 +249,22 @@ __global__ void __launch_bounds__(Cfg<EPI, CG, BN>::kThreads, 1)
                     ptx::mbar_wait(&full_bar[stage], phase);
                     ptx::tc_fence_after();
                     const uint32_t sa = ptx::smem_u32(smem + stage * C::kStageBytes);
-                    const uint64_t da = ptx::umma_desc_k_sw128(sa), db = ptx::umma_desc_k_sw128(sa + kABytes);
+                    if (C::kRowReuse && geo.reuse) {
+                        // tap dy reads the 128 pixels that start dy+1 image rows into the haloed box (W * 128 B: a multiple of 1024)
 #pragma unroll
-                    for (int k = 0; k < BK / UMMA_K; ++k) {
-                        // advance 32 B (16 bf16) inside the 128 B swizzle row: +2 in 16-byte address units
-                        ptx::umma_bf16_ss<CG>(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                        for (int dyi = 0; dyi < 3; ++dyi) {
+                            const uint64_t da = ptx::umma_desc_k_sw128(sa + dyi * geo.img_w * 128);
+                            const uint64_t db = ptx::umma_desc_k_sw128(sa + C::kAStage + dyi * C::kBBytes);
+#pragma unroll
+                            for (int k = 0; k < BK / UMMA_K; ++k) ptx::umma_bf16_ss<CG>(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | dyi | k) != 0 ? 1u : 0u);
+                        }
+                    } else {
+                        const uint64_t da = ptx::umma_desc_k_sw128(sa), db = ptx::umma_desc_k_sw128(sa + C::kAStage);
+#pragma unroll
+                        for (int k = 0; k < BK / UMMA_K; ++k) {
+                            // advance 32 B (16 bf16) inside the 128 B swizzle row: +2 in 16-byte address units
+                            ptx::umma_bf16_ss<CG>(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                        }
                     }
                     // free the smem stage (in both CTAs) once these MMAs have retired
                     if constexpr (CG == 1) ptx::umma_commit<1>(&empty_bar[stage]);
@@ -488,7 +531,7 @@ int make_tile_map(CUtensorMap* map, const void* base, int esize, int64_t rows, i
 }
 
 // bf16 NHWC [B][H][W][C] activation tensor, box {64 channels, W, 128/W rows, 1 image}, 128-byte swizzle, zero fill outside.
-static int make_nhwc_map(CUtensorMap* map, const void* base, int64_t B, int64_t H, int64_t W, int64_t C) {
+static int make_nhwc_map(CUtensorMap* map, const void* base, int64_t B, int64_t H, int64_t W, int64_t C, int halo_rows = 0) {
     EncodeTiledFn enc = get_encode_fn();
     if (!enc) {
         set_error("cuTensorMapEncodeTiled entry point unavailable");
@@ -501,7 +544,7 @@ static int make_nhwc_map(CUtensorMap* map, const void* base, int64_t B, int64_t 
     }
     cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
     cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
-    cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)W, (cuuint32_t)(BM / W), 1};
+    cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)W, (cuuint32_t)(BM / W + halo_rows), 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -536,17 +579,19 @@ struct Problem {
 
 template <int EPI, int CG, bool CONV, int BN>
 static int launch_gemm(const Problem& p, cudaStream_t stream) {
-    using C = Cfg<EPI, CG, BN>;
+    using C = Cfg<EPI, CG, BN, CONV>;
     BSI_ENSURE_SMEM((k_gemm_bf16<EPI, CG, CONV, BN>), C::kSmemBytes);
     CUtensorMap ma, ma2, mw, mc, mr;
     int rc;
     ConvGeom geo{};
     if (CONV) {
-        rc = make_nhwc_map(&ma, p.A, p.img_b, p.img_h, p.img_w, p.c1);
+        // W * 128 B must keep the shifted descriptors 1024-byte aligned (W % 8 == 0) and the haloed box must fit the stage
+        geo.reuse = C::kRowReuse && p.taps == 9 && p.img_w <= kReuseMaxW && p.img_w % 8 == 0;
+        rc = make_nhwc_map(&ma, p.A, p.img_b, p.img_h, p.img_w, p.c1, geo.reuse ? 2 : 0);
         if (rc != BSI_OK) return rc;
         ma2 = ma;
         if (p.A2) {
-            rc = make_nhwc_map(&ma2, p.A2, p.img_b, p.img_h, p.img_w, p.c2);
+            rc = make_nhwc_map(&ma2, p.A2, p.img_b, p.img_h, p.img_w, p.c2, geo.reuse ? 2 : 0);
             if (rc != BSI_OK) return rc;
         }
         geo.taps = p.taps, geo.cb1 = p.c1 / BK, geo.cbt = (p.c1 + (p.A2 ? p.c2 : 0)) / BK;
@@ -569,7 +614,8 @@ static int launch_gemm(const Problem& p, cudaStream_t stream) {
         rc = make_tile_map(&mr, p.resid, 4, p.M, p.N, p.ldc, p.batch, p.stride_c, BM);
         if (rc != BSI_OK) return rc;
     }
-    const int m_tiles = (p.M + BM * CG - 1) / (BM * CG), n_tiles = (p.N + BN - 1) / BN, k_blocks = (p.K + BK - 1) / BK;
+    const int m_tiles = (p.M + BM * CG - 1) / (BM * CG), n_tiles = (p.N + BN - 1) / BN;
+    const int k_blocks = geo.reuse ? 3 * geo.cbt : (p.K + BK - 1) / BK;  // row-reuse stages carry three taps each
     const int total = p.batch * m_tiles * n_tiles;
     const int max_workers = sm_count() / CG;
     const int workers = total < max_workers ? total : max_workers;

@@ -101,6 +101,24 @@ def test_conv3x3_and_1x1_vs_torch(cg):
         call("bsi_gemm_force_cta_group", 0)
 
 
+@pytest.mark.parametrize("cg", [2, 1])
+@pytest.mark.parametrize("Hh,Ww", [(16, 16), (16, 8), (4, 64)], ids=["w16", "w8", "w64_no_row_reuse"])
+def test_conv3x3_other_image_widths(Hh, Ww, cg):
+    """The narrow-N convolution stages one haloed A box per (dx, channel block) and reads the three dy taps through smem
+    descriptors W pixels apart: check the other legal row widths, and W = 64 where the box does not fit and every tap is loaded."""
+    call("bsi_gemm_force_cta_group", cg)
+    try:
+        B, C, N = 5, 128, 128
+        x = rnd(f"cw.x{Ww}", (B, Hh, Ww, C)).bfloat16()
+        w = rnd("cw.w", (N, C, 3, 3), 1 / math.sqrt(9 * C))
+        bias = rnd("cw.b", (N,), 0.1)
+        y = torch.full((B * Hh * Ww, N), float("nan"), device=dev())
+        conv(x, pack_weight(w), y, bias, L.EPI_BIAS_F32, 9)
+        report(f"conv3x3 W={Ww} cg{cg}", y, ref_conv(x, w, bias, 1), 2e-3, 2e-3)
+    finally:
+        call("bsi_gemm_force_cta_group", 0)
+
+
 def test_groupnorm_act_and_input_and_decode():
     B, HW, C = 3, 1024, 128
     x = rnd("gn.x", (B, HW, C), 2.0) + 0.3
