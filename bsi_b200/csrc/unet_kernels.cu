@@ -2,7 +2,13 @@
 // that are not GEMMs: GroupNorm(+SiLU) -> bf16 NHWC operand, input builder (c_in scaling + Fourier features + NCHW->NHWC),
 // 1x1 decode convolution back to NCHW, conv-weight packing, and the single-head S=1024, d=128 attention of the centre block.
 // Activations are NHWC so that a 3x3 convolution is an implicit GEMM over shifted TMA boxes (gemm_sm100.cu, CONV mode).
+#include <cooperative_groups.h>
+#include <stdlib.h>
+
 #include "common.cuh"
+#include "ptx_sm100.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace bsi {
 
@@ -64,6 +70,94 @@ __global__ void __launch_bounds__(kGnThreads)
             *reinterpret_cast<uint2*>(ab + (size_t)p * C + cq * 4) = make_uint2(pack_bf16(y[0], y[1]), pack_bf16(y[2], y[3]));
             if (rb) *reinterpret_cast<uint2*>(rb + (size_t)p * C + cq * 4) = make_uint2(pack_bf16(in[0], in[1]), pack_bf16(in[2], in[3]));
         }
+    }
+}
+
+// Cluster variant: an image is split over the 8 CTAs of a thread-block cluster.  Each CTA pulls its contiguous slice
+// (HW/8 pixels x C channels, <= 64 KB) into shared memory with one bulk copy, so HBM is read exactly once with the whole
+// slice in flight; the per-group sums are combined across the cluster through distributed shared memory (fixed order:
+// deterministic) and the normalised activation is produced from the smem copy.  Three CTAs fit an SM, which overlaps one
+// CTA's copy with another's reduction / cluster barrier / stores.  4 B read + 2 (or 4) B written per element, nothing else.
+constexpr int kGnClusterThreads = 256;
+constexpr int kGnClusterSize = 8;
+constexpr int kGnSliceBytes = 64 * 1024;
+__global__ void __launch_bounds__(kGnClusterThreads, 3)
+    k_groupnorm_act_cluster(__nv_bfloat16* __restrict__ act, __nv_bfloat16* __restrict__ raw, const float* __restrict__ x,
+                            const float* __restrict__ gamma, const float* __restrict__ beta, int HW, int C, int cpg, float eps, int apply_silu) {
+    extern __shared__ __align__(128) uint8_t gn_raw[];
+    // [slice fp32] | [stripes][C][2] partials | [C] mean | [C] rstd | [groups][2] doubles (this CTA's group sums) | mbarrier
+    cg::cluster_group cluster = cg::this_cluster();
+    const int quads = C >> 2, stripes = kGnClusterThreads / quads;
+    const int cq = threadIdx.x % quads, ps = threadIdx.x / quads;
+    const int rank = (int)cluster.block_rank(), img = blockIdx.x / kGnClusterSize;
+    const int pix = HW / kGnClusterSize;  // pixels of this CTA
+    const size_t base = ((size_t)img * HW + (size_t)rank * pix) * C;
+    float* s_x = reinterpret_cast<float*>(gn_raw);
+    float* s_partial = s_x + (size_t)pix * C;
+    float* s_mean = s_partial + stripes * C * 2;
+    float* s_rstd = s_mean + C;
+    double* s_part = reinterpret_cast<double*>(s_rstd + C);
+    const int groups = C / cpg;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(s_part + 2 * groups);
+    if (threadIdx.x == 0) {
+        ptx::mbar_init(bar, 1);
+        ptx::fence_mbar_init();
+        const uint32_t bytes = (uint32_t)pix * C * 4;
+        ptx::mbar_arrive_expect_tx(bar, bytes);
+        ptx::bulk_load_1d(s_x, x + base, bytes, bar);
+    }
+    __syncthreads();
+    ptx::mbar_wait(bar, 0);
+    float s[4] = {0.f, 0.f, 0.f, 0.f}, ss[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int p = ps; p < pix; p += stripes) {
+        const float4 v = *reinterpret_cast<const float4*>(s_x + (size_t)p * C + cq * 4);
+        s[0] += v.x, s[1] += v.y, s[2] += v.z, s[3] += v.w;
+        ss[0] = fmaf(v.x, v.x, ss[0]), ss[1] = fmaf(v.y, v.y, ss[1]), ss[2] = fmaf(v.z, v.z, ss[2]), ss[3] = fmaf(v.w, v.w, ss[3]);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        s_partial[(ps * C + cq * 4 + j) * 2] = s[j];
+        s_partial[(ps * C + cq * 4 + j) * 2 + 1] = ss[j];
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < groups) {
+        double a = 0.0, b = 0.0;
+        for (int c = threadIdx.x * cpg; c < (threadIdx.x + 1) * cpg; ++c)
+            for (int st = 0; st < stripes; ++st) a += s_partial[(st * C + c) * 2], b += s_partial[(st * C + c) * 2 + 1];
+        s_part[threadIdx.x * 2] = a, s_part[threadIdx.x * 2 + 1] = b;
+    }
+    cluster.sync();
+    if ((int)threadIdx.x < groups) {
+        double a = 0.0, b = 0.0;
+        for (int r = 0; r < kGnClusterSize; ++r) {
+            const double* remote = cluster.map_shared_rank(s_part, r);
+            a += remote[threadIdx.x * 2], b += remote[threadIdx.x * 2 + 1];
+        }
+        const double n = (double)HW * cpg, mean = a / n;
+        const double var = fmax(b / n - mean * mean, 0.0);
+        const float rstd = rsqrtf((float)var + eps);
+        for (int c = threadIdx.x * cpg; c < (threadIdx.x + 1) * cpg; ++c) s_mean[c] = (float)mean, s_rstd[c] = rstd;
+    }
+    cluster.sync();  // also keeps every CTA's partials alive until all peers have read them
+    const float4 g4 = *reinterpret_cast<const float4*>(gamma + cq * 4), b4 = *reinterpret_cast<const float4*>(beta + cq * 4);
+    const float m[4] = {s_mean[cq * 4], s_mean[cq * 4 + 1], s_mean[cq * 4 + 2], s_mean[cq * 4 + 3]};
+    const float r[4] = {s_rstd[cq * 4], s_rstd[cq * 4 + 1], s_rstd[cq * 4 + 2], s_rstd[cq * 4 + 3]};
+    const float g[4] = {g4.x, g4.y, g4.z, g4.w}, be[4] = {b4.x, b4.y, b4.z, b4.w};
+    __nv_bfloat16* ab = act + base;
+    __nv_bfloat16* rb = raw ? raw + base : nullptr;
+#pragma unroll 4
+    for (int p = ps; p < pix; p += stripes) {
+        const float4 v = *reinterpret_cast<const float4*>(s_x + (size_t)p * C + cq * 4);
+        const float in[4] = {v.x, v.y, v.z, v.w};
+        float y[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float t = fmaf((in[j] - m[j]) * r[j], g[j], be[j]);
+            y[j] = apply_silu ? __fdividef(t, 1.0f + __expf(-t)) : t;
+        }
+        const size_t off = (size_t)p * C + cq * 4;
+        *reinterpret_cast<uint2*>(ab + off) = make_uint2(pack_bf16(y[0], y[1]), pack_bf16(y[2], y[3]));
+        if (rb) *reinterpret_cast<uint2*>(rb + off) = make_uint2(pack_bf16(in[0], in[1]), pack_bf16(in[2], in[3]));
     }
 }
 
@@ -278,6 +372,26 @@ int bsi_groupnorm_act_bf16(void* act_bf16, void* raw_bf16, const float* x, const
                   "bsi_groupnorm_act_bf16: unsupported channel count %d / group size %d", C, channels_per_group);
     const int stripes = kGnThreads / (C / 4);
     const int smem = (stripes * C * 2 + 2 * C) * (int)sizeof(float);
+    // cluster path: the image split over 2, 4 or 8 CTAs fits the threads' registers (<= 16 float4 each)
+    // cluster path: the image splits into 8 contiguous slices of <= 64 KB that each CTA stages in shared memory
+    static const bool use_cluster = [] { const char* e = getenv("BSI_GN_CLUSTER"); return !(e && e[0] == '0'); }();
+    const int cstripes = kGnClusterThreads / (C / 4);
+    if (use_cluster && kGnClusterThreads % (C / 4) == 0 && C / channels_per_group <= kGnClusterThreads && HW % kGnClusterSize == 0 &&
+        (int64_t)(HW / kGnClusterSize) * C * 4 <= kGnSliceBytes && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+        const int slice = (HW / kGnClusterSize) * C * 4;
+        const int smem_c = slice + (cstripes * C * 2 + 2 * C) * (int)sizeof(float) + 2 * (C / channels_per_group) * (int)sizeof(double) + 16;
+        BSI_ENSURE_SMEM(k_groupnorm_act_cluster, smem_c);
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3((unsigned)B * kGnClusterSize), cfg.blockDim = dim3(kGnClusterThreads), cfg.dynamicSmemBytes = smem_c, cfg.stream = (cudaStream_t)stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = kGnClusterSize, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr, cfg.numAttrs = 1;
+        BSI_CUDA_OK(cudaLaunchKernelEx(&cfg, k_groupnorm_act_cluster, (__nv_bfloat16*)act_bf16, (__nv_bfloat16*)raw_bf16, x, gamma, beta, (int)HW, (int)C,
+                                       (int)channels_per_group, eps, (int)apply_silu));
+        BSI_LAUNCH_OK("k_groupnorm_act_cluster");
+        return BSI_OK;
+    }
     if (smem > 48 * 1024) BSI_ENSURE_SMEM(k_groupnorm_act, smem);
     k_groupnorm_act<<<B, kGnThreads, smem, (cudaStream_t)stream>>>((__nv_bfloat16*)act_bf16, (__nv_bfloat16*)raw_bf16, x, gamma, beta, HW, C,
                                                                   channels_per_group, eps, apply_silu);
