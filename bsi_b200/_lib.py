@@ -68,7 +68,7 @@ class AdamWArgs(C.Structure):
         ("param", C.c_void_p), ("grad", C.c_void_p), ("exp_avg", C.c_void_p), ("exp_avg_sq", C.c_void_p), ("ema", C.c_void_p),
         ("param_bf16", C.c_void_p), ("grad_sumsq", C.c_void_p), ("numel", C.c_int64), ("step", C.c_int64),
         ("lr", C.c_double), ("beta1", C.c_double), ("beta2", C.c_double), ("eps", C.c_double), ("weight_decay", C.c_double),
-        ("max_norm", C.c_float), ("ema_weight", C.c_float), ("ema_mode", C.c_int32), ("zero_grad", C.c_int32),
+        ("max_norm", C.c_float), ("grad_scale", C.c_float), ("ema_weight", C.c_float), ("ema_mode", C.c_int32), ("zero_grad", C.c_int32),
     ]  # fmt: skip
 
 

@@ -7,7 +7,9 @@
 // The arithmetic follows torch's single-tensor AdamW op by op, each result rounded to fp32 like the eager ops do:
 //   p.mul_(1 - lr*wd); m.lerp_(g, 1-b1); v.mul_(b2).addcmul_(g, g, value=1-b2);
 //   denom = (v.sqrt() / sqrt(1-b2^t)).add_(eps); p.addcdiv_(m, denom, value=-lr/(1-b1^t))
-// with g = grad * min(max_norm / (||grad|| + 1e-6), 1) as torch.nn.utils.clip_grad_norm_ scales it.
+// with g = grad * min(max_norm / (||grad|| + 1e-6), 1) as torch.nn.utils.clip_grad_norm_ scales it.  Under data parallelism
+// the gradient arena is summed over ranks by ONE all-reduce (bsi_b200/optim.py) and the 1/world_size of
+// DistributedDataParallel (bsi/tasks/bsi.py:163-166) is applied here as grad_scale instead of in a pass of its own.
 #include "common.cuh"
 
 namespace bsi {
@@ -62,13 +64,14 @@ struct StepConsts {
     float eps;
     float neg_step;     // -lr / (1 - beta1^t)
     float max_norm;     // <= 0: no clipping
+    float grad_scale;   // 1/world_size after a sum all-reduce of the gradient arena (DDP's average), else 1
     float ema_weight;   // 1 - decay
     int ema_mode;       // 0 none, 1 copy, 2 lerp
     int zero_grad;
 };
 
 __device__ __forceinline__ float adamw_one(float& p, float g, float& m, float& v, const StepConsts& c, float coef) {
-    g = __fmul_rn(g, coef);
+    g = __fmul_rn(__fmul_rn(g, c.grad_scale), coef);
     p = __fmul_rn(p, c.decay_mul);
     m = torch_lerp(m, g, c.w1);
     v = __fmaf_rn(__fmul_rn(c.w2, g), g, __fmul_rn(v, c.beta2));  // addcmul: (value*g)*g + v*beta2 in one FMA
@@ -83,7 +86,7 @@ __global__ void __launch_bounds__(kOThreads)
                 const StepConsts c) {
     float coef = 1.0f;
     if (c.max_norm > 0.0f) {
-        const float total_norm = __fsqrt_rn(grad_sumsq[0]);
+        const float total_norm = __fmul_rn(__fsqrt_rn(grad_sumsq[0]), c.grad_scale);  // norm of the averaged gradient
         coef = fminf(__fdiv_rn(c.max_norm, __fadd_rn(total_norm, 1e-6f)), 1.0f);
     }
     float4* p4 = reinterpret_cast<float4*>(param);
@@ -171,6 +174,7 @@ int bsi_adamw_ema_step(const bsi_adamw_args* a, void* stream) {
     c.eps = (float)a->eps;
     c.neg_step = (float)(-(a->lr / bc1));
     c.max_norm = a->max_norm;
+    c.grad_scale = a->grad_scale > 0.0f ? a->grad_scale : 1.0f;
     c.ema_weight = a->ema_weight, c.ema_mode = a->ema_mode, c.zero_grad = a->zero_grad;
     k_adamw_ema<<<stream_grid(a->numel / 4), kOThreads, 0, (cudaStream_t)stream>>>(a->param, a->grad, a->exp_avg, a->exp_avg_sq, a->ema,
                                                                                    (__nv_bfloat16*)a->param_bf16, a->grad_sumsq, a->numel / 4, c);

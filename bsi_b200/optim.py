@@ -196,7 +196,9 @@ class AdamW(torch.optim.Optimizer):
         self._sumsq = torch.zeros(1, dtype=torch.float32, device=dev)
         self._ws = torch.empty(int(self._lib.bsi_grad_sumsq_workspace_floats()), dtype=torch.float32, device=dev)
         self._t = 0
+        self._last_scale = 1.0
         self._ema: EMA | None = None
+        self._grad_scale = 1.0  # 1/world_size once all_reduce_grads() has summed the arena over ranks
         self._clean_version = -1  # version counter of the gradient arena right after the kernel zeroed it
         for i, p in enumerate(plist):
             p.grad = self._g.view(i)
@@ -218,7 +220,17 @@ class AdamW(torch.optim.Optimizer):
 
     def total_grad_norm(self) -> Tensor:
         """Device scalar: the gradient norm the last ``step()`` clipped against (``clip_grad_norm_``'s return value)."""
-        return self._sumsq.sqrt()
+        return self._sumsq.sqrt() * self._last_scale
+
+    def all_reduce_grads(self, group=None) -> None:
+        """Data-parallel gradient exchange (``DistributedDataParallel`` of bsi/tasks/bsi.py:163-166) as ONE sum all-reduce over
+        the flat gradient arena (NCCL over NVLink); the division by the world size is folded into the next ``step()``.
+        Call between ``backward()`` and ``step()`` with the model *not* wrapped in DDP."""
+        import torch.distributed as dist
+
+        self._gather_grads()
+        dist.all_reduce(self._g.flat, op=dist.ReduceOp.SUM, group=group)
+        self._grad_scale = 1.0 / dist.get_world_size(group)
 
     def _gather_grads(self) -> None:
         """Gradients normally accumulate straight into the arena (``p.grad`` is a view of it).  If something replaced
@@ -260,9 +272,10 @@ class AdamW(torch.optim.Optimizer):
             ema=L.ptr(self._ema_arena.flat) if self._ema is not None else None, param_bf16=L.ptr(self._bf16) if self._bf16 is not None else None,
             grad_sumsq=L.ptr(self._sumsq) if clip else None, numel=self._p.numel, step=self._t, lr=float(g0["lr"]), beta1=float(g0["betas"][0]),
             beta2=float(g0["betas"][1]), eps=float(g0["eps"]), weight_decay=float(g0["weight_decay"]),
-            max_norm=float(self.max_grad_norm) if clip else 0.0, ema_weight=float(weight), ema_mode=int(mode), zero_grad=1,
+            max_norm=float(self.max_grad_norm) if clip else 0.0, grad_scale=float(self._grad_scale), ema_weight=float(weight), ema_mode=int(mode), zero_grad=1,
         )
         L.check(self._lib.bsi_adamw_ema_step(ctypes.byref(a), st), "bsi_adamw_ema_step")
+        self._last_scale, self._grad_scale = self._grad_scale, 1.0
         self._clean_version = self._g.flat._version  # the kernel left the gradients zeroed; autograd accumulation bumps the counter
         for p in self._params:
             self.state[p]["step"] += 1

@@ -332,6 +332,8 @@ typedef struct bsi_adamw_args {
     int64_t step;            /* optimizer step, counted from 1 (bias correction) */
     double lr, beta1, beta2, eps, weight_decay;
     float max_norm;          /* clip_grad_norm_(max_norm, 2): g *= min(max_norm / (||g|| + 1e-6), 1); <= 0 disables */
+    float grad_scale;        /* gradients are multiplied by this first (1/world_size after a sum all-reduce: DDP's mean,
+                                bsi/tasks/bsi.py:163-166); 0 means 1 */
     float ema_weight;        /* 1 - current_decay (EMA.get_current_decay, ema_pytorch.py:308-314) */
     int32_t ema_mode;        /* 0 none, 1 ema = param (copy_params_from_model_to_ema), 2 ema.lerp_(param, ema_weight) */
     int32_t zero_grad;       /* 1: leave the gradient arena zeroed (optimizer.zero_grad(set_to_none=False)) */
