@@ -295,6 +295,9 @@ class BSI(nn.Module):
         sigma = torch.rsqrt(lam).contiguous()
         if self.noise_source != "torch" and _seed is None:
             _seed = self._draw_seed(generator)
+        if R == 0:  # empty batch: nothing to draw (torch.randn of an empty shape consumes no random numbers either)
+            mu = torch.empty((*lambda_.shape, *self.data_shape), **self.tensor_args)
+            return (mu, torch.empty_like(mu)) if _c_in is not None else mu
         nz, _keep = self._noise((*lambda_.shape, *self.data_shape), generator, _draw, 0, _seed)
         mu = torch.empty((*lambda_.shape, *self.data_shape), **self.tensor_args)
         model_in = torch.empty_like(mu) if _c_in is not None else None
@@ -326,6 +329,8 @@ class BSI(nn.Module):
         """sum_d (x - x_hat)^2 for mu ~ q(.|x, lambda_[n,B]) and the model evaluated at t_flat -> [n,B]."""
         self._check_precond()
         n, B = lambda_.shape
+        if B == 0:
+            return _cuda_f32(x, "x").new_zeros((n, 0))
         if self.preconditioning == "edm":
             c_skip, c_out, c_in = self._edm_preconditioning(t_flat)
             mu, model_in = self._sample_q_mu_lambda(x, lambda_, generator, _c_in=c_in, _draw=draw)
@@ -342,6 +347,8 @@ class BSI(nn.Module):
         dev = self._require_cuda()
         x = _cuda_f32(x, "x")
         B, D = x.shape[0], self._numel
+        if B == 0:
+            return x.new_zeros((n_samples, 0))
         lam_M = x.new_full((n_samples, B), float(self.lambda_0 + self.alpha_M))
         t_one = x.new_ones(n_samples * B)
         if self.preconditioning == "edm":
@@ -446,6 +453,11 @@ class BSI(nn.Module):
         if philox and seed is None:
             seed = self._draw_seed(generator)
         shape = (n, *self.data_shape)
+        if n == 0:  # the reference returns empty tensors (every op of its loop accepts an empty batch)
+            empty = torch.empty(shape, **self.tensor_args)
+            if history:
+                return empty.new_empty((k + 1, *shape)), empty.new_empty((k + 1, *shape)), empty.new_empty((k, *shape))
+            return empty
         precond = 1 if self.preconditioning == "edm" else 0
         sigma0 = torch.rsqrt(lam[:1]).contiguous()
         if self._is_native_denoiser() and philox and not history:

@@ -1,5 +1,7 @@
 """BSI public API with a caller-owned PyTorch denoiser (config 1: README toy Conv2d) vs the CPU oracle and goldens."""
 
+import math
+
 import pytest
 import torch
 
@@ -130,3 +132,56 @@ def test_cpu_tensors_are_rejected_loudly():
         bsi.sample(2)
     with pytest.raises(BsiNativeError):
         Discretization.image_8bit().bucketize(torch.zeros(4))
+
+
+def test_finite_elbo_vs_oracle_with_custom_schedule():
+    """finite_elbo (bsi/bsi.py:184-215,249-274; eval_elbo.py -k <int>): same RNG consumption as the reference
+    (randn recon -> randint steps -> randn measure) replayed into the oracle, default and cosine-like custom schedule."""
+    bsi, sd = make(k=32)
+    f = lambda mu, t: O.toy_conv_forward(sd, mu, t)
+    x = H.det_images("toy.x", 8, (3, 32, 32), seed=2)
+    for name, t_grid in (("default", None), ("custom", torch.sin(torch.linspace(0.0, 1.0, 21) * (math.pi / 2)) ** 2)):
+        k = 32 if t_grid is None else len(t_grid) - 1
+        with torch.inference_mode():
+            e, b, ex = bsi.finite_elbo(x.to(dev()), 2, 5, torch.Generator(device=dev()).manual_seed(11), t=None if t_grid is None else t_grid.to(dev()))
+            gen = torch.Generator(device=dev()).manual_seed(11)
+            eps_r = torch.randn((2, 8, 3, 32, 32), device=dev(), generator=gen).cpu()
+            idx = torch.randint(0, k, (5, 8), device=dev(), generator=gen).cpu()
+            eps_m = torch.randn((5, 8, 3, 32, 32), device=dev(), generator=gen).cpu()
+            grid = torch.linspace(0.0, 1.0, 33) if t_grid is None else t_grid
+            l_r = O.recon_loss(f, C32, x, 2, eps_r, O.GRID_8BIT)
+            l_m = O.finite_measure_loss(f, C32, x, grid, idx, eps_m)
+            e_ref, b_ref, _ = O.combine_elbo(l_r, l_m, 3072)
+        report(f"finite l_measure ({name})", ex["l_measure"], l_m, 1e-4, 1e-3)
+        report(f"finite l_recon ({name})", ex["l_recon"], l_r, 1e-4, 1e-2)
+        assert float((b.cpu() - b_ref).abs().max()) < 1e-3, name
+
+
+def test_edge_cases_empty_single_and_ragged_batches():
+    """Empty and ragged inputs behave like the reference: sample(0) is an empty tensor of the data shape, odd batch sizes and
+    k = 1 work, and a data shape whose element count the vectorised kernels cannot handle fails loudly instead of silently."""
+    from bsi_b200._lib import BsiNativeError
+
+    bsi, sd = make(k=4)
+    f = lambda mu, t: O.toy_conv_forward(sd, mu, t)
+    with torch.inference_mode():
+        empty = bsi.sample(0, torch.Generator(device=dev()).manual_seed(1))
+        assert empty.shape == (0, 3, 32, 32) and empty.dtype == torch.float32
+        for n in (1, 3, 7):
+            out = bsi.sample(n, torch.Generator(device=dev()).manual_seed(2))
+            gen = torch.Generator(device=dev()).manual_seed(2)
+            eps = torch.stack([torch.randn((n, 3, 32, 32), device=dev(), generator=gen) for _ in range(5)]).cpu()
+            ref = O.sample_with_noise(f, C32, torch.linspace(0.0, 1.0, 5), eps)
+            report(f"sample n={n}", out, ref, 1e-5, 1e-5)
+        x = H.det_images("toy.x", 5, (3, 32, 32), seed=2)
+        e, b, ex = bsi.elbo(x.to(dev()), 1, 3, torch.Generator(device=dev()).manual_seed(4))
+        assert b.shape == (5,) and ex["l_measure"].shape == (3, 5) and torch.isfinite(b).all()
+        e0, b0, ex0 = bsi.elbo(x[:0].to(dev()), 1, 2, torch.Generator(device=dev()).manual_seed(4))
+        assert b0.shape == (0,) and ex0["l_recon"].shape == (1, 0)
+    one, _ = make(k=1)
+    with torch.inference_mode():
+        assert torch.isfinite(one.sample(2, torch.Generator(device=dev()).manual_seed(3))).all()
+    model = torch.nn.Identity()
+    odd = BSI(model, data_shape=(1, 5, 5), k=4, discretization=Discretization.image_8bit(), **HYPER).to(dev())
+    with torch.inference_mode(), pytest.raises((BsiNativeError, RuntimeError), match="multiple of 4"):
+        odd.sample(2, torch.Generator(device=dev()).manual_seed(1))
