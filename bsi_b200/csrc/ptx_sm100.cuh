@@ -137,6 +137,12 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void*
                  "r"(c0), "r"(c1), "r"(c2)
                  : "memory");
 }
+// TMA store with reduction: global[tile] += smem tile (element type of the tensor map; fp32 here)
+__device__ __forceinline__ void tma_reduce_add_3d(const CUtensorMap* map, const void* src, int c0, int c1, int c2) {
+    asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(map),
+                 "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void tma_store_wait_read() {

@@ -309,6 +309,13 @@ int bsi_unet_forward(const bsi_unet* e, float* out, const float* mu, bsi_rowref 
                      int32_t cond_sample_rows, int32_t cond_step_rows, const int32_t* step_ptr, int32_t B, void* workspace, int64_t workspace_bytes,
                      void* stream);
 
+/* Weight-gradient GEMM (backward of nn.Linear, bsi/models/dit.py:33-34,71-76,79-81; groundwork for config 5):
+ *     dW[n][k] += sum_m dY[m][n] * X[m][k]     dY bf16 [M][N] (pitch ldy), X bf16 [M][K] (pitch ldx), dW fp32 [N][K] (pitch ldw)
+ * Accumulates into dW (autograd's "+="); the M range is split over `splits` work items per tile (0 = automatic) whose
+ * partial sums are combined by TMA reduce-add, so the fp32 summation order across splits is not fixed. */
+int bsi_gemm_wgrad_bf16(float* dW, const void* dY_bf16, const void* X_bf16, int32_t M, int32_t N, int32_t K, int32_t ldy, int32_t ldx,
+                        int32_t ldw, int32_t splits, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Optimizer side of the training step over flat fp32 arenas of `numel` elements
  * (numel % 4 == 0).  Replaces, in two launches, Lightning's clip_grad_norm_ (config/train.yaml:40),
