@@ -1,0 +1,232 @@
+// Elementwise / reduction kernels of the DiT training path (backward of bsi/models/dit.py:50-55,87-103).
+// All HBM-bound; the GEMMs around them are bsi_gemm_bf16 (forward, data gradient with transposed weights) and
+// bsi_gemm_wgrad_bf16 (weight gradient).
+//   gate_residual            x += gate[b] * branch                        (torch.addcmul(x, gate, branch), dit.py:93-102)
+//   gate_residual_backward   dbranch = gate[b] * dx ; dgate[b] = sum_t dx * branch
+//   gelu / gelu_backward     nn.GELU(approximate="tanh") on the bf16 pre-activation (dit.py:75)
+//   layernorm_mod_backward   backward of modulate(LayerNorm(x), shift, scale) (dit.py:50-55) and of the affine decoder LayerNorm (:164):
+//                            dx += rstd * (g - mean(g) - xhat * mean(g * xhat)), g = da * (1 + scale)   [or da * gamma]
+//                            dscale[b] = sum_t da * xhat, dshift[b] = sum_t da   (per-CTA partial sums, fixed order)
+#include "common.cuh"
+
+namespace bsi {
+
+constexpr int kTrThreads = 256;
+
+__device__ __forceinline__ float2 bf16x2_to_float2(uint32_t v) { return make_float2(__uint_as_float(v << 16), __uint_as_float(v & 0xffff0000u)); }
+
+// ------------------------------------------------------------------ x += gate * branch
+__global__ void __launch_bounds__(kTrThreads) k_gate_residual(float* __restrict__ x, const __nv_bfloat16* __restrict__ br, bsi_rowref gate, int T, int64_t M, int D) {
+    const int64_t quads = M * (D / 4);
+    for (int64_t i = (int64_t)blockIdx.x * kTrThreads + threadIdx.x; i < quads; i += (int64_t)gridDim.x * kTrThreads) {
+        const int64_t row = i / (D / 4);
+        const int c = (int)(i - row * (D / 4)) * 4;
+        const float4 g = gate.base ? *reinterpret_cast<const float4*>(rowref_ptr(gate, row / T, 0) + c) : make_float4(1.f, 1.f, 1.f, 1.f);
+        const uint2 b = *reinterpret_cast<const uint2*>(br + row * D + c);
+        const float2 b0 = bf16x2_to_float2(b.x), b1 = bf16x2_to_float2(b.y);
+        float4 v = *reinterpret_cast<float4*>(x + row * D + c);
+        v.x = fmaf(g.x, b0.x, v.x), v.y = fmaf(g.y, b0.y, v.y), v.z = fmaf(g.z, b1.x, v.z), v.w = fmaf(g.w, b1.y, v.w);
+        *reinterpret_cast<float4*>(x + row * D + c) = v;
+    }
+}
+
+// ------------------------------------------------------------------ dbranch = gate * dx, dgate[b] = sum_t dx * branch
+// grid (D / 512, B): a thread owns two adjacent columns of one sample and walks its T token rows (coalesced across the CTA)
+__global__ void __launch_bounds__(kTrThreads) k_gate_residual_backward(__nv_bfloat16* __restrict__ dbr, float* __restrict__ dgate, const float* __restrict__ dx,
+                                                                       const __nv_bfloat16* __restrict__ br, bsi_rowref gate, int T, int D) {
+    const int c = (blockIdx.x * kTrThreads + threadIdx.x) * 2;
+    if (c >= D) return;
+    const int64_t b = blockIdx.y;
+    const float2 g = gate.base ? *reinterpret_cast<const float2*>(rowref_ptr(gate, b, 0) + c) : make_float2(1.f, 1.f);
+    float a0 = 0.f, a1 = 0.f;
+#pragma unroll 4
+    for (int t = 0; t < T; ++t) {
+        const int64_t off = (b * T + t) * D + c;
+        const float2 d = *reinterpret_cast<const float2*>(dx + off);
+        const float2 v = bf16x2_to_float2(*reinterpret_cast<const uint32_t*>(br + off));
+        a0 = fmaf(d.x, v.x, a0), a1 = fmaf(d.y, v.y, a1);
+        *reinterpret_cast<uint32_t*>(dbr + off) = pack_bf16(g.x * d.x, g.y * d.y);
+    }
+    if (dgate) *reinterpret_cast<float2*>(dgate + b * D + c) = make_float2(a0, a1);
+}
+
+// ------------------------------------------------------------------ GELU (tanh) forward / backward on bf16
+__device__ __forceinline__ float gelu_fwd(float x) {
+    const float u = 0.7978845608028654f * fmaf(0.044715f * x * x, x, x);
+    return 0.5f * x * (1.0f + tanhf(u));
+}
+__device__ __forceinline__ float gelu_grad(float x) {
+    const float x2 = x * x;
+    const float t = tanhf(0.7978845608028654f * fmaf(0.044715f * x2, x, x));
+    const float du = 0.7978845608028654f * fmaf(3.0f * 0.044715f, x2, 1.0f);
+    return 0.5f * (1.0f + t) + 0.5f * x * (1.0f - t * t) * du;
+}
+template <bool BWD>
+__global__ void __launch_bounds__(kTrThreads) k_gelu(__nv_bfloat16* __restrict__ out, const __nv_bfloat16* __restrict__ up, const __nv_bfloat16* __restrict__ pre, int64_t n8) {
+    for (int64_t i = (int64_t)blockIdx.x * kTrThreads + threadIdx.x; i < n8; i += (int64_t)gridDim.x * kTrThreads) {
+        const uint4 p = reinterpret_cast<const uint4*>(pre)[i];
+        uint4 u = make_uint4(0, 0, 0, 0);
+        if (BWD) u = reinterpret_cast<const uint4*>(up)[i];
+        const uint32_t pw[4] = {p.x, p.y, p.z, p.w}, uw[4] = {u.x, u.y, u.z, u.w};
+        uint32_t ow[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float2 x = bf16x2_to_float2(pw[j]);
+            if (BWD) {
+                const float2 g = bf16x2_to_float2(uw[j]);
+                ow[j] = pack_bf16(g.x * gelu_grad(x.x), g.y * gelu_grad(x.y));
+            } else {
+                ow[j] = pack_bf16(gelu_fwd(x.x), gelu_fwd(x.y));
+            }
+        }
+        reinterpret_cast<uint4*>(out)[i] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+    }
+}
+
+// ------------------------------------------------------------------ LayerNorm (+ modulation / affine) backward
+// One warp per row (row in registers), a CTA of 8 warps owns `rows_per_cta` consecutive rows (all of one sample) and writes one
+// partial row of dscale / dshift sums; the host adds the partials of a sample (fixed order -> deterministic).
+template <int NV>
+__global__ void __launch_bounds__(kTrThreads, 2)
+    k_layernorm_mod_backward(float* __restrict__ dx_io, float* __restrict__ dscale_part, float* __restrict__ dshift_part, const __nv_bfloat16* __restrict__ da,
+                             const float* __restrict__ x, bsi_rowref scale, const float* __restrict__ gamma, int rows_per_sample, int rows_per_cta,
+                             int64_t M, float eps) {
+    constexpr int dim = 128 * NV;
+    extern __shared__ float ln_smem[];  // [8 warps][2][dim]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t row0 = (int64_t)blockIdx.x * rows_per_cta;
+    float4 ps[NV], ph[NV];  // per-lane partial sums of da * xhat and da over this warp's rows
+#pragma unroll
+    for (int i = 0; i < NV; ++i) ps[i] = ph[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4* p_mul = gamma ? reinterpret_cast<const float4*>(gamma) : reinterpret_cast<const float4*>(rowref_ptr(scale, row0 / rows_per_sample, 0));
+    const float one = gamma ? 0.0f : 1.0f;
+    for (int r = warp; r < rows_per_cta; r += kTrThreads / 32) {
+        const int64_t row = row0 + r;
+        if (row >= M) break;
+        const float4* xr = reinterpret_cast<const float4*>(x + row * dim);
+        const uint2* ar = reinterpret_cast<const uint2*>(da + row * dim);
+        float4 v[NV], g[NV];
+        float s = 0.0f;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            v[i] = xr[lane + 32 * i];
+            s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+        }
+        const float mean = warp_sum(s) * (1.0f / dim);
+        float ss = 0.0f;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            v[i].x -= mean, v[i].y -= mean, v[i].z -= mean, v[i].w -= mean;
+            ss += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
+        }
+        const float rstd = rsqrtf(warp_sum(ss) * (1.0f / dim) + eps);
+        float sg = 0.0f, sgx = 0.0f;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            v[i].x *= rstd, v[i].y *= rstd, v[i].z *= rstd, v[i].w *= rstd;  // xhat
+            const uint2 a = ar[lane + 32 * i];
+            const float2 a0 = bf16x2_to_float2(a.x), a1 = bf16x2_to_float2(a.y);
+            const float4 m = p_mul[lane + 32 * i];
+            ps[i].x = fmaf(a0.x, v[i].x, ps[i].x), ps[i].y = fmaf(a0.y, v[i].y, ps[i].y), ps[i].z = fmaf(a1.x, v[i].z, ps[i].z), ps[i].w = fmaf(a1.y, v[i].w, ps[i].w);
+            ph[i].x += a0.x, ph[i].y += a0.y, ph[i].z += a1.x, ph[i].w += a1.y;
+            g[i] = make_float4(a0.x * (m.x + one), a0.y * (m.y + one), a1.x * (m.z + one), a1.y * (m.w + one));
+            sg += (g[i].x + g[i].y) + (g[i].z + g[i].w);
+            sgx += (g[i].x * v[i].x + g[i].y * v[i].y) + (g[i].z * v[i].z + g[i].w * v[i].w);
+        }
+        const float mg = warp_sum(sg) * (1.0f / dim), mgx = warp_sum(sgx) * (1.0f / dim);
+        float4* dr = reinterpret_cast<float4*>(dx_io + row * dim);
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            float4 d = dr[lane + 32 * i];
+            d.x += rstd * (g[i].x - mg - v[i].x * mgx), d.y += rstd * (g[i].y - mg - v[i].y * mgx);
+            d.z += rstd * (g[i].z - mg - v[i].z * mgx), d.w += rstd * (g[i].w - mg - v[i].w * mgx);
+            dr[lane + 32 * i] = d;
+        }
+    }
+    float4* sm = reinterpret_cast<float4*>(ln_smem);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        sm[(warp * 2 + 0) * (dim / 4) + lane + 32 * i] = ps[i];
+        sm[(warp * 2 + 1) * (dim / 4) + lane + 32 * i] = ph[i];
+    }
+    __syncthreads();
+    for (int q = threadIdx.x; q < 2 * (dim / 4); q += kTrThreads) {
+        const int which = q / (dim / 4), col = q - which * (dim / 4);
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int w = 0; w < kTrThreads / 32; ++w) {
+            const float4 t = sm[(w * 2 + which) * (dim / 4) + col];
+            acc.x += t.x, acc.y += t.y, acc.z += t.z, acc.w += t.w;
+        }
+        float* dst = which == 0 ? dscale_part : dshift_part;
+        reinterpret_cast<float4*>(dst + (int64_t)blockIdx.x * dim)[col] = acc;
+    }
+}
+
+static unsigned tr_grid(int64_t work) {
+    const int64_t need = (work + kTrThreads - 1) / kTrThreads, cap = (int64_t)sm_count() * 8;
+    return (unsigned)(need < cap ? need : cap);
+}
+
+}  // namespace bsi
+
+using namespace bsi;
+
+extern "C" {
+
+int bsi_gate_residual(float* x, const void* branch_bf16, bsi_rowref gate, int32_t rows_per_sample, int64_t M, int32_t D, void* stream) {
+    BSI_CHECK_ARG(x && branch_bf16 && M > 0 && D > 0 && D % 4 == 0 && rows_per_sample > 0, "bsi_gate_residual: bad arguments (D=%d must be a multiple of 4)", D);
+    k_gate_residual<<<tr_grid(M * (D / 4)), kTrThreads, 0, (cudaStream_t)stream>>>(x, (const __nv_bfloat16*)branch_bf16, gate, rows_per_sample, M, D);
+    BSI_LAUNCH_OK("k_gate_residual");
+    return BSI_OK;
+}
+
+int bsi_gate_residual_backward(void* dbranch_bf16, float* dgate, const float* dx, const void* branch_bf16, bsi_rowref gate, int32_t rows_per_sample,
+                               int32_t B, int32_t D, void* stream) {
+    BSI_CHECK_ARG(dbranch_bf16 && dx && branch_bf16 && B > 0 && D > 0 && D % 2 == 0 && rows_per_sample > 0, "bsi_gate_residual_backward: bad arguments");
+    dim3 grid((D / 2 + kTrThreads - 1) / kTrThreads, B);
+    k_gate_residual_backward<<<grid, kTrThreads, 0, (cudaStream_t)stream>>>((__nv_bfloat16*)dbranch_bf16, dgate, dx, (const __nv_bfloat16*)branch_bf16, gate,
+                                                                          rows_per_sample, D);
+    BSI_LAUNCH_OK("k_gate_residual_backward");
+    return BSI_OK;
+}
+
+int bsi_gelu_bf16(void* out_bf16, const void* pre_bf16, int64_t numel, void* stream) {
+    BSI_CHECK_ARG(out_bf16 && pre_bf16 && numel > 0 && numel % 8 == 0, "bsi_gelu_bf16: numel (%lld) must be a positive multiple of 8", (long long)numel);
+    k_gelu<false><<<tr_grid(numel / 8), kTrThreads, 0, (cudaStream_t)stream>>>((__nv_bfloat16*)out_bf16, nullptr, (const __nv_bfloat16*)pre_bf16, numel / 8);
+    BSI_LAUNCH_OK("k_gelu");
+    return BSI_OK;
+}
+
+int bsi_gelu_backward_bf16(void* dpre_bf16, const void* dout_bf16, const void* pre_bf16, int64_t numel, void* stream) {
+    BSI_CHECK_ARG(dpre_bf16 && dout_bf16 && pre_bf16 && numel > 0 && numel % 8 == 0, "bsi_gelu_backward_bf16: numel (%lld) must be a positive multiple of 8",
+                  (long long)numel);
+    k_gelu<true><<<tr_grid(numel / 8), kTrThreads, 0, (cudaStream_t)stream>>>((__nv_bfloat16*)dpre_bf16, (const __nv_bfloat16*)dout_bf16,
+                                                                             (const __nv_bfloat16*)pre_bf16, numel / 8);
+    BSI_LAUNCH_OK("k_gelu_backward");
+    return BSI_OK;
+}
+
+int bsi_layernorm_mod_backward(float* dx_io, float* dscale_part, float* dshift_part, const void* da_bf16, const float* x, bsi_rowref scale, const float* gamma,
+                               int32_t rows_per_sample, int32_t rows_per_cta, int64_t M, int32_t dim, float eps, void* stream) {
+    BSI_CHECK_ARG(dx_io && dscale_part && dshift_part && da_bf16 && x && M > 0, "bsi_layernorm_mod_backward: null pointer or empty input");
+    BSI_CHECK_ARG(gamma || (scale.base && rows_per_sample > 0), "bsi_layernorm_mod_backward: need either gamma or scale");
+    BSI_CHECK_ARG(dim % 128 == 0 && dim >= 128 && dim <= 1024, "bsi_layernorm_mod_backward: dim=%d must be a multiple of 128 in [128,1024]", dim);
+    BSI_CHECK_ARG(rows_per_cta > 0 && (gamma || rows_per_sample % rows_per_cta == 0), "bsi_layernorm_mod_backward: rows_per_cta must divide rows_per_sample");
+    const int grid = (int)((M + rows_per_cta - 1) / rows_per_cta);
+    const int smem = (kTrThreads / 32) * 2 * dim * (int)sizeof(float);
+#define BSI_LNB_CASE(NV)                                                                                                                      \
+    case NV:                                                                                                                                  \
+        BSI_ENSURE_SMEM(k_layernorm_mod_backward<NV>, smem);                                                                                   \
+        k_layernorm_mod_backward<NV><<<grid, kTrThreads, smem, (cudaStream_t)stream>>>(dx_io, dscale_part, dshift_part, (const __nv_bfloat16*)da_bf16, x, \
+                                                                                       scale, gamma, rows_per_sample, rows_per_cta, M, eps); \
+        break;
+    switch (dim / 128) {
+        BSI_LNB_CASE(1) BSI_LNB_CASE(2) BSI_LNB_CASE(3) BSI_LNB_CASE(4) BSI_LNB_CASE(5) BSI_LNB_CASE(6) BSI_LNB_CASE(7) BSI_LNB_CASE(8)
+        default: set_error("unsupported dim %d", dim); return BSI_ERR_UNSUPPORTED;
+    }
+#undef BSI_LNB_CASE
+    BSI_LAUNCH_OK("k_layernorm_mod_backward");
+    return BSI_OK;
+}
+
+}  // extern "C"

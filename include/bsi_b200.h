@@ -316,6 +316,21 @@ int bsi_unet_forward(const bsi_unet* e, float* out, const float* mu, bsi_rowref 
 int bsi_gemm_wgrad_bf16(float* dW, const void* dY_bf16, const void* X_bf16, int32_t M, int32_t N, int32_t K, int32_t ldy, int32_t ldx,
                         int32_t ldw, int32_t splits, void* stream);
 
+/* Elementwise / reduction pieces of the DiT backward (bsi/models/dit.py:50-55,87-103; config 5 groundwork). */
+/* x[row] += gate[row / rows_per_sample] * branch[row]   (torch.addcmul(x, gate, branch); gate.base == NULL: gate = 1) */
+int bsi_gate_residual(float* x, const void* branch_bf16, bsi_rowref gate, int32_t rows_per_sample, int64_t M, int32_t D, void* stream);
+/* dbranch = gate * dx (bf16);  dgate[b][d] = sum_t dx[b,t,d] * branch[b,t,d]  (dgate may be NULL) */
+int bsi_gate_residual_backward(void* dbranch_bf16, float* dgate, const float* dx, const void* branch_bf16, bsi_rowref gate, int32_t rows_per_sample,
+                               int32_t B, int32_t D, void* stream);
+/* nn.GELU(approximate="tanh") on a bf16 pre-activation, and its backward dpre = dout * gelu'(pre). */
+int bsi_gelu_bf16(void* out_bf16, const void* pre_bf16, int64_t numel, void* stream);
+int bsi_gelu_backward_bf16(void* dpre_bf16, const void* dout_bf16, const void* pre_bf16, int64_t numel, void* stream);
+/* Backward of a = LayerNorm(x) * (1 + scale[b]) + shift[b]  (gamma == NULL)  or  a = LayerNorm(x) * gamma + beta  (gamma != NULL):
+ *   dx_io[row] += dL/dx;  dscale_part / dshift_part [ceil(M / rows_per_cta)][dim]: per-CTA partial sums of da*xhat and da over
+ *   rows_per_cta consecutive rows (rows_per_cta divides rows_per_sample); the caller adds the partials of a sample. */
+int bsi_layernorm_mod_backward(float* dx_io, float* dscale_part, float* dshift_part, const void* da_bf16, const float* x, bsi_rowref scale,
+                               const float* gamma, int32_t rows_per_sample, int32_t rows_per_cta, int64_t M, int32_t dim, float eps, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Optimizer side of the training step over flat fp32 arenas of `numel` elements
  * (numel % 4 == 0).  Replaces, in two launches, Lightning's clip_grad_norm_ (config/train.yaml:40),

@@ -4,6 +4,7 @@ weights -- each against torch fp32 matmuls of the same bf16-rounded operands."""
 
 import pytest
 import torch
+import torch.nn.functional as F
 
 from gpu_util import call, dev, report, sync
 from bsi_b200 import _lib as L
@@ -55,3 +56,80 @@ def test_dgrad_through_forward_kernel_with_transposed_weights():
     zero = torch.zeros(K, device=dev())
     gemm(dy, wt, dx, zero, L.EPI_BIAS_F32)
     report("dgrad", dx, dy.float() @ w.bfloat16().float(), 1e-3, 1e-3)
+
+
+def test_gate_residual_forward_backward_vs_autograd():
+    B, T, D = 3, 256, 384
+    M = B * T
+    x0 = rnd("gr.x", (M, D))
+    br = rnd("gr.br", (M, D)).bfloat16()
+    tab = rnd("gr.tab", (B, 6 * D), 0.7)  # gate lives inside the [B, 6D] modulation table (column block 2), like dit.py:89
+    gate = L.rowref(tab, 6 * D, 0, 2 * D)
+    x = x0.clone()
+    call("bsi_gate_residual", L.ptr(x), L.ptr(br), gate, T, M, D, L.stream_ptr())
+    sync()
+    g = tab[:, 2 * D : 3 * D].clone().requires_grad_(True)
+    brf = br.float().requires_grad_(True)
+    ref = torch.addcmul(x0.reshape(B, T, D), g[:, None], brf.reshape(B, T, D)).reshape(M, D)
+    report("gate_residual", x, ref, 1e-6, 1e-6)
+    dx = rnd("gr.dx", (M, D))
+    ref.backward(dx)
+    dbr = torch.zeros((M, D), dtype=torch.bfloat16, device=dev())
+    dgate = torch.zeros((B, D), device=dev())
+    call("bsi_gate_residual_backward", L.ptr(dbr), L.ptr(dgate), L.ptr(dx), L.ptr(br), gate, T, B, D, L.stream_ptr())
+    sync()
+    report("dbranch", dbr, brf.grad, 1e-2, 1e-3)
+    report("dgate", dgate, g.grad, 1e-4, 1e-4)
+
+
+def test_gelu_forward_backward_vs_autograd():
+    n = 8 * 5000
+    pre = rnd("ge.pre", (n,), 4.0).bfloat16()
+    up = rnd("ge.up", (n,)).bfloat16()
+    h = torch.zeros_like(pre)
+    call("bsi_gelu_bf16", L.ptr(h), L.ptr(pre), n, L.stream_ptr())
+    p = pre.float().requires_grad_(True)
+    ref = F.gelu(p, approximate="tanh")
+    ref.backward(up.float())
+    dpre = torch.zeros_like(pre)
+    call("bsi_gelu_backward_bf16", L.ptr(dpre), L.ptr(up), L.ptr(pre), n, L.stream_ptr())
+    sync()
+    report("gelu", h, ref, 1e-2, 1e-3)
+    report("gelu backward", dpre, p.grad, 1e-2, 1e-3)
+
+
+@pytest.mark.parametrize("dim", [128, 1024])
+def test_layernorm_mod_backward_vs_autograd(dim):
+    B, T, rpc = 3, 256, 32
+    M = B * T
+    x = rnd(f"lb.x{dim}", (M, dim), 1.5) + 0.3
+    da = rnd(f"lb.da{dim}", (M, dim)).bfloat16()
+    tab = rnd(f"lb.t{dim}", (B, 6 * dim), 0.5)
+    dx0 = rnd(f"lb.dx{dim}", (M, dim))
+    # modulated variant
+    xr = x.clone().requires_grad_(True)
+    sc = tab[:, dim : 2 * dim].clone().requires_grad_(True)
+    sh = tab[:, :dim].clone().requires_grad_(True)
+    a = torch.addcmul(sh[:, None], sc[:, None] + 1, F.layer_norm(xr, (dim,), eps=1e-5).reshape(B, T, dim)).reshape(M, dim)
+    a.backward(da.float())
+    dx = dx0.clone()
+    parts = torch.zeros((2, M // rpc, dim), device=dev())
+    call("bsi_layernorm_mod_backward", L.ptr(dx), L.ptr(parts[0]), L.ptr(parts[1]), L.ptr(da), L.ptr(x), L.rowref(tab, 6 * dim, 0, dim), None, T, rpc, M, dim,
+         1e-5, L.stream_ptr())
+    sync()
+    report(f"ln-mod dx {dim}", dx, dx0 + xr.grad, 1e-4, 1e-4)
+    report(f"ln-mod dscale {dim}", parts[0].reshape(B, T // rpc, dim).sum(1), sc.grad, 1e-4, 1e-3)
+    report(f"ln-mod dshift {dim}", parts[1].reshape(B, T // rpc, dim).sum(1), sh.grad, 1e-4, 1e-3)
+    # affine variant (patch decoder LayerNorm)
+    gamma = (rnd(f"lb.g{dim}", (dim,), 0.3) + 1).requires_grad_(True)
+    beta = rnd(f"lb.b{dim}", (dim,), 0.2).requires_grad_(True)
+    xr2 = x.clone().requires_grad_(True)
+    F.layer_norm(xr2, (dim,), gamma, beta, 1e-5).backward(da.float())
+    dx = torch.zeros_like(x)
+    parts.zero_()
+    call("bsi_layernorm_mod_backward", L.ptr(dx), L.ptr(parts[0]), L.ptr(parts[1]), L.ptr(da), L.ptr(x), L.RowRef(None, 0, 0), L.ptr(gamma.detach()), T, rpc, M, dim,
+         1e-5, L.stream_ptr())
+    sync()
+    report(f"ln-affine dx {dim}", dx, xr2.grad, 1e-4, 1e-4)
+    report(f"ln-affine dgamma {dim}", parts[0].sum(0), gamma.grad, 1e-4, 2e-3)
+    report(f"ln-affine dbeta {dim}", parts[1].sum(0), beta.grad, 1e-4, 2e-3)
