@@ -62,7 +62,8 @@ __device__ __forceinline__ float gelu_grad(float x) {
     return 0.5f * (1.0f + t) + 0.5f * x * (1.0f - t * t) * du;
 }
 template <bool BWD>
-__global__ void __launch_bounds__(kTrThreads) k_gelu(__nv_bfloat16* __restrict__ out, const __nv_bfloat16* __restrict__ up, const __nv_bfloat16* __restrict__ pre, int64_t n8) {
+// (out may alias up: the backward runs in place on the upstream gradient)
+__global__ void __launch_bounds__(kTrThreads) k_gelu(__nv_bfloat16* out, const __nv_bfloat16* up, const __nv_bfloat16* __restrict__ pre, int64_t n8) {
     for (int64_t i = (int64_t)blockIdx.x * kTrThreads + threadIdx.x; i < n8; i += (int64_t)gridDim.x * kTrThreads) {
         const uint4 p = reinterpret_cast<const uint4*>(pre)[i];
         uint4 u = make_uint4(0, 0, 0, 0);

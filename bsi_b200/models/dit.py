@@ -84,6 +84,19 @@ class DenoisingDiT(NativeDenoiser):
                                 fourier_features.n_max if fourier_features is not None else -1)
         self._init_native()
 
+    def forward_scaled(self, mu: Tensor, t: Tensor, in_scale: Tensor | None) -> Tensor:
+        """Inference: the fused engine.  Under autograd with trainable parameters: the differentiable path of
+        ``dit_train`` (same kernels driven one by one, activations saved, native dgrad / wgrad GEMMs)."""
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            from .dit_train import forward_train
+
+            if not mu.is_cuda:
+                raise L.BsiNativeError("DenoisingDiT runs on CUDA only (no CPU fallback)")
+            if tuple(mu.shape[1:]) != self.data_shape:
+                raise ValueError(f"expected input of shape [B, {self.data_shape}], got {tuple(mu.shape)}")
+            return forward_train(self, mu, t, in_scale)
+        return super().forward_scaled(mu, t, in_scale)
+
     def _named_tensors(self):
         yield from self.state_dict(keep_vars=True).items()
         yield "dit.patch_pos_embedding", self.dit.patch_pos_embedding

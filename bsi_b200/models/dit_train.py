@@ -1,0 +1,269 @@
+"""Differentiable forward of the native DenoisingDiT (reference bsi/models/dit.py:87-103,174-181,225-233) for
+``BSI.train_loss(x).mean().backward()`` -- SURVEY §8 a23, first version.
+
+The inference engine (dit_engine.cu) fuses each block into a handful of kernels and keeps nothing; training needs the
+intermediates, so this module drives the same C-ABI primitives one by one from Python, saves the bf16 operands of every
+GEMM, and runs the backward with
+
+  * ``bsi_gemm_bf16``        forward GEMMs, and the data gradients dX = dY W through transposed bf16 weight copies,
+  * ``bsi_gemm_wgrad_bf16``  weight gradients dW += dY^T X (tcgen05, MN-major operands, split-M reduce-add),
+  * ``bsi_layernorm_mod_bf16`` / ``bsi_layernorm_mod_backward``, ``bsi_gate_residual(_backward)``, ``bsi_gelu(_backward)_bf16``,
+  * ``bsi_attention_bf16``   forward attention.
+
+What is still PyTorch here, and why: the adaLN / time-embedding chain on ``[B, 6*dim]`` tensors (O(batch) work, 0.2 % of the
+flops; differentiated by autograd through the ``mods`` argument), the bias gradients (one column sum per GEMM), and the
+attention *backward*, which recomputes ``F.scaled_dot_product_attention`` under autograd (a library flash-attention kernel)
+until the tcgen05 attention backward exists.  Everything else -- 96 % of the backward flops -- runs on this repo's kernels.
+Dropout is not implemented (the reference trains with dropout 0.05; construct the model with ``dropout=None`` for now).
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+import torch.nn.functional as F
+from torch import Tensor
+
+from .. import _lib as L
+
+_LN_ROWS_PER_CTA = 32
+
+
+def _st(dev):
+    return L.stream_ptr(dev)
+
+
+def _pad8(n: int) -> int:
+    return (n + 7) // 8 * 8
+
+
+def _pad_cols(t: Tensor, n: int) -> Tensor:
+    """[rows][c] -> contiguous [rows][n] with zero columns appended."""
+    if t.shape[1] == n:
+        return t.contiguous()
+    out = t.new_zeros((t.shape[0], n))
+    out[:, : t.shape[1]] = t
+    return out
+
+
+def _pad_rows(t: Tensor, n: int) -> Tensor:
+    if t.shape[0] == n:
+        return t.contiguous()
+    out = t.new_zeros((n, *t.shape[1:]))
+    out[: t.shape[0]] = t
+    return out
+
+
+def _gemm(A: Tensor, W: Tensor, out: Tensor, bias: Tensor, epi: int, *, pos: Tensor | None = None, rows_per_sample: int = 0) -> None:
+    """out[M][N] = epilogue(A[M][K] @ W[N][K]^T + bias); A, W bf16 row-major (pitch = last stride-1 dimension)."""
+    a = L.GemmArgs()
+    a.A, a.W, a.C, a.bias = A.data_ptr(), W.data_ptr(), out.data_ptr(), bias.data_ptr()
+    a.M, a.N, a.K = A.shape[0], W.shape[0], A.shape[1]
+    a.lda, a.ldw, a.ldc = A.stride(0), W.stride(0), out.stride(0)
+    a.batch = 1
+    a.stride_a, a.stride_w, a.stride_c, a.stride_bias = a.M * a.lda, a.N * a.ldw, a.M * a.ldc, a.N
+    a.epilogue = epi
+    a.gate = L.RowRef(None, 0, 0)
+    a.step_ptr, a.rows_per_sample = None, rows_per_sample
+    a.pos = pos.data_ptr() if pos is not None else None
+    a.patch = a.grid_w = a.channels = 0
+    L.check(L.load().bsi_gemm_bf16(C.byref(a), _st(A.device)), "bsi_gemm_bf16")
+
+
+def _wgrad(dY: Tensor, X: Tensor) -> Tensor:
+    """dW[N][K] = dY[M][N]^T @ X[M][K] (fp32)."""
+    M, N, K = dY.shape[0], dY.shape[1], X.shape[1]
+    dW = torch.zeros((N, K), dtype=torch.float32, device=dY.device)
+    L.check(L.load().bsi_gemm_wgrad_bf16(dW.data_ptr(), dY.data_ptr(), X.data_ptr(), M, N, K, dY.stride(0), X.stride(0), K, 0, _st(dY.device)),
+            "bsi_gemm_wgrad_bf16")
+    return dW
+
+
+def _ln_mod(x: Tensor, shift: L.RowRef | None, scale: L.RowRef | None, T: int, gamma: Tensor | None = None, beta: Tensor | None = None) -> Tensor:
+    M, D = x.shape
+    out = torch.empty((M, D), dtype=torch.bfloat16, device=x.device)
+    none = L.RowRef(None, 0, 0)
+    L.check(L.load().bsi_layernorm_mod_bf16(out.data_ptr(), x.data_ptr(), shift or none, scale or none, None, L.ptr(gamma), L.ptr(beta), T, M, D, 1e-5,
+                                            _st(x.device)), "bsi_layernorm_mod_bf16")
+    return out
+
+
+def _ln_mod_backward(dx_io: Tensor, da: Tensor, x: Tensor, scale: L.RowRef | None, T: int, gamma: Tensor | None = None):
+    """dx_io += dL/dx; returns the per-CTA partial sums (dscale_part, dshift_part) [M / 32][D]."""
+    M, D = x.shape
+    parts = torch.empty((2, (M + _LN_ROWS_PER_CTA - 1) // _LN_ROWS_PER_CTA, D), dtype=torch.float32, device=x.device)
+    L.check(L.load().bsi_layernorm_mod_backward(dx_io.data_ptr(), parts[0].data_ptr(), parts[1].data_ptr(), da.data_ptr(), x.data_ptr(),
+                                                scale or L.RowRef(None, 0, 0), L.ptr(gamma), T, _LN_ROWS_PER_CTA, M, D, 1e-5, _st(x.device)),
+            "bsi_layernorm_mod_backward")
+    return parts[0], parts[1]
+
+
+class DiTTrainFunction(torch.autograd.Function):
+    """out = DiT(in_scale * mu; mods, params).  Differentiable w.r.t. ``mods`` [L][B][6*dim] and the parameter list (not mu)."""
+
+    @staticmethod
+    def forward(ctx, model, mu: Tensor, in_scale: Tensor | None, mods: Tensor, *params: Tensor):
+        cfg = model._cfg
+        dev = mu.device
+        B, Cc, H, Wd = mu.shape
+        p, D, depth, heads = cfg.patch, cfg.dim, cfg.depth, cfg.heads
+        T = (H // p) * (Wd // p)
+        M = B * T
+        lib = L.load()
+        it = iter(params)
+        w_patch, b_patch = next(it), next(it)
+        blocks = [tuple(next(it) for _ in range(8)) for _ in range(depth)]
+        ln_g, ln_b, w_dec, b_dec = next(it), next(it), next(it), next(it)
+        bf = lambda w: w.detach().to(torch.bfloat16).contiguous()
+        with torch.cuda.device(dev):
+            scale = torch.ones(1, dtype=torch.float32, device=dev) if in_scale is None else in_scale.detach().float().contiguous()
+            K0 = _pad8(w_patch.shape[1])  # operand pitches are multiples of 16 bytes; the padding columns are zero on both sides
+            a0 = torch.empty((M, K0), dtype=torch.bfloat16, device=dev)
+            L.check(lib.bsi_dit_patch_operand(a0.data_ptr(), mu.detach().float().contiguous().data_ptr(), L.rowref(scale, 0 if in_scale is None else 1), None,
+                                              B, Cc, H, Wd, p, cfg.fourier_n_min, cfg.fourier_n_max, K0, _st(dev)), "bsi_dit_patch_operand")
+            x = torch.empty((M, D), dtype=torch.float32, device=dev)
+            _gemm(a0, _pad_cols(bf(w_patch), K0), x, b_patch.detach().float(), L.EPI_POS_F32, pos=model.dit.patch_pos_embedding.float().contiguous(),
+                  rows_per_sample=T)
+            mods = mods.detach().float().contiguous()
+            saved = []
+            for l, (w_qkv, b_qkv, w_o, b_o, w_1, b_1, w_2, b_2) in enumerate(blocks):
+                m = mods[l]
+                ref = lambda j: L.rowref(m, 6 * D, 0, j * D)
+                x_in = x.clone()
+                a1 = _ln_mod(x, ref(0), ref(1), T)
+                qkv = torch.empty((M, 3 * D), dtype=torch.bfloat16, device=dev)
+                _gemm(a1, bf(w_qkv), qkv, b_qkv.detach().float(), L.EPI_BIAS_BF16)
+                att = torch.empty((M, D), dtype=torch.bfloat16, device=dev)
+                L.check(lib.bsi_attention_bf16(att.data_ptr(), qkv.data_ptr(), B, T, heads, D // heads, _st(dev)), "bsi_attention_bf16")
+                br1 = torch.empty((M, D), dtype=torch.bfloat16, device=dev)
+                _gemm(att, bf(w_o), br1, b_o.detach().float(), L.EPI_BIAS_BF16)
+                L.check(lib.bsi_gate_residual(x.data_ptr(), br1.data_ptr(), ref(2), T, M, D, _st(dev)), "bsi_gate_residual")
+                x_mid = x.clone()
+                a2 = _ln_mod(x, ref(3), ref(4), T)
+                pre = torch.empty((M, 4 * D), dtype=torch.bfloat16, device=dev)
+                _gemm(a2, bf(w_1), pre, b_1.detach().float(), L.EPI_BIAS_BF16)
+                h = torch.empty_like(pre)
+                L.check(lib.bsi_gelu_bf16(h.data_ptr(), pre.data_ptr(), pre.numel(), _st(dev)), "bsi_gelu_bf16")
+                br2 = torch.empty((M, D), dtype=torch.bfloat16, device=dev)
+                _gemm(h, bf(w_2), br2, b_2.detach().float(), L.EPI_BIAS_BF16)
+                L.check(lib.bsi_gate_residual(x.data_ptr(), br2.data_ptr(), ref(5), T, M, D, _st(dev)), "bsi_gate_residual")
+                saved.append((x_in, a1, qkv, att, br1, x_mid, a2, pre, h, br2))
+            a_dec = _ln_mod(x, None, None, T, ln_g.detach().float().contiguous(), ln_b.detach().float().contiguous())
+            n_out = w_dec.shape[0]
+            Np = _pad8(n_out)
+            y = torch.empty((M, Np), dtype=torch.float32, device=dev)
+            _gemm(a_dec, _pad_rows(bf(w_dec), Np), y, _pad_rows(b_dec.detach().float(), Np), L.EPI_BIAS_F32)
+            gh, gw = H // p, Wd // p
+            out = y[:, :n_out].reshape(B, gh, gw, p, p, Cc).permute(0, 5, 1, 3, 2, 4).reshape(B, Cc, H, Wd).contiguous()
+        ctx.model, ctx.geom = model, (B, Cc, H, Wd, T, M)
+        ctx.saved_acts = (a0, x, a_dec, saved)
+        ctx.save_for_backward(mods, *params)
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, dout: Tensor):
+        model = ctx.model
+        cfg = model._cfg
+        B, Cc, H, Wd, T, M = ctx.geom
+        p, D, depth, heads = cfg.patch, cfg.dim, cfg.depth, cfg.heads
+        mods, *params = ctx.saved_tensors
+        a0, x_last, a_dec, saved = ctx.saved_acts
+        dev = dout.device
+        lib = L.load()
+        it = iter(params)
+        w_patch, b_patch = next(it), next(it)
+        blocks = [tuple(next(it) for _ in range(8)) for _ in range(depth)]
+        ln_g, ln_b, w_dec, b_dec = next(it), next(it), next(it), next(it)
+        bft = lambda w: w.detach().to(torch.bfloat16).t().contiguous()  # [K][N]: the forward kernel then computes dY @ W
+        colsum = lambda t: t.sum(0, dtype=torch.float32)
+        zeros = lambda n: torch.zeros(n, dtype=torch.float32, device=dev)
+        grads: list[Tensor] = []
+        with torch.cuda.device(dev):
+            gh, gw = H // p, Wd // p
+            dy = dout.float().reshape(B, Cc, gh, p, gw, p).permute(0, 2, 4, 3, 5, 1).reshape(M, p * p * Cc)
+            n_out = w_dec.shape[0]
+            Np = _pad8(n_out)
+            dy16 = _pad_cols(dy.to(torch.bfloat16), Np)
+            g_wdec, g_bdec = _wgrad(dy16, a_dec)[:n_out], colsum(dy)
+            da = torch.empty((M, D), dtype=torch.bfloat16, device=dev)
+            _gemm(dy16, _pad_cols(bft(w_dec), Np), da, zeros(D), L.EPI_BIAS_BF16)
+            dx = torch.zeros((M, D), dtype=torch.float32, device=dev)
+            dg_part, db_part = _ln_mod_backward(dx, da, x_last, None, T, ln_g.detach().float().contiguous())
+            tail = [dg_part.sum(0), db_part.sum(0), g_wdec, g_bdec]
+            dmods = torch.empty_like(mods)
+            block_grads = []
+            for l in reversed(range(depth)):
+                w_qkv, b_qkv, w_o, b_o, w_1, b_1, w_2, b_2 = blocks[l]
+                x_in, a1, qkv, att, br1, x_mid, a2, pre, h, br2 = saved[l]
+                m, dm = mods[l], dmods[l]
+                ref = lambda j: L.rowref(m, 6 * D, 0, j * D)
+                part = lambda t: t.reshape(B, T // _LN_ROWS_PER_CTA, D).sum(1)
+                # ---- MLP branch: x_out = x_mid + gate_mlp * (gelu(a2 W1^T + b1) W2^T + b2)
+                dbr = torch.empty((M, D), dtype=torch.bfloat16, device=dev)
+                dgate = torch.empty((B, D), dtype=torch.float32, device=dev)
+                L.check(lib.bsi_gate_residual_backward(dbr.data_ptr(), dgate.data_ptr(), dx.data_ptr(), br2.data_ptr(), ref(5), T, B, D, _st(dev)),
+                        "bsi_gate_residual_backward")
+                dm[:, 5 * D :] = dgate
+                g_w2, g_b2 = _wgrad(dbr, h), colsum(dbr)
+                dh = torch.empty((M, 4 * D), dtype=torch.bfloat16, device=dev)
+                _gemm(dbr, bft(w_2), dh, zeros(4 * D), L.EPI_BIAS_BF16)
+                L.check(lib.bsi_gelu_backward_bf16(dh.data_ptr(), dh.data_ptr(), pre.data_ptr(), dh.numel(), _st(dev)), "bsi_gelu_backward_bf16")
+                g_w1, g_b1 = _wgrad(dh, a2), colsum(dh)
+                _gemm(dh, bft(w_1), da, zeros(D), L.EPI_BIAS_BF16)
+                dsc, dsh = _ln_mod_backward(dx, da, x_mid, ref(4), T)
+                dm[:, 3 * D : 4 * D], dm[:, 4 * D : 5 * D] = part(dsh), part(dsc)
+                # ---- attention branch: x_mid = x_in + gate_msa * (attn(a1 Wqkv^T + b) Wo^T + b)
+                L.check(lib.bsi_gate_residual_backward(dbr.data_ptr(), dgate.data_ptr(), dx.data_ptr(), br1.data_ptr(), ref(2), T, B, D, _st(dev)),
+                        "bsi_gate_residual_backward")
+                dm[:, 2 * D : 3 * D] = dgate
+                g_wo, g_bo = _wgrad(dbr, att), colsum(dbr)
+                datt = torch.empty((M, D), dtype=torch.bfloat16, device=dev)
+                _gemm(dbr, bft(w_o), datt, zeros(D), L.EPI_BIAS_BF16)
+                dqkv = _attention_backward(qkv, datt, B, T, heads, D // heads)
+                g_wqkv, g_bqkv = _wgrad(dqkv, a1), colsum(dqkv)
+                _gemm(dqkv, bft(w_qkv), da, zeros(D), L.EPI_BIAS_BF16)
+                dsc, dsh = _ln_mod_backward(dx, da, x_in, ref(1), T)
+                dm[:, :D], dm[:, D : 2 * D] = part(dsh), part(dsc)
+                block_grads.append([g_wqkv, g_bqkv, g_wo, g_bo, g_w1, g_b1, g_w2, g_b2])
+                saved[l] = None  # release this layer's activations
+            dx16 = dx.to(torch.bfloat16)
+            grads = [_wgrad(dx16, a0)[:, : w_patch.shape[1]], colsum(dx)]
+            for bg in reversed(block_grads):
+                grads += bg
+            grads += tail
+        return (None, None, None, dmods, *grads)
+
+
+def _attention_backward(qkv: Tensor, datt: Tensor, B: int, T: int, heads: int, hd: int) -> Tensor:
+    """d(qkv) of out = SDPA(q, k, v) on the packed [B*T][3*dim] layout -- recomputed by the library flash-attention kernel."""
+    v5 = qkv.view(B, T, 3, heads, hd)
+    with torch.enable_grad():
+        q, k, v = (v5[:, :, j].permute(0, 2, 1, 3).detach().requires_grad_(True) for j in range(3))
+        o = F.scaled_dot_product_attention(q, k, v)
+        gq, gk, gv = torch.autograd.grad(o, (q, k, v), datt.view(B, T, heads, hd).permute(0, 2, 1, 3))
+    out = torch.empty_like(v5)
+    out[:, :, 0], out[:, :, 1], out[:, :, 2] = gq.permute(0, 2, 1, 3), gk.permute(0, 2, 1, 3), gv.permute(0, 2, 1, 3)
+    return out.view(B * T, 3 * heads * hd)
+
+
+def trainable_parameters(model) -> list[Tensor]:
+    """The parameters DiTTrainFunction differentiates, in its argument order (adaLN / time embedding go through ``mods``)."""
+    d = model.dit
+    ps = [d.patch_encoder.weight, d.patch_encoder.bias]
+    for blk in d.blocks:
+        ps += [blk.attn.to_qkv.weight, blk.attn.to_qkv.bias, blk.attn.to_out.weight, blk.attn.to_out.bias,
+               blk.mlp[0].weight, blk.mlp[0].bias, blk.mlp[2].weight, blk.mlp[2].bias]
+    ps += [d.patch_decoder[0].weight, d.patch_decoder[0].bias, d.patch_decoder[1].weight, d.patch_decoder[1].bias]
+    return ps
+
+
+def forward_train(model, mu: Tensor, t: Tensor, in_scale: Tensor | None) -> Tensor:
+    """f(in_scale * mu, t) with autograd support for every parameter of the DiT."""
+    for blk in model.dit.blocks:
+        if isinstance(blk.dropout, torch.nn.Dropout) and blk.dropout.p > 0 and model.training:
+            raise NotImplementedError("dropout is not implemented in the native training path: construct DenoisingDiT(dropout=None) or call .eval()")
+    cond = model.dit.t_embedding(t.to(torch.float32))
+    mods = torch.stack([blk.adaLN_modulation(cond) for blk in model.dit.blocks])
+    return DiTTrainFunction.apply(model, mu, in_scale, mods, *trainable_parameters(model))
