@@ -1,8 +1,9 @@
 // Elementwise / reduction kernels of the DiT training path (backward of bsi/models/dit.py:50-55,87-103).
 // All HBM-bound; the GEMMs around them are bsi_gemm_bf16 (forward, data gradient with transposed weights) and
 // bsi_gemm_wgrad_bf16 (weight gradient).
-//   gate_residual            x += gate[b] * branch                        (torch.addcmul(x, gate, branch), dit.py:93-102)
-//   gate_residual_backward   dbranch = gate[b] * dx ; dgate[b] = sum_t dx * branch
+//   gate_residual            x_out = x + gate[b] * branch                 (torch.addcmul(x, gate, branch), dit.py:93-102)
+//   gate_residual_backward   dbranch = gate[b] * dx ; dgate[b] = sum_t dx * branch ; per-sample column sums of dbranch (bias gradient)
+//   colsum_bf16              partial column sums of a bf16 matrix (bias gradients of the other linears)
 //   gelu / gelu_backward     nn.GELU(approximate="tanh") on the bf16 pre-activation (dit.py:75)
 //   layernorm_mod_backward   backward of modulate(LayerNorm(x), shift, scale) (dit.py:50-55) and of the affine decoder LayerNorm (:164):
 //                            dx += rstd * (g - mean(g) - xhat * mean(g * xhat)), g = da * (1 + scale)   [or da * gamma]
@@ -16,7 +17,7 @@ constexpr int kTrThreads = 256;
 __device__ __forceinline__ float2 bf16x2_to_float2(uint32_t v) { return make_float2(__uint_as_float(v << 16), __uint_as_float(v & 0xffff0000u)); }
 
 // ------------------------------------------------------------------ x += gate * branch
-__global__ void __launch_bounds__(kTrThreads) k_gate_residual(float* __restrict__ x, const __nv_bfloat16* __restrict__ br, bsi_rowref gate, int T, int64_t M, int D) {
+__global__ void __launch_bounds__(kTrThreads) k_gate_residual(float* x_out, const float* x, const __nv_bfloat16* __restrict__ br, bsi_rowref gate, int T, int64_t M, int D) {
     const int64_t quads = M * (D / 4);
     for (int64_t i = (int64_t)blockIdx.x * kTrThreads + threadIdx.x; i < quads; i += (int64_t)gridDim.x * kTrThreads) {
         const int64_t row = i / (D / 4);
@@ -24,30 +25,35 @@ __global__ void __launch_bounds__(kTrThreads) k_gate_residual(float* __restrict_
         const float4 g = gate.base ? *reinterpret_cast<const float4*>(rowref_ptr(gate, row / T, 0) + c) : make_float4(1.f, 1.f, 1.f, 1.f);
         const uint2 b = *reinterpret_cast<const uint2*>(br + row * D + c);
         const float2 b0 = bf16x2_to_float2(b.x), b1 = bf16x2_to_float2(b.y);
-        float4 v = *reinterpret_cast<float4*>(x + row * D + c);
+        float4 v = *reinterpret_cast<const float4*>(x + row * D + c);
         v.x = fmaf(g.x, b0.x, v.x), v.y = fmaf(g.y, b0.y, v.y), v.z = fmaf(g.z, b1.x, v.z), v.w = fmaf(g.w, b1.y, v.w);
-        *reinterpret_cast<float4*>(x + row * D + c) = v;
+        *reinterpret_cast<float4*>(x_out + row * D + c) = v;
     }
 }
 
 // ------------------------------------------------------------------ dbranch = gate * dx, dgate[b] = sum_t dx * branch
 // grid (D / 512, B): a thread owns two adjacent columns of one sample and walks its T token rows (coalesced across the CTA)
-__global__ void __launch_bounds__(kTrThreads) k_gate_residual_backward(__nv_bfloat16* __restrict__ dbr, float* __restrict__ dgate, const float* __restrict__ dx,
-                                                                       const __nv_bfloat16* __restrict__ br, bsi_rowref gate, int T, int D) {
+__global__ void __launch_bounds__(kTrThreads) k_gate_residual_backward(__nv_bfloat16* __restrict__ dbr, float* __restrict__ dgate, float* __restrict__ dbias_part,
+                                                                       const float* __restrict__ dx, const __nv_bfloat16* __restrict__ br, bsi_rowref gate, int T,
+                                                                       int D) {
     const int c = (blockIdx.x * kTrThreads + threadIdx.x) * 2;
     if (c >= D) return;
     const int64_t b = blockIdx.y;
     const float2 g = gate.base ? *reinterpret_cast<const float2*>(rowref_ptr(gate, b, 0) + c) : make_float2(1.f, 1.f);
-    float a0 = 0.f, a1 = 0.f;
+    float a0 = 0.f, a1 = 0.f, s0 = 0.f, s1 = 0.f;
 #pragma unroll 4
     for (int t = 0; t < T; ++t) {
         const int64_t off = (b * T + t) * D + c;
         const float2 d = *reinterpret_cast<const float2*>(dx + off);
         const float2 v = bf16x2_to_float2(*reinterpret_cast<const uint32_t*>(br + off));
         a0 = fmaf(d.x, v.x, a0), a1 = fmaf(d.y, v.y, a1);
-        *reinterpret_cast<uint32_t*>(dbr + off) = pack_bf16(g.x * d.x, g.y * d.y);
+        const uint32_t o = pack_bf16(g.x * d.x, g.y * d.y);
+        const float2 of = bf16x2_to_float2(o);  // the bias gradient sums what the weight-gradient GEMM sees (bf16-rounded)
+        s0 += of.x, s1 += of.y;
+        *reinterpret_cast<uint32_t*>(dbr + off) = o;
     }
     if (dgate) *reinterpret_cast<float2*>(dgate + b * D + c) = make_float2(a0, a1);
+    if (dbias_part) *reinterpret_cast<float2*>(dbias_part + b * D + c) = make_float2(s0, s1);
 }
 
 // ------------------------------------------------------------------ GELU (tanh) forward / backward on bf16
@@ -163,6 +169,22 @@ __global__ void __launch_bounds__(kTrThreads, 2)
     }
 }
 
+// ------------------------------------------------------------------ column sums of a bf16 [M][N] matrix (bias gradients)
+// grid (N / 512, ceil(M / rows_per_cta)): a thread owns two adjacent columns and walks rows_per_cta rows; partial[chunk][N]
+__global__ void __launch_bounds__(kTrThreads) k_colsum_bf16(float* __restrict__ partial, const __nv_bfloat16* __restrict__ a, int64_t M, int N, int64_t ld,
+                                                            int rows_per_cta) {
+    const int c = (blockIdx.x * kTrThreads + threadIdx.x) * 2;
+    if (c >= N) return;
+    const int64_t r0 = (int64_t)blockIdx.y * rows_per_cta, r1 = min(r0 + rows_per_cta, M);
+    float s0 = 0.f, s1 = 0.f;
+#pragma unroll 8
+    for (int64_t r = r0; r < r1; ++r) {
+        const float2 v = bf16x2_to_float2(*reinterpret_cast<const uint32_t*>(a + r * ld + c));
+        s0 += v.x, s1 += v.y;
+    }
+    *reinterpret_cast<float2*>(partial + (int64_t)blockIdx.y * N + c) = make_float2(s0, s1);
+}
+
 static unsigned tr_grid(int64_t work) {
     const int64_t need = (work + kTrThreads - 1) / kTrThreads, cap = (int64_t)sm_count() * 8;
     return (unsigned)(need < cap ? need : cap);
@@ -174,20 +196,28 @@ using namespace bsi;
 
 extern "C" {
 
-int bsi_gate_residual(float* x, const void* branch_bf16, bsi_rowref gate, int32_t rows_per_sample, int64_t M, int32_t D, void* stream) {
-    BSI_CHECK_ARG(x && branch_bf16 && M > 0 && D > 0 && D % 4 == 0 && rows_per_sample > 0, "bsi_gate_residual: bad arguments (D=%d must be a multiple of 4)", D);
-    k_gate_residual<<<tr_grid(M * (D / 4)), kTrThreads, 0, (cudaStream_t)stream>>>(x, (const __nv_bfloat16*)branch_bf16, gate, rows_per_sample, M, D);
+int bsi_gate_residual(float* x_out, const float* x, const void* branch_bf16, bsi_rowref gate, int32_t rows_per_sample, int64_t M, int32_t D, void* stream) {
+    BSI_CHECK_ARG(x_out && x && branch_bf16 && M > 0 && D > 0 && D % 4 == 0 && rows_per_sample > 0, "bsi_gate_residual: bad arguments (D=%d must be a multiple of 4)", D);
+    k_gate_residual<<<tr_grid(M * (D / 4)), kTrThreads, 0, (cudaStream_t)stream>>>(x_out, x, (const __nv_bfloat16*)branch_bf16, gate, rows_per_sample, M, D);
     BSI_LAUNCH_OK("k_gate_residual");
     return BSI_OK;
 }
 
-int bsi_gate_residual_backward(void* dbranch_bf16, float* dgate, const float* dx, const void* branch_bf16, bsi_rowref gate, int32_t rows_per_sample,
-                               int32_t B, int32_t D, void* stream) {
+int bsi_gate_residual_backward(void* dbranch_bf16, float* dgate, float* dbias_part, const float* dx, const void* branch_bf16, bsi_rowref gate,
+                               int32_t rows_per_sample, int32_t B, int32_t D, void* stream) {
     BSI_CHECK_ARG(dbranch_bf16 && dx && branch_bf16 && B > 0 && D > 0 && D % 2 == 0 && rows_per_sample > 0, "bsi_gate_residual_backward: bad arguments");
     dim3 grid((D / 2 + kTrThreads - 1) / kTrThreads, B);
-    k_gate_residual_backward<<<grid, kTrThreads, 0, (cudaStream_t)stream>>>((__nv_bfloat16*)dbranch_bf16, dgate, dx, (const __nv_bfloat16*)branch_bf16, gate,
-                                                                          rows_per_sample, D);
+    k_gate_residual_backward<<<grid, kTrThreads, 0, (cudaStream_t)stream>>>((__nv_bfloat16*)dbranch_bf16, dgate, dbias_part, dx,
+                                                                          (const __nv_bfloat16*)branch_bf16, gate, rows_per_sample, D);
     BSI_LAUNCH_OK("k_gate_residual_backward");
+    return BSI_OK;
+}
+
+int bsi_colsum_bf16(float* partial, const void* a_bf16, int64_t M, int32_t N, int64_t ld, int32_t rows_per_cta, void* stream) {
+    BSI_CHECK_ARG(partial && a_bf16 && M > 0 && N > 0 && N % 2 == 0 && ld >= N && ld % 2 == 0 && rows_per_cta > 0, "bsi_colsum_bf16: bad arguments");
+    dim3 grid((N / 2 + kTrThreads - 1) / kTrThreads, (unsigned)((M + rows_per_cta - 1) / rows_per_cta));
+    k_colsum_bf16<<<grid, kTrThreads, 0, (cudaStream_t)stream>>>(partial, (const __nv_bfloat16*)a_bf16, M, N, ld, rows_per_cta);
+    BSI_LAUNCH_OK("k_colsum_bf16");
     return BSI_OK;
 }
 

@@ -125,12 +125,13 @@ class DiTTrainFunction(torch.autograd.Function):
             x = torch.empty((M, D), dtype=torch.float32, device=dev)
             _gemm(a0, _pad_cols(bf(w_patch), K0), x, b_patch.detach().float(), L.EPI_POS_F32, pos=model.dit.patch_pos_embedding.float().contiguous(),
                   rows_per_sample=T)
+            ctx.mods_dtype = mods.dtype
             mods = mods.detach().float().contiguous()
             saved = []
             for l, (w_qkv, b_qkv, w_o, b_o, w_1, b_1, w_2, b_2) in enumerate(blocks):
                 m = mods[l]
                 ref = lambda j: L.rowref(m, 6 * D, 0, j * D)
-                x_in = x.clone()
+                x_in = x
                 a1 = _ln_mod(x, ref(0), ref(1), T)
                 qkv = torch.empty((M, 3 * D), dtype=torch.bfloat16, device=dev)
                 _gemm(a1, bf(w_qkv), qkv, b_qkv.detach().float(), L.EPI_BIAS_BF16)
@@ -138,8 +139,9 @@ class DiTTrainFunction(torch.autograd.Function):
                 L.check(lib.bsi_attention_bf16(att.data_ptr(), qkv.data_ptr(), B, T, heads, D // heads, _st(dev)), "bsi_attention_bf16")
                 br1 = torch.empty((M, D), dtype=torch.bfloat16, device=dev)
                 _gemm(att, bf(w_o), br1, b_o.detach().float(), L.EPI_BIAS_BF16)
-                L.check(lib.bsi_gate_residual(x.data_ptr(), br1.data_ptr(), ref(2), T, M, D, _st(dev)), "bsi_gate_residual")
-                x_mid = x.clone()
+                x_mid = torch.empty_like(x)  # out of place: x_in stays alive as this layer's saved input
+                L.check(lib.bsi_gate_residual(x_mid.data_ptr(), x.data_ptr(), br1.data_ptr(), ref(2), T, M, D, _st(dev)), "bsi_gate_residual")
+                x = x_mid
                 a2 = _ln_mod(x, ref(3), ref(4), T)
                 pre = torch.empty((M, 4 * D), dtype=torch.bfloat16, device=dev)
                 _gemm(a2, bf(w_1), pre, b_1.detach().float(), L.EPI_BIAS_BF16)
@@ -147,7 +149,8 @@ class DiTTrainFunction(torch.autograd.Function):
                 L.check(lib.bsi_gelu_bf16(h.data_ptr(), pre.data_ptr(), pre.numel(), _st(dev)), "bsi_gelu_bf16")
                 br2 = torch.empty((M, D), dtype=torch.bfloat16, device=dev)
                 _gemm(h, bf(w_2), br2, b_2.detach().float(), L.EPI_BIAS_BF16)
-                L.check(lib.bsi_gate_residual(x.data_ptr(), br2.data_ptr(), ref(5), T, M, D, _st(dev)), "bsi_gate_residual")
+                x = torch.empty_like(x_mid)
+                L.check(lib.bsi_gate_residual(x.data_ptr(), x_mid.data_ptr(), br2.data_ptr(), ref(5), T, M, D, _st(dev)), "bsi_gate_residual")
                 saved.append((x_in, a1, qkv, att, br1, x_mid, a2, pre, h, br2))
             a_dec = _ln_mod(x, None, None, T, ln_g.detach().float().contiguous(), ln_b.detach().float().contiguous())
             n_out = w_dec.shape[0]
@@ -177,7 +180,13 @@ class DiTTrainFunction(torch.autograd.Function):
         blocks = [tuple(next(it) for _ in range(8)) for _ in range(depth)]
         ln_g, ln_b, w_dec, b_dec = next(it), next(it), next(it), next(it)
         bft = lambda w: w.detach().to(torch.bfloat16).t().contiguous()  # [K][N]: the forward kernel then computes dY @ W
-        colsum = lambda t: t.sum(0, dtype=torch.float32)
+        def colsum(t: Tensor) -> Tensor:
+            if t.dtype != torch.bfloat16:
+                return t.sum(0, dtype=torch.float32)
+            parts = torch.empty(((t.shape[0] + 255) // 256, t.shape[1]), dtype=torch.float32, device=dev)
+            L.check(lib.bsi_colsum_bf16(parts.data_ptr(), t.data_ptr(), t.shape[0], t.shape[1], t.stride(0), 256, _st(dev)), "bsi_colsum_bf16")
+            return parts.sum(0)
+
         zeros = lambda n: torch.zeros(n, dtype=torch.float32, device=dev)
         grads: list[Tensor] = []
         with torch.cuda.device(dev):
@@ -203,10 +212,11 @@ class DiTTrainFunction(torch.autograd.Function):
                 # ---- MLP branch: x_out = x_mid + gate_mlp * (gelu(a2 W1^T + b1) W2^T + b2)
                 dbr = torch.empty((M, D), dtype=torch.bfloat16, device=dev)
                 dgate = torch.empty((B, D), dtype=torch.float32, device=dev)
-                L.check(lib.bsi_gate_residual_backward(dbr.data_ptr(), dgate.data_ptr(), dx.data_ptr(), br2.data_ptr(), ref(5), T, B, D, _st(dev)),
-                        "bsi_gate_residual_backward")
+                dbias = torch.empty((B, D), dtype=torch.float32, device=dev)
+                L.check(lib.bsi_gate_residual_backward(dbr.data_ptr(), dgate.data_ptr(), dbias.data_ptr(), dx.data_ptr(), br2.data_ptr(), ref(5), T, B, D,
+                                                       _st(dev)), "bsi_gate_residual_backward")
                 dm[:, 5 * D :] = dgate
-                g_w2, g_b2 = _wgrad(dbr, h), colsum(dbr)
+                g_w2, g_b2 = _wgrad(dbr, h), dbias.sum(0)
                 dh = torch.empty((M, 4 * D), dtype=torch.bfloat16, device=dev)
                 _gemm(dbr, bft(w_2), dh, zeros(4 * D), L.EPI_BIAS_BF16)
                 L.check(lib.bsi_gelu_backward_bf16(dh.data_ptr(), dh.data_ptr(), pre.data_ptr(), dh.numel(), _st(dev)), "bsi_gelu_backward_bf16")
@@ -215,10 +225,10 @@ class DiTTrainFunction(torch.autograd.Function):
                 dsc, dsh = _ln_mod_backward(dx, da, x_mid, ref(4), T)
                 dm[:, 3 * D : 4 * D], dm[:, 4 * D : 5 * D] = part(dsh), part(dsc)
                 # ---- attention branch: x_mid = x_in + gate_msa * (attn(a1 Wqkv^T + b) Wo^T + b)
-                L.check(lib.bsi_gate_residual_backward(dbr.data_ptr(), dgate.data_ptr(), dx.data_ptr(), br1.data_ptr(), ref(2), T, B, D, _st(dev)),
-                        "bsi_gate_residual_backward")
+                L.check(lib.bsi_gate_residual_backward(dbr.data_ptr(), dgate.data_ptr(), dbias.data_ptr(), dx.data_ptr(), br1.data_ptr(), ref(2), T, B, D,
+                                                       _st(dev)), "bsi_gate_residual_backward")
                 dm[:, 2 * D : 3 * D] = dgate
-                g_wo, g_bo = _wgrad(dbr, att), colsum(dbr)
+                g_wo, g_bo = _wgrad(dbr, att), dbias.sum(0)
                 datt = torch.empty((M, D), dtype=torch.bfloat16, device=dev)
                 _gemm(dbr, bft(w_o), datt, zeros(D), L.EPI_BIAS_BF16)
                 dqkv = _attention_backward(qkv, datt, B, T, heads, D // heads)
@@ -233,7 +243,7 @@ class DiTTrainFunction(torch.autograd.Function):
             for bg in reversed(block_grads):
                 grads += bg
             grads += tail
-        return (None, None, None, dmods, *grads)
+        return (None, None, None, dmods.to(ctx.mods_dtype), *grads)
 
 
 def _attention_backward(qkv: Tensor, datt: Tensor, B: int, T: int, heads: int, hd: int) -> Tensor:
@@ -265,5 +275,7 @@ def forward_train(model, mu: Tensor, t: Tensor, in_scale: Tensor | None) -> Tens
         if isinstance(blk.dropout, torch.nn.Dropout) and blk.dropout.p > 0 and model.training:
             raise NotImplementedError("dropout is not implemented in the native training path: construct DenoisingDiT(dropout=None) or call .eval()")
     cond = model.dit.t_embedding(t.to(torch.float32))
-    mods = torch.stack([blk.adaLN_modulation(cond) for blk in model.dit.blocks])
+    # the conditioning chain runs on bf16 tensor cores like the inference engine's (and the reference under bf16 autocast)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        mods = torch.stack([blk.adaLN_modulation(cond) for blk in model.dit.blocks])
     return DiTTrainFunction.apply(model, mu, in_scale, mods, *trainable_parameters(model))

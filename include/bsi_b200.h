@@ -317,11 +317,13 @@ int bsi_gemm_wgrad_bf16(float* dW, const void* dY_bf16, const void* X_bf16, int3
                         int32_t ldw, int32_t splits, void* stream);
 
 /* Elementwise / reduction pieces of the DiT backward (bsi/models/dit.py:50-55,87-103; config 5 groundwork). */
-/* x[row] += gate[row / rows_per_sample] * branch[row]   (torch.addcmul(x, gate, branch); gate.base == NULL: gate = 1) */
-int bsi_gate_residual(float* x, const void* branch_bf16, bsi_rowref gate, int32_t rows_per_sample, int64_t M, int32_t D, void* stream);
-/* dbranch = gate * dx (bf16);  dgate[b][d] = sum_t dx[b,t,d] * branch[b,t,d]  (dgate may be NULL) */
-int bsi_gate_residual_backward(void* dbranch_bf16, float* dgate, const float* dx, const void* branch_bf16, bsi_rowref gate, int32_t rows_per_sample,
-                               int32_t B, int32_t D, void* stream);
+/* x_out[row] = x[row] + gate[row / rows_per_sample] * branch[row]   (torch.addcmul(x, gate, branch); x_out may be x; gate.base == NULL: gate = 1) */
+int bsi_gate_residual(float* x_out, const float* x, const void* branch_bf16, bsi_rowref gate, int32_t rows_per_sample, int64_t M, int32_t D, void* stream);
+/* dbranch = gate * dx (bf16);  dgate[b][d] = sum_t dx[b,t,d] * branch[b,t,d];  dbias_part[b][d] = sum_t dbranch[b,t,d]  (either may be NULL) */
+int bsi_gate_residual_backward(void* dbranch_bf16, float* dgate, float* dbias_part, const float* dx, const void* branch_bf16, bsi_rowref gate,
+                               int32_t rows_per_sample, int32_t B, int32_t D, void* stream);
+/* partial[chunk][n] = sum of a[r][n] over the chunk's rows_per_cta rows (bias gradient = sum over chunks); a bf16 [M][N], pitch ld */
+int bsi_colsum_bf16(float* partial, const void* a_bf16, int64_t M, int32_t N, int64_t ld, int32_t rows_per_cta, void* stream);
 /* nn.GELU(approximate="tanh") on a bf16 pre-activation, and its backward dpre = dout * gelu'(pre). */
 int bsi_gelu_bf16(void* out_bf16, const void* pre_bf16, int64_t numel, void* stream);
 int bsi_gelu_backward_bf16(void* dpre_bf16, const void* dout_bf16, const void* pre_bf16, int64_t numel, void* stream);

@@ -66,20 +66,34 @@ def test_gate_residual_forward_backward_vs_autograd():
     tab = rnd("gr.tab", (B, 6 * D), 0.7)  # gate lives inside the [B, 6D] modulation table (column block 2), like dit.py:89
     gate = L.rowref(tab, 6 * D, 0, 2 * D)
     x = x0.clone()
-    call("bsi_gate_residual", L.ptr(x), L.ptr(br), gate, T, M, D, L.stream_ptr())
+    call("bsi_gate_residual", L.ptr(x), L.ptr(x), L.ptr(br), gate, T, M, D, L.stream_ptr())
+    x_new = torch.zeros_like(x0)
+    call("bsi_gate_residual", L.ptr(x_new), L.ptr(x0), L.ptr(br), gate, T, M, D, L.stream_ptr())
     sync()
     g = tab[:, 2 * D : 3 * D].clone().requires_grad_(True)
     brf = br.float().requires_grad_(True)
     ref = torch.addcmul(x0.reshape(B, T, D), g[:, None], brf.reshape(B, T, D)).reshape(M, D)
     report("gate_residual", x, ref, 1e-6, 1e-6)
+    assert torch.equal(x_new, x)  # out of place == in place
     dx = rnd("gr.dx", (M, D))
     ref.backward(dx)
     dbr = torch.zeros((M, D), dtype=torch.bfloat16, device=dev())
     dgate = torch.zeros((B, D), device=dev())
-    call("bsi_gate_residual_backward", L.ptr(dbr), L.ptr(dgate), L.ptr(dx), L.ptr(br), gate, T, B, D, L.stream_ptr())
+    dbias = torch.zeros((B, D), device=dev())
+    call("bsi_gate_residual_backward", L.ptr(dbr), L.ptr(dgate), L.ptr(dbias), L.ptr(dx), L.ptr(br), gate, T, B, D, L.stream_ptr())
     sync()
     report("dbranch", dbr, brf.grad, 1e-2, 1e-3)
     report("dgate", dgate, g.grad, 1e-4, 1e-4)
+    report("bias gradient of the branch", dbias.sum(0), dbr.float().sum(0), 1e-5, 1e-4)
+
+
+def test_colsum_bf16():
+    M, N = 1000, 384
+    a = rnd("cs.a", (M, 2 * N)).bfloat16()[:, N:]  # strided view (pitch 2N)
+    parts = torch.zeros(((M + 255) // 256, N), device=dev())
+    call("bsi_colsum_bf16", L.ptr(parts), a.data_ptr(), M, N, 2 * N, 256, L.stream_ptr())
+    sync()
+    report("colsum", parts.sum(0), a.float().sum(0), 1e-5, 1e-4)
 
 
 def test_gelu_forward_backward_vs_autograd():
