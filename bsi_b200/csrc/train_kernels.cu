@@ -185,6 +185,28 @@ __global__ void __launch_bounds__(kTrThreads) k_colsum_bf16(float* __restrict__ 
     *reinterpret_cast<float2*>(partial + (int64_t)blockIdx.y * N + c) = make_float2(s0, s1);
 }
 
+// ------------------------------------------------------------------ fp32 weight -> bf16 copy and bf16 transposed copy in one pass
+// in [R][C] fp32 -> out [R][ld_out] bf16 (forward operand, optional) and out_t [C][ld_t] bf16 (operand of the data-gradient GEMM);
+// 32 x 32 tiles through shared memory so that both global accesses are coalesced.  block (32, 8).
+__global__ void __launch_bounds__(256) k_cast_transpose_bf16(__nv_bfloat16* __restrict__ out, __nv_bfloat16* __restrict__ out_t, const float* __restrict__ in,
+                                                             int R, int Cc, int ld_out, int ld_t) {
+    __shared__ float tile[32][33];
+    const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    for (int j = threadIdx.y; j < 32; j += 8) {
+        const int r = r0 + j, c = c0 + threadIdx.x;
+        const float v = (r < R && c < Cc) ? in[(int64_t)r * Cc + c] : 0.0f;
+        tile[j][threadIdx.x] = v;
+        if (out && r < R && c < Cc) out[(int64_t)r * ld_out + c] = __float2bfloat16(v);
+    }
+    __syncthreads();
+    if (out_t) {
+        for (int j = threadIdx.y; j < 32; j += 8) {
+            const int c = c0 + j, r = r0 + threadIdx.x;
+            if (c < Cc && r < R) out_t[(int64_t)c * ld_t + r] = __float2bfloat16(tile[threadIdx.x][j]);
+        }
+    }
+}
+
 static unsigned tr_grid(int64_t work) {
     const int64_t need = (work + kTrThreads - 1) / kTrThreads, cap = (int64_t)sm_count() * 8;
     return (unsigned)(need < cap ? need : cap);
@@ -218,6 +240,15 @@ int bsi_colsum_bf16(float* partial, const void* a_bf16, int64_t M, int32_t N, in
     dim3 grid((N / 2 + kTrThreads - 1) / kTrThreads, (unsigned)((M + rows_per_cta - 1) / rows_per_cta));
     k_colsum_bf16<<<grid, kTrThreads, 0, (cudaStream_t)stream>>>(partial, (const __nv_bfloat16*)a_bf16, M, N, ld, rows_per_cta);
     BSI_LAUNCH_OK("k_colsum_bf16");
+    return BSI_OK;
+}
+
+int bsi_cast_transpose_bf16(void* out_bf16, void* out_t_bf16, const float* in, int32_t rows, int32_t cols, int32_t ld_out, int32_t ld_t, void* stream) {
+    BSI_CHECK_ARG((out_bf16 || out_t_bf16) && in && rows > 0 && cols > 0 && (!out_bf16 || ld_out >= cols) && (!out_t_bf16 || ld_t >= rows),
+                  "bsi_cast_transpose_bf16: bad arguments");
+    dim3 grid((cols + 31) / 32, (rows + 31) / 32), block(32, 8);
+    k_cast_transpose_bf16<<<grid, block, 0, (cudaStream_t)stream>>>((__nv_bfloat16*)out_bf16, (__nv_bfloat16*)out_t_bf16, in, rows, cols, ld_out, ld_t);
+    BSI_LAUNCH_OK("k_cast_transpose_bf16");
     return BSI_OK;
 }
 

@@ -115,7 +115,19 @@ class DiTTrainFunction(torch.autograd.Function):
         w_patch, b_patch = next(it), next(it)
         blocks = [tuple(next(it) for _ in range(8)) for _ in range(depth)]
         ln_g, ln_b, w_dec, b_dec = next(it), next(it), next(it), next(it)
-        bf = lambda w: w.detach().to(torch.bfloat16).contiguous()
+        wts: list[Tensor] = []  # transposed bf16 weights, in parameter order, for the data-gradient GEMMs of the backward
+
+        def bf(w: Tensor, pad_rows: int = 0, pad_cols: int = 0) -> Tensor:
+            """bf16 copy [N'][K'] (zero padded) for the forward GEMM; its transpose [K'][N'] is produced in the same pass."""
+            n, k = w.shape
+            n_p, k_p = max(n, pad_rows), max(k, pad_cols)
+            alloc = torch.zeros if (n_p != n or k_p != k) else torch.empty
+            w16, wt16 = alloc((n_p, k_p), dtype=torch.bfloat16, device=dev), alloc((k_p, n_p), dtype=torch.bfloat16, device=dev)
+            L.check(lib.bsi_cast_transpose_bf16(w16.data_ptr(), wt16.data_ptr(), w.detach().float().contiguous().data_ptr(), n, k, k_p, n_p, _st(dev)),
+                    "bsi_cast_transpose_bf16")
+            wts.append(wt16)
+            return w16
+
         with torch.cuda.device(dev):
             scale = torch.ones(1, dtype=torch.float32, device=dev) if in_scale is None else in_scale.detach().float().contiguous()
             K0 = _pad8(w_patch.shape[1])  # operand pitches are multiples of 16 bytes; the padding columns are zero on both sides
@@ -123,7 +135,7 @@ class DiTTrainFunction(torch.autograd.Function):
             L.check(lib.bsi_dit_patch_operand(a0.data_ptr(), mu.detach().float().contiguous().data_ptr(), L.rowref(scale, 0 if in_scale is None else 1), None,
                                               B, Cc, H, Wd, p, cfg.fourier_n_min, cfg.fourier_n_max, K0, _st(dev)), "bsi_dit_patch_operand")
             x = torch.empty((M, D), dtype=torch.float32, device=dev)
-            _gemm(a0, _pad_cols(bf(w_patch), K0), x, b_patch.detach().float(), L.EPI_POS_F32, pos=model.dit.patch_pos_embedding.float().contiguous(),
+            _gemm(a0, bf(w_patch, pad_cols=K0), x, b_patch.detach().float(), L.EPI_POS_F32, pos=model.dit.patch_pos_embedding.float().contiguous(),
                   rows_per_sample=T)
             ctx.mods_dtype = mods.dtype
             mods = mods.detach().float().contiguous()
@@ -156,11 +168,11 @@ class DiTTrainFunction(torch.autograd.Function):
             n_out = w_dec.shape[0]
             Np = _pad8(n_out)
             y = torch.empty((M, Np), dtype=torch.float32, device=dev)
-            _gemm(a_dec, _pad_rows(bf(w_dec), Np), y, _pad_rows(b_dec.detach().float(), Np), L.EPI_BIAS_F32)
+            _gemm(a_dec, bf(w_dec, pad_rows=Np), y, _pad_rows(b_dec.detach().float(), Np), L.EPI_BIAS_F32)
             gh, gw = H // p, Wd // p
             out = y[:, :n_out].reshape(B, gh, gw, p, p, Cc).permute(0, 5, 1, 3, 2, 4).reshape(B, Cc, H, Wd).contiguous()
         ctx.model, ctx.geom = model, (B, Cc, H, Wd, T, M)
-        ctx.saved_acts = (a0, x, a_dec, saved)
+        ctx.saved_acts = (a0, x, a_dec, saved, wts)
         ctx.save_for_backward(mods, *params)
         return out
 
@@ -172,14 +184,15 @@ class DiTTrainFunction(torch.autograd.Function):
         B, Cc, H, Wd, T, M = ctx.geom
         p, D, depth, heads = cfg.patch, cfg.dim, cfg.depth, cfg.heads
         mods, *params = ctx.saved_tensors
-        a0, x_last, a_dec, saved = ctx.saved_acts
+        a0, x_last, a_dec, saved, wts = ctx.saved_acts
+        wt_blocks = [wts[1 + 4 * l : 5 + 4 * l] for l in range(depth)]  # [patch | (qkv, out, mlp1, mlp2) per block | decoder]
+        wt_dec = wts[-1]
         dev = dout.device
         lib = L.load()
         it = iter(params)
         w_patch, b_patch = next(it), next(it)
         blocks = [tuple(next(it) for _ in range(8)) for _ in range(depth)]
         ln_g, ln_b, w_dec, b_dec = next(it), next(it), next(it), next(it)
-        bft = lambda w: w.detach().to(torch.bfloat16).t().contiguous()  # [K][N]: the forward kernel then computes dY @ W
         def colsum(t: Tensor) -> Tensor:
             if t.dtype != torch.bfloat16:
                 return t.sum(0, dtype=torch.float32)
@@ -197,7 +210,7 @@ class DiTTrainFunction(torch.autograd.Function):
             dy16 = _pad_cols(dy.to(torch.bfloat16), Np)
             g_wdec, g_bdec = _wgrad(dy16, a_dec)[:n_out], colsum(dy)
             da = torch.empty((M, D), dtype=torch.bfloat16, device=dev)
-            _gemm(dy16, _pad_cols(bft(w_dec), Np), da, zeros(D), L.EPI_BIAS_BF16)
+            _gemm(dy16, wt_dec, da, zeros(D), L.EPI_BIAS_BF16)  # W^T [D][Np]: the forward kernel computes dY @ W
             dx = torch.zeros((M, D), dtype=torch.float32, device=dev)
             dg_part, db_part = _ln_mod_backward(dx, da, x_last, None, T, ln_g.detach().float().contiguous())
             tail = [dg_part.sum(0), db_part.sum(0), g_wdec, g_bdec]
@@ -206,6 +219,7 @@ class DiTTrainFunction(torch.autograd.Function):
             for l in reversed(range(depth)):
                 w_qkv, b_qkv, w_o, b_o, w_1, b_1, w_2, b_2 = blocks[l]
                 x_in, a1, qkv, att, br1, x_mid, a2, pre, h, br2 = saved[l]
+                wt_qkv, wt_o, wt_1, wt_2 = wt_blocks[l]
                 m, dm = mods[l], dmods[l]
                 ref = lambda j: L.rowref(m, 6 * D, 0, j * D)
                 part = lambda t: t.reshape(B, T // _LN_ROWS_PER_CTA, D).sum(1)
@@ -218,10 +232,10 @@ class DiTTrainFunction(torch.autograd.Function):
                 dm[:, 5 * D :] = dgate
                 g_w2, g_b2 = _wgrad(dbr, h), dbias.sum(0)
                 dh = torch.empty((M, 4 * D), dtype=torch.bfloat16, device=dev)
-                _gemm(dbr, bft(w_2), dh, zeros(4 * D), L.EPI_BIAS_BF16)
+                _gemm(dbr, wt_2, dh, zeros(4 * D), L.EPI_BIAS_BF16)
                 L.check(lib.bsi_gelu_backward_bf16(dh.data_ptr(), dh.data_ptr(), pre.data_ptr(), dh.numel(), _st(dev)), "bsi_gelu_backward_bf16")
                 g_w1, g_b1 = _wgrad(dh, a2), colsum(dh)
-                _gemm(dh, bft(w_1), da, zeros(D), L.EPI_BIAS_BF16)
+                _gemm(dh, wt_1, da, zeros(D), L.EPI_BIAS_BF16)
                 dsc, dsh = _ln_mod_backward(dx, da, x_mid, ref(4), T)
                 dm[:, 3 * D : 4 * D], dm[:, 4 * D : 5 * D] = part(dsh), part(dsc)
                 # ---- attention branch: x_mid = x_in + gate_msa * (attn(a1 Wqkv^T + b) Wo^T + b)
@@ -230,10 +244,10 @@ class DiTTrainFunction(torch.autograd.Function):
                 dm[:, 2 * D : 3 * D] = dgate
                 g_wo, g_bo = _wgrad(dbr, att), dbias.sum(0)
                 datt = torch.empty((M, D), dtype=torch.bfloat16, device=dev)
-                _gemm(dbr, bft(w_o), datt, zeros(D), L.EPI_BIAS_BF16)
+                _gemm(dbr, wt_o, datt, zeros(D), L.EPI_BIAS_BF16)
                 dqkv = _attention_backward(qkv, datt, B, T, heads, D // heads)
                 g_wqkv, g_bqkv = _wgrad(dqkv, a1), colsum(dqkv)
-                _gemm(dqkv, bft(w_qkv), da, zeros(D), L.EPI_BIAS_BF16)
+                _gemm(dqkv, wt_qkv, da, zeros(D), L.EPI_BIAS_BF16)
                 dsc, dsh = _ln_mod_backward(dx, da, x_in, ref(1), T)
                 dm[:, :D], dm[:, D : 2 * D] = part(dsh), part(dsc)
                 block_grads.append([g_wqkv, g_bqkv, g_wo, g_bo, g_w1, g_b1, g_w2, g_b2])

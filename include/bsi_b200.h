@@ -322,6 +322,9 @@ int bsi_gate_residual(float* x_out, const float* x, const void* branch_bf16, bsi
 /* dbranch = gate * dx (bf16);  dgate[b][d] = sum_t dx[b,t,d] * branch[b,t,d];  dbias_part[b][d] = sum_t dbranch[b,t,d]  (either may be NULL) */
 int bsi_gate_residual_backward(void* dbranch_bf16, float* dgate, float* dbias_part, const float* dx, const void* branch_bf16, bsi_rowref gate,
                                int32_t rows_per_sample, int32_t B, int32_t D, void* stream);
+/* fp32 [rows][cols] -> bf16 copy out[rows][ld_out] and bf16 transposed copy out_t[cols][ld_t] in one pass (either may be NULL;
+ * padding beyond cols / rows is left untouched: allocate it zeroed).  The transposed weight is the operand of dX = dY W. */
+int bsi_cast_transpose_bf16(void* out_bf16, void* out_t_bf16, const float* in, int32_t rows, int32_t cols, int32_t ld_out, int32_t ld_t, void* stream);
 /* partial[chunk][n] = sum of a[r][n] over the chunk's rows_per_cta rows (bias gradient = sum over chunks); a bf16 [M][N], pitch ld */
 int bsi_colsum_bf16(float* partial, const void* a_bf16, int64_t M, int32_t N, int64_t ld, int32_t rows_per_cta, void* stream);
 /* nn.GELU(approximate="tanh") on a bf16 pre-activation, and its backward dpre = dout * gelu'(pre). */

@@ -147,3 +147,14 @@ def test_layernorm_mod_backward_vs_autograd(dim):
     report(f"ln-affine dx {dim}", dx, xr2.grad, 1e-4, 1e-4)
     report(f"ln-affine dgamma {dim}", parts[0].sum(0), gamma.grad, 1e-4, 2e-3)
     report(f"ln-affine dbeta {dim}", parts[1].sum(0), beta.grad, 1e-4, 2e-3)
+
+
+def test_cast_transpose_bf16():
+    R, Cc = 100, 84  # ragged on both sides of the 32 x 32 tiles, padded pitches
+    w = rnd("ct.w", (R, Cc))
+    out = torch.zeros((R, 88), dtype=torch.bfloat16, device=dev())
+    out_t = torch.zeros((Cc, 104), dtype=torch.bfloat16, device=dev())
+    call("bsi_cast_transpose_bf16", L.ptr(out), L.ptr(out_t), L.ptr(w), R, Cc, 88, 104, L.stream_ptr())
+    sync()
+    assert torch.equal(out[:, :Cc], w.bfloat16()) and float(out[:, Cc:].abs().max()) == 0.0
+    assert torch.equal(out_t[:, :R], w.bfloat16().t()) and float(out_t[:, R:].abs().max()) == 0.0
