@@ -1,13 +1,18 @@
-"""Config-5 probe: one optimisation step of DiT-L/4 on imagenet64 shapes through the native training path --
-BSI.train_loss(x).mean().backward() + fused clip/AdamW/EMA -- timed with CUDA events.  Prints one JSON line.
+"""Config-5 probe: optimisation steps of DiT-L/4 on imagenet64 shapes through the native training path --
+BSI.train_loss(x).mean().backward() [+ one NCCL all-reduce over the flat gradient arena] + fused clip/AdamW/EMA -- timed with
+CUDA events, max over ranks.  The global batch is fixed (strong scaling, like the reference's data loader which divides the batch
+by the world size, bsi/data/h5image.py:309-312); a rank whose share exceeds --micro accumulates gradients over micro-batches.
 
-    python tools/gpu_train.py [batch] [depth]
+    python tools/gpu_train.py [--global-batch 1024] [--micro 256] [--depth 24] [--steps 3] [--profile]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P tools/gpu_train.py ...
 """
+import argparse
 import json
+import os
 import sys
-import time
 
 import torch
+import torch.distributed as dist
 
 sys.path.insert(0, ".")
 from bsi_b200 import BSI, Discretization  # noqa: E402
@@ -15,11 +20,25 @@ from bsi_b200 import optim as NO  # noqa: E402
 from bsi_b200.models import DenoisingDiT  # noqa: E402
 from bsi_b200.nn import FourierFeatures  # noqa: E402
 
-B = int(sys.argv[1]) if len(sys.argv) > 1 else 128
-depth = int(sys.argv[2]) if len(sys.argv) > 2 else 24
-dev = torch.device("cuda:0")
-torch.manual_seed(0)
-model = DenoisingDiT((3, 64, 64), 4, 1024, depth, 16, dropout=None, fourier_features=FourierFeatures(n_min=6, n_max=8)).to(dev).train()
+ap = argparse.ArgumentParser()
+ap.add_argument("--global-batch", type=int, default=128)
+ap.add_argument("--micro", type=int, default=256)
+ap.add_argument("--depth", type=int, default=24)
+ap.add_argument("--steps", type=int, default=3)
+ap.add_argument("--profile", action="store_true")
+a = ap.parse_args()
+
+world, rank, local_rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
+dev = torch.device("cuda", local_rank)
+torch.cuda.set_device(dev)
+if world > 1:
+    dist.init_process_group("nccl", device_id=dev)
+local = a.global_batch // world
+micro = min(a.micro, local)
+assert local % micro == 0 and a.global_batch % world == 0
+
+torch.manual_seed(0)  # identical replicas on every rank
+model = DenoisingDiT((3, 64, 64), 4, 1024, a.depth, 16, dropout=None, fourier_features=FourierFeatures(n_min=6, n_max=8)).to(dev).train()
 with torch.no_grad():
     for blk in model.dit.blocks:  # adaLN-Zero would make every block the identity
         torch.nn.init.normal_(blk.adaLN_modulation[-1].weight, std=0.02)
@@ -29,38 +48,49 @@ bsi = BSI(model, data_shape=(3, 64, 64), k=256, discretization=Discretization.im
 ema = NO.create_ema(model, beta=0.9999, update_after_step=1000, update_every=1)
 opt = NO.AdamW(model.parameters(), lr=1e-3, weight_decay=0.01, max_grad_norm=1.0)
 opt.attach_ema(ema)
-gen = torch.Generator(device=dev).manual_seed(2)
-x = torch.randint(0, 256, (B, 3, 64, 64), device=dev, generator=gen).float() * (2 / 255) - 1
+gen = torch.Generator(device=dev).manual_seed(2 + rank)
+x = torch.randint(0, 256, (local, 3, 64, 64), device=dev, generator=gen).float() * (2 / 255) - 1
 
 
 def step():
     opt.zero_grad()
-    loss = bsi.train_loss(x, gen).mean()
-    loss.backward()
+    total = 0.0
+    for i in range(0, local, micro):
+        # mean over the global batch = sum of micro-batch sums / global batch (after the all-reduce's 1/world)
+        loss = bsi.train_loss(x[i : i + micro], gen).sum() * (world / a.global_batch)
+        loss.backward()
+        total += loss.detach()
+    if world > 1:
+        opt.all_reduce_grads()
     opt.step()
     ema.update()
-    return loss
+    return total
 
 
 for _ in range(2):
     loss = step()
 torch.cuda.synchronize()
+if world > 1:
+    dist.barrier()
 torch.cuda.reset_peak_memory_stats()
-a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-n = 3
-t0 = time.perf_counter()
-a.record()
-for _ in range(n):
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(a.steps):
     loss = step()
-b.record()
+e1.record()
 torch.cuda.synchronize()
-ms = a.elapsed_time(b) / n
-flops = B * 3 * (161.26e9 * depth / 24 + 0.352e9)  # forward + dgrad + wgrad per sample
-print(json.dumps(dict(what="imagenet64-dit train step (native path)", batch=B, depth=depth, ms=ms, samples_per_s=B / ms * 1e3, tflops=flops / ms / 1e9,
-                      wall_ms=(time.perf_counter() - t0) / n * 1e3, peak_mem_gb=torch.cuda.max_memory_allocated() / 2**30, loss=float(loss),
-                      params=sum(p.numel() for p in model.parameters()))))
+ms = torch.tensor([e0.elapsed_time(e1) / a.steps], device=dev)
+if world > 1:
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+ms = float(ms)
+flops = a.global_batch * 3 * (161.26e9 * a.depth / 24 + 0.352e9)  # forward + dgrad + wgrad per sample
+if rank == 0:
+    print(json.dumps(dict(what="imagenet64-dit train step (native path)", n_gpus=world, global_batch=a.global_batch, per_gpu_batch=local, micro_batch=micro,
+                          depth=a.depth, ms_per_step=ms, samples_per_s=a.global_batch / ms * 1e3, tflops_total=flops / ms / 1e9,
+                          tflops_per_gpu=flops / ms / 1e9 / world, peak_mem_gb=torch.cuda.max_memory_allocated() / 2**30, loss=float(loss),
+                          grad_norm=float(opt.total_grad_norm()), params=sum(p.numel() for p in model.parameters()))), flush=True)
 
-if len(sys.argv) > 3 and sys.argv[3] == "profile":
+if a.profile and rank == 0:
     from torch.profiler import ProfilerActivity, profile
 
     with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
@@ -72,3 +102,5 @@ if len(sys.argv) > 3 and sys.argv[3] == "profile":
     for name, ms_k, cnt in rows[:32]:
         print(f"{ms_k:8.2f} ms {100 * ms_k / tot:5.1f}% n={cnt:5d}  {name[:110]}")
     print(f"total device time {tot:.1f} ms")
+if world > 1:
+    dist.destroy_process_group()
