@@ -8,12 +8,13 @@ GEMM, and runs the backward with
   * ``bsi_gemm_bf16``        forward GEMMs, and the data gradients dX = dY W through transposed bf16 weight copies,
   * ``bsi_gemm_wgrad_bf16``  weight gradients dW += dY^T X (tcgen05, MN-major operands, split-M reduce-add),
   * ``bsi_layernorm_mod_bf16`` / ``bsi_layernorm_mod_backward``, ``bsi_gate_residual(_backward)``, ``bsi_gelu(_backward)_bf16``,
-  * ``bsi_attention_bf16``   forward attention.
+  * ``bsi_attention_bf16``   forward attention,
+
+  * ``bsi_attention_backward_bf16``  attention backward (two deterministic mma.sync kernels that recompute the scores).
 
 What is still PyTorch here, and why: the adaLN / time-embedding chain on ``[B, 6*dim]`` tensors (O(batch) work, 0.2 % of the
-flops; differentiated by autograd through the ``mods`` argument), the bias gradients (one column sum per GEMM), and the
-attention *backward*, which recomputes ``F.scaled_dot_product_attention`` under autograd (a library flash-attention kernel)
-until the tcgen05 attention backward exists.  Everything else -- 96 % of the backward flops -- runs on this repo's kernels.
+flops; differentiated by autograd through the ``mods`` argument, under bf16 autocast) and the final sums of per-CTA partial
+reductions (``[B, chunks, D]`` buffers).  Every pass over a token-sized tensor runs on this repo's kernels.
 Dropout is not implemented (the reference trains with dropout 0.05; construct the model with ``dropout=None`` for now).
 """
 
@@ -22,7 +23,6 @@ from __future__ import annotations
 import ctypes as C
 
 import torch
-import torch.nn.functional as F
 from torch import Tensor
 
 from .. import _lib as L
@@ -245,7 +245,7 @@ class DiTTrainFunction(torch.autograd.Function):
                 g_wo, g_bo = _wgrad(dbr, att), dbias.sum(0)
                 datt = torch.empty((M, D), dtype=torch.bfloat16, device=dev)
                 _gemm(dbr, wt_o, datt, zeros(D), L.EPI_BIAS_BF16)
-                dqkv = _attention_backward(qkv, datt, B, T, heads, D // heads)
+                dqkv = _attention_backward(qkv, att, datt, B, T, heads, D // heads)
                 g_wqkv, g_bqkv = _wgrad(dqkv, a1), colsum(dqkv)
                 _gemm(dqkv, wt_qkv, da, zeros(D), L.EPI_BIAS_BF16)
                 dsc, dsh = _ln_mod_backward(dx, da, x_in, ref(1), T)
@@ -260,16 +260,13 @@ class DiTTrainFunction(torch.autograd.Function):
         return (None, None, None, dmods.to(ctx.mods_dtype), *grads)
 
 
-def _attention_backward(qkv: Tensor, datt: Tensor, B: int, T: int, heads: int, hd: int) -> Tensor:
-    """d(qkv) of out = SDPA(q, k, v) on the packed [B*T][3*dim] layout -- recomputed by the library flash-attention kernel."""
-    v5 = qkv.view(B, T, 3, heads, hd)
-    with torch.enable_grad():
-        q, k, v = (v5[:, :, j].permute(0, 2, 1, 3).detach().requires_grad_(True) for j in range(3))
-        o = F.scaled_dot_product_attention(q, k, v)
-        gq, gk, gv = torch.autograd.grad(o, (q, k, v), datt.view(B, T, heads, hd).permute(0, 2, 1, 3))
-    out = torch.empty_like(v5)
-    out[:, :, 0], out[:, :, 1], out[:, :, 2] = gq.permute(0, 2, 1, 3), gk.permute(0, 2, 1, 3), gv.permute(0, 2, 1, 3)
-    return out.view(B * T, 3 * heads * hd)
+def _attention_backward(qkv: Tensor, att: Tensor, datt: Tensor, B: int, T: int, heads: int, hd: int) -> Tensor:
+    """d(qkv) of att = attention(qkv) on the packed [B*T][3*dim] layout (two mma.sync kernels, attention_bwd.cu)."""
+    dqkv = torch.empty_like(qkv)
+    ws = torch.empty((2, B * heads * T), dtype=torch.float32, device=qkv.device)
+    L.check(L.load().bsi_attention_backward_bf16(dqkv.data_ptr(), ws[0].data_ptr(), ws[1].data_ptr(), qkv.data_ptr(), att.data_ptr(), datt.data_ptr(),
+                                                 B, T, heads, hd, _st(qkv.device)), "bsi_attention_backward_bf16")
+    return dqkv
 
 
 def trainable_parameters(model) -> list[Tensor]:

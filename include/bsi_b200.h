@@ -208,6 +208,12 @@ int bsi_attention_bf16(void* out_bf16, const void* qkv_bf16, int32_t B, int32_t 
 /* Test hook: T = 256 runs the tcgen05 kernel (scores in TMEM); 1 forces the warp-level mma.sync kernel used for other T. */
 int bsi_attention_force_legacy(int32_t on);
 
+/* Backward of bsi_attention_bf16 on the same packed layouts (autograd of dit.py:36-47): dqkv bf16 [B*T][3*dim] from the saved qkv,
+ * the saved forward output and the upstream gradient dout bf16 [B*T][dim].  lse_ws / dsum_ws: B*heads*T floats of scratch each
+ * (log-sum-exp of the scaled scores and sum_c dout*out per query row; written by the first kernel, read by the second). */
+int bsi_attention_backward_bf16(void* dqkv_bf16, float* lse_ws, float* dsum_ws, const void* qkv_bf16, const void* out_bf16, const void* dout_bf16,
+                                int32_t B, int32_t T, int32_t heads, int32_t head_dim, void* stream);
+
 /* Patch-embed operand (dit.py:149-153,228-231; fourier_features.py:24-36):
  *   A[b*T + tok][(py*p+px)*Cin + c] = bf16( feature_c( scale[b] * mu[b,:,y,x] ) )
  * Cin = C*(1 + 2*(n_max-n_min+1)) when n_max >= n_min else C; feature order: raw channels, then

@@ -158,3 +158,27 @@ def test_cast_transpose_bf16():
     sync()
     assert torch.equal(out[:, :Cc], w.bfloat16()) and float(out[:, Cc:].abs().max()) == 0.0
     assert torch.equal(out_t[:, :R], w.bfloat16().t()) and float(out_t[:, R:].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("B,T,heads", [(2, 256, 2), (3, 128, 4), (2, 512, 1)])
+def test_attention_backward_vs_autograd(B, T, heads):
+    hd, dim = 64, heads * 64
+    qkv = rnd(f"ab.qkv{T}", (B * T, 3 * dim), 2.0).bfloat16()
+    dout = rnd(f"ab.do{T}", (B * T, dim)).bfloat16()
+    out = torch.zeros((B * T, dim), dtype=torch.bfloat16, device=dev())
+    call("bsi_attention_bf16", L.ptr(out), L.ptr(qkv), B, T, heads, hd, L.stream_ptr())
+    dqkv = torch.full((B * T, 3 * dim), float("nan"), dtype=torch.bfloat16, device=dev())
+    ws = torch.zeros((2, B * heads * T), device=dev())
+    call("bsi_attention_backward_bf16", L.ptr(dqkv), L.ptr(ws[0]), L.ptr(ws[1]), L.ptr(qkv), L.ptr(out), L.ptr(dout), B, T, heads, hd, L.stream_ptr())
+    sync()
+    q, k, v = (t.detach().requires_grad_(True) for t in qkv.float().reshape(B, T, 3, heads, hd).permute(2, 0, 3, 1, 4))
+    o = F.scaled_dot_product_attention(q, k, v)
+    o.backward(dout.float().reshape(B, T, heads, hd).permute(0, 2, 1, 3))
+    ref = torch.stack((q.grad, k.grad, v.grad)).permute(1, 3, 0, 2, 4).reshape(B * T, 3 * dim)
+    lse_ref = torch.logsumexp((q @ k.transpose(-1, -2)).detach() / 8.0, dim=-1) * 1.4426950408889634
+    report("log-sum-exp (base 2)", ws[0].reshape(B, heads, T), lse_ref, 1e-4, 1e-3)
+    for name, sl in (("dq", slice(0, dim)), ("dk", slice(dim, 2 * dim)), ("dv", slice(2 * dim, 3 * dim))):
+        got, want = dqkv[:, sl].float(), ref[:, sl]
+        rel = float((got - want).norm() / want.norm())
+        assert rel < 1.5e-2, f"{name}: relative L2 error {rel}"
+        report(name, got, want, 5e-2, 2e-2 * float(want.abs().max()))
