@@ -22,6 +22,7 @@ SPECS = {
     "small64": O.DiTSpec((3, 64, 64), 4, 128, 2, 2),
     "nofourier32": O.DiTSpec((3, 32, 32), 2, 128, 1, 2, fourier=None),
     "wide": O.DiTSpec((3, 32, 32), 2, 256, 1, 4),
+    "L2x64": O.DiTSpec((3, 64, 64), 4, 1024, 2, 16),  # DiT-L width and head count (the 2-CTA 256x256 GEMM tiles, 16 heads), 2 blocks
 }
 
 
