@@ -32,8 +32,13 @@ __device__ __forceinline__ void mma_bf16(float (&d)[4], const uint32_t (&a)[4], 
         : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
+// DROP: attention dropout of the training path (F.scaled_dot_product_attention(dropout_p), dit.py:43-44): the softmax is normalised
+// over all keys, then each probability is kept with probability 1 - p and rescaled; the mask is a pure function of
+// (seed, head-of-sample, query, key) so that the backward kernels (attention_bwd.cu) regenerate it.
+template <bool DROP>
 __global__ void __launch_bounds__(kAttThreads, 2)
-    k_attention_mma(__nv_bfloat16* __restrict__ out, const __nv_bfloat16* __restrict__ qkv, int T, int dim, float scale_log2) {
+    k_attention_mma(__nv_bfloat16* __restrict__ out, const __nv_bfloat16* __restrict__ qkv, int T, int dim, float scale_log2, uint32_t drop_thresh,
+                    uint32_t drop_seed, float drop_inv) {
     extern __shared__ __align__(128) uint8_t att_smem[];
     const uint32_t sQ = (uint32_t)__cvta_generic_to_shared(att_smem), sK = sQ + kQRows * 128, sV = sK + T * 128;
     const int q0 = blockIdx.x * kQRows, h = blockIdx.y, b = blockIdx.z;
@@ -114,6 +119,18 @@ __global__ void __launch_bounds__(kAttThreads, 2)
         }
 #pragma unroll
         for (int r = 0; r < 2; ++r) l_run[r] = l_run[r] * corr[r] + rs[r];
+        if constexpr (DROP) {
+            const uint32_t sd = mix32(drop_seed ^ ((uint32_t)(b * gridDim.y + h) * 0x9E3779B9u));
+            const uint32_t qa = (uint32_t)(q0 + warp * 16 + (lane >> 2)) * T, qb = qa + 8u * T;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const uint32_t key = kc * 64 + j * 8 + 2 * (lane & 3);
+                s[j][0] = dropout_keep(sd, qa + key, drop_thresh) ? s[j][0] * drop_inv : 0.0f;
+                s[j][1] = dropout_keep(sd, qa + key + 1, drop_thresh) ? s[j][1] * drop_inv : 0.0f;
+                s[j][2] = dropout_keep(sd, qb + key, drop_thresh) ? s[j][2] * drop_inv : 0.0f;
+                s[j][3] = dropout_keep(sd, qb + key + 1, drop_thresh) ? s[j][3] * drop_inv : 0.0f;
+            }
+        }
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             o[j][0] *= corr[0], o[j][1] *= corr[0];
@@ -184,11 +201,29 @@ extern "C" int bsi_attention_bf16(void* out_bf16, const void* qkv_bf16, int32_t 
     if (T == 256 && !g_force_legacy_attention) return attention_tcgen05(out_bf16, qkv_bf16, B, heads, (cudaStream_t)stream);
     const int dim = heads * head_dim;
     const int smem = (kQRows + 2 * T) * 128;
-    BSI_ENSURE_SMEM(k_attention_mma, smem);
+    BSI_ENSURE_SMEM(k_attention_mma<false>, smem);
     const float scale_log2 = 1.4426950408889634f / sqrtf((float)head_dim);
     dim3 grid(T / kQRows, heads, B);
-    k_attention_mma<<<grid, kAttThreads, smem, (cudaStream_t)stream>>>((__nv_bfloat16*)out_bf16, (const __nv_bfloat16*)qkv_bf16, T, dim,
-                                                                      scale_log2);
+    k_attention_mma<false><<<grid, kAttThreads, smem, (cudaStream_t)stream>>>((__nv_bfloat16*)out_bf16, (const __nv_bfloat16*)qkv_bf16, T, dim,
+                                                                             scale_log2, 0u, 0u, 1.0f);
     BSI_LAUNCH_OK("k_attention_mma");
+    return BSI_OK;
+}
+
+extern "C" int bsi_attention_dropout_bf16(void* out_bf16, const void* qkv_bf16, int32_t B, int32_t T, int32_t heads, int32_t head_dim, float drop_p,
+                                          uint32_t drop_seed, void* stream) {
+    BSI_CHECK_ARG(out_bf16 && qkv_bf16 && B > 0 && heads > 0 && drop_p > 0.0f && drop_p < 1.0f, "bsi_attention_dropout_bf16: bad arguments");
+    if (head_dim != kHd || T % kQRows != 0 || T > 512) {
+        set_error("bsi_attention_dropout_bf16: only head_dim=64 and T in {128,256,384,512} are implemented (got head_dim=%d T=%d)", head_dim, T);
+        return BSI_ERR_UNSUPPORTED;
+    }
+    const int dim = heads * head_dim;
+    const int smem = (kQRows + 2 * T) * 128;
+    BSI_ENSURE_SMEM(k_attention_mma<true>, smem);
+    const float scale_log2 = 1.4426950408889634f / sqrtf((float)head_dim);
+    dim3 grid(T / kQRows, heads, B);
+    k_attention_mma<true><<<grid, kAttThreads, smem, (cudaStream_t)stream>>>((__nv_bfloat16*)out_bf16, (const __nv_bfloat16*)qkv_bf16, T, dim, scale_log2,
+                                                                            dropout_thresh(drop_p), drop_seed, 1.0f / (1.0f - drop_p));
+    BSI_LAUNCH_OK("k_attention_mma<dropout>");
     return BSI_OK;
 }

@@ -104,7 +104,7 @@ __device__ __forceinline__ void store_rows(const float (&acc)[8][4], float scale
 __global__ void __launch_bounds__(ab::kThreads, 1)
     k_attention_bwd_q(__nv_bfloat16* __restrict__ dqkv, float* __restrict__ lse, float* __restrict__ dsum, const __nv_bfloat16* __restrict__ qkv,
                       const __nv_bfloat16* __restrict__ out, const __nv_bfloat16* __restrict__ dout, int T, int dim, int heads, float scale_log2,
-                      float scale) {
+                      float scale, uint32_t drop_thresh, uint32_t drop_seed, float drop_inv) {
     using namespace ab;
     extern __shared__ __align__(128) uint8_t ab_smem[];
     const uint32_t sQ = (uint32_t)__cvta_generic_to_shared(ab_smem), sdO = sQ + kRows * 128, sO = sdO + kRows * 128, sK = sO + kRows * 128,
@@ -198,6 +198,18 @@ __global__ void __launch_bounds__(ab::kThreads, 1)
         float s[8][4], dp[8][4];
         mm_abt(s, qf, sK, kc * 64, lane);
         mm_abt(dp, dof, sV, kc * 64, lane);
+        if (drop_thresh) {  // dP = mask/(1-p) o (dO V^T): the forward dropped these probabilities (attention.cu, k_attention_mma<true>)
+            const uint32_t sd = mix32(drop_seed ^ ((uint32_t)(b * heads + h) * 0x9E3779B9u));
+            const uint32_t qa = (uint32_t)(q0 + r0 + g) * T, qb = qa + 8u * T;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const uint32_t key = kc * 64 + j * 8 + 2 * (lane & 3);
+                dp[j][0] = dropout_keep(sd, qa + key, drop_thresh) ? dp[j][0] * drop_inv : 0.0f;
+                dp[j][1] = dropout_keep(sd, qa + key + 1, drop_thresh) ? dp[j][1] * drop_inv : 0.0f;
+                dp[j][2] = dropout_keep(sd, qb + key, drop_thresh) ? dp[j][2] * drop_inv : 0.0f;
+                dp[j][3] = dropout_keep(sd, qb + key + 1, drop_thresh) ? dp[j][3] * drop_inv : 0.0f;
+            }
+        }
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             s[j][0] = exp2f(fmaf(s[j][0], scale_log2, -lse2[0])) * (dp[j][0] - dr[0]);
@@ -212,7 +224,8 @@ __global__ void __launch_bounds__(ab::kThreads, 1)
 
 __global__ void __launch_bounds__(ab::kThreads, 1)
     k_attention_bwd_kv(__nv_bfloat16* __restrict__ dqkv, const float* __restrict__ lse, const float* __restrict__ dsum, const __nv_bfloat16* __restrict__ qkv,
-                       const __nv_bfloat16* __restrict__ dout, int T, int dim, int heads, float scale_log2, float scale) {
+                       const __nv_bfloat16* __restrict__ dout, int T, int dim, int heads, float scale_log2, float scale, uint32_t drop_thresh,
+                       uint32_t drop_seed, float drop_inv) {
     using namespace ab;
     extern __shared__ __align__(128) uint8_t ab_smem[];
     const uint32_t sK = (uint32_t)__cvta_generic_to_shared(ab_smem), sV = sK + kRows * 128, sQ = sV + kRows * 128, sdO = sQ + T * 128;
@@ -240,6 +253,7 @@ __global__ void __launch_bounds__(ab::kThreads, 1)
     float dk[8][4], dv[8][4];
 #pragma unroll
     for (int j = 0; j < 8; ++j) dk[j][0] = dk[j][1] = dk[j][2] = dk[j][3] = dv[j][0] = dv[j][1] = dv[j][2] = dv[j][3] = 0.0f;
+    const uint32_t sd = mix32(drop_seed ^ ((uint32_t)(b * heads + h) * 0x9E3779B9u));
     for (int qc = 0; qc < T / 64; ++qc) {
         float s[8][4], dp[8][4];
         mm_abt(s, kf, sQ, qc * 64, lane);     // S^T: rows = this warp's keys, columns = queries of the chunk
@@ -250,8 +264,17 @@ __global__ void __launch_bounds__(ab::kThreads, 1)
             const float l0 = sL[c], l1 = sL[c + 1], d0 = sD[c], d1 = sD[c + 1];
             s[j][0] = exp2f(fmaf(s[j][0], scale_log2, -l0)), s[j][1] = exp2f(fmaf(s[j][1], scale_log2, -l1));
             s[j][2] = exp2f(fmaf(s[j][2], scale_log2, -l0)), s[j][3] = exp2f(fmaf(s[j][3], scale_log2, -l1));
-            dp[j][0] = s[j][0] * (dp[j][0] - d0), dp[j][1] = s[j][1] * (dp[j][1] - d1);
-            dp[j][2] = s[j][2] * (dp[j][2] - d0), dp[j][3] = s[j][3] * (dp[j][3] - d1);
+            float m00 = 1.0f, m01 = 1.0f, m10 = 1.0f, m11 = 1.0f;  // mask/(1-p) of (key row g | g+8, query column c | c+1)
+            if (drop_thresh) {
+                const uint32_t ka = (uint32_t)(k0 + r0 + (lane >> 2)), kb = ka + 8u;
+                m00 = dropout_keep(sd, (uint32_t)c * T + ka, drop_thresh) ? drop_inv : 0.0f;
+                m01 = dropout_keep(sd, (uint32_t)(c + 1) * T + ka, drop_thresh) ? drop_inv : 0.0f;
+                m10 = dropout_keep(sd, (uint32_t)c * T + kb, drop_thresh) ? drop_inv : 0.0f;
+                m11 = dropout_keep(sd, (uint32_t)(c + 1) * T + kb, drop_thresh) ? drop_inv : 0.0f;
+            }
+            dp[j][0] = s[j][0] * (dp[j][0] * m00 - d0), dp[j][1] = s[j][1] * (dp[j][1] * m01 - d1);
+            dp[j][2] = s[j][2] * (dp[j][2] * m10 - d0), dp[j][3] = s[j][3] * (dp[j][3] * m11 - d1);
+            s[j][0] *= m00, s[j][1] *= m01, s[j][2] *= m10, s[j][3] *= m11;  // dV uses the dropped probabilities
         }
         mm_pb(dv, s, sdO, qc * 64, lane);  // dV += P^T dO
         mm_pb(dk, dp, sQ, qc * 64, lane);  // dK += dS^T Q
@@ -266,8 +289,11 @@ __global__ void __launch_bounds__(ab::kThreads, 1)
 using namespace bsi;
 
 extern "C" int bsi_attention_backward_bf16(void* dqkv_bf16, float* lse_ws, float* dsum_ws, const void* qkv_bf16, const void* out_bf16, const void* dout_bf16,
-                                           int32_t B, int32_t T, int32_t heads, int32_t head_dim, void* stream) {
-    BSI_CHECK_ARG(dqkv_bf16 && lse_ws && dsum_ws && qkv_bf16 && out_bf16 && dout_bf16 && B > 0 && heads > 0, "bsi_attention_backward_bf16: bad arguments");
+                                           int32_t B, int32_t T, int32_t heads, int32_t head_dim, float drop_p, uint32_t drop_seed, void* stream) {
+    BSI_CHECK_ARG(dqkv_bf16 && lse_ws && dsum_ws && qkv_bf16 && out_bf16 && dout_bf16 && B > 0 && heads > 0 && drop_p >= 0.0f && drop_p < 1.0f,
+                  "bsi_attention_backward_bf16: bad arguments");
+    const uint32_t drop_thresh = dropout_thresh(drop_p);
+    const float drop_inv = drop_p > 0.0f ? 1.0f / (1.0f - drop_p) : 1.0f;
     if (head_dim != ab::kHd || T % ab::kRows != 0 || T > 512) {
         set_error("bsi_attention_backward_bf16: only head_dim=64 and T in {128,256,384,512} are implemented (got head_dim=%d T=%d)", head_dim, T);
         return BSI_ERR_UNSUPPORTED;
@@ -279,11 +305,12 @@ extern "C" int bsi_attention_backward_bf16(void* dqkv_bf16, float* lse_ws, float
     BSI_ENSURE_SMEM(k_attention_bwd_q, smem_q);
     k_attention_bwd_q<<<grid, ab::kThreads, smem_q, (cudaStream_t)stream>>>((__nv_bfloat16*)dqkv_bf16, lse_ws, dsum_ws, (const __nv_bfloat16*)qkv_bf16,
                                                                            (const __nv_bfloat16*)out_bf16, (const __nv_bfloat16*)dout_bf16, T, dim, heads,
-                                                                           scale_log2, scale);
+                                                                           scale_log2, scale, drop_thresh, drop_seed, drop_inv);
     BSI_LAUNCH_OK("k_attention_bwd_q");
     BSI_ENSURE_SMEM(k_attention_bwd_kv, smem_kv);
     k_attention_bwd_kv<<<grid, ab::kThreads, smem_kv, (cudaStream_t)stream>>>((__nv_bfloat16*)dqkv_bf16, lse_ws, dsum_ws, (const __nv_bfloat16*)qkv_bf16,
-                                                                             (const __nv_bfloat16*)dout_bf16, T, dim, heads, scale_log2, scale);
+                                                                             (const __nv_bfloat16*)dout_bf16, T, dim, heads, scale_log2, scale, drop_thresh, drop_seed,
+                                                                             drop_inv);
     BSI_LAUNCH_OK("k_attention_bwd_kv");
     return BSI_OK;
 }

@@ -85,6 +85,20 @@ __device__ __forceinline__ float warp_max(float v) {
     return v;
 }
 
+// Counter-based dropout mask (training path): keep element `idx` of the stream keyed by `seed` with probability 1 - p, where
+// thresh = round(p * 2^32).  murmur3's 32-bit finaliser over a Weyl-multiplied index: stateless, so the forward and both backward
+// kernels regenerate the identical mask from (seed, index) instead of storing it (tests/helpers.py restates it in Python).
+__host__ __device__ __forceinline__ uint32_t mix32(uint32_t x) {
+    x ^= x >> 16;
+    x *= 0x85ebca6bu;
+    x ^= x >> 13;
+    x *= 0xc2b2ae35u;
+    x ^= x >> 16;
+    return x;
+}
+__host__ __device__ __forceinline__ bool dropout_keep(uint32_t seed, uint32_t idx, uint32_t thresh) { return mix32(idx * 0x9E3779B9u + seed) >= thresh; }
+__host__ __device__ __forceinline__ uint32_t dropout_thresh(float p) { return p <= 0.0f ? 0u : (uint32_t)((double)p * 4294967296.0); }
+
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
     __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<uint32_t*>(&v);

@@ -12,7 +12,7 @@ template <int NV>  // NV float4 per lane: dim = 128 * NV
 __global__ void __launch_bounds__(kLnThreads, 2)
     k_layernorm_mod(__nv_bfloat16* __restrict__ out, const float* __restrict__ x, bsi_rowref shift, bsi_rowref scale,
                     const int32_t* __restrict__ step_ptr, const float* __restrict__ gamma, const float* __restrict__ beta,
-                    int rows_per_sample, int64_t M, float eps) {
+                    int rows_per_sample, int64_t M, float eps, uint32_t drop_thresh, uint32_t drop_seed, float drop_inv) {
     constexpr int dim = 128 * NV;
     const int lane = threadIdx.x & 31;
     const int64_t warps_total = (int64_t)gridDim.x * (kLnThreads / 32);
@@ -53,6 +53,13 @@ __global__ void __launch_bounds__(kLnThreads, 2)
             float y1 = fmaf((v[i].y - mean) * rstd, m.y + one, a.y);
             float y2 = fmaf((v[i].z - mean) * rstd, m.z + one, a.z);
             float y3 = fmaf((v[i].w - mean) * rstd, m.w + one, a.w);
+            if (drop_thresh) {  // nn.Dropout on the modulated activations (training, dit.py:101): element index = row * dim + column
+                const uint32_t e = (uint32_t)row * dim + (lane + 32 * i) * 4;
+                y0 = dropout_keep(drop_seed, e, drop_thresh) ? y0 * drop_inv : 0.0f;
+                y1 = dropout_keep(drop_seed, e + 1, drop_thresh) ? y1 * drop_inv : 0.0f;
+                y2 = dropout_keep(drop_seed, e + 2, drop_thresh) ? y2 * drop_inv : 0.0f;
+                y3 = dropout_keep(drop_seed, e + 3, drop_thresh) ? y3 * drop_inv : 0.0f;
+            }
             o[lane + 32 * i] = make_uint2(pack_bf16(y0, y1), pack_bf16(y2, y3));
         }
     }
@@ -62,9 +69,11 @@ __global__ void __launch_bounds__(kLnThreads, 2)
 
 using namespace bsi;
 
-extern "C" int bsi_layernorm_mod_bf16(void* out_bf16, const float* x, bsi_rowref shift, bsi_rowref scale, const int32_t* step_ptr,
-                                      const float* gamma, const float* beta, int32_t rows_per_sample, int64_t M, int32_t dim,
-                                      float eps, void* stream) {
+static int layernorm_mod_launch(void* out_bf16, const float* x, bsi_rowref shift, bsi_rowref scale, const int32_t* step_ptr, const float* gamma,
+                                const float* beta, int32_t rows_per_sample, int64_t M, int32_t dim, float eps, float drop_p, uint32_t drop_seed,
+                                void* stream) {
+    const uint32_t drop_thresh = dropout_thresh(drop_p);
+    const float drop_inv = drop_p > 0.0f ? 1.0f / (1.0f - drop_p) : 1.0f;
     BSI_CHECK_ARG(out_bf16 && x && M > 0, "bsi_layernorm_mod_bf16: null pointer or empty input");
     BSI_CHECK_ARG((gamma && beta) || (shift.base && scale.base && rows_per_sample > 0),
                   "bsi_layernorm_mod_bf16: need either gamma/beta or shift/scale");
@@ -80,7 +89,7 @@ extern "C" int bsi_layernorm_mod_bf16(void* out_bf16, const float* x, bsi_rowref
     cfg.attrs = attr, cfg.numAttrs = use_pdl() ? 1 : 0;
 #define BSI_LN_CASE(NV)                                                                                                         \
     case NV:                                                                                                                    \
-        BSI_CUDA_OK(cudaLaunchKernelEx(&cfg, k_layernorm_mod<NV>, o, x, shift, scale, step_ptr, gamma, beta, rows_per_sample, M, eps)); \
+        BSI_CUDA_OK(cudaLaunchKernelEx(&cfg, k_layernorm_mod<NV>, o, x, shift, scale, step_ptr, gamma, beta, rows_per_sample, M, eps, drop_thresh, drop_seed, drop_inv)); \
         break;
     switch (dim / 128) {
         BSI_LN_CASE(1) BSI_LN_CASE(2) BSI_LN_CASE(3) BSI_LN_CASE(4) BSI_LN_CASE(5) BSI_LN_CASE(6) BSI_LN_CASE(7) BSI_LN_CASE(8)
@@ -90,4 +99,16 @@ extern "C" int bsi_layernorm_mod_bf16(void* out_bf16, const float* x, bsi_rowref
 #undef BSI_LN_CASE
     BSI_LAUNCH_OK("k_layernorm_mod");
     return BSI_OK;
+}
+
+extern "C" int bsi_layernorm_mod_bf16(void* out_bf16, const float* x, bsi_rowref shift, bsi_rowref scale, const int32_t* step_ptr,
+                                      const float* gamma, const float* beta, int32_t rows_per_sample, int64_t M, int32_t dim,
+                                      float eps, void* stream) {
+    return layernorm_mod_launch(out_bf16, x, shift, scale, step_ptr, gamma, beta, rows_per_sample, M, dim, eps, 0.0f, 0u, stream);
+}
+
+extern "C" int bsi_layernorm_mod_dropout_bf16(void* out_bf16, const float* x, bsi_rowref shift, bsi_rowref scale, int32_t rows_per_sample, int64_t M,
+                                              int32_t dim, float eps, float drop_p, uint32_t drop_seed, void* stream) {
+    BSI_CHECK_ARG(drop_p >= 0.0f && drop_p < 1.0f && M * dim < (int64_t)1 << 32, "bsi_layernorm_mod_dropout_bf16: p in [0,1) and M*dim < 2^32 required");
+    return layernorm_mod_launch(out_bf16, x, shift, scale, nullptr, nullptr, nullptr, rows_per_sample, M, dim, eps, drop_p, drop_seed, stream);
 }

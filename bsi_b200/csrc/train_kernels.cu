@@ -97,7 +97,7 @@ template <int NV>
 __global__ void __launch_bounds__(kTrThreads, 2)
     k_layernorm_mod_backward(float* __restrict__ dx_io, float* __restrict__ dscale_part, float* __restrict__ dshift_part, const __nv_bfloat16* __restrict__ da,
                              const float* __restrict__ x, bsi_rowref scale, const float* __restrict__ gamma, int rows_per_sample, int rows_per_cta,
-                             int64_t M, float eps) {
+                             int64_t M, float eps, uint32_t drop_thresh, uint32_t drop_seed, float drop_inv) {
     constexpr int dim = 128 * NV;
     extern __shared__ float ln_smem[];  // [8 warps][2][dim]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -132,7 +132,14 @@ __global__ void __launch_bounds__(kTrThreads, 2)
         for (int i = 0; i < NV; ++i) {
             v[i].x *= rstd, v[i].y *= rstd, v[i].z *= rstd, v[i].w *= rstd;  // xhat
             const uint2 a = ar[lane + 32 * i];
-            const float2 a0 = bf16x2_to_float2(a.x), a1 = bf16x2_to_float2(a.y);
+            float2 a0 = bf16x2_to_float2(a.x), a1 = bf16x2_to_float2(a.y);
+            if (drop_thresh) {  // the forward dropped / rescaled these outputs: the same mask applies to their gradient
+                const uint32_t e = (uint32_t)row * dim + (lane + 32 * i) * 4;
+                a0.x = dropout_keep(drop_seed, e, drop_thresh) ? a0.x * drop_inv : 0.0f;
+                a0.y = dropout_keep(drop_seed, e + 1, drop_thresh) ? a0.y * drop_inv : 0.0f;
+                a1.x = dropout_keep(drop_seed, e + 2, drop_thresh) ? a1.x * drop_inv : 0.0f;
+                a1.y = dropout_keep(drop_seed, e + 3, drop_thresh) ? a1.y * drop_inv : 0.0f;
+            }
             const float4 m = p_mul[lane + 32 * i];
             ps[i].x = fmaf(a0.x, v[i].x, ps[i].x), ps[i].y = fmaf(a0.y, v[i].y, ps[i].y), ps[i].z = fmaf(a1.x, v[i].z, ps[i].z), ps[i].w = fmaf(a1.y, v[i].w, ps[i].w);
             ph[i].x += a0.x, ph[i].y += a0.y, ph[i].z += a1.x, ph[i].w += a1.y;
@@ -269,7 +276,11 @@ int bsi_gelu_backward_bf16(void* dpre_bf16, const void* dout_bf16, const void* p
 }
 
 int bsi_layernorm_mod_backward(float* dx_io, float* dscale_part, float* dshift_part, const void* da_bf16, const float* x, bsi_rowref scale, const float* gamma,
-                               int32_t rows_per_sample, int32_t rows_per_cta, int64_t M, int32_t dim, float eps, void* stream) {
+                               int32_t rows_per_sample, int32_t rows_per_cta, int64_t M, int32_t dim, float eps, float drop_p, uint32_t drop_seed,
+                               void* stream) {
+    BSI_CHECK_ARG(drop_p >= 0.0f && drop_p < 1.0f && (drop_p == 0.0f || M * dim < (int64_t)1 << 32), "bsi_layernorm_mod_backward: bad dropout arguments");
+    const uint32_t drop_thresh = dropout_thresh(drop_p);
+    const float drop_inv = drop_p > 0.0f ? 1.0f / (1.0f - drop_p) : 1.0f;
     BSI_CHECK_ARG(dx_io && dscale_part && dshift_part && da_bf16 && x && M > 0, "bsi_layernorm_mod_backward: null pointer or empty input");
     BSI_CHECK_ARG(gamma || (scale.base && rows_per_sample > 0), "bsi_layernorm_mod_backward: need either gamma or scale");
     BSI_CHECK_ARG(dim % 128 == 0 && dim >= 128 && dim <= 1024, "bsi_layernorm_mod_backward: dim=%d must be a multiple of 128 in [128,1024]", dim);
@@ -280,7 +291,7 @@ int bsi_layernorm_mod_backward(float* dx_io, float* dscale_part, float* dshift_p
     case NV:                                                                                                                                  \
         BSI_ENSURE_SMEM(k_layernorm_mod_backward<NV>, smem);                                                                                   \
         k_layernorm_mod_backward<NV><<<grid, kTrThreads, smem, (cudaStream_t)stream>>>(dx_io, dscale_part, dshift_part, (const __nv_bfloat16*)da_bf16, x, \
-                                                                                       scale, gamma, rows_per_sample, rows_per_cta, M, eps); \
+                                                                                       scale, gamma, rows_per_sample, rows_per_cta, M, eps, drop_thresh, drop_seed, drop_inv); \
         break;
     switch (dim / 128) {
         BSI_LNB_CASE(1) BSI_LNB_CASE(2) BSI_LNB_CASE(3) BSI_LNB_CASE(4) BSI_LNB_CASE(5) BSI_LNB_CASE(6) BSI_LNB_CASE(7) BSI_LNB_CASE(8)

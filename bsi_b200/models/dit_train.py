@@ -15,7 +15,8 @@ GEMM, and runs the backward with
 What is still PyTorch here, and why: the adaLN / time-embedding chain on ``[B, 6*dim]`` tensors (O(batch) work, 0.2 % of the
 flops; differentiated by autograd through the ``mods`` argument, under bf16 autocast) and the final sums of per-CTA partial
 reductions (``[B, chunks, D]`` buffers).  Every pass over a token-sized tensor runs on this repo's kernels.
-Dropout is not implemented (the reference trains with dropout 0.05; construct the model with ``dropout=None`` for now).
+Dropout (the reference's experiments train with 0.05) is fused into the attention and LayerNorm kernels through a stateless hash
+mask (csrc/common.cuh ``dropout_keep``), which the backward kernels regenerate.
 """
 
 from __future__ import annotations
@@ -80,21 +81,28 @@ def _wgrad(dY: Tensor, X: Tensor) -> Tensor:
     return dW
 
 
-def _ln_mod(x: Tensor, shift: L.RowRef | None, scale: L.RowRef | None, T: int, gamma: Tensor | None = None, beta: Tensor | None = None) -> Tensor:
+def _ln_mod(x: Tensor, shift: L.RowRef | None, scale: L.RowRef | None, T: int, gamma: Tensor | None = None, beta: Tensor | None = None,
+            drop: tuple[float, int] = (0.0, 0)) -> Tensor:
     M, D = x.shape
     out = torch.empty((M, D), dtype=torch.bfloat16, device=x.device)
     none = L.RowRef(None, 0, 0)
+    if drop[0] > 0:
+        L.check(L.load().bsi_layernorm_mod_dropout_bf16(out.data_ptr(), x.data_ptr(), shift, scale, T, M, D, 1e-5, drop[0], drop[1], _st(x.device)),
+                "bsi_layernorm_mod_dropout_bf16")
+        return out
     L.check(L.load().bsi_layernorm_mod_bf16(out.data_ptr(), x.data_ptr(), shift or none, scale or none, None, L.ptr(gamma), L.ptr(beta), T, M, D, 1e-5,
                                             _st(x.device)), "bsi_layernorm_mod_bf16")
     return out
 
 
-def _ln_mod_backward(dx_io: Tensor, da: Tensor, x: Tensor, scale: L.RowRef | None, T: int, gamma: Tensor | None = None):
+def _ln_mod_backward(dx_io: Tensor, da: Tensor, x: Tensor, scale: L.RowRef | None, T: int, gamma: Tensor | None = None,
+                     drop: tuple[float, int] = (0.0, 0)):
     """dx_io += dL/dx; returns the per-CTA partial sums (dscale_part, dshift_part) [M / 32][D]."""
     M, D = x.shape
     parts = torch.empty((2, (M + _LN_ROWS_PER_CTA - 1) // _LN_ROWS_PER_CTA, D), dtype=torch.float32, device=x.device)
     L.check(L.load().bsi_layernorm_mod_backward(dx_io.data_ptr(), parts[0].data_ptr(), parts[1].data_ptr(), da.data_ptr(), x.data_ptr(),
-                                                scale or L.RowRef(None, 0, 0), L.ptr(gamma), T, _LN_ROWS_PER_CTA, M, D, 1e-5, _st(x.device)),
+                                                scale or L.RowRef(None, 0, 0), L.ptr(gamma), T, _LN_ROWS_PER_CTA, M, D, 1e-5, drop[0], drop[1],
+                                                _st(x.device)),
             "bsi_layernorm_mod_backward")
     return parts[0], parts[1]
 
@@ -103,7 +111,7 @@ class DiTTrainFunction(torch.autograd.Function):
     """out = DiT(in_scale * mu; mods, params).  Differentiable w.r.t. ``mods`` [L][B][6*dim] and the parameter list (not mu)."""
 
     @staticmethod
-    def forward(ctx, model, mu: Tensor, in_scale: Tensor | None, mods: Tensor, *params: Tensor):
+    def forward(ctx, model, mu: Tensor, in_scale: Tensor | None, drop: tuple[float, int], mods: Tensor, *params: Tensor):
         cfg = model._cfg
         dev = mu.device
         B, Cc, H, Wd = mu.shape
@@ -128,6 +136,7 @@ class DiTTrainFunction(torch.autograd.Function):
             wts.append(wt16)
             return w16
 
+        drop_p, drop_seed = drop
         with torch.cuda.device(dev):
             scale = torch.ones(1, dtype=torch.float32, device=dev) if in_scale is None else in_scale.detach().float().contiguous()
             K0 = _pad8(w_patch.shape[1])  # operand pitches are multiples of 16 bytes; the padding columns are zero on both sides
@@ -148,13 +157,17 @@ class DiTTrainFunction(torch.autograd.Function):
                 qkv = torch.empty((M, 3 * D), dtype=torch.bfloat16, device=dev)
                 _gemm(a1, bf(w_qkv), qkv, b_qkv.detach().float(), L.EPI_BIAS_BF16)
                 att = torch.empty((M, D), dtype=torch.bfloat16, device=dev)
-                L.check(lib.bsi_attention_bf16(att.data_ptr(), qkv.data_ptr(), B, T, heads, D // heads, _st(dev)), "bsi_attention_bf16")
+                if drop_p > 0:
+                    L.check(lib.bsi_attention_dropout_bf16(att.data_ptr(), qkv.data_ptr(), B, T, heads, D // heads, drop_p, _layer_seed(drop_seed, 2 * l),
+                                                           _st(dev)), "bsi_attention_dropout_bf16")
+                else:
+                    L.check(lib.bsi_attention_bf16(att.data_ptr(), qkv.data_ptr(), B, T, heads, D // heads, _st(dev)), "bsi_attention_bf16")
                 br1 = torch.empty((M, D), dtype=torch.bfloat16, device=dev)
                 _gemm(att, bf(w_o), br1, b_o.detach().float(), L.EPI_BIAS_BF16)
                 x_mid = torch.empty_like(x)  # out of place: x_in stays alive as this layer's saved input
                 L.check(lib.bsi_gate_residual(x_mid.data_ptr(), x.data_ptr(), br1.data_ptr(), ref(2), T, M, D, _st(dev)), "bsi_gate_residual")
                 x = x_mid
-                a2 = _ln_mod(x, ref(3), ref(4), T)
+                a2 = _ln_mod(x, ref(3), ref(4), T, drop=(drop_p, _layer_seed(drop_seed, 2 * l + 1)))
                 pre = torch.empty((M, 4 * D), dtype=torch.bfloat16, device=dev)
                 _gemm(a2, bf(w_1), pre, b_1.detach().float(), L.EPI_BIAS_BF16)
                 h = torch.empty_like(pre)
@@ -171,7 +184,7 @@ class DiTTrainFunction(torch.autograd.Function):
             _gemm(a_dec, bf(w_dec, pad_rows=Np), y, _pad_rows(b_dec.detach().float(), Np), L.EPI_BIAS_F32)
             gh, gw = H // p, Wd // p
             out = y[:, :n_out].reshape(B, gh, gw, p, p, Cc).permute(0, 5, 1, 3, 2, 4).reshape(B, Cc, H, Wd).contiguous()
-        ctx.model, ctx.geom = model, (B, Cc, H, Wd, T, M)
+        ctx.model, ctx.geom, ctx.drop = model, (B, Cc, H, Wd, T, M), drop
         ctx.saved_acts = (a0, x, a_dec, saved, wts)
         ctx.save_for_backward(mods, *params)
         return out
@@ -184,6 +197,7 @@ class DiTTrainFunction(torch.autograd.Function):
         B, Cc, H, Wd, T, M = ctx.geom
         p, D, depth, heads = cfg.patch, cfg.dim, cfg.depth, cfg.heads
         mods, *params = ctx.saved_tensors
+        drop_p, drop_seed = ctx.drop
         a0, x_last, a_dec, saved, wts = ctx.saved_acts
         wt_blocks = [wts[1 + 4 * l : 5 + 4 * l] for l in range(depth)]  # [patch | (qkv, out, mlp1, mlp2) per block | decoder]
         wt_dec = wts[-1]
@@ -236,7 +250,7 @@ class DiTTrainFunction(torch.autograd.Function):
                 L.check(lib.bsi_gelu_backward_bf16(dh.data_ptr(), dh.data_ptr(), pre.data_ptr(), dh.numel(), _st(dev)), "bsi_gelu_backward_bf16")
                 g_w1, g_b1 = _wgrad(dh, a2), colsum(dh)
                 _gemm(dh, wt_1, da, zeros(D), L.EPI_BIAS_BF16)
-                dsc, dsh = _ln_mod_backward(dx, da, x_mid, ref(4), T)
+                dsc, dsh = _ln_mod_backward(dx, da, x_mid, ref(4), T, drop=(drop_p, _layer_seed(drop_seed, 2 * l + 1)))
                 dm[:, 3 * D : 4 * D], dm[:, 4 * D : 5 * D] = part(dsh), part(dsc)
                 # ---- attention branch: x_mid = x_in + gate_msa * (attn(a1 Wqkv^T + b) Wo^T + b)
                 L.check(lib.bsi_gate_residual_backward(dbr.data_ptr(), dgate.data_ptr(), dbias.data_ptr(), dx.data_ptr(), br1.data_ptr(), ref(2), T, B, D,
@@ -245,7 +259,7 @@ class DiTTrainFunction(torch.autograd.Function):
                 g_wo, g_bo = _wgrad(dbr, att), dbias.sum(0)
                 datt = torch.empty((M, D), dtype=torch.bfloat16, device=dev)
                 _gemm(dbr, wt_o, datt, zeros(D), L.EPI_BIAS_BF16)
-                dqkv = _attention_backward(qkv, att, datt, B, T, heads, D // heads)
+                dqkv = _attention_backward(qkv, att, datt, B, T, heads, D // heads, (drop_p, _layer_seed(drop_seed, 2 * l)))
                 g_wqkv, g_bqkv = _wgrad(dqkv, a1), colsum(dqkv)
                 _gemm(dqkv, wt_qkv, da, zeros(D), L.EPI_BIAS_BF16)
                 dsc, dsh = _ln_mod_backward(dx, da, x_in, ref(1), T)
@@ -257,15 +271,15 @@ class DiTTrainFunction(torch.autograd.Function):
             for bg in reversed(block_grads):
                 grads += bg
             grads += tail
-        return (None, None, None, dmods.to(ctx.mods_dtype), *grads)
+        return (None, None, None, None, dmods.to(ctx.mods_dtype), *grads)
 
 
-def _attention_backward(qkv: Tensor, att: Tensor, datt: Tensor, B: int, T: int, heads: int, hd: int) -> Tensor:
+def _attention_backward(qkv: Tensor, att: Tensor, datt: Tensor, B: int, T: int, heads: int, hd: int, drop: tuple[float, int] = (0.0, 0)) -> Tensor:
     """d(qkv) of att = attention(qkv) on the packed [B*T][3*dim] layout (two mma.sync kernels, attention_bwd.cu)."""
     dqkv = torch.empty_like(qkv)
     ws = torch.empty((2, B * heads * T), dtype=torch.float32, device=qkv.device)
     L.check(L.load().bsi_attention_backward_bf16(dqkv.data_ptr(), ws[0].data_ptr(), ws[1].data_ptr(), qkv.data_ptr(), att.data_ptr(), datt.data_ptr(),
-                                                 B, T, heads, hd, _st(qkv.device)), "bsi_attention_backward_bf16")
+                                                 B, T, heads, hd, drop[0], drop[1], _st(qkv.device)), "bsi_attention_backward_bf16")
     return dqkv
 
 
@@ -280,13 +294,28 @@ def trainable_parameters(model) -> list[Tensor]:
     return ps
 
 
-def forward_train(model, mu: Tensor, t: Tensor, in_scale: Tensor | None) -> Tensor:
-    """f(in_scale * mu, t) with autograd support for every parameter of the DiT."""
-    for blk in model.dit.blocks:
-        if isinstance(blk.dropout, torch.nn.Dropout) and blk.dropout.p > 0 and model.training:
-            raise NotImplementedError("dropout is not implemented in the native training path: construct DenoisingDiT(dropout=None) or call .eval()")
+def _layer_seed(seed: int, k: int) -> int:
+    """Distinct 32-bit stream key per (call, layer, site) from the call's seed (host-side integer hash)."""
+    x = (seed + 0x9E3779B9 * (k + 1)) & 0xFFFFFFFF
+    x ^= x >> 16
+    x = (x * 0x85EBCA6B) & 0xFFFFFFFF
+    x ^= x >> 13
+    x = (x * 0xC2B2AE35) & 0xFFFFFFFF
+    return x ^ (x >> 16)
+
+
+def forward_train(model, mu: Tensor, t: Tensor, in_scale: Tensor | None, seed: int | None = None) -> Tensor:
+    """f(in_scale * mu, t) with autograd support for every parameter of the DiT.
+
+    In ``train()`` mode with ``dropout=p`` the reference's two dropout sites are active (dit.py:43-44 on the attention
+    probabilities, :101 on the MLP input); their masks are stateless hashes of a per-call seed drawn from torch's CPU
+    generator (or ``seed``), regenerated in the backward kernels instead of being stored."""
+    blk0 = model.dit.blocks[0]
+    drop_p = float(blk0.dropout.p) if model.training and isinstance(blk0.dropout, torch.nn.Dropout) else 0.0
+    if drop_p > 0 and seed is None:
+        seed = int(torch.randint(0, 2**31 - 1, (1,)).item())  # CPU generator: no device synchronisation
     cond = model.dit.t_embedding(t.to(torch.float32))
     # the conditioning chain runs on bf16 tensor cores like the inference engine's (and the reference under bf16 autocast)
     with torch.autocast("cuda", dtype=torch.bfloat16):
         mods = torch.stack([blk.adaLN_modulation(cond) for blk in model.dit.blocks])
-    return DiTTrainFunction.apply(model, mu, in_scale, mods, *trainable_parameters(model))
+    return DiTTrainFunction.apply(model, mu, in_scale, (drop_p, int(seed or 0)), mods, *trainable_parameters(model))

@@ -212,7 +212,15 @@ int bsi_attention_force_legacy(int32_t on);
  * the saved forward output and the upstream gradient dout bf16 [B*T][dim].  lse_ws / dsum_ws: B*heads*T floats of scratch each
  * (log-sum-exp of the scaled scores and sum_c dout*out per query row; written by the first kernel, read by the second). */
 int bsi_attention_backward_bf16(void* dqkv_bf16, float* lse_ws, float* dsum_ws, const void* qkv_bf16, const void* out_bf16, const void* dout_bf16,
-                                int32_t B, int32_t T, int32_t heads, int32_t head_dim, void* stream);
+                                int32_t B, int32_t T, int32_t heads, int32_t head_dim, float drop_p, uint32_t drop_seed, void* stream);
+/* Training-mode attention with dropout on the probabilities (F.scaled_dot_product_attention(dropout_p), dit.py:43-44).  The keep mask
+ * is a stateless hash of (drop_seed, head of sample, query, key) -- mix32 in csrc/common.cuh -- which bsi_attention_backward_bf16
+ * regenerates from the same (drop_p, drop_seed); drop_p = 0 there means the forward ran without dropout. */
+int bsi_attention_dropout_bf16(void* out_bf16, const void* qkv_bf16, int32_t B, int32_t T, int32_t heads, int32_t head_dim, float drop_p,
+                               uint32_t drop_seed, void* stream);
+/* bsi_layernorm_mod_bf16 followed by nn.Dropout(drop_p) on its output (dit.py:101), mask = hash of (drop_seed, row * dim + column). */
+int bsi_layernorm_mod_dropout_bf16(void* out_bf16, const float* x, bsi_rowref shift, bsi_rowref scale, int32_t rows_per_sample, int64_t M,
+                                   int32_t dim, float eps, float drop_p, uint32_t drop_seed, void* stream);
 
 /* Patch-embed operand (dit.py:149-153,228-231; fourier_features.py:24-36):
  *   A[b*T + tok][(py*p+px)*Cin + c] = bf16( feature_c( scale[b] * mu[b,:,y,x] ) )
@@ -338,9 +346,11 @@ int bsi_gelu_bf16(void* out_bf16, const void* pre_bf16, int64_t numel, void* str
 int bsi_gelu_backward_bf16(void* dpre_bf16, const void* dout_bf16, const void* pre_bf16, int64_t numel, void* stream);
 /* Backward of a = LayerNorm(x) * (1 + scale[b]) + shift[b]  (gamma == NULL)  or  a = LayerNorm(x) * gamma + beta  (gamma != NULL):
  *   dx_io[row] += dL/dx;  dscale_part / dshift_part [ceil(M / rows_per_cta)][dim]: per-CTA partial sums of da*xhat and da over
- *   rows_per_cta consecutive rows (rows_per_cta divides rows_per_sample); the caller adds the partials of a sample. */
+ *   rows_per_cta consecutive rows (rows_per_cta divides rows_per_sample); the caller adds the partials of a sample.
+ *   drop_p > 0: the forward was bsi_layernorm_mod_dropout_bf16 with the same (drop_p, drop_seed). */
 int bsi_layernorm_mod_backward(float* dx_io, float* dscale_part, float* dshift_part, const void* da_bf16, const float* x, bsi_rowref scale,
-                               const float* gamma, int32_t rows_per_sample, int32_t rows_per_cta, int64_t M, int32_t dim, float eps, void* stream);
+                               const float* gamma, int32_t rows_per_sample, int32_t rows_per_cta, int64_t M, int32_t dim, float eps, float drop_p,
+                               uint32_t drop_seed, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Optimizer side of the training step over flat fp32 arenas of `numel` elements

@@ -172,6 +172,33 @@ def optim_grad(i: int, step: int) -> torch.Tensor:
     return det_uniform(f"optim.g{i}.{step}", OPTIM_SHAPES[i]) * scale
 
 
+def _mix32(x: torch.Tensor) -> torch.Tensor:
+    """csrc/common.cuh mix32 on int64 tensors holding uint32 values."""
+    m = 0xFFFFFFFF
+    x = x & m
+    x = x ^ (x >> 16)
+    x = (x * 0x85EBCA6B) & m
+    x = x ^ (x >> 13)
+    x = (x * 0xC2B2AE35) & m
+    return x ^ (x >> 16)
+
+
+def dropout_keep(seed: int, idx: torch.Tensor, p: float) -> torch.Tensor:
+    """Keep mask of the native kernels' stateless dropout (csrc/common.cuh dropout_keep) for element indices `idx` (int64)."""
+    thresh = int(float(np.float32(p)) * 4294967296.0)
+    return _mix32((idx * 0x9E3779B9 + seed) & 0xFFFFFFFF) >= thresh
+
+
+def attention_dropout_mask(seed: int, B: int, heads: int, T: int, p: float) -> torch.Tensor:
+    """[B, heads, T(query), T(key)] keep mask of bsi_attention_dropout_bf16 / bsi_attention_backward_bf16."""
+    bh = torch.arange(B * heads, dtype=torch.int64)
+    sd = _mix32((seed ^ ((bh * 0x9E3779B9) & 0xFFFFFFFF)) & 0xFFFFFFFF)
+    idx = torch.arange(T * T, dtype=torch.int64)
+    thresh = int(float(np.float32(p)) * 4294967296.0)
+    keep = _mix32((idx[None, :] * 0x9E3779B9 + sd[:, None]) & 0xFFFFFFFF) >= thresh
+    return keep.reshape(B, heads, T, T)
+
+
 def import_reference():
     """Import the real reference package (build container only)."""
     if REFERENCE_DIR not in sys.path:

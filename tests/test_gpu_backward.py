@@ -6,6 +6,7 @@ import pytest
 import torch
 import torch.nn.functional as F
 
+import helpers as H
 from gpu_util import call, dev, report, sync
 from bsi_b200 import _lib as L
 from test_gpu_gemm import gemm, rnd
@@ -129,7 +130,7 @@ def test_layernorm_mod_backward_vs_autograd(dim):
     dx = dx0.clone()
     parts = torch.zeros((2, M // rpc, dim), device=dev())
     call("bsi_layernorm_mod_backward", L.ptr(dx), L.ptr(parts[0]), L.ptr(parts[1]), L.ptr(da), L.ptr(x), L.rowref(tab, 6 * dim, 0, dim), None, T, rpc, M, dim,
-         1e-5, L.stream_ptr())
+         1e-5, 0.0, 0, L.stream_ptr())
     sync()
     report(f"ln-mod dx {dim}", dx, dx0 + xr.grad, 1e-4, 1e-4)
     report(f"ln-mod dscale {dim}", parts[0].reshape(B, T // rpc, dim).sum(1), sc.grad, 1e-4, 1e-3)
@@ -142,7 +143,7 @@ def test_layernorm_mod_backward_vs_autograd(dim):
     dx = torch.zeros_like(x)
     parts.zero_()
     call("bsi_layernorm_mod_backward", L.ptr(dx), L.ptr(parts[0]), L.ptr(parts[1]), L.ptr(da), L.ptr(x), L.RowRef(None, 0, 0), L.ptr(gamma.detach()), T, rpc, M, dim,
-         1e-5, L.stream_ptr())
+         1e-5, 0.0, 0, L.stream_ptr())
     sync()
     report(f"ln-affine dx {dim}", dx, xr2.grad, 1e-4, 1e-4)
     report(f"ln-affine dgamma {dim}", parts[0].sum(0), gamma.grad, 1e-4, 2e-3)
@@ -169,7 +170,7 @@ def test_attention_backward_vs_autograd(B, T, heads):
     call("bsi_attention_bf16", L.ptr(out), L.ptr(qkv), B, T, heads, hd, L.stream_ptr())
     dqkv = torch.full((B * T, 3 * dim), float("nan"), dtype=torch.bfloat16, device=dev())
     ws = torch.zeros((2, B * heads * T), device=dev())
-    call("bsi_attention_backward_bf16", L.ptr(dqkv), L.ptr(ws[0]), L.ptr(ws[1]), L.ptr(qkv), L.ptr(out), L.ptr(dout), B, T, heads, hd, L.stream_ptr())
+    call("bsi_attention_backward_bf16", L.ptr(dqkv), L.ptr(ws[0]), L.ptr(ws[1]), L.ptr(qkv), L.ptr(out), L.ptr(dout), B, T, heads, hd, 0.0, 0, L.stream_ptr())
     sync()
     q, k, v = (t.detach().requires_grad_(True) for t in qkv.float().reshape(B, T, 3, heads, hd).permute(2, 0, 3, 1, 4))
     o = F.scaled_dot_product_attention(q, k, v)
@@ -182,3 +183,59 @@ def test_attention_backward_vs_autograd(B, T, heads):
         rel = float((got - want).norm() / want.norm())
         assert rel < 1.5e-2, f"{name}: relative L2 error {rel}"
         report(name, got, want, 5e-2, 2e-2 * float(want.abs().max()))
+
+
+def test_layernorm_dropout_forward_backward_with_restated_mask():
+    """nn.Dropout on the modulated activations (dit.py:101): the kernels' stateless mask is restated in Python (helpers.dropout_keep)
+    and fed to torch autograd as an explicit tensor."""
+    B, T, dim, rpc, p, seed = 2, 256, 256, 32, 0.3, 0xC0FFEE
+    M = B * T
+    x = rnd("ld.x", (M, dim), 1.2)
+    tab = rnd("ld.t", (B, 6 * dim), 0.5)
+    out = torch.zeros((M, dim), dtype=torch.bfloat16, device=dev())
+    call("bsi_layernorm_mod_dropout_bf16", L.ptr(out), L.ptr(x), L.rowref(tab, 6 * dim, 0, 0), L.rowref(tab, 6 * dim, 0, dim), T, M, dim, 1e-5, p, seed,
+         L.stream_ptr())
+    keep = H.dropout_keep(seed, torch.arange(M * dim, dtype=torch.int64), p).reshape(M, dim).to(dev())
+    assert abs(float(keep.float().mean()) - (1 - p)) < 5e-3
+    xr = x.clone().requires_grad_(True)
+    a = torch.addcmul(tab[:, None, :dim], tab[:, None, dim : 2 * dim] + 1, F.layer_norm(xr, (dim,), eps=1e-5).reshape(B, T, dim)).reshape(M, dim)
+    ref = a * keep / (1 - p)
+    sync()
+    report("ln dropout forward", out, ref, 1e-2, 1e-2)
+    assert torch.equal(out == 0, ~keep | (ref.bfloat16() == 0))  # exactly the restated mask
+    da = rnd("ld.da", (M, dim)).bfloat16()
+    ref.backward(da.float())
+    dx = torch.zeros_like(x)
+    parts = torch.zeros((2, M // rpc, dim), device=dev())
+    call("bsi_layernorm_mod_backward", L.ptr(dx), L.ptr(parts[0]), L.ptr(parts[1]), L.ptr(da), L.ptr(x), L.rowref(tab, 6 * dim, 0, dim), None, T, rpc, M, dim,
+         1e-5, p, seed, L.stream_ptr())
+    sync()
+    report("ln dropout backward dx", dx, xr.grad, 1e-4, 1e-4)
+
+
+@pytest.mark.parametrize("B,T,heads,p", [(2, 256, 2, 0.05), (1, 128, 3, 0.5)])
+def test_attention_dropout_forward_backward_with_restated_mask(B, T, heads, p):
+    """Attention dropout (F.scaled_dot_product_attention(dropout_p), dit.py:43-44) forward and backward against torch autograd with
+    the kernels' mask restated in Python."""
+    hd, dim, seed = 64, heads * 64, 20261017
+    qkv = rnd(f"ad.qkv{T}", (B * T, 3 * dim), 2.0).bfloat16()
+    dout = rnd(f"ad.do{T}", (B * T, dim)).bfloat16()
+    out = torch.zeros((B * T, dim), dtype=torch.bfloat16, device=dev())
+    call("bsi_attention_dropout_bf16", L.ptr(out), L.ptr(qkv), B, T, heads, hd, p, seed, L.stream_ptr())
+    dqkv = torch.full((B * T, 3 * dim), float("nan"), dtype=torch.bfloat16, device=dev())
+    ws = torch.zeros((2, B * heads * T), device=dev())
+    call("bsi_attention_backward_bf16", L.ptr(dqkv), L.ptr(ws[0]), L.ptr(ws[1]), L.ptr(qkv), L.ptr(out), L.ptr(dout), B, T, heads, hd, p, seed, L.stream_ptr())
+    sync()
+    keep = H.attention_dropout_mask(seed, B, heads, T, p).to(dev())
+    assert abs(float(keep.float().mean()) - (1 - p)) < 1e-2
+    q, k, v = (t.detach().requires_grad_(True) for t in qkv.float().reshape(B, T, 3, heads, hd).permute(2, 0, 3, 1, 4))
+    prob = torch.softmax(q @ k.transpose(-1, -2) / 8.0, dim=-1) * keep / (1 - p)
+    o = prob @ v
+    o.backward(dout.float().reshape(B, T, heads, hd).permute(0, 2, 1, 3))
+    o_ref = o.detach().permute(0, 2, 1, 3).reshape(B * T, dim)
+    assert float((out.float() - o_ref).norm() / o_ref.norm()) < 1e-2
+    ref = torch.stack((q.grad, k.grad, v.grad)).permute(1, 3, 0, 2, 4).reshape(B * T, 3 * dim)
+    for name, sl in (("dq", slice(0, dim)), ("dk", slice(dim, 2 * dim)), ("dv", slice(2 * dim, 3 * dim))):
+        got, want = dqkv[:, sl].float(), ref[:, sl]
+        rel = float((got - want).norm() / want.norm())
+        assert rel < 2e-2, f"{name}: relative L2 error {rel}"

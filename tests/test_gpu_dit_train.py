@@ -63,7 +63,7 @@ def test_forward_and_all_gradients_vs_oracle_autograd(name):
     assert not bad, f"gradient mismatch (relative L2): {bad}"
 
 
-def test_inference_path_is_unchanged_and_dropout_is_rejected():
+def test_inference_path_is_unchanged():
     spec = SPECS["small64"]
     m, sd = build(spec)
     mu = H.det_uniform("dt.inf.mu", (2, *spec.data_shape)).to(dev())
@@ -73,12 +73,40 @@ def test_inference_path_is_unchanged_and_dropout_is_rejected():
     y_tr = m(mu, t)
     assert not y_inf.requires_grad and y_tr.requires_grad
     assert rel(y_tr, y_inf) < 1e-2  # same kernels, fused differently (fp32 adaLN chain in the training path)
+
+
+def test_dropout_in_training_mode():
+    """dropout=0.05 as in config/experiment/imagenet64.yaml:39: train() applies the two dropout sites (stateless masks keyed by a
+    per-call seed), eval() is the identity, a fixed seed reproduces forward and gradients bit for bit."""
+    from bsi_b200.models.dit_train import forward_train
+
+    spec = SPECS["small64"]
+    m, sd = build(spec)
     ff = FourierFeatures(n_min=6, n_max=8)
-    md = DenoisingDiT(spec.data_shape, spec.patch, spec.dim, spec.depth, spec.heads, dropout=0.05, fourier_features=ff).to(dev()).train()
-    with pytest.raises(NotImplementedError, match="dropout"):
-        md(mu, t)
+    md = DenoisingDiT(spec.data_shape, spec.patch, spec.dim, spec.depth, spec.heads, dropout=0.05, fourier_features=ff)
+    md.load_state_dict(sd)
+    md = md.to(dev()).train()
+    mu = H.det_uniform("dt.drop.mu", (2, *spec.data_shape)).to(dev())
+    t = torch.tensor([0.3, 0.9], device=dev())
+    y_plain = m(mu, t)
+    y1 = forward_train(md, mu, t, None, seed=11)
+    y1.square().sum().backward()
+    g1 = [p.grad.clone() for p in md.parameters()]
+    md.zero_grad()
+    y2 = forward_train(md, mu, t, None, seed=11)
+    y2.square().sum().backward()
+    y3 = forward_train(md, mu, t, None, seed=12)
+    assert torch.equal(y1, y2) and all(torch.equal(a, p.grad) for a, p in zip(g1, md.parameters()))
+    assert not torch.equal(y1, y3)
+    assert 1e-3 < rel(y1, y_plain) < 0.5  # dropout perturbs the output, moderately at p = 0.05
+    assert all(torch.isfinite(g).all() and float(g.abs().max()) > 0 for g in g1)
+    torch.manual_seed(5)
+    ya = md(mu, t)
+    torch.manual_seed(5)
+    yb = md(mu, t)
+    assert torch.equal(ya, yb) and not torch.equal(ya, md(mu, t))  # seeds come from torch's CPU generator
     md.eval()
-    assert md(mu, t).requires_grad  # eval(): dropout is the identity, training through the model is allowed
+    assert rel(md(mu, t), y_plain) == 0.0  # eval(): no dropout, same result as the dropout-free model
 
 
 def test_train_loss_backward_through_native_dit():

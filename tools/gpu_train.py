@@ -26,6 +26,7 @@ ap.add_argument("--micro", type=int, default=256)
 ap.add_argument("--depth", type=int, default=24)
 ap.add_argument("--steps", type=int, default=3)
 ap.add_argument("--profile", action="store_true")
+ap.add_argument("--dropout", type=float, default=0.0, help="0.05 in config/experiment/imagenet64.yaml")
 a = ap.parse_args()
 
 world, rank, local_rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
@@ -38,7 +39,7 @@ micro = min(a.micro, local)
 assert local % micro == 0 and a.global_batch % world == 0
 
 torch.manual_seed(0)  # identical replicas on every rank
-model = DenoisingDiT((3, 64, 64), 4, 1024, a.depth, 16, dropout=None, fourier_features=FourierFeatures(n_min=6, n_max=8)).to(dev).train()
+model = DenoisingDiT((3, 64, 64), 4, 1024, a.depth, 16, dropout=a.dropout or None, fourier_features=FourierFeatures(n_min=6, n_max=8)).to(dev).train()
 with torch.no_grad():
     for blk in model.dit.blocks:  # adaLN-Zero would make every block the identity
         torch.nn.init.normal_(blk.adaLN_modulation[-1].weight, std=0.02)
@@ -86,7 +87,7 @@ ms = float(ms)
 flops = a.global_batch * 3 * (161.26e9 * a.depth / 24 + 0.352e9)  # forward + dgrad + wgrad per sample
 if rank == 0:
     print(json.dumps(dict(what="imagenet64-dit train step (native path)", n_gpus=world, global_batch=a.global_batch, per_gpu_batch=local, micro_batch=micro,
-                          depth=a.depth, ms_per_step=ms, samples_per_s=a.global_batch / ms * 1e3, tflops_total=flops / ms / 1e9,
+                          depth=a.depth, dropout=a.dropout, ms_per_step=ms, samples_per_s=a.global_batch / ms * 1e3, tflops_total=flops / ms / 1e9,
                           tflops_per_gpu=flops / ms / 1e9 / world, peak_mem_gb=torch.cuda.max_memory_allocated() / 2**30, loss=float(loss),
                           grad_norm=float(opt.total_grad_norm()), params=sum(p.numel() for p in model.parameters()))), flush=True)
 
