@@ -72,10 +72,10 @@ def _gemm(A: Tensor, W: Tensor, out: Tensor, bias: Tensor, epi: int, *, pos: Ten
     L.check(L.load().bsi_gemm_bf16(C.byref(a), _st(A.device)), "bsi_gemm_bf16")
 
 
-def _wgrad(dY: Tensor, X: Tensor) -> Tensor:
-    """dW[N][K] = dY[M][N]^T @ X[M][K] (fp32)."""
+def _wgrad(dY: Tensor, X: Tensor, into: Tensor | None = None) -> Tensor:
+    """dW[N][K] (+)= dY[M][N]^T @ X[M][K] (fp32): a fresh tensor, or accumulated in place into `into` (a gradient-arena slice)."""
     M, N, K = dY.shape[0], dY.shape[1], X.shape[1]
-    dW = torch.zeros((N, K), dtype=torch.float32, device=dY.device)
+    dW = into if into is not None else torch.zeros((N, K), dtype=torch.float32, device=dY.device)
     L.check(L.load().bsi_gemm_wgrad_bf16(dW.data_ptr(), dY.data_ptr(), X.data_ptr(), M, N, K, dY.stride(0), X.stride(0), K, 0, _st(dY.device)),
             "bsi_gemm_wgrad_bf16")
     return dW
@@ -216,18 +216,44 @@ class DiTTrainFunction(torch.autograd.Function):
 
         zeros = lambda n: torch.zeros(n, dtype=torch.float32, device=dev)
         grads: list[Tensor] = []
+        sink = getattr(model, "_grad_sink", None)
+
+        def emit_w(p: Tensor, dY: Tensor, X: Tensor, rows: int | None = None, cols: int | None = None):
+            """Weight gradient of `p`: accumulated by the GEMM straight into the optimizer's arena when one is attached (returns
+            None: autograd has nothing left to add), else returned as a tensor."""
+            view = sink.grad_view(p) if sink is not None else None
+            if view is not None and rows is None and cols is None:
+                _wgrad(dY, X, into=view)
+                return None
+            g = _wgrad(dY, X)
+            g = g[:rows] if rows is not None else g
+            g = g[:, :cols] if cols is not None else g
+            if view is not None:
+                view.add_(g)
+                return None
+            return g
+
+        def emit_b(p: Tensor, g: Tensor):
+            view = sink.grad_view(p) if sink is not None else None
+            if view is not None:
+                view.add_(g)
+                return None
+            return g
+
         with torch.cuda.device(dev):
             gh, gw = H // p, Wd // p
             dy = dout.float().reshape(B, Cc, gh, p, gw, p).permute(0, 2, 4, 3, 5, 1).reshape(M, p * p * Cc)
             n_out = w_dec.shape[0]
             Np = _pad8(n_out)
             dy16 = _pad_cols(dy.to(torch.bfloat16), Np)
-            g_wdec, g_bdec = _wgrad(dy16, a_dec)[:n_out], colsum(dy)
+            g_wdec, g_bdec = emit_w(w_dec, dy16, a_dec, rows=n_out), emit_b(b_dec, colsum(dy))
             da = torch.empty((M, D), dtype=torch.bfloat16, device=dev)
             _gemm(dy16, wt_dec, da, zeros(D), L.EPI_BIAS_BF16)  # W^T [D][Np]: the forward kernel computes dY @ W
             dx = torch.zeros((M, D), dtype=torch.float32, device=dev)
             dg_part, db_part = _ln_mod_backward(dx, da, x_last, None, T, ln_g.detach().float().contiguous())
-            tail = [dg_part.sum(0), db_part.sum(0), g_wdec, g_bdec]
+            tail = [emit_b(ln_g, dg_part.sum(0)), emit_b(ln_b, db_part.sum(0)), g_wdec, g_bdec]
+            if sink is not None:
+                sink.grads_ready([ln_g, ln_b, w_dec, b_dec])
             dmods = torch.empty_like(mods)
             block_grads = []
             for l in reversed(range(depth)):
@@ -244,11 +270,11 @@ class DiTTrainFunction(torch.autograd.Function):
                 L.check(lib.bsi_gate_residual_backward(dbr.data_ptr(), dgate.data_ptr(), dbias.data_ptr(), dx.data_ptr(), br2.data_ptr(), ref(5), T, B, D,
                                                        _st(dev)), "bsi_gate_residual_backward")
                 dm[:, 5 * D :] = dgate
-                g_w2, g_b2 = _wgrad(dbr, h), dbias.sum(0)
+                g_w2, g_b2 = emit_w(w_2, dbr, h), emit_b(b_2, dbias.sum(0))
                 dh = torch.empty((M, 4 * D), dtype=torch.bfloat16, device=dev)
                 _gemm(dbr, wt_2, dh, zeros(4 * D), L.EPI_BIAS_BF16)
                 L.check(lib.bsi_gelu_backward_bf16(dh.data_ptr(), dh.data_ptr(), pre.data_ptr(), dh.numel(), _st(dev)), "bsi_gelu_backward_bf16")
-                g_w1, g_b1 = _wgrad(dh, a2), colsum(dh)
+                g_w1, g_b1 = emit_w(w_1, dh, a2), emit_b(b_1, colsum(dh))
                 _gemm(dh, wt_1, da, zeros(D), L.EPI_BIAS_BF16)
                 dsc, dsh = _ln_mod_backward(dx, da, x_mid, ref(4), T, drop=(drop_p, _layer_seed(drop_seed, 2 * l + 1)))
                 dm[:, 3 * D : 4 * D], dm[:, 4 * D : 5 * D] = part(dsh), part(dsc)
@@ -256,18 +282,22 @@ class DiTTrainFunction(torch.autograd.Function):
                 L.check(lib.bsi_gate_residual_backward(dbr.data_ptr(), dgate.data_ptr(), dbias.data_ptr(), dx.data_ptr(), br1.data_ptr(), ref(2), T, B, D,
                                                        _st(dev)), "bsi_gate_residual_backward")
                 dm[:, 2 * D : 3 * D] = dgate
-                g_wo, g_bo = _wgrad(dbr, att), dbias.sum(0)
+                g_wo, g_bo = emit_w(w_o, dbr, att), emit_b(b_o, dbias.sum(0))
                 datt = torch.empty((M, D), dtype=torch.bfloat16, device=dev)
                 _gemm(dbr, wt_o, datt, zeros(D), L.EPI_BIAS_BF16)
                 dqkv = _attention_backward(qkv, att, datt, B, T, heads, D // heads, (drop_p, _layer_seed(drop_seed, 2 * l)))
-                g_wqkv, g_bqkv = _wgrad(dqkv, a1), colsum(dqkv)
+                g_wqkv, g_bqkv = emit_w(w_qkv, dqkv, a1), emit_b(b_qkv, colsum(dqkv))
                 _gemm(dqkv, wt_qkv, da, zeros(D), L.EPI_BIAS_BF16)
                 dsc, dsh = _ln_mod_backward(dx, da, x_in, ref(1), T)
                 dm[:, :D], dm[:, D : 2 * D] = part(dsh), part(dsc)
                 block_grads.append([g_wqkv, g_bqkv, g_wo, g_bo, g_w1, g_b1, g_w2, g_b2])
+                if sink is not None:  # this block's eight tensors are final: their all-reduce can overlap the remaining layers
+                    sink.grads_ready([w_qkv, b_qkv, w_o, b_o, w_1, b_1, w_2, b_2])
                 saved[l] = None  # release this layer's activations
             dx16 = dx.to(torch.bfloat16)
-            grads = [_wgrad(dx16, a0)[:, : w_patch.shape[1]], colsum(dx)]
+            grads = [emit_w(w_patch, dx16, a0, cols=w_patch.shape[1]), emit_b(b_patch, colsum(dx))]
+            if sink is not None:
+                sink.grads_ready([w_patch, b_patch])
             for bg in reversed(block_grads):
                 grads += bg
             grads += tail

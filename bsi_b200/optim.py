@@ -196,6 +196,8 @@ class AdamW(torch.optim.Optimizer):
         self._sumsq = torch.zeros(1, dtype=torch.float32, device=dev)
         self._ws = torch.empty(int(self._lib.bsi_grad_sumsq_workspace_floats()), dtype=torch.float32, device=dev)
         self._t = 0
+        self._pending, self._reduced, self._index = [], [], {}
+        self._overlap, self._sync, self._group = False, True, None
         self._last_scale = 1.0
         self._ema: EMA | None = None
         self._grad_scale = 1.0  # 1/world_size once all_reduce_grads() has summed the arena over ranks
@@ -223,14 +225,70 @@ class AdamW(torch.optim.Optimizer):
         return self._sumsq.sqrt() * self._last_scale
 
     def all_reduce_grads(self, group=None) -> None:
-        """Data-parallel gradient exchange (``DistributedDataParallel`` of bsi/tasks/bsi.py:163-166) as ONE sum all-reduce over
+        """Data-parallel gradient exchange (``DistributedDataParallel`` of bsi/tasks/bsi.py:163-166) as sum all-reduces over
         the flat gradient arena (NCCL over NVLink); the division by the world size is folded into the next ``step()``.
-        Call between ``backward()`` and ``step()`` with the model *not* wrapped in DDP."""
+        Call between ``backward()`` and ``step()`` with the model *not* wrapped in DDP.  Ranges that ``attach_model`` already
+        reduced during the backward pass are skipped; everything else goes out as one collective per remaining range."""
         import torch.distributed as dist
 
         self._gather_grads()
-        dist.all_reduce(self._g.flat, op=dist.ReduceOp.SUM, group=group)
+        done = sorted(self._reduced)
+        start = 0
+        for a, b in done + [(self._g.numel, self._g.numel)]:
+            if a > start:
+                dist.all_reduce(self._g.flat[start:a], op=dist.ReduceOp.SUM, group=group)
+            start = max(start, b)
+        for h in self._pending:
+            h.wait()
+        self._pending, self._reduced = [], []
         self._grad_scale = 1.0 / dist.get_world_size(group)
+
+    # --- direct gradient sink for the native training path (bsi_b200/models/dit_train.py)
+    def attach_model(self, model, overlap: bool = True, group=None) -> None:
+        """Let the native ``DenoisingDiT`` backward write weight gradients straight into this optimizer's gradient arena (the
+        weight-gradient GEMM accumulates in place: no temporaries, no autograd ``+=`` pass) and, under ``torch.distributed``,
+        start the all-reduce of each transformer block's gradient range as soon as the block's backward is done, so that the
+        exchange overlaps the rest of the backward pass (what DDP's bucketed hooks do, bsi/tasks/bsi.py:163-166)."""
+        model._grad_sink = self
+        self._overlap, self._group = overlap, group
+        self._index = {id(p): i for i, p in enumerate(self._params)}
+
+    def no_sync(self):
+        """Context manager for gradient accumulation: backward passes inside it do not start all-reduces (like DDP.no_sync)."""
+        opt = self
+
+        class _NoSync:
+            def __enter__(self):
+                opt._sync = False
+
+            def __exit__(self, *exc):
+                opt._sync = True
+
+        return _NoSync()
+
+    def grad_view(self, p: Tensor) -> Tensor | None:
+        """The arena slice that is ``p``'s gradient (None if ``p`` is not managed here or its ``.grad`` was replaced)."""
+        i = self._index.get(id(p))
+        if i is None:
+            return None
+        v = self._g.view(i)
+        if p.grad is None or p.grad.data_ptr() != v.data_ptr():
+            p.grad = v
+        return v
+
+    def grads_ready(self, params: list[Tensor]) -> None:
+        """Called by the backward when the gradients of ``params`` (a contiguous run of the arena) are final for this step."""
+        import torch.distributed as dist
+
+        if not (self._overlap and self._sync and dist.is_available() and dist.is_initialized() and dist.get_world_size(self._group) > 1):
+            return
+        idx = sorted(self._index[id(p)] for p in params)
+        if idx != list(range(idx[0], idx[-1] + 1)):
+            return  # not contiguous in the arena: leave it to all_reduce_grads
+        a = self._g.offsets[idx[0]]
+        b = self._g.offsets[idx[-1]] + (self._g.shapes[idx[-1]].numel() + _ALIGN - 1) // _ALIGN * _ALIGN
+        self._pending.append(dist.all_reduce(self._g.flat[a:b], op=dist.ReduceOp.SUM, group=self._group, async_op=True))
+        self._reduced.append((a, b))
 
     def _gather_grads(self) -> None:
         """Gradients normally accumulate straight into the arena (``p.grad`` is a view of it).  If something replaced

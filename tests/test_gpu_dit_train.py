@@ -129,3 +129,27 @@ def test_train_loss_backward_through_native_dit():
     bad = {k: rel(p.grad, ref_sd[k].grad) for k, p in m.state_dict(keep_vars=True).items()}
     bad = {k: v for k, v in bad.items() if not v < 5e-2}
     assert not bad, f"train_loss gradient mismatch (relative L2): {bad}"
+
+
+def test_gradient_sink_equals_autograd_path():
+    """AdamW.attach_model: the backward accumulates weight gradients straight into the optimizer's arena (no autograd += pass);
+    the arena must hold exactly what the autograd path produces, also when two backward passes accumulate."""
+    from bsi_b200 import optim as NO
+
+    spec = SPECS["small64"]
+    mu = 1.5 * H.det_uniform("dt.sink.mu", (2, *spec.data_shape)).to(dev())
+    t = torch.tensor([0.25, 0.8], device=dev())
+    w = H.det_uniform("dt.sink.w", (2, *spec.data_shape)).to(dev())
+    grads = {}
+    for sink in (False, True):
+        m, _ = build(spec)
+        opt = NO.AdamW(m.parameters(), lr=1e-3)
+        if sink:
+            opt.attach_model(m)
+        for _ in range(2):  # gradient accumulation over two passes
+            (m(mu, t) * w).sum().backward()
+        sync()
+        grads[sink] = [p.grad.clone() for p in m.parameters()]
+        assert all(p.grad.data_ptr() == opt._g.view(i).data_ptr() for i, p in enumerate(m.parameters()))
+    for a, b in zip(grads[False], grads[True]):
+        assert rel(b, a) < 1e-5  # same kernels; only the fp32 accumulation order of the split-M partial tiles differs

@@ -80,7 +80,7 @@ def test_two_rank_step_equals_ddp_average():
         report(f"ddp ema {i}", res[0][1][i], side.ema[i], 2e-6, 1e-8)
 
 
-def _train_worker(rank, world, port, q):
+def _train_worker(rank, world, port, q, sink=False):
     """One data-parallel optimisation step of the native DiT: each rank differentiates train_loss on its half of the batch."""
     import torch.distributed as dist
 
@@ -101,6 +101,8 @@ def _train_worker(rank, world, port, q):
               preconditioning="edm").to(dev)
     bsi.noise_source = "torch"
     opt = NO.AdamW(model.parameters(), lr=1e-3, weight_decay=0.01, max_grad_norm=1.0)
+    if sink:
+        opt.attach_model(model)  # gradients straight into the arena, per-block all-reduce started during the backward
     x = H.det_images("mt.x", 8, spec.data_shape, seed=2).to(dev)
     # both layouts see the same per-sample lambdas and noise: the 8-sample single-process run and the two 4-sample halves
     lam = H.det_uniform("mt.lam", (1, 8)).to(dev).abs() * 5 + 0.05
@@ -132,7 +134,8 @@ def _train_worker(rank, world, port, q):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
-def test_native_dit_data_parallel_step_equals_single_process():
+@pytest.mark.parametrize("sink", [False, True], ids=["allreduce_after_backward", "overlapped_per_block"])
+def test_native_dit_data_parallel_step_equals_single_process(sink):
     import torch.multiprocessing as mp
 
     ctx = mp.get_context("spawn")
@@ -143,7 +146,7 @@ def test_native_dit_data_parallel_step_equals_single_process():
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
         s.close()
-        procs = [ctx.Process(target=_train_worker, args=(r, world, port, q)) for r in range(world)]
+        procs = [ctx.Process(target=_train_worker, args=(r, world, port, q, sink)) for r in range(world)]
         [p.start() for p in procs]
         for _ in procs:
             w, r, params, grads, norm = q.get(timeout=300)

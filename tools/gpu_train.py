@@ -26,6 +26,7 @@ ap.add_argument("--micro", type=int, default=256)
 ap.add_argument("--depth", type=int, default=24)
 ap.add_argument("--steps", type=int, default=3)
 ap.add_argument("--profile", action="store_true")
+ap.add_argument("--no-sink", action="store_true", help="gradients through autograd, one all-reduce after backward")
 ap.add_argument("--dropout", type=float, default=0.0, help="0.05 in config/experiment/imagenet64.yaml")
 a = ap.parse_args()
 
@@ -49,6 +50,8 @@ bsi = BSI(model, data_shape=(3, 64, 64), k=256, discretization=Discretization.im
 ema = NO.create_ema(model, beta=0.9999, update_after_step=1000, update_every=1)
 opt = NO.AdamW(model.parameters(), lr=1e-3, weight_decay=0.01, max_grad_norm=1.0)
 opt.attach_ema(ema)
+if not a.no_sink:
+    opt.attach_model(model)  # weight gradients straight into the arena; per-block all-reduce overlapped with the backward
 gen = torch.Generator(device=dev).manual_seed(2 + rank)
 x = torch.randint(0, 256, (local, 3, 64, 64), device=dev, generator=gen).float() * (2 / 255) - 1
 
@@ -59,7 +62,11 @@ def step():
     for i in range(0, local, micro):
         # mean over the global batch = sum of micro-batch sums / global batch (after the all-reduce's 1/world)
         loss = bsi.train_loss(x[i : i + micro], gen).sum() * (world / a.global_batch)
-        loss.backward()
+        if i + micro < local:
+            with opt.no_sync():  # gradient accumulation: only the last micro-batch starts the all-reduces
+                loss.backward()
+        else:
+            loss.backward()
         total += loss.detach()
     if world > 1:
         opt.all_reduce_grads()
