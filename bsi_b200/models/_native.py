@@ -25,6 +25,15 @@ class NativeDenoiser(nn.Module):
     def _fn(self, name: str):
         return getattr(L.load(), self._api + name)
 
+    def __getstate__(self):
+        """Copies (``copy.deepcopy`` for the EMA model, bsi/tasks/ema_pytorch.py:203-236) and pickles carry the parameters only:
+        the engine handle, the packed arena, workspaces / CUDA graphs and an attached optimizer sink belong to this instance and
+        are rebuilt lazily by the copy's first call."""
+        state = self.__dict__.copy()
+        state.update(_engine=None, _arena=None, _packed_sig=None, _scratch={})
+        state.pop("_grad_sink", None)
+        return state
+
     def __del__(self):
         eng = getattr(self, "_engine", None)
         if eng:

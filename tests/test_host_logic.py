@@ -239,3 +239,19 @@ def test_flat_arena_layout_and_cpu_rejection():
     assert v.shape == (4, 4, 3) and float(arena.flat[72:120].sum()) == 144.0 and float(arena.flat.sum()) == 144.0
     with pytest.raises(RuntimeError, match="no CPU path"):
         NO.FlatArena.adopt([torch.nn.Parameter(torch.zeros(4))])
+
+
+def test_native_denoiser_copies_and_pickles_without_its_native_handles():
+    """create_ema deep-copies the model (bsi/tasks/ema_pytorch.py:203-236); a copy must not share (or choke on) the engine handle."""
+    import copy
+    import ctypes
+    import pickle
+
+    from bsi_b200.models import DenoisingDiT
+
+    m = DenoisingDiT((3, 32, 32), 2, 128, 1, 2)
+    m._engine, m._packed_sig, m._scratch = ctypes.c_void_p(0), ("stale",), {"workspace": torch.zeros(3)}  # as after a first forward (null handle)
+    for c in (copy.deepcopy(m), pickle.loads(pickle.dumps(m))):
+        assert c._engine is None and c._arena is None and c._packed_sig is None and c._scratch == {}
+        assert all(torch.equal(a, b) and a.data_ptr() != b.data_ptr() for a, b in zip(m.state_dict().values(), c.state_dict().values()))
+    m._engine = None
