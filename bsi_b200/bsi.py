@@ -234,8 +234,18 @@ class BSI(nn.Module):
         dev = generator.device if generator is not None else "cpu"
         return int(torch.randint(0, 2**62, (), generator=generator, device=dev, dtype=torch.int64).item())
 
+    def _native(self):
+        """The native denoiser behind ``self.model``: the model itself, or the ``ema_model`` of an EMA wrapper whose call just
+        delegates to it (bsi/tasks/ema_pytorch.py:436-437; ``BSITraining`` builds its evaluation ``BSI`` around that wrapper,
+        bsi/tasks/bsi.py:115-118) -- so sampling / ELBO with EMA weights also take the fused native path."""
+        m = self.model
+        if getattr(m, "bsi_native", False):
+            return m
+        inner = getattr(m, "ema_model", None)
+        return inner if getattr(inner, "bsi_native", False) else None
+
     def _is_native_denoiser(self) -> bool:
-        return getattr(self.model, "bsi_native", False)
+        return self._native() is not None
 
     # ---- EDM preconditioning (reference bsi/bsi.py:375-403) ---------------------------------
     def _edm_preconditioning(self, t: Tensor):
@@ -248,7 +258,7 @@ class BSI(nn.Module):
         """f = model(c_in * mu, t); the scaling is fused into the native DiT's operand builder when possible."""
         dev = mu.device
         if self._is_native_denoiser() and not torch.is_grad_enabled():
-            return self.model.forward_scaled(mu, t, c_in)
+            return self._native().forward_scaled(mu, t, c_in)
         if c_in is None:
             return self.model(mu, t)
         scaled = torch.empty_like(mu)
@@ -462,7 +472,7 @@ class BSI(nn.Module):
         sigma0 = torch.rsqrt(lam[:1]).contiguous()
         if self._is_native_denoiser() and philox and not history:
             # whole loop on the device: CUDA graph of (denoiser forward + fused step), replayed k times
-            return self.model.sample_loop(n, sigma0, coef, c_in, t_rows, k, seed, sample_offset, precond)
+            return self._native().sample_loop(n, sigma0, coef, c_in, t_rows, k, seed, sample_offset, precond)
         mu = torch.empty(shape, **self.tensor_args)
         with torch.cuda.device(dev):
             nz, _keep = self._noise(shape, generator, 0, sample_offset, seed)

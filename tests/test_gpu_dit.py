@@ -239,3 +239,19 @@ def test_full_width_dit_l_properties():
         assert torch.equal(xa, xb), "denoiser output of a sample depends on its batch neighbours"
         idx = Discretization.image_8bit().bucketize(x)
         assert torch.equal(idx, ((x + 1) * 127.5).round().long()), "8-bit bin indices of grid data must be exact"
+
+
+def test_ema_wrapper_takes_the_native_sampler():
+    """BSITraining evaluates with BSI(model=EMA(...)) (bsi/tasks/bsi.py:115-118): the wrapper's call delegates to ema_model, so the
+    fused native sampler must be used for it and give the same samples as the unwrapped model with the same weights."""
+    from bsi_b200.optim import create_ema
+
+    bsi, m, sd, spec = make_bsi("small64", k=8, noise="philox")
+    with torch.inference_mode():
+        direct = bsi.sample(4, seed=9)  # first forward: the engine exists before the EMA copy is made
+    ema = create_ema(m, beta=0.9999, update_after_step=0, update_every=1).to(dev())
+    ema_bsi = BSI(ema, data_shape=spec.data_shape, k=8, discretization=Discretization.image_8bit(), **HYPER).to(dev())
+    assert ema_bsi._native() is ema.ema_model and ema.ema_model._engine is None  # the copy carries no native handle of the original
+    with torch.inference_mode():
+        via_ema = ema_bsi.sample(4, seed=9)
+    assert torch.equal(direct, via_ema)
