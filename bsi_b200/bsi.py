@@ -239,10 +239,13 @@ class BSI(nn.Module):
         delegates to it (bsi/tasks/ema_pytorch.py:436-437; ``BSITraining`` builds its evaluation ``BSI`` around that wrapper,
         bsi/tasks/bsi.py:115-118) -- so sampling / ELBO with EMA weights also take the fused native path."""
         m = self.model
-        if getattr(m, "bsi_native", False):
-            return m
-        inner = getattr(m, "ema_model", None)
-        return inner if getattr(inner, "bsi_native", False) else None
+        for _ in range(3):  # EMA(ema_model=...) and DistributedDataParallel(module=...) (bsi/tasks/bsi.py:163-166) only delegate
+            if getattr(m, "bsi_native", False):
+                return m
+            m = getattr(m, "ema_model", None) or getattr(m, "module", None)
+            if m is None:
+                return None
+        return None
 
     def _is_native_denoiser(self) -> bool:
         return self._native() is not None

@@ -255,3 +255,20 @@ def test_native_denoiser_copies_and_pickles_without_its_native_handles():
         assert c._engine is None and c._arena is None and c._packed_sig is None and c._scratch == {}
         assert all(torch.equal(a, b) and a.data_ptr() != b.data_ptr() for a, b in zip(m.state_dict().values(), c.state_dict().values()))
     m._engine = None
+
+
+def test_native_denoiser_is_found_behind_ema_and_ddp_style_wrappers():
+    from bsi_b200 import BSI
+    from bsi_b200.models import DenoisingDiT
+
+    class Wrapper(torch.nn.Module):
+        def __init__(self, attr, inner):
+            super().__init__()
+            setattr(self, attr, inner)
+
+    m = DenoisingDiT((3, 32, 32), 2, 128, 1, 2)
+    hyper = dict(data_shape=(3, 32, 32), lambda_0=1e-2, alpha_M=1e6, alpha_R=2e6, k=4)
+    assert BSI(m, **hyper)._native() is m
+    assert BSI(Wrapper("ema_model", m), **hyper)._native() is m
+    assert BSI(Wrapper("module", Wrapper("ema_model", m)), **hyper)._native() is m
+    assert BSI(torch.nn.Identity(), **hyper)._native() is None and BSI(Wrapper("module", torch.nn.Identity()), **hyper)._native() is None
