@@ -267,7 +267,7 @@ def test_native_denoiser_is_found_behind_ema_and_ddp_style_wrappers():
             setattr(self, attr, inner)
 
     m = DenoisingDiT((3, 32, 32), 2, 128, 1, 2)
-    hyper = dict(data_shape=(3, 32, 32), lambda_0=1e-2, alpha_M=1e6, alpha_R=2e6, k=4)
+    hyper = dict(data_shape=(3, 32, 32), lambda_0=1e-2, alpha_M=1e6, alpha_R=2e6, k=4, preconditioning="edm")
     assert BSI(m, **hyper)._native() is m
     assert BSI(Wrapper("ema_model", m), **hyper)._native() is m
     assert BSI(Wrapper("module", Wrapper("ema_model", m)), **hyper)._native() is m
