@@ -30,6 +30,16 @@ __all__ = ["AdamW", "EMA", "create_ema", "FlatArena"]
 _ALIGN = 4  # elements: every tensor starts on a 16-byte boundary so the kernels can use float4
 
 
+def unreduced_ranges(done: list[tuple[int, int]], numel: int) -> list[tuple[int, int]]:
+    """Complement of the element ranges `done` (already all-reduced during the backward) inside [0, numel)."""
+    out, start = [], 0
+    for a, b in sorted(done) + [(numel, numel)]:
+        if a > start:
+            out.append((start, a))
+        start = max(start, b)
+    return out
+
+
 class FlatArena:
     """One contiguous fp32 CUDA buffer holding a list of tensors back to back (each padded to 4 elements).
 
@@ -232,12 +242,8 @@ class AdamW(torch.optim.Optimizer):
         import torch.distributed as dist
 
         self._gather_grads()
-        done = sorted(self._reduced)
-        start = 0
-        for a, b in done + [(self._g.numel, self._g.numel)]:
-            if a > start:
-                dist.all_reduce(self._g.flat[start:a], op=dist.ReduceOp.SUM, group=group)
-            start = max(start, b)
+        for a, b in unreduced_ranges(self._reduced, self._g.numel):
+            dist.all_reduce(self._g.flat[a:b], op=dist.ReduceOp.SUM, group=group)
         for h in self._pending:
             h.wait()
         self._pending, self._reduced = [], []

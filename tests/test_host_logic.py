@@ -5,6 +5,7 @@ import os
 import socket
 
 import pytest
+import numpy as np
 import torch
 
 import helpers as H
@@ -272,3 +273,48 @@ def test_native_denoiser_is_found_behind_ema_and_ddp_style_wrappers():
     assert BSI(Wrapper("ema_model", m), **hyper)._native() is m
     assert BSI(Wrapper("module", Wrapper("ema_model", m)), **hyper)._native() is m
     assert BSI(torch.nn.Identity(), **hyper)._native() is None and BSI(Wrapper("module", torch.nn.Identity()), **hyper)._native() is None
+
+
+def _gloo_exchange_worker(rank, world, port, q):
+    """The gradient exchange of AdamW.all_reduce_grads on a CPU arena: some ranges were reduced "during the backward" (here: up
+    front), the remaining ones afterwards -- every element must be summed over ranks exactly once."""
+    import torch.distributed as dist
+
+    from bsi_b200.optim import FlatArena, unreduced_ranges
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    arena = FlatArena([torch.Size(s) for s in H.OPTIM_SHAPES], torch.device("cpu"))
+    for i in range(len(H.OPTIM_SHAPES)):
+        arena.view(i).copy_(H.optim_grad(i, rank))
+    early = [(arena.offsets[1], arena.offsets[2]), (arena.offsets[3], arena.numel)]  # tensors 1 and 3 "finished early"
+    for a, b in early:
+        dist.all_reduce(arena.flat[a:b])
+    for a, b in unreduced_ranges(early, arena.numel):
+        dist.all_reduce(arena.flat[a:b])
+    q.put((rank, arena.flat.numpy().copy()))
+    dist.destroy_process_group()
+
+
+def test_gradient_exchange_ranges_gloo_world2():
+    import torch.multiprocessing as mp
+
+    from bsi_b200.optim import FlatArena, unreduced_ranges
+
+    assert unreduced_ranges([], 10) == [(0, 10)]
+    assert unreduced_ranges([(4, 6), (0, 2)], 10) == [(2, 4), (6, 10)]
+    assert unreduced_ranges([(0, 10)], 10) == [] and unreduced_ranges([(2, 5), (4, 8)], 8) == [(0, 2)]
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_gloo_exchange_worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in procs]
+    res = dict(q.get(timeout=120) for _ in procs)
+    [p.join(60) for p in procs]
+    ref = FlatArena([torch.Size(s) for s in H.OPTIM_SHAPES], torch.device("cpu"))
+    for i in range(len(H.OPTIM_SHAPES)):
+        ref.view(i).copy_(H.optim_grad(i, 0) + H.optim_grad(i, 1))
+    assert np.array_equal(res[0], res[1]) and np.array_equal(res[0], ref.flat.numpy())
