@@ -115,8 +115,8 @@ class NativeDenoiser(nn.Module):
             raise L.BsiNativeError(f"{type(self).__name__} runs on CUDA only (no CPU fallback)")
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
             raise NotImplementedError(
-                f"bsi_b200.{type(self).__name__} has no backward kernels yet: call it under torch.no_grad()/inference_mode() "
-                "or with parameters frozen (training through the native denoisers is scheduled after the sampling path)"
+                f"bsi_b200.{type(self).__name__} has no backward kernels yet (only DenoisingDiT is differentiable): call it under "
+                "torch.no_grad()/inference_mode() or with parameters frozen, or train the reference's PyTorch module inside bsi_b200.BSI"
             )
         if tuple(mu.shape[1:]) != self.data_shape:
             raise ValueError(f"expected input of shape [B, {self.data_shape}], got {tuple(mu.shape)}")
