@@ -80,7 +80,7 @@ def test_two_rank_step_equals_ddp_average():
         report(f"ddp ema {i}", res[0][1][i], side.ema[i], 2e-6, 1e-8)
 
 
-def _train_worker(rank, world, port, q, sink=False):
+def _train_worker(rank, world, port, q, mode="allreduce"):
     """One data-parallel optimisation step of the native DiT: each rank differentiates train_loss on its half of the batch."""
     import torch.distributed as dist
 
@@ -101,8 +101,13 @@ def _train_worker(rank, world, port, q, sink=False):
               preconditioning="edm").to(dev)
     bsi.noise_source = "torch"
     opt = NO.AdamW(model.parameters(), lr=1e-3, weight_decay=0.01, max_grad_norm=1.0)
-    if sink:
+    if mode == "sink":
         opt.attach_model(model)  # gradients straight into the arena, per-block all-reduce started during the backward
+    net = model
+    if mode == "ddp" and world > 1:  # the reference's own arrangement (BSITraining.configure_ddp, bsi/tasks/bsi.py:163-166)
+        from torch.nn.parallel import DistributedDataParallel
+
+        net = DistributedDataParallel(model, device_ids=[rank], static_graph=True)
     x = H.det_images("mt.x", 8, spec.data_shape, seed=2).to(dev)
     # both layouts see the same per-sample lambdas and noise: the 8-sample single-process run and the two 4-sample halves
     lam = H.det_uniform("mt.lam", (1, 8)).to(dev).abs() * 5 + 0.05
@@ -115,15 +120,15 @@ def _train_worker(rank, world, port, q, sink=False):
         t = bsi.p_lambda.cdf(lam_l).flatten()
         c_skip, c_out, c_in = bsi._edm_preconditioning(t)
         mu = x[lo:hi] * ((lam_l - bsi.lambda_0) / lam_l).reshape(-1, 1, 1, 1) + torch.rsqrt(lam_l).reshape(-1, 1, 1, 1) * eps[lo:hi]
-        f = model.forward_scaled(mu, t, c_in)
+        f = net(mu * c_in.reshape(-1, 1, 1, 1), t)
         x_hat = c_skip.reshape(-1, 1, 1, 1) * mu + c_out.reshape(-1, 1, 1, 1) * f
         err = (x[lo:hi] - x_hat).square().flatten(1).sum(1)
         return (0.5 * bsi.p_lambda.reciprocal_pdf(lam_l).flatten() * err).sum() / 8  # mean over the GLOBAL batch
 
     opt.zero_grad()
     (local_loss() * world).backward()  # all_reduce_grads averages over ranks, so each rank contributes world * (its share of the mean)
-    if world > 1:
-        opt.all_reduce_grads()
+    if world > 1 and mode != "ddp":
+        opt.all_reduce_grads()  # (DistributedDataParallel has already averaged the gradients in its hooks)
     grads = [(p.grad * opt._grad_scale).cpu().numpy() for p in model.parameters()]  # what the optimizer kernel is about to consume
     opt.step()
     torch.cuda.synchronize()
@@ -134,8 +139,8 @@ def _train_worker(rank, world, port, q, sink=False):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
-@pytest.mark.parametrize("sink", [False, True], ids=["allreduce_after_backward", "overlapped_per_block"])
-def test_native_dit_data_parallel_step_equals_single_process(sink):
+@pytest.mark.parametrize("mode", ["allreduce", "sink", "ddp"], ids=["allreduce_after_backward", "overlapped_per_block", "torch_ddp_wrapper"])
+def test_native_dit_data_parallel_step_equals_single_process(mode):
     import torch.multiprocessing as mp
 
     ctx = mp.get_context("spawn")
@@ -146,7 +151,7 @@ def test_native_dit_data_parallel_step_equals_single_process(sink):
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
         s.close()
-        procs = [ctx.Process(target=_train_worker, args=(r, world, port, q, sink)) for r in range(world)]
+        procs = [ctx.Process(target=_train_worker, args=(r, world, port, q, mode)) for r in range(world)]
         [p.start() for p in procs]
         for _ in procs:
             w, r, params, grads, norm = q.get(timeout=300)
