@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(kTrThreads) k_gelu(__nv_bfloat16* out, const _
 // One warp per row (row in registers), a CTA of 8 warps owns `rows_per_cta` consecutive rows (all of one sample) and writes one
 // partial row of dscale / dshift sums; the host adds the partials of a sample (fixed order -> deterministic).
 template <int NV>
-__global__ void __launch_bounds__(kTrThreads, 2)
+__global__ void __launch_bounds__(kTrThreads, NV >= 6 ? 1 : 2)  // dim >= 768: the row, its gradient and two partial-sum rows need > 128 registers
     k_layernorm_mod_backward(float* __restrict__ dx_io, float* __restrict__ dscale_part, float* __restrict__ dshift_part, const __nv_bfloat16* __restrict__ da,
                              const float* __restrict__ x, bsi_rowref scale, const float* __restrict__ gamma, int rows_per_sample, int rows_per_cta,
                              int64_t M, float eps, uint32_t drop_thresh, uint32_t drop_seed, float drop_inv) {

@@ -97,14 +97,14 @@ def _ln_mod(x: Tensor, shift: L.RowRef | None, scale: L.RowRef | None, T: int, g
 
 def _ln_mod_backward(dx_io: Tensor, da: Tensor, x: Tensor, scale: L.RowRef | None, T: int, gamma: Tensor | None = None,
                      drop: tuple[float, int] = (0.0, 0)):
-    """dx_io += dL/dx; returns the per-CTA partial sums (dscale_part, dshift_part) [M / 32][D]."""
+    """dx_io += dL/dx; returns the per-CTA partial sums [2 (dscale, dshift)][M / 32][D]."""
     M, D = x.shape
     parts = torch.empty((2, (M + _LN_ROWS_PER_CTA - 1) // _LN_ROWS_PER_CTA, D), dtype=torch.float32, device=x.device)
     L.check(L.load().bsi_layernorm_mod_backward(dx_io.data_ptr(), parts[0].data_ptr(), parts[1].data_ptr(), da.data_ptr(), x.data_ptr(),
                                                 scale or L.RowRef(None, 0, 0), L.ptr(gamma), T, _LN_ROWS_PER_CTA, M, D, 1e-5, drop[0], drop[1],
                                                 _st(x.device)),
             "bsi_layernorm_mod_backward")
-    return parts[0], parts[1]
+    return parts
 
 
 class DiTTrainFunction(torch.autograd.Function):
@@ -250,8 +250,8 @@ class DiTTrainFunction(torch.autograd.Function):
             da = torch.empty((M, D), dtype=torch.bfloat16, device=dev)
             _gemm(dy16, wt_dec, da, zeros(D), L.EPI_BIAS_BF16)  # W^T [D][Np]: the forward kernel computes dY @ W
             dx = torch.zeros((M, D), dtype=torch.float32, device=dev)
-            dg_part, db_part = _ln_mod_backward(dx, da, x_last, None, T, ln_g.detach().float().contiguous())
-            tail = [emit_b(ln_g, dg_part.sum(0)), emit_b(ln_b, db_part.sum(0)), g_wdec, g_bdec]
+            dgb = _ln_mod_backward(dx, da, x_last, None, T, ln_g.detach().float().contiguous()).sum(1)  # [2][D]: dgamma, dbeta
+            tail = [emit_b(ln_g, dgb[0]), emit_b(ln_b, dgb[1]), g_wdec, g_bdec]
             if sink is not None:
                 sink.grads_ready([ln_g, ln_b, w_dec, b_dec])
             dmods = torch.empty_like(mods)
@@ -262,7 +262,7 @@ class DiTTrainFunction(torch.autograd.Function):
                 wt_qkv, wt_o, wt_1, wt_2 = wt_blocks[l]
                 m, dm = mods[l], dmods[l]
                 ref = lambda j: L.rowref(m, 6 * D, 0, j * D)
-                part = lambda t: t.reshape(B, T // _LN_ROWS_PER_CTA, D).sum(1)
+                part = lambda t: t.reshape(2, B, T // _LN_ROWS_PER_CTA, D).sum(2)  # per-sample (dscale, dshift) from the CTA partials
                 # ---- MLP branch: x_out = x_mid + gate_mlp * (gelu(a2 W1^T + b1) W2^T + b2)
                 dbr = torch.empty((M, D), dtype=torch.bfloat16, device=dev)
                 dgate = torch.empty((B, D), dtype=torch.float32, device=dev)
@@ -276,8 +276,8 @@ class DiTTrainFunction(torch.autograd.Function):
                 L.check(lib.bsi_gelu_backward_bf16(dh.data_ptr(), dh.data_ptr(), pre.data_ptr(), dh.numel(), _st(dev)), "bsi_gelu_backward_bf16")
                 g_w1, g_b1 = emit_w(w_1, dh, a2), emit_b(b_1, colsum(dh))
                 _gemm(dh, wt_1, da, zeros(D), L.EPI_BIAS_BF16)
-                dsc, dsh = _ln_mod_backward(dx, da, x_mid, ref(4), T, drop=(drop_p, _layer_seed(drop_seed, 2 * l + 1)))
-                dm[:, 3 * D : 4 * D], dm[:, 4 * D : 5 * D] = part(dsh), part(dsc)
+                dsc, dsh = part(_ln_mod_backward(dx, da, x_mid, ref(4), T, drop=(drop_p, _layer_seed(drop_seed, 2 * l + 1))))
+                dm[:, 3 * D : 4 * D], dm[:, 4 * D : 5 * D] = dsh, dsc
                 # ---- attention branch: x_mid = x_in + gate_msa * (attn(a1 Wqkv^T + b) Wo^T + b)
                 L.check(lib.bsi_gate_residual_backward(dbr.data_ptr(), dgate.data_ptr(), dbias.data_ptr(), dx.data_ptr(), br1.data_ptr(), ref(2), T, B, D,
                                                        _st(dev)), "bsi_gate_residual_backward")
@@ -288,8 +288,8 @@ class DiTTrainFunction(torch.autograd.Function):
                 dqkv = _attention_backward(qkv, att, datt, B, T, heads, D // heads, (drop_p, _layer_seed(drop_seed, 2 * l)))
                 g_wqkv, g_bqkv = emit_w(w_qkv, dqkv, a1), emit_b(b_qkv, colsum(dqkv))
                 _gemm(dqkv, wt_qkv, da, zeros(D), L.EPI_BIAS_BF16)
-                dsc, dsh = _ln_mod_backward(dx, da, x_in, ref(1), T)
-                dm[:, :D], dm[:, D : 2 * D] = part(dsh), part(dsc)
+                dsc, dsh = part(_ln_mod_backward(dx, da, x_in, ref(1), T))
+                dm[:, :D], dm[:, D : 2 * D] = dsh, dsc
                 block_grads.append([g_wqkv, g_bqkv, g_wo, g_bo, g_w1, g_b1, g_w2, g_b2])
                 if sink is not None:  # this block's eight tensors are final: their all-reduce can overlap the remaining layers
                     sink.grads_ready([w_qkv, b_qkv, w_o, b_o, w_1, b_1, w_2, b_2])
