@@ -31,6 +31,68 @@ __global__ void __launch_bounds__(kTrThreads) k_gate_residual(float* x_out, cons
     }
 }
 
+// ------------------------------------------------------------------ x_out = x + gate * branch, then LayerNorm + modulation of x_out -> bf16
+// The residual update at the end of one branch and the LayerNorm that opens the next one (dit.py:93-102) in one pass: the row
+// is read once, kept in registers for the statistics, and written once as fp32 (saved for the backward) and once as bf16.
+template <int NV>
+__global__ void __launch_bounds__(kTrThreads, 2)
+    k_gate_residual_layernorm(__nv_bfloat16* __restrict__ out, float* __restrict__ x_out, const float* __restrict__ x, const __nv_bfloat16* __restrict__ br,
+                              bsi_rowref gate, bsi_rowref shift, bsi_rowref scale, const float* __restrict__ gamma, const float* __restrict__ beta,
+                              int rows_per_sample, int64_t M, float eps, uint32_t drop_thresh, uint32_t drop_seed, float drop_inv) {
+    constexpr int dim = 128 * NV;
+    const int lane = threadIdx.x & 31;
+    const int64_t warps_total = (int64_t)gridDim.x * (kTrThreads / 32);
+    for (int64_t row = (int64_t)blockIdx.x * (kTrThreads / 32) + (threadIdx.x >> 5); row < M; row += warps_total) {
+        const int64_t sample = row / rows_per_sample;
+        const float4* xr = reinterpret_cast<const float4*>(x + row * dim);
+        const uint2* brr = reinterpret_cast<const uint2*>(br + row * dim);
+        const float4* gr = gate.base ? reinterpret_cast<const float4*>(rowref_ptr(gate, sample, 0)) : nullptr;
+        float4* xo = reinterpret_cast<float4*>(x_out + row * dim);
+        float4 v[NV];
+        float s = 0.0f;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            v[i] = xr[lane + 32 * i];
+            const uint2 b = brr[lane + 32 * i];
+            const float2 b0 = bf16x2_to_float2(b.x), b1 = bf16x2_to_float2(b.y);
+            const float4 g = gr ? gr[lane + 32 * i] : make_float4(1.f, 1.f, 1.f, 1.f);
+            v[i].x = fmaf(g.x, b0.x, v[i].x), v[i].y = fmaf(g.y, b0.y, v[i].y), v[i].z = fmaf(g.z, b1.x, v[i].z), v[i].w = fmaf(g.w, b1.y, v[i].w);
+            xo[lane + 32 * i] = v[i];
+            s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+        }
+        const float mean = warp_sum(s) * (1.0f / dim);
+        float ss = 0.0f;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+            ss += (a * a + b * b) + (c * c + d * d);
+        }
+        const float rstd = rsqrtf(warp_sum(ss) * (1.0f / dim) + eps);
+        const float4 *p_mul, *p_add;
+        if (gamma) {
+            p_mul = reinterpret_cast<const float4*>(gamma), p_add = reinterpret_cast<const float4*>(beta);
+        } else {
+            p_mul = reinterpret_cast<const float4*>(rowref_ptr(scale, sample, 0)), p_add = reinterpret_cast<const float4*>(rowref_ptr(shift, sample, 0));
+        }
+        const float one = gamma ? 0.0f : 1.0f;
+        uint2* o = reinterpret_cast<uint2*>(out + row * dim);
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const float4 m = p_mul[lane + 32 * i], a = p_add[lane + 32 * i];
+            float y0 = fmaf((v[i].x - mean) * rstd, m.x + one, a.x), y1 = fmaf((v[i].y - mean) * rstd, m.y + one, a.y);
+            float y2 = fmaf((v[i].z - mean) * rstd, m.z + one, a.z), y3 = fmaf((v[i].w - mean) * rstd, m.w + one, a.w);
+            if (drop_thresh) {
+                const uint32_t e = (uint32_t)row * dim + (lane + 32 * i) * 4;
+                y0 = dropout_keep(drop_seed, e, drop_thresh) ? y0 * drop_inv : 0.0f;
+                y1 = dropout_keep(drop_seed, e + 1, drop_thresh) ? y1 * drop_inv : 0.0f;
+                y2 = dropout_keep(drop_seed, e + 2, drop_thresh) ? y2 * drop_inv : 0.0f;
+                y3 = dropout_keep(drop_seed, e + 3, drop_thresh) ? y3 * drop_inv : 0.0f;
+            }
+            o[lane + 32 * i] = make_uint2(pack_bf16(y0, y1), pack_bf16(y2, y3));
+        }
+    }
+}
+
 // ------------------------------------------------------------------ dbranch = gate * dx, dgate[b] = sum_t dx * branch
 // grid (D / 512, B): a thread owns two adjacent columns of one sample and walks its T token rows (coalesced across the CTA)
 __global__ void __launch_bounds__(kTrThreads) k_gate_residual_backward(__nv_bfloat16* __restrict__ dbr, float* __restrict__ dgate, float* __restrict__ dbias_part,
@@ -229,6 +291,32 @@ int bsi_gate_residual(float* x_out, const float* x, const void* branch_bf16, bsi
     BSI_CHECK_ARG(x_out && x && branch_bf16 && M > 0 && D > 0 && D % 4 == 0 && rows_per_sample > 0, "bsi_gate_residual: bad arguments (D=%d must be a multiple of 4)", D);
     k_gate_residual<<<tr_grid(M * (D / 4)), kTrThreads, 0, (cudaStream_t)stream>>>(x_out, x, (const __nv_bfloat16*)branch_bf16, gate, rows_per_sample, M, D);
     BSI_LAUNCH_OK("k_gate_residual");
+    return BSI_OK;
+}
+
+int bsi_gate_residual_layernorm_bf16(void* out_bf16, float* x_out, const float* x, const void* branch_bf16, bsi_rowref gate, bsi_rowref shift, bsi_rowref scale,
+                                     const float* gamma, const float* beta, int32_t rows_per_sample, int64_t M, int32_t dim, float eps, float drop_p,
+                                     uint32_t drop_seed, void* stream) {
+    BSI_CHECK_ARG(out_bf16 && x_out && x && branch_bf16 && M > 0 && rows_per_sample > 0, "bsi_gate_residual_layernorm_bf16: null pointer or empty input");
+    BSI_CHECK_ARG((gamma && beta) || (shift.base && scale.base), "bsi_gate_residual_layernorm_bf16: need either gamma/beta or shift/scale");
+    BSI_CHECK_ARG(dim % 128 == 0 && dim >= 128 && dim <= 1024, "bsi_gate_residual_layernorm_bf16: dim=%d must be a multiple of 128 in [128,1024]", dim);
+    BSI_CHECK_ARG(drop_p >= 0.0f && drop_p < 1.0f && (drop_p == 0.0f || M * dim < (int64_t)1 << 32), "bsi_gate_residual_layernorm_bf16: bad dropout arguments");
+    const uint32_t drop_thresh = dropout_thresh(drop_p);
+    const float drop_inv = drop_p > 0.0f ? 1.0f / (1.0f - drop_p) : 1.0f;
+    const int64_t blocks = (M + (kTrThreads / 32) - 1) / (kTrThreads / 32), cap = (int64_t)sm_count() * 8;
+    const int grid = (int)(blocks < cap ? blocks : cap);
+#define BSI_GRL_CASE(NV)                                                                                                                          \
+    case NV:                                                                                                                                      \
+        k_gate_residual_layernorm<NV><<<grid, kTrThreads, 0, (cudaStream_t)stream>>>((__nv_bfloat16*)out_bf16, x_out, x, (const __nv_bfloat16*)branch_bf16, \
+                                                                                     gate, shift, scale, gamma, beta, rows_per_sample, M, eps, drop_thresh, \
+                                                                                     drop_seed, drop_inv);                                       \
+        break;
+    switch (dim / 128) {
+        BSI_GRL_CASE(1) BSI_GRL_CASE(2) BSI_GRL_CASE(3) BSI_GRL_CASE(4) BSI_GRL_CASE(5) BSI_GRL_CASE(6) BSI_GRL_CASE(7) BSI_GRL_CASE(8)
+        default: set_error("unsupported dim %d", dim); return BSI_ERR_UNSUPPORTED;
+    }
+#undef BSI_GRL_CASE
+    BSI_LAUNCH_OK("k_gate_residual_layernorm");
     return BSI_OK;
 }
 

@@ -149,11 +149,22 @@ class DiTTrainFunction(torch.autograd.Function):
             ctx.mods_dtype = mods.dtype
             mods = mods.detach().float().contiguous()
             saved = []
+            none = L.RowRef(None, 0, 0)
+
+            def gate_ln(x_in: Tensor, br: Tensor, gate, shift, scale, gamma=None, beta=None, drop_site=(0.0, 0)):
+                """x_out = x_in + gate * br and the LayerNorm (+ modulation / affine, + dropout) of x_out, one pass (train_kernels.cu)."""
+                x_out = torch.empty_like(x_in)  # out of place: x_in stays alive as a saved activation
+                a = torch.empty((M, D), dtype=torch.bfloat16, device=dev)
+                L.check(lib.bsi_gate_residual_layernorm_bf16(a.data_ptr(), x_out.data_ptr(), x_in.data_ptr(), br.data_ptr(), gate, shift or none, scale or none,
+                                                             L.ptr(gamma), L.ptr(beta), T, M, D, 1e-5, drop_site[0], drop_site[1], _st(dev)),
+                        "bsi_gate_residual_layernorm_bf16")
+                return x_out, a
+
+            a1 = _ln_mod(x, L.rowref(mods[0], 6 * D, 0, 0), L.rowref(mods[0], 6 * D, 0, D), T)
             for l, (w_qkv, b_qkv, w_o, b_o, w_1, b_1, w_2, b_2) in enumerate(blocks):
                 m = mods[l]
                 ref = lambda j: L.rowref(m, 6 * D, 0, j * D)
                 x_in = x
-                a1 = _ln_mod(x, ref(0), ref(1), T)
                 qkv = torch.empty((M, 3 * D), dtype=torch.bfloat16, device=dev)
                 _gemm(a1, bf(w_qkv), qkv, b_qkv.detach().float(), L.EPI_BIAS_BF16)
                 att = torch.empty((M, D), dtype=torch.bfloat16, device=dev)
@@ -164,20 +175,19 @@ class DiTTrainFunction(torch.autograd.Function):
                     L.check(lib.bsi_attention_bf16(att.data_ptr(), qkv.data_ptr(), B, T, heads, D // heads, _st(dev)), "bsi_attention_bf16")
                 br1 = torch.empty((M, D), dtype=torch.bfloat16, device=dev)
                 _gemm(att, bf(w_o), br1, b_o.detach().float(), L.EPI_BIAS_BF16)
-                x_mid = torch.empty_like(x)  # out of place: x_in stays alive as this layer's saved input
-                L.check(lib.bsi_gate_residual(x_mid.data_ptr(), x.data_ptr(), br1.data_ptr(), ref(2), T, M, D, _st(dev)), "bsi_gate_residual")
-                x = x_mid
-                a2 = _ln_mod(x, ref(3), ref(4), T, drop=(drop_p, _layer_seed(drop_seed, 2 * l + 1)))
+                x_mid, a2 = gate_ln(x, br1, ref(2), ref(3), ref(4), drop_site=(drop_p, _layer_seed(drop_seed, 2 * l + 1)))
                 pre = torch.empty((M, 4 * D), dtype=torch.bfloat16, device=dev)
                 _gemm(a2, bf(w_1), pre, b_1.detach().float(), L.EPI_BIAS_BF16)
                 h = torch.empty_like(pre)
                 L.check(lib.bsi_gelu_bf16(h.data_ptr(), pre.data_ptr(), pre.numel(), _st(dev)), "bsi_gelu_bf16")
                 br2 = torch.empty((M, D), dtype=torch.bfloat16, device=dev)
                 _gemm(h, bf(w_2), br2, b_2.detach().float(), L.EPI_BIAS_BF16)
-                x = torch.empty_like(x_mid)
-                L.check(lib.bsi_gate_residual(x.data_ptr(), x_mid.data_ptr(), br2.data_ptr(), ref(5), T, M, D, _st(dev)), "bsi_gate_residual")
                 saved.append((x_in, a1, qkv, att, br1, x_mid, a2, pre, h, br2))
-            a_dec = _ln_mod(x, None, None, T, ln_g.detach().float().contiguous(), ln_b.detach().float().contiguous())
+                if l + 1 < depth:  # the MLP branch's residual update opens the next block's attention LayerNorm ...
+                    nxt = mods[l + 1]
+                    x, a1 = gate_ln(x_mid, br2, ref(5), L.rowref(nxt, 6 * D, 0, 0), L.rowref(nxt, 6 * D, 0, D))
+                else:  # ... or the affine LayerNorm of the patch decoder
+                    x, a_dec = gate_ln(x_mid, br2, ref(5), None, None, ln_g.detach().float().contiguous(), ln_b.detach().float().contiguous())
             n_out = w_dec.shape[0]
             Np = _pad8(n_out)
             y = torch.empty((M, Np), dtype=torch.float32, device=dev)

@@ -333,6 +333,11 @@ int bsi_gemm_wgrad_bf16(float* dW, const void* dY_bf16, const void* X_bf16, int3
 /* Elementwise / reduction pieces of the DiT backward (bsi/models/dit.py:50-55,87-103; config 5 groundwork). */
 /* x_out[row] = x[row] + gate[row / rows_per_sample] * branch[row]   (torch.addcmul(x, gate, branch); x_out may be x; gate.base == NULL: gate = 1) */
 int bsi_gate_residual(float* x_out, const float* x, const void* branch_bf16, bsi_rowref gate, int32_t rows_per_sample, int64_t M, int32_t D, void* stream);
+/* bsi_gate_residual followed by bsi_layernorm_mod(_dropout)_bf16 on its result, in one pass over the row (dit.py:93-102):
+ *   x_out = x + gate * branch (fp32, may alias x);  out = dropout(LayerNorm(x_out) * (1 + scale) + shift)   [or * gamma + beta] */
+int bsi_gate_residual_layernorm_bf16(void* out_bf16, float* x_out, const float* x, const void* branch_bf16, bsi_rowref gate, bsi_rowref shift,
+                                     bsi_rowref scale, const float* gamma, const float* beta, int32_t rows_per_sample, int64_t M, int32_t dim, float eps,
+                                     float drop_p, uint32_t drop_seed, void* stream);
 /* dbranch = gate * dx (bf16);  dgate[b][d] = sum_t dx[b,t,d] * branch[b,t,d];  dbias_part[b][d] = sum_t dbranch[b,t,d]  (either may be NULL) */
 int bsi_gate_residual_backward(void* dbranch_bf16, float* dgate, float* dbias_part, const float* dx, const void* branch_bf16, bsi_rowref gate,
                                int32_t rows_per_sample, int32_t B, int32_t D, void* stream);

@@ -239,3 +239,33 @@ def test_attention_dropout_forward_backward_with_restated_mask(B, T, heads, p):
         got, want = dqkv[:, sl].float(), ref[:, sl]
         rel = float((got - want).norm() / want.norm())
         assert rel < 2e-2, f"{name}: relative L2 error {rel}"
+
+
+@pytest.mark.parametrize("dim", [128, 1024])
+def test_gate_residual_layernorm_fused_equals_the_two_kernels(dim):
+    """x_out = x + gate * branch and LayerNorm(+modulation / affine, + dropout) of x_out in one pass == the two separate kernels, bit for bit."""
+    B, T = 3, 256
+    M = B * T
+    x = rnd(f"gl.x{dim}", (M, dim), 1.3)
+    br = rnd(f"gl.br{dim}", (M, dim)).bfloat16()
+    tab = rnd(f"gl.t{dim}", (B, 6 * dim), 0.5)
+    gate, shift, scale = (L.rowref(tab, 6 * dim, 0, j * dim) for j in (2, 3, 4))
+    none = L.RowRef(None, 0, 0)
+    gamma, beta = rnd(f"gl.g{dim}", (dim,), 0.3) + 1, rnd(f"gl.b{dim}", (dim,), 0.2)
+    for variant in ("modulated", "dropout", "affine"):
+        p, seed = (0.2, 77) if variant == "dropout" else (0.0, 0)
+        x_sep = torch.zeros_like(x)
+        call("bsi_gate_residual", L.ptr(x_sep), L.ptr(x), L.ptr(br), gate, T, M, dim, L.stream_ptr())
+        a_sep = torch.zeros((M, dim), dtype=torch.bfloat16, device=dev())
+        if variant == "affine":
+            call("bsi_layernorm_mod_bf16", L.ptr(a_sep), L.ptr(x_sep), none, none, None, L.ptr(gamma), L.ptr(beta), T, M, dim, 1e-5, L.stream_ptr())
+        elif variant == "dropout":
+            call("bsi_layernorm_mod_dropout_bf16", L.ptr(a_sep), L.ptr(x_sep), shift, scale, T, M, dim, 1e-5, p, seed, L.stream_ptr())
+        else:
+            call("bsi_layernorm_mod_bf16", L.ptr(a_sep), L.ptr(x_sep), shift, scale, None, None, None, T, M, dim, 1e-5, L.stream_ptr())
+        x_f, a_f = torch.zeros_like(x), torch.zeros_like(a_sep)
+        aff = variant == "affine"
+        call("bsi_gate_residual_layernorm_bf16", L.ptr(a_f), L.ptr(x_f), L.ptr(x), L.ptr(br), gate, none if aff else shift, none if aff else scale,
+             L.ptr(gamma) if aff else None, L.ptr(beta) if aff else None, T, M, dim, 1e-5, p, seed, L.stream_ptr())
+        sync()
+        assert torch.equal(x_f, x_sep) and torch.equal(a_f, a_sep), variant
