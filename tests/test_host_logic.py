@@ -318,3 +318,24 @@ def test_gradient_exchange_ranges_gloo_world2():
     for i in range(len(H.OPTIM_SHAPES)):
         ref.view(i).copy_(H.optim_grad(i, 0) + H.optim_grad(i, 1))
     assert np.array_equal(res[0], res[1]) and np.array_equal(res[0], ref.flat.numpy())
+
+
+def test_training_path_covers_every_parameter_exactly_once():
+    """dit_train differentiates the GEMM / LayerNorm parameters itself and leaves the adaLN chain to autograd through `mods`:
+    together they must cover every parameter of the model exactly once, in the arena order AdamW.grads_ready relies on."""
+    from bsi_b200.models import DenoisingDiT
+    from bsi_b200.models.dit_train import _layer_seed, trainable_parameters
+
+    m = DenoisingDiT((3, 32, 32), 2, 128, 3, 2)
+    direct = trainable_parameters(m)
+    ada = [p for blk in m.dit.blocks for p in blk.adaLN_modulation.parameters()]
+    everything = list(m.parameters())
+    assert len({id(p) for p in direct}) == len(direct) and not ({id(p) for p in direct} & {id(p) for p in ada})
+    assert {id(p) for p in direct} | {id(p) for p in ada} == {id(p) for p in everything}
+    index = {id(p): i for i, p in enumerate(everything)}
+    for l in range(3):  # a block's eight GEMM tensors are one contiguous run of the parameter list (one all-reduce range)
+        run = [index[id(p)] for p in direct[2 + 8 * l : 10 + 8 * l]]
+        assert run == list(range(run[0], run[0] + 8))
+    assert [index[id(p)] for p in direct[-4:]] == list(range(len(everything) - 4, len(everything)))
+    seeds = {_layer_seed(s, k) for s in (0, 1, 12345) for k in range(48)}
+    assert len(seeds) == 3 * 48 and all(0 <= x < 2**32 for x in seeds)  # distinct dropout streams per (call, layer, site)
