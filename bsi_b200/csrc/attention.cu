@@ -38,7 +38,7 @@ __device__ __forceinline__ void mma_bf16(float (&d)[4], const uint32_t (&a)[4], 
 template <bool DROP>
 __global__ void __launch_bounds__(kAttThreads, 2)
     k_attention_mma(__nv_bfloat16* __restrict__ out, const __nv_bfloat16* __restrict__ qkv, int T, int dim, float scale_log2, uint32_t drop_thresh,
-                    uint32_t drop_seed, float drop_inv) {
+                    uint32_t drop_seed, float drop_inv, float* __restrict__ lse) {
     extern __shared__ __align__(128) uint8_t att_smem[];
     const uint32_t sQ = (uint32_t)__cvta_generic_to_shared(att_smem), sK = sQ + kQRows * 128, sV = sK + T * 128;
     const int q0 = blockIdx.x * kQRows, h = blockIdx.y, b = blockIdx.z;
@@ -160,6 +160,11 @@ __global__ void __launch_bounds__(kAttThreads, 2)
     const float inv0 = 1.0f / l_run[0], inv1 = 1.0f / l_run[1];
     __syncwarp();
     const int g = lane >> 2, t4 = lane & 3;
+    if (lse && t4 == 0) {  // log2 of sum_j exp(scale * s_j) per query row: lets the backward skip its statistics pass
+        float* lrow = lse + ((size_t)b * gridDim.y + h) * T + q0 + r0;
+        lrow[g] = fmaf(m_run[0], scale_log2, log2f(l_run[0]));
+        lrow[g + 8] = fmaf(m_run[1], scale_log2, log2f(l_run[1]));
+    }
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         // column pair (j*8 + 2*t4, +1) lives in 16-byte chunk j at byte offset 4*t4
@@ -205,13 +210,13 @@ extern "C" int bsi_attention_bf16(void* out_bf16, const void* qkv_bf16, int32_t 
     const float scale_log2 = 1.4426950408889634f / sqrtf((float)head_dim);
     dim3 grid(T / kQRows, heads, B);
     k_attention_mma<false><<<grid, kAttThreads, smem, (cudaStream_t)stream>>>((__nv_bfloat16*)out_bf16, (const __nv_bfloat16*)qkv_bf16, T, dim,
-                                                                             scale_log2, 0u, 0u, 1.0f);
+                                                                             scale_log2, 0u, 0u, 1.0f, nullptr);
     BSI_LAUNCH_OK("k_attention_mma");
     return BSI_OK;
 }
 
-extern "C" int bsi_attention_dropout_bf16(void* out_bf16, const void* qkv_bf16, int32_t B, int32_t T, int32_t heads, int32_t head_dim, float drop_p,
-                                          uint32_t drop_seed, void* stream) {
+extern "C" int bsi_attention_dropout_bf16(void* out_bf16, float* lse_out, const void* qkv_bf16, int32_t B, int32_t T, int32_t heads, int32_t head_dim,
+                                          float drop_p, uint32_t drop_seed, void* stream) {
     BSI_CHECK_ARG(out_bf16 && qkv_bf16 && B > 0 && heads > 0 && drop_p > 0.0f && drop_p < 1.0f, "bsi_attention_dropout_bf16: bad arguments");
     if (head_dim != kHd || T % kQRows != 0 || T > 512) {
         set_error("bsi_attention_dropout_bf16: only head_dim=64 and T in {128,256,384,512} are implemented (got head_dim=%d T=%d)", head_dim, T);
@@ -223,7 +228,7 @@ extern "C" int bsi_attention_dropout_bf16(void* out_bf16, const void* qkv_bf16, 
     const float scale_log2 = 1.4426950408889634f / sqrtf((float)head_dim);
     dim3 grid(T / kQRows, heads, B);
     k_attention_mma<true><<<grid, kAttThreads, smem, (cudaStream_t)stream>>>((__nv_bfloat16*)out_bf16, (const __nv_bfloat16*)qkv_bf16, T, dim, scale_log2,
-                                                                            dropout_thresh(drop_p), drop_seed, 1.0f / (1.0f - drop_p));
+                                                                            dropout_thresh(drop_p), drop_seed, 1.0f / (1.0f - drop_p), lse_out);
     BSI_LAUNCH_OK("k_attention_mma<dropout>");
     return BSI_OK;
 }

@@ -104,7 +104,7 @@ __device__ __forceinline__ void store_rows(const float (&acc)[8][4], float scale
 __global__ void __launch_bounds__(ab::kThreads, 1)
     k_attention_bwd_q(__nv_bfloat16* __restrict__ dqkv, float* __restrict__ lse, float* __restrict__ dsum, const __nv_bfloat16* __restrict__ qkv,
                       const __nv_bfloat16* __restrict__ out, const __nv_bfloat16* __restrict__ dout, int T, int dim, int heads, float scale_log2,
-                      float scale, uint32_t drop_thresh, uint32_t drop_seed, float drop_inv) {
+                      float scale, uint32_t drop_thresh, uint32_t drop_seed, float drop_inv, int have_lse) {
     using namespace ab;
     extern __shared__ __align__(128) uint8_t ab_smem[];
     const uint32_t sQ = (uint32_t)__cvta_generic_to_shared(ab_smem), sdO = sQ + kRows * 128, sO = sdO + kRows * 128, sK = sO + kRows * 128,
@@ -150,9 +150,9 @@ __global__ void __launch_bounds__(ab::kThreads, 1)
     load_frags(qf, sQ, r0, lane);
     load_frags(dof, sdO, r0, lane);
 
-    // ---- pass 1: log-sum-exp of the warp's 16 rows (thread: rows g and g + 8)
+    // ---- pass 1: log-sum-exp of the warp's 16 rows (thread: rows g and g + 8) -- skipped when the forward kernel saved it
     float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.0f, 0.0f};
-    for (int kc = 0; kc < T / 64; ++kc) {
+    for (int kc = 0; kc < (have_lse ? 0 : T / 64); ++kc) {
         float s[8][4];
         mm_abt(s, qf, sK, kc * 64, lane);
         float mx[2] = {-INFINITY, -INFINITY};
@@ -184,7 +184,10 @@ __global__ void __launch_bounds__(ab::kThreads, 1)
         l_run[r] += __shfl_xor_sync(0xffffffffu, l_run[r], 2);
         lse2[r] = fmaf(m_run[r], scale_log2, log2f(l_run[r]));  // log2 of sum_j exp(scale * s_j)
     }
-    if ((lane & 3) == 0) {
+    if (have_lse) {
+        lse2[0] = lse[((size_t)b * heads + h) * T + q0 + r0 + g];
+        lse2[1] = lse[((size_t)b * heads + h) * T + q0 + r0 + g + 8];
+    } else if ((lane & 3) == 0) {
         lse[((size_t)b * heads + h) * T + q0 + r0 + g] = lse2[0];
         lse[((size_t)b * heads + h) * T + q0 + r0 + g + 8] = lse2[1];
     }
@@ -289,7 +292,8 @@ __global__ void __launch_bounds__(ab::kThreads, 1)
 using namespace bsi;
 
 extern "C" int bsi_attention_backward_bf16(void* dqkv_bf16, float* lse_ws, float* dsum_ws, const void* qkv_bf16, const void* out_bf16, const void* dout_bf16,
-                                           int32_t B, int32_t T, int32_t heads, int32_t head_dim, float drop_p, uint32_t drop_seed, void* stream) {
+                                           int32_t B, int32_t T, int32_t heads, int32_t head_dim, float drop_p, uint32_t drop_seed, int32_t lse_valid,
+                                           void* stream) {
     BSI_CHECK_ARG(dqkv_bf16 && lse_ws && dsum_ws && qkv_bf16 && out_bf16 && dout_bf16 && B > 0 && heads > 0 && drop_p >= 0.0f && drop_p < 1.0f,
                   "bsi_attention_backward_bf16: bad arguments");
     const uint32_t drop_thresh = dropout_thresh(drop_p);
@@ -305,7 +309,7 @@ extern "C" int bsi_attention_backward_bf16(void* dqkv_bf16, float* lse_ws, float
     BSI_ENSURE_SMEM(k_attention_bwd_q, smem_q);
     k_attention_bwd_q<<<grid, ab::kThreads, smem_q, (cudaStream_t)stream>>>((__nv_bfloat16*)dqkv_bf16, lse_ws, dsum_ws, (const __nv_bfloat16*)qkv_bf16,
                                                                            (const __nv_bfloat16*)out_bf16, (const __nv_bfloat16*)dout_bf16, T, dim, heads,
-                                                                           scale_log2, scale, drop_thresh, drop_seed, drop_inv);
+                                                                           scale_log2, scale, drop_thresh, drop_seed, drop_inv, lse_valid);
     BSI_LAUNCH_OK("k_attention_bwd_q");
     BSI_ENSURE_SMEM(k_attention_bwd_kv, smem_kv);
     k_attention_bwd_kv<<<grid, ab::kThreads, smem_kv, (cudaStream_t)stream>>>((__nv_bfloat16*)dqkv_bf16, lse_ws, dsum_ws, (const __nv_bfloat16*)qkv_bf16,

@@ -168,9 +168,11 @@ class DiTTrainFunction(torch.autograd.Function):
                 qkv = torch.empty((M, 3 * D), dtype=torch.bfloat16, device=dev)
                 _gemm(a1, bf(w_qkv), qkv, b_qkv.detach().float(), L.EPI_BIAS_BF16)
                 att = torch.empty((M, D), dtype=torch.bfloat16, device=dev)
-                if drop_p > 0:
-                    L.check(lib.bsi_attention_dropout_bf16(att.data_ptr(), qkv.data_ptr(), B, T, heads, D // heads, drop_p, _layer_seed(drop_seed, 2 * l),
-                                                           _st(dev)), "bsi_attention_dropout_bf16")
+                lse = None
+                if drop_p > 0:  # the dropout forward also saves the softmax statistics, which spares the backward a recomputation pass
+                    lse = torch.empty(B * heads * T, dtype=torch.float32, device=dev)
+                    L.check(lib.bsi_attention_dropout_bf16(att.data_ptr(), lse.data_ptr(), qkv.data_ptr(), B, T, heads, D // heads, drop_p,
+                                                           _layer_seed(drop_seed, 2 * l), _st(dev)), "bsi_attention_dropout_bf16")
                 else:
                     L.check(lib.bsi_attention_bf16(att.data_ptr(), qkv.data_ptr(), B, T, heads, D // heads, _st(dev)), "bsi_attention_bf16")
                 br1 = torch.empty((M, D), dtype=torch.bfloat16, device=dev)
@@ -182,7 +184,7 @@ class DiTTrainFunction(torch.autograd.Function):
                 L.check(lib.bsi_gelu_bf16(h.data_ptr(), pre.data_ptr(), pre.numel(), _st(dev)), "bsi_gelu_bf16")
                 br2 = torch.empty((M, D), dtype=torch.bfloat16, device=dev)
                 _gemm(h, bf(w_2), br2, b_2.detach().float(), L.EPI_BIAS_BF16)
-                saved.append((x_in, a1, qkv, att, br1, x_mid, a2, pre, h, br2))
+                saved.append((x_in, a1, qkv, att, br1, x_mid, a2, pre, h, br2, lse))
                 if l + 1 < depth:  # the MLP branch's residual update opens the next block's attention LayerNorm ...
                     nxt = mods[l + 1]
                     x, a1 = gate_ln(x_mid, br2, ref(5), L.rowref(nxt, 6 * D, 0, 0), L.rowref(nxt, 6 * D, 0, D))
@@ -268,7 +270,7 @@ class DiTTrainFunction(torch.autograd.Function):
             block_grads = []
             for l in reversed(range(depth)):
                 w_qkv, b_qkv, w_o, b_o, w_1, b_1, w_2, b_2 = blocks[l]
-                x_in, a1, qkv, att, br1, x_mid, a2, pre, h, br2 = saved[l]
+                x_in, a1, qkv, att, br1, x_mid, a2, pre, h, br2, lse = saved[l]
                 wt_qkv, wt_o, wt_1, wt_2 = wt_blocks[l]
                 m, dm = mods[l], dmods[l]
                 ref = lambda j: L.rowref(m, 6 * D, 0, j * D)
@@ -295,7 +297,7 @@ class DiTTrainFunction(torch.autograd.Function):
                 g_wo, g_bo = emit_w(w_o, dbr, att), emit_b(b_o, dbias.sum(0))
                 datt = torch.empty((M, D), dtype=torch.bfloat16, device=dev)
                 _gemm(dbr, wt_o, datt, zeros(D), L.EPI_BIAS_BF16)
-                dqkv = _attention_backward(qkv, att, datt, B, T, heads, D // heads, (drop_p, _layer_seed(drop_seed, 2 * l)))
+                dqkv = _attention_backward(qkv, att, datt, B, T, heads, D // heads, (drop_p, _layer_seed(drop_seed, 2 * l)), lse)
                 g_wqkv, g_bqkv = emit_w(w_qkv, dqkv, a1), emit_b(b_qkv, colsum(dqkv))
                 _gemm(dqkv, wt_qkv, da, zeros(D), L.EPI_BIAS_BF16)
                 dsc, dsh = part(_ln_mod_backward(dx, da, x_in, ref(1), T))
@@ -314,12 +316,14 @@ class DiTTrainFunction(torch.autograd.Function):
         return (None, None, None, None, dmods.to(ctx.mods_dtype), *grads)
 
 
-def _attention_backward(qkv: Tensor, att: Tensor, datt: Tensor, B: int, T: int, heads: int, hd: int, drop: tuple[float, int] = (0.0, 0)) -> Tensor:
+def _attention_backward(qkv: Tensor, att: Tensor, datt: Tensor, B: int, T: int, heads: int, hd: int, drop: tuple[float, int] = (0.0, 0),
+                        lse: Tensor | None = None) -> Tensor:
     """d(qkv) of att = attention(qkv) on the packed [B*T][3*dim] layout (two mma.sync kernels, attention_bwd.cu)."""
     dqkv = torch.empty_like(qkv)
     ws = torch.empty((2, B * heads * T), dtype=torch.float32, device=qkv.device)
-    L.check(L.load().bsi_attention_backward_bf16(dqkv.data_ptr(), ws[0].data_ptr(), ws[1].data_ptr(), qkv.data_ptr(), att.data_ptr(), datt.data_ptr(),
-                                                 B, T, heads, hd, drop[0], drop[1], _st(qkv.device)), "bsi_attention_backward_bf16")
+    lse_ws = lse if lse is not None else ws[0]
+    L.check(L.load().bsi_attention_backward_bf16(dqkv.data_ptr(), lse_ws.data_ptr(), ws[1].data_ptr(), qkv.data_ptr(), att.data_ptr(), datt.data_ptr(),
+                                                 B, T, heads, hd, drop[0], drop[1], int(lse is not None), _st(qkv.device)), "bsi_attention_backward_bf16")
     return dqkv
 
 

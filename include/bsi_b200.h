@@ -210,14 +210,17 @@ int bsi_attention_force_legacy(int32_t on);
 
 /* Backward of bsi_attention_bf16 on the same packed layouts (autograd of dit.py:36-47): dqkv bf16 [B*T][3*dim] from the saved qkv,
  * the saved forward output and the upstream gradient dout bf16 [B*T][dim].  lse_ws / dsum_ws: B*heads*T floats of scratch each
- * (log-sum-exp of the scaled scores and sum_c dout*out per query row; written by the first kernel, read by the second). */
+ * (log2-sum-exp of the scaled scores and sum_c dout*out per query row; written by the first kernel, read by the second).
+ * lse_valid != 0: lse_ws already holds the statistics (saved by bsi_attention_dropout_bf16) and the recomputation pass is skipped. */
 int bsi_attention_backward_bf16(void* dqkv_bf16, float* lse_ws, float* dsum_ws, const void* qkv_bf16, const void* out_bf16, const void* dout_bf16,
-                                int32_t B, int32_t T, int32_t heads, int32_t head_dim, float drop_p, uint32_t drop_seed, void* stream);
+                                int32_t B, int32_t T, int32_t heads, int32_t head_dim, float drop_p, uint32_t drop_seed, int32_t lse_valid,
+                                void* stream);
 /* Training-mode attention with dropout on the probabilities (F.scaled_dot_product_attention(dropout_p), dit.py:43-44).  The keep mask
  * is a stateless hash of (drop_seed, head of sample, query, key) -- mix32 in csrc/common.cuh -- which bsi_attention_backward_bf16
- * regenerates from the same (drop_p, drop_seed); drop_p = 0 there means the forward ran without dropout. */
-int bsi_attention_dropout_bf16(void* out_bf16, const void* qkv_bf16, int32_t B, int32_t T, int32_t heads, int32_t head_dim, float drop_p,
-                               uint32_t drop_seed, void* stream);
+ * regenerates from the same (drop_p, drop_seed); drop_p = 0 there means the forward ran without dropout.  lse_out (optional,
+ * B*heads*T floats): log2-sum-exp per query row for the backward's lse_valid fast path. */
+int bsi_attention_dropout_bf16(void* out_bf16, float* lse_out, const void* qkv_bf16, int32_t B, int32_t T, int32_t heads, int32_t head_dim,
+                               float drop_p, uint32_t drop_seed, void* stream);
 /* bsi_layernorm_mod_bf16 followed by nn.Dropout(drop_p) on its output (dit.py:101), mask = hash of (drop_seed, row * dim + column). */
 int bsi_layernorm_mod_dropout_bf16(void* out_bf16, const float* x, bsi_rowref shift, bsi_rowref scale, int32_t rows_per_sample, int64_t M,
                                    int32_t dim, float eps, float drop_p, uint32_t drop_seed, void* stream);

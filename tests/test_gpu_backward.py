@@ -170,7 +170,7 @@ def test_attention_backward_vs_autograd(B, T, heads):
     call("bsi_attention_bf16", L.ptr(out), L.ptr(qkv), B, T, heads, hd, L.stream_ptr())
     dqkv = torch.full((B * T, 3 * dim), float("nan"), dtype=torch.bfloat16, device=dev())
     ws = torch.zeros((2, B * heads * T), device=dev())
-    call("bsi_attention_backward_bf16", L.ptr(dqkv), L.ptr(ws[0]), L.ptr(ws[1]), L.ptr(qkv), L.ptr(out), L.ptr(dout), B, T, heads, hd, 0.0, 0, L.stream_ptr())
+    call("bsi_attention_backward_bf16", L.ptr(dqkv), L.ptr(ws[0]), L.ptr(ws[1]), L.ptr(qkv), L.ptr(out), L.ptr(dout), B, T, heads, hd, 0.0, 0, 0, L.stream_ptr())
     sync()
     q, k, v = (t.detach().requires_grad_(True) for t in qkv.float().reshape(B, T, 3, heads, hd).permute(2, 0, 3, 1, 4))
     o = F.scaled_dot_product_attention(q, k, v)
@@ -221,11 +221,17 @@ def test_attention_dropout_forward_backward_with_restated_mask(B, T, heads, p):
     qkv = rnd(f"ad.qkv{T}", (B * T, 3 * dim), 2.0).bfloat16()
     dout = rnd(f"ad.do{T}", (B * T, dim)).bfloat16()
     out = torch.zeros((B * T, dim), dtype=torch.bfloat16, device=dev())
-    call("bsi_attention_dropout_bf16", L.ptr(out), L.ptr(qkv), B, T, heads, hd, p, seed, L.stream_ptr())
+    lse = torch.zeros(B * heads * T, device=dev())
+    call("bsi_attention_dropout_bf16", L.ptr(out), L.ptr(lse), L.ptr(qkv), B, T, heads, hd, p, seed, L.stream_ptr())
     dqkv = torch.full((B * T, 3 * dim), float("nan"), dtype=torch.bfloat16, device=dev())
     ws = torch.zeros((2, B * heads * T), device=dev())
-    call("bsi_attention_backward_bf16", L.ptr(dqkv), L.ptr(ws[0]), L.ptr(ws[1]), L.ptr(qkv), L.ptr(out), L.ptr(dout), B, T, heads, hd, p, seed, L.stream_ptr())
+    call("bsi_attention_backward_bf16", L.ptr(dqkv), L.ptr(ws[0]), L.ptr(ws[1]), L.ptr(qkv), L.ptr(out), L.ptr(dout), B, T, heads, hd, p, seed, 0, L.stream_ptr())
+    # fast path: the statistics saved by the forward kernel replace the recomputation pass -- same result up to the rounding of lse
+    dqkv_fast = torch.full_like(dqkv, float("nan"))
+    call("bsi_attention_backward_bf16", L.ptr(dqkv_fast), L.ptr(lse), L.ptr(ws[1]), L.ptr(qkv), L.ptr(out), L.ptr(dout), B, T, heads, hd, p, seed, 1, L.stream_ptr())
     sync()
+    report("saved vs recomputed log-sum-exp", lse, ws[0], 1e-5, 1e-4)
+    report("backward with saved statistics", dqkv_fast, dqkv, 2e-2, 1e-3)
     keep = H.attention_dropout_mask(seed, B, heads, T, p).to(dev())
     assert abs(float(keep.float().mean()) - (1 - p)) < 1e-2
     q, k, v = (t.detach().requires_grad_(True) for t in qkv.float().reshape(B, T, 3, heads, hd).permute(2, 0, 3, 1, 4))
