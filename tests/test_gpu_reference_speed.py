@@ -65,3 +65,42 @@ def test_dit_l_forward_native_vs_pytorch_on_the_same_gpu():
     print(json.dumps(res))
     assert res["rel_l2_native_vs_pytorch_bf16"] < 2e-2
     assert res["speedup_vs_bf16_autocast"] > 1.0, res
+
+
+def test_dit_l_forward_backward_native_vs_pytorch_autograd():
+    """Same comparison for the training direction (config 5's denoiser work): forward + backward of DiT-L/4 at batch 64."""
+    B = 64
+    spec = O.DiTSpec((3, 64, 64), 4, 1024, 24, 16)
+    torch.manual_seed(0)
+    m = DenoisingDiT(spec.data_shape, spec.patch, spec.dim, spec.depth, spec.heads, dropout=None, fourier_features=FourierFeatures(n_min=6, n_max=8))
+    with torch.no_grad():
+        for blk in m.dit.blocks:
+            torch.nn.init.normal_(blk.adaLN_modulation[-1].weight, std=0.02)
+            torch.nn.init.normal_(blk.adaLN_modulation[-1].bias, std=0.02)
+    m = m.to(dev()).train()
+    sd = {k: v.detach().clone().requires_grad_(v.is_floating_point() and k in dict(m.named_parameters())) for k, v in m.state_dict().items()}
+    mu = torch.randn((B, *spec.data_shape), device=dev())
+    t = torch.rand(B, device=dev())
+    w = torch.randn_like(mu)
+
+    def native():
+        m.zero_grad(set_to_none=True)
+        (m(mu, t) * w).sum().backward()
+
+    def pytorch():
+        for v in sd.values():
+            v.grad = None
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            y = O.dit_forward(sd, spec, mu, t)
+        (y.float() * w).sum().backward()
+
+    res = {"batch": B, "native_fwd_bwd_ms": _time(native), "pytorch_bf16_autocast_fwd_bwd_ms": _time(pytorch)}
+    res["speedup"] = res["pytorch_bf16_autocast_fwd_bwd_ms"] / res["native_fwd_bwd_ms"]
+    g_native = m.dit.blocks[11].mlp[0].weight.grad
+    g_ref = sd["dit.blocks.11.mlp.0.weight"].grad
+    res["rel_l2_grad_mlp_block11"] = float((g_native - g_ref).norm() / g_ref.norm())
+    os.makedirs(OUT_DIR, exist_ok=True)
+    with open(os.path.join(OUT_DIR, "reference_on_gpu_train.json"), "w") as fh:
+        json.dump(res, fh)
+    print(json.dumps(res))
+    assert res["rel_l2_grad_mlp_block11"] < 5e-2
