@@ -104,3 +104,33 @@ def test_dit_l_forward_backward_native_vs_pytorch_autograd():
         json.dump(res, fh)
     print(json.dumps(res))
     assert res["rel_l2_grad_mlp_block11"] < 5e-2
+
+
+def test_unet_forward_native_vs_pytorch_on_the_same_gpu():
+    """cifar10-vdm's VDM U-Net (dim 128, 32 levels, batch 256): the oracle's functional forward on CUDA (cuDNN convolutions, channels-last
+    is PyTorch's business) under bf16 autocast vs the native engine."""
+    from bsi_b200.models import DenoisingVDMUNet, NyquistPositionalEmbedding
+
+    B = 256
+    spec = O.UNetSpec((3, 32, 32), dim=128, levels=32)
+    m = DenoisingVDMUNet(spec.data_shape, NyquistPositionalEmbedding(32, 100), "silu", 128, 32, 4, n_attention_heads=1, dropout=0.1,
+                         fourier_features=FourierFeatures(n_min=6, n_max=8))
+    m.load_state_dict(H.det_state_dict(H.unet_shapes(spec), seed=1))
+    m = m.to(dev()).eval().requires_grad_(False)
+    sd = {k: v.detach() for k, v in m.state_dict().items()}
+    mu = torch.randn((B, *spec.data_shape), device=dev())
+    t = torch.rand(B, device=dev())
+    res = {"batch": B}
+    with torch.inference_mode():
+        y_native = m(mu, t)
+        res["native_ms"] = _time(lambda: m(mu, t))
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            y_ref = O.unet_forward(sd, spec, mu, t).float()
+            res["pytorch_bf16_autocast_ms"] = _time(lambda: O.unet_forward(sd, spec, mu, t))
+    res["speedup_vs_bf16_autocast"] = res["pytorch_bf16_autocast_ms"] / res["native_ms"]
+    res["rel_l2_native_vs_pytorch_bf16"] = float((y_native - y_ref).norm() / y_ref.norm())
+    os.makedirs(OUT_DIR, exist_ok=True)
+    with open(os.path.join(OUT_DIR, "reference_on_gpu_unet.json"), "w") as fh:
+        json.dump(res, fh)
+    print(json.dumps(res))
+    assert res["rel_l2_native_vs_pytorch_bf16"] < 5e-2
