@@ -3,7 +3,7 @@
 TAG=${1:-r01}
 mkdir -p gpurun_out
 bash tools/gpu_round.sh noprobe
-bash tools/gpu_one.sh test_gpu_unet test_gpu_optim test_gpu_multi test_gpu_backward test_gpu_dit_train
+bash tools/gpu_one.sh test_gpu_unet test_gpu_optim test_gpu_multi test_gpu_backward test_gpu_dit_train test_gpu_reference_speed
 python __graft_entry__.py smoke > gpurun_out/smoke_$TAG.log 2>&1; echo "smoke exit $?"; tail -2 gpurun_out/smoke_$TAG.log
 python bench.py --steps 2 --warmup 3 > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err; echo "bench exit $?"; tail -c 1800 gpurun_out/bench_$TAG.json
 python tools/gpu_elbo.py > gpurun_out/elbo_$TAG.log 2>&1; tail -2 gpurun_out/elbo_$TAG.log
