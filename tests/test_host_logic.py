@@ -339,3 +339,22 @@ def test_training_path_covers_every_parameter_exactly_once():
     assert [index[id(p)] for p in direct[-4:]] == list(range(len(everything) - 4, len(everything)))
     seeds = {_layer_seed(s, k) for s in (0, 1, 12345) for k in range(48)}
     assert len(seeds) == 3 * 48 and all(0 <= x < 2**32 for x in seeds)  # distinct dropout streams per (call, layer, site)
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (CPU oracle port; here with a 2-block model to stay fast) prints ONE JSON line with the keys
+    the driver reads: impl, metric/unit, value, cpu_baseline describing the run, an e2e object with zero transfer bytes."""
+    import json
+    import subprocess
+    import sys
+
+    out = subprocess.run([sys.executable, os.path.join(H.ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0", "--depth", "2"],
+                         capture_output=True, text=True, timeout=300, cwd=H.ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "BSI.sample samples/sec" and d["unit"] == "samples/s" and d["higher_is_better"] is True
+    assert d["value"] > 0 and d["cpu_baseline"]["value"] == d["value"] and d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"] == {"value": d["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["vs_baseline"] is None and d["gpu_launches"] == 0 and "workload" in d["config"]
