@@ -358,3 +358,21 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert d["value"] > 0 and d["cpu_baseline"]["value"] == d["value"] and d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"] == {"value": d["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["vs_baseline"] is None and d["gpu_launches"] == 0 and "workload" in d["config"]
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the behaviour of a machine without a GPU")
+def test_native_arm_fails_loudly_without_a_gpu():
+    """No CPU fallback anywhere on the product path: bench.py's native arm and the BSI API refuse to run without CUDA."""
+    import subprocess
+    import sys
+
+    from bsi_b200 import BSI, Discretization
+    from bsi_b200._lib import BsiNativeError
+
+    out = subprocess.run([sys.executable, os.path.join(H.ROOT, "bench.py"), "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=300,
+                         cwd=H.ROOT)
+    assert out.returncode != 0 and "no CPU fallback" in (out.stderr + out.stdout)
+    bsi = BSI(torch.nn.Identity(), data_shape=(3, 32, 32), lambda_0=1e-2, alpha_M=1e6, alpha_R=2e6, k=4, preconditioning="edm",
+              discretization=Discretization.image_8bit())
+    with pytest.raises((BsiNativeError, RuntimeError)):
+        bsi.sample(2)
