@@ -79,6 +79,7 @@ _vp, _i32, _i64, _f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
 # name -> (restype, argtypes); must list every symbol of include/bsi_b200.h (checked by tests/test_abi.py)
 SIGNATURES = {
     "bsi_attention_backward_bf16": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _f32, C.c_uint32, _i32, _vp]),
+    "bsi_attention_lse_bf16": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp]),
     "bsi_attention_dropout_bf16": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _f32, C.c_uint32, _vp]),
     "bsi_layernorm_mod_dropout_bf16": (C.c_int, [_vp, _vp, RowRef, RowRef, _i32, _i64, _i32, _f32, _f32, C.c_uint32, _vp]),
     "bsi_gate_residual": (C.c_int, [_vp, _vp, _vp, RowRef, _i32, _i64, _i32, _vp]),

@@ -183,7 +183,7 @@ __global__ void __launch_bounds__(kAttThreads, 2)
     }
 }
 
-int attention_tcgen05(void* out_bf16, const void* qkv_bf16, int B, int heads, cudaStream_t stream);  // attention_sm100.cu
+int attention_tcgen05(void* out_bf16, const void* qkv_bf16, int B, int heads, float* lse, cudaStream_t stream);  // attention_sm100.cu
 static int g_force_legacy_attention = 0;
 
 }  // namespace bsi
@@ -203,7 +203,7 @@ extern "C" int bsi_attention_bf16(void* out_bf16, const void* qkv_bf16, int32_t 
         set_error("bsi_attention_bf16: only head_dim=64 and T in {128,256,384,512} are implemented (got head_dim=%d T=%d)", head_dim, T);
         return BSI_ERR_UNSUPPORTED;
     }
-    if (T == 256 && !g_force_legacy_attention) return attention_tcgen05(out_bf16, qkv_bf16, B, heads, (cudaStream_t)stream);
+    if (T == 256 && !g_force_legacy_attention) return attention_tcgen05(out_bf16, qkv_bf16, B, heads, nullptr, (cudaStream_t)stream);
     const int dim = heads * head_dim;
     const int smem = (kQRows + 2 * T) * 128;
     BSI_ENSURE_SMEM(k_attention_mma<false>, smem);
@@ -211,6 +211,26 @@ extern "C" int bsi_attention_bf16(void* out_bf16, const void* qkv_bf16, int32_t 
     dim3 grid(T / kQRows, heads, B);
     k_attention_mma<false><<<grid, kAttThreads, smem, (cudaStream_t)stream>>>((__nv_bfloat16*)out_bf16, (const __nv_bfloat16*)qkv_bf16, T, dim,
                                                                              scale_log2, 0u, 0u, 1.0f, nullptr);
+    BSI_LAUNCH_OK("k_attention_mma");
+    return BSI_OK;
+}
+
+// Training forward without dropout: the attention output plus the per-row log2-sum-exp the backward needs (lse_valid fast path).
+extern "C" int bsi_attention_lse_bf16(void* out_bf16, float* lse_out, const void* qkv_bf16, int32_t B, int32_t T, int32_t heads, int32_t head_dim,
+                                      void* stream) {
+    BSI_CHECK_ARG(out_bf16 && lse_out && qkv_bf16 && B > 0 && heads > 0, "bsi_attention_lse_bf16: bad arguments");
+    if (head_dim != kHd || T % kQRows != 0 || T > 512) {
+        set_error("bsi_attention_lse_bf16: only head_dim=64 and T in {128,256,384,512} are implemented (got head_dim=%d T=%d)", head_dim, T);
+        return BSI_ERR_UNSUPPORTED;
+    }
+    if (T == 256 && !g_force_legacy_attention) return attention_tcgen05(out_bf16, qkv_bf16, B, heads, lse_out, (cudaStream_t)stream);
+    const int dim = heads * head_dim;
+    const int smem = (kQRows + 2 * T) * 128;
+    BSI_ENSURE_SMEM(k_attention_mma<false>, smem);
+    const float scale_log2 = 1.4426950408889634f / sqrtf((float)head_dim);
+    dim3 grid(T / kQRows, heads, B);
+    k_attention_mma<false><<<grid, kAttThreads, smem, (cudaStream_t)stream>>>((__nv_bfloat16*)out_bf16, (const __nv_bfloat16*)qkv_bf16, T, dim, scale_log2,
+                                                                             0u, 0u, 1.0f, lse_out);
     BSI_LAUNCH_OK("k_attention_mma");
     return BSI_OK;
 }

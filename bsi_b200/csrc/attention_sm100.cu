@@ -39,9 +39,12 @@ __device__ __forceinline__ float ex2_approx(float x) {
 }
 __device__ __forceinline__ void softmax_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
+// LSE: also store log2(sum_j exp(scale * s_j)) per query row (training forward: spares the attention backward its statistics pass);
+// the inference instantiation <false> is unchanged.
+template <bool LSE>
 __global__ void __launch_bounds__(att::kThreads, 2)
     k_attention_tc(const __grid_constant__ CUtensorMap map_qkv, const __grid_constant__ CUtensorMap map_out, const int dim, const int heads,
-                   const int total_items, const float scale_log2) {
+                   const int total_items, const float scale_log2, float* __restrict__ lse) {
     using namespace att;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -213,7 +216,11 @@ __global__ void __launch_bounds__(att::kThreads, 2)
             if (lane == 0) ptx::mbar_arrive(bar_ofree);  // the TMEM tile may be overwritten by the next item's S
             if (threadIdx.x == 0) ptx::tma_store_wait_read<0>();  // previous item's store has drained the staging tile
             softmax_bar();  // also orders the s_sum exchange (written before bar_p above)
-            const float inv = 1.0f / (sum + s_sum[(hf ^ 1) * QB + r]);
+            const float total = sum + s_sum[(hf ^ 1) * QB + r];
+            const float inv = 1.0f / total;
+            if constexpr (LSE) {
+                if (hf == 0) lse[((size_t)(row0 / T) * heads + h) * T + qblk * QB + r] = moff + log2f(total);
+            }
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
                 uint32_t w[4];
@@ -240,10 +247,11 @@ __global__ void __launch_bounds__(att::kThreads, 2)
     }
 }
 
-int attention_tcgen05(void* out_bf16, const void* qkv_bf16, int B, int heads, cudaStream_t stream) {
+int attention_tcgen05(void* out_bf16, const void* qkv_bf16, int B, int heads, float* lse, cudaStream_t stream) {
     using namespace att;
     const int dim = heads * HD;
-    BSI_ENSURE_SMEM(k_attention_tc, kSmem);
+    if (lse) BSI_ENSURE_SMEM(k_attention_tc<true>, kSmem);
+    else BSI_ENSURE_SMEM(k_attention_tc<false>, kSmem);
     CUtensorMap mq, mo;
     int rc = make_tile_map(&mq, qkv_bf16, 2, (int64_t)B * T, 3 * dim, 3 * dim, 1, 0, QB);
     if (rc != BSI_OK) return rc;
@@ -257,7 +265,8 @@ int attention_tcgen05(void* out_bf16, const void* qkv_bf16, int B, int heads, cu
     cudaLaunchAttribute attr[1];
     fill_pdl_attr(&attr[0]);
     cfg.attrs = attr, cfg.numAttrs = use_pdl() ? 1 : 0;
-    BSI_CUDA_OK(cudaLaunchKernelEx(&cfg, k_attention_tc, mq, mo, dim, heads, total, scale_log2));
+    if (lse) BSI_CUDA_OK(cudaLaunchKernelEx(&cfg, k_attention_tc<true>, mq, mo, dim, heads, total, scale_log2, lse));
+    else BSI_CUDA_OK(cudaLaunchKernelEx(&cfg, k_attention_tc<false>, mq, mo, dim, heads, total, scale_log2, (float*)nullptr));
     BSI_LAUNCH_OK("k_attention_tc");
     return BSI_OK;
 }

@@ -168,13 +168,13 @@ class DiTTrainFunction(torch.autograd.Function):
                 qkv = torch.empty((M, 3 * D), dtype=torch.bfloat16, device=dev)
                 _gemm(a1, bf(w_qkv), qkv, b_qkv.detach().float(), L.EPI_BIAS_BF16)
                 att = torch.empty((M, D), dtype=torch.bfloat16, device=dev)
-                lse = None
-                if drop_p > 0:  # the dropout forward also saves the softmax statistics, which spares the backward a recomputation pass
-                    lse = torch.empty(B * heads * T, dtype=torch.float32, device=dev)
+                lse = torch.empty(B * heads * T, dtype=torch.float32, device=dev)  # softmax statistics: spare the backward a recomputation pass
+                if drop_p > 0:
                     L.check(lib.bsi_attention_dropout_bf16(att.data_ptr(), lse.data_ptr(), qkv.data_ptr(), B, T, heads, D // heads, drop_p,
                                                            _layer_seed(drop_seed, 2 * l), _st(dev)), "bsi_attention_dropout_bf16")
                 else:
-                    L.check(lib.bsi_attention_bf16(att.data_ptr(), qkv.data_ptr(), B, T, heads, D // heads, _st(dev)), "bsi_attention_bf16")
+                    L.check(lib.bsi_attention_lse_bf16(att.data_ptr(), lse.data_ptr(), qkv.data_ptr(), B, T, heads, D // heads, _st(dev)),
+                            "bsi_attention_lse_bf16")
                 br1 = torch.empty((M, D), dtype=torch.bfloat16, device=dev)
                 _gemm(att, bf(w_o), br1, b_o.detach().float(), L.EPI_BIAS_BF16)
                 x_mid, a2 = gate_ln(x, br1, ref(2), ref(3), ref(4), drop_site=(drop_p, _layer_seed(drop_seed, 2 * l + 1)))

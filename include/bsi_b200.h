@@ -215,6 +215,9 @@ int bsi_attention_force_legacy(int32_t on);
 int bsi_attention_backward_bf16(void* dqkv_bf16, float* lse_ws, float* dsum_ws, const void* qkv_bf16, const void* out_bf16, const void* dout_bf16,
                                 int32_t B, int32_t T, int32_t heads, int32_t head_dim, float drop_p, uint32_t drop_seed, int32_t lse_valid,
                                 void* stream);
+/* bsi_attention_bf16 that also stores the per-row log2-sum-exp of the scaled scores (lse_out: B*heads*T floats) for the
+ * lse_valid fast path of bsi_attention_backward_bf16 (training forward without dropout). */
+int bsi_attention_lse_bf16(void* out_bf16, float* lse_out, const void* qkv_bf16, int32_t B, int32_t T, int32_t heads, int32_t head_dim, void* stream);
 /* Training-mode attention with dropout on the probabilities (F.scaled_dot_product_attention(dropout_p), dit.py:43-44).  The keep mask
  * is a stateless hash of (drop_seed, head of sample, query, key) -- mix32 in csrc/common.cuh -- which bsi_attention_backward_bf16
  * regenerates from the same (drop_p, drop_seed); drop_p = 0 there means the forward ran without dropout.  lse_out (optional,

@@ -231,7 +231,8 @@ def test_attention_dropout_forward_backward_with_restated_mask(B, T, heads, p):
     call("bsi_attention_backward_bf16", L.ptr(dqkv_fast), L.ptr(lse), L.ptr(ws[1]), L.ptr(qkv), L.ptr(out), L.ptr(dout), B, T, heads, hd, p, seed, 1, L.stream_ptr())
     sync()
     report("saved vs recomputed log-sum-exp", lse, ws[0], 1e-5, 1e-4)
-    report("backward with saved statistics", dqkv_fast, dqkv, 2e-2, 1e-3)
+    report("backward with saved statistics", dqkv_fast, dqkv, 2e-2, 4e-3)
+    assert float((dqkv_fast.float() - dqkv.float()).norm() / dqkv.float().norm()) < 2e-3
     keep = H.attention_dropout_mask(seed, B, heads, T, p).to(dev())
     assert abs(float(keep.float().mean()) - (1 - p)) < 1e-2
     q, k, v = (t.detach().requires_grad_(True) for t in qkv.float().reshape(B, T, 3, heads, hd).permute(2, 0, 3, 1, 4))
@@ -275,3 +276,30 @@ def test_gate_residual_layernorm_fused_equals_the_two_kernels(dim):
              L.ptr(gamma) if aff else None, L.ptr(beta) if aff else None, T, M, dim, 1e-5, p, seed, L.stream_ptr())
         sync()
         assert torch.equal(x_f, x_sep) and torch.equal(a_f, a_sep), variant
+
+
+@pytest.mark.parametrize("T", [256, 128], ids=["tcgen05", "mma_sync"])
+def test_attention_forward_with_saved_statistics(T):
+    """bsi_attention_lse_bf16 == bsi_attention_bf16 bit for bit, plus the log2-sum-exp the backward's fast path consumes."""
+    B, heads, hd = 3, 4, 64
+    dim = heads * hd
+    qkv = rnd(f"al.qkv{T}", (B * T, 3 * dim), 2.0).bfloat16()
+    dout = rnd(f"al.do{T}", (B * T, dim)).bfloat16()
+    out0 = torch.zeros((B * T, dim), dtype=torch.bfloat16, device=dev())
+    out1 = torch.zeros_like(out0)
+    lse = torch.zeros(B * heads * T, device=dev())
+    call("bsi_attention_bf16", L.ptr(out0), L.ptr(qkv), B, T, heads, hd, L.stream_ptr())
+    call("bsi_attention_lse_bf16", L.ptr(out1), L.ptr(lse), L.ptr(qkv), B, T, heads, hd, L.stream_ptr())
+    sync()
+    assert torch.equal(out0, out1)
+    q, k, _ = qkv.float().reshape(B, T, 3, heads, hd).permute(2, 0, 3, 1, 4)
+    ref = torch.logsumexp(q @ k.transpose(-1, -2) / 8.0, dim=-1) * 1.4426950408889634
+    report("saved log2-sum-exp", lse.reshape(B, heads, T), ref, 1e-4, 1e-3)
+    ws = torch.zeros((2, B * heads * T), device=dev())
+    slow, fast = torch.zeros_like(qkv), torch.zeros_like(qkv)
+    call("bsi_attention_backward_bf16", L.ptr(slow), L.ptr(ws[0]), L.ptr(ws[1]), L.ptr(qkv), L.ptr(out0), L.ptr(dout), B, T, heads, hd, 0.0, 0, 0, L.stream_ptr())
+    call("bsi_attention_backward_bf16", L.ptr(fast), L.ptr(lse), L.ptr(ws[1]), L.ptr(qkv), L.ptr(out0), L.ptr(dout), B, T, heads, hd, 0.0, 0, 1, L.stream_ptr())
+    sync()
+    # the saved and the recomputed statistics differ in the last bits, which moves a bf16 gradient by at most one ulp of the tensor's range
+    report("backward with saved statistics", fast, slow, 2e-2, 4e-3)
+    assert float((fast.float() - slow.float()).norm() / slow.float().norm()) < 2e-3
