@@ -48,14 +48,18 @@ int sm_count();
 bool use_pdl();
 void fill_pdl_attr(cudaLaunchAttribute* attr);
 
-// Opt a kernel into `bytes` of dynamic shared memory, once per (call site, device).
+// Opt a kernel into `bytes` of dynamic shared memory, once per (call site, device).  The limit is only ever raised: another
+// call site of the same kernel may already have asked for more (the cache below is per call site, the attribute per kernel).
 #define BSI_ENSURE_SMEM(kernel, bytes)                                                                            \
     do {                                                                                                          \
         static int _done[64] = {0};                                                                               \
         int _dev = 0;                                                                                             \
         BSI_CUDA_OK(cudaGetDevice(&_dev));                                                                        \
         if (_dev >= 0 && _dev < 64 && _done[_dev] < (bytes)) {                                                    \
-            BSI_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (bytes)));      \
+            cudaFuncAttributes _fa;                                                                               \
+            BSI_CUDA_OK(cudaFuncGetAttributes(&_fa, kernel));                                                     \
+            const int _want = (int)(bytes) > _fa.maxDynamicSharedSizeBytes ? (int)(bytes) : _fa.maxDynamicSharedSizeBytes; \
+            BSI_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, _want));        \
             _done[_dev] = (bytes);                                                                                \
         }                                                                                                         \
     } while (0)

@@ -303,3 +303,22 @@ def test_attention_forward_with_saved_statistics(T):
     # the saved and the recomputed statistics differ in the last bits, which moves a bf16 gradient by at most one ulp of the tensor's range
     report("backward with saved statistics", fast, slow, 2e-2, 4e-3)
     assert float((fast.float() - slow.float()).norm() / slow.float().norm()) < 2e-3
+
+
+def test_shared_memory_opt_in_is_never_lowered_by_another_entry_point():
+    """Regression: bsi_attention_lse_bf16 (T = 128, 48 KB) and the mma.sync path of bsi_attention_bf16 (T = 512, 144 KB) launch the same
+    kernel from two call sites; the smaller request must not lower the kernel's dynamic shared memory limit again."""
+    heads, hd = 2, 64
+    dim = heads * hd
+    call("bsi_attention_force_legacy", 1)
+    try:
+        for T in (512, 128, 512):
+            qkv = rnd(f"sm.qkv{T}", (T, 3 * dim)).bfloat16()
+            out = torch.zeros((T, dim), dtype=torch.bfloat16, device=dev())
+            lse = torch.zeros(heads * T, device=dev())
+            call("bsi_attention_bf16", L.ptr(out), L.ptr(qkv), 1, T, heads, hd, L.stream_ptr())
+            call("bsi_attention_lse_bf16", L.ptr(out), L.ptr(lse), L.ptr(qkv), 1, T, heads, hd, L.stream_ptr())
+            sync()
+            assert torch.isfinite(out.float()).all()
+    finally:
+        call("bsi_attention_force_legacy", 0)
