@@ -20,7 +20,7 @@ class RowRef(C.Structure):
 
 
 class Noise(C.Structure):
-    _fields_ = [("eps", C.c_void_p), ("seed", C.c_uint64), ("sample_base", C.c_uint64), ("draw", C.c_int32)]
+    _fields_ = [("eps", C.c_void_p), ("seed", C.c_uint64), ("sample_base", C.c_uint64), ("draw", C.c_int32), ("key_ptr", C.c_void_p)]
 
 
 class GemmArgs(C.Structure):
@@ -199,7 +199,11 @@ def rowref(t: torch.Tensor | None, sample_stride: int = 0, step_stride: int = 0,
     return RowRef(ptr(t) + 4 * offset, sample_stride, step_stride)
 
 
-def noise(eps: torch.Tensor | None = None, seed: int = 0, sample_base: int = 0, draw: int = 0) -> Noise:
+def noise(eps: torch.Tensor | None = None, seed: int = 0, sample_base: int = 0, draw: int = 0, key: torch.Tensor | None = None) -> Noise:
+    """bsi_noise: injected `eps`, or Philox keyed by (seed, sample_base) -- by value, or read on the device from `key`
+    (int64[2] CUDA tensor {seed, sample_base}) so that a captured graph can be replayed with another key."""
     if eps is not None:
         assert eps.dtype == torch.float32
-    return Noise(ptr(eps), seed & 0xFFFFFFFFFFFFFFFF, sample_base, draw)
+    if key is not None:
+        assert key.dtype == torch.int64 and key.numel() == 2 and key.is_cuda
+    return Noise(ptr(eps), seed & 0xFFFFFFFFFFFFFFFF, sample_base, draw, ptr(key))

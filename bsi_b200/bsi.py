@@ -27,7 +27,7 @@ from torch import Tensor, nn
 
 from . import _lib as L
 
-__all__ = ["BSI", "Discretization", "LogUniform", "broadcast_right"]
+__all__ = ["BSI", "Discretization", "LogUniform", "ReplayNoise", "broadcast_right"]
 
 
 def _cuda_f32(x: Tensor, what: str) -> Tensor:
@@ -122,6 +122,35 @@ class LogUniform:
 
     def icdf(self, quantile: Tensor) -> Tensor:
         return torch.exp(self.diff_ln_high_ln_low * quantile + self.ln_low)
+
+
+class ReplayNoise:
+    """Stands in for the ``generator`` argument and hands out PRE-DRAWN tensors in the order the reference consumes its
+    generator (``randn`` / ``rand`` / ``randperm`` / ``randint`` calls of bsi/bsi.py:224-226,264,283-284,325,332,415,430-434).
+
+    Parity hook: the stored draws of a reference run (tests/golden/full.pt) are injected into the CUDA path, so losses
+    and bits-per-dim are compared on exactly the noise and lambda grid the reference used."""
+
+    def __init__(self, draws):
+        self._draws = list(draws)
+
+    def take(self, shape, device) -> Tensor:
+        if not self._draws:
+            raise RuntimeError("ReplayNoise exhausted: the call consumed more random draws than were recorded")
+        d = self._draws.pop(0)
+        if tuple(d.shape) != tuple(shape):
+            raise RuntimeError(f"ReplayNoise: next recorded draw has shape {tuple(d.shape)}, the call asked for {tuple(shape)}")
+        return d.to(device)
+
+    @property
+    def remaining(self) -> int:
+        return len(self._draws)
+
+
+def _randn(shape, generator, **tensor_args) -> Tensor:
+    if isinstance(generator, ReplayNoise):
+        return generator.take(shape, tensor_args["device"]).to(tensor_args["dtype"]).contiguous()
+    return torch.randn(shape, **tensor_args, generator=generator)
 
 
 # ----------------------------------------------------------------------------- autograd bridge
@@ -225,10 +254,13 @@ class BSI(nn.Module):
 
     def _noise(self, shape, generator, draw: int, sample_base: int = 0, seed: int | None = None):
         """bsi_noise for one draw: injected torch.randn (parity) or Philox keyed by `seed`."""
-        if self.noise_source == "torch":
-            eps = torch.randn(shape, **self.tensor_args, generator=generator)
+        if self.noise_source == "torch" or isinstance(generator, ReplayNoise):
+            eps = _randn(shape, generator, **self.tensor_args)
             return L.noise(eps=eps), eps
         return L.noise(seed=seed, sample_base=sample_base, draw=draw), None
+
+    def _philox(self, generator) -> bool:
+        return self.noise_source != "torch" and not isinstance(generator, ReplayNoise)
 
     def _draw_seed(self, generator) -> int:
         dev = generator.device if generator is not None else "cpu"
@@ -306,7 +338,13 @@ class BSI(nn.Module):
         lam = lambda_.reshape(-1)
         gamma = ((lam - self.lambda_0) / lam).contiguous()
         sigma = torch.rsqrt(lam).contiguous()
-        if self.noise_source != "torch" and _seed is None:
+        if x.ndim < 1 or lambda_.ndim < 1 or lambda_.shape[-1] != B:
+            # the reference would broadcast a mismatched lambda inside torch (or fail there); the kernels index x[r % B] and the
+            # per-row coefficient vectors directly, so a shape that does not end in the batch axis is rejected here
+            raise ValueError(f"lambda_ must have shape [..., batch={B}], got {tuple(lambda_.shape)}")
+        if _c_in is not None and _c_in.numel() != R:
+            raise ValueError(f"c_in has {_c_in.numel()} elements for {R} (sample, data point) rows")
+        if self._philox(generator) and _seed is None:
             _seed = self._draw_seed(generator)
         if R == 0:  # empty batch: nothing to draw (torch.randn of an empty shape consumes no random numbers either)
             mu = torch.empty((*lambda_.shape, *self.data_shape), **self.tensor_args)
@@ -328,12 +366,18 @@ class BSI(nn.Module):
     def _sample_lambda(self, n_samples: int, batch_size: int, generator=None) -> Tensor:
         if self.low_discrepancy_sampling:
             # low-discrepancy grid of the VDM paper: one random offset, a permuted regular grid
-            offset = torch.rand((), **self.tensor_args, generator=generator)
             total = n_samples * batch_size
-            grid = torch.randperm(total, device=self.tensor_args["device"], generator=generator) / (1 + total)
+            if isinstance(generator, ReplayNoise):
+                dev = self.tensor_args["device"]
+                offset, perm = generator.take((), dev).to(self.tensor_args["dtype"]), generator.take((total,), dev)
+            else:
+                offset = torch.rand((), **self.tensor_args, generator=generator)
+                perm = torch.randperm(total, device=self.tensor_args["device"], generator=generator)
+            grid = perm / (1 + total)
             t = torch.remainder(grid.reshape(n_samples, batch_size) + offset, 1)
         else:
-            # the reference draws the transposed shape here (bsi/bsi.py:441-445); mirrored as is
+            # the reference draws the transposed shape here (bsi/bsi.py:441-445); mirrored as is.  Only n_samples == batch_size
+            # survives the shape checks of the loss methods below (the reference broadcasts or fails inside torch instead)
             t = torch.rand((batch_size, n_samples), **self.tensor_args, generator=generator)
         return self.p_lambda.icdf(t)
 
@@ -341,6 +385,12 @@ class BSI(nn.Module):
     def _errors(self, x: Tensor, lambda_: Tensor, t_flat: Tensor, generator, draw: int) -> Tensor:
         """sum_d (x - x_hat)^2 for mu ~ q(.|x, lambda_[n,B]) and the model evaluated at t_flat -> [n,B]."""
         self._check_precond()
+        if lambda_.ndim != 2 or lambda_.shape[1] != len(x) or t_flat.numel() != lambda_.numel():
+            raise ValueError(
+                f"lambda_ must be [n_samples, batch={len(x)}] with one time per entry, got lambda_ {tuple(lambda_.shape)} and "
+                f"{t_flat.numel()} times (low_discrepancy_sampling=False draws the reference's transposed [batch, n_samples] grid, "
+                "bsi/bsi.py:441-445, which only fits when n_samples == batch)"
+            )
         n, B = lambda_.shape
         if B == 0:
             return _cuda_f32(x, "x").new_zeros((n, 0))
@@ -404,7 +454,10 @@ class BSI(nn.Module):
         lambda_ = self.p_lambda.icdf(t)
         alpha = lambda_.diff()
         k = len(alpha)
-        i = torch.randint(0, k, (n_samples, len(x)), device=x.device, generator=generator)
+        if isinstance(generator, ReplayNoise):
+            i = generator.take((n_samples, len(x)), x.device)
+        else:
+            i = torch.randint(0, k, (n_samples, len(x)), device=x.device, generator=generator)
         err = self._errors(x, lambda_[i], t[i].flatten(end_dim=1), generator, draw=1)
         return (0.5 * k) * alpha[i] * err
 
@@ -462,7 +515,7 @@ class BSI(nn.Module):
         k, lam, coef, c_in, t_rows = self._step_table(t)
         D = self._numel
         lib, st = L.load(), L.stream_ptr(dev)
-        philox = self.noise_source != "torch"
+        philox = self._philox(generator)
         if philox and seed is None:
             seed = self._draw_seed(generator)
         shape = (n, *self.data_shape)
@@ -475,7 +528,7 @@ class BSI(nn.Module):
         sigma0 = torch.rsqrt(lam[:1]).contiguous()
         if self._is_native_denoiser() and philox and not history:
             # whole loop on the device: CUDA graph of (denoiser forward + fused step), replayed k times
-            return self._native().sample_loop(n, sigma0, coef, c_in, t_rows, k, seed, sample_offset, precond)
+            return self._native().sample_loop(n, sigma0, coef, c_in, t_rows, k, seed, sample_offset, precond, plans=self._plans)
         mu = torch.empty(shape, **self.tensor_args)
         with torch.cuda.device(dev):
             nz, _keep = self._noise(shape, generator, 0, sample_offset, seed)
@@ -488,7 +541,8 @@ class BSI(nn.Module):
             for i in range(k):
                 ti = t_rows[i].expand(n)
                 f = _cuda_f32(self._denoise(mu, ti, c_in[i].expand(n) if precond else None), "denoiser output")
-                nz, _keep = self._noise(shape, generator, 1 + i, sample_offset, seed)
+                # Philox counter of step i is draw + step = 1 + i, the same as in the captured graph (draw = 1, device step counter)
+                nz, _keep = self._noise(shape, generator, 1, sample_offset, seed)
                 L.check(
                     lib.bsi_step_fused(
                         L.ptr(mu), L.ptr(f), L.ptr(coef), None, i, precond, nz,

@@ -31,10 +31,20 @@ def denoiser_state_dict(ckpt: Mapping[str, Any], which: str = "ema") -> dict[str
 
 
 def _data_shape(config: Mapping[str, Any]) -> tuple[int, int, int]:
-    name = str(config["data"].get("name", config["data"].get("_target_", ""))).lower()
-    if "64" in name:
-        return (3, 64, 64)
-    return (3, 32, 32)  # cifar10, imagenet32
+    """``datamodule.data_shape()`` of the run (bsi/tasks/bsi.py:103) from the resolved data config, with the data modules'
+    own rules: ImageNetDataModule -> (3, n, n) (bsi/data/imagenet.py:148-149, config/data/imagenet.yaml ``n``);
+    CIFAR10DataModule -> (3, 32, 32) (bsi/data/cifar10.py:148-149).  The weights cannot tell: the DiT's positional table is
+    a non-persistent buffer, so the token grid is not in the state_dict."""
+    data = config["data"]
+    target = str(data.get("_target_", ""))
+    if target.endswith("ImageNetDataModule") or ("n" in data and not target):
+        n = int(data["n"])
+        return (3, n, n)
+    if target.endswith("CIFAR10DataModule"):
+        return (3, int(data.get("height", 32)), int(data.get("width", 32)))
+    if "data_shape" in data:  # explicit override for checkpoints of other data modules
+        return tuple(int(v) for v in data["data_shape"])
+    raise KeyError(f"cannot derive the data shape from the checkpoint's data config (_target_={target!r}); add data.data_shape")
 
 
 def build_denoiser(model_cfg: Mapping[str, Any], data_shape) -> torch.nn.Module:

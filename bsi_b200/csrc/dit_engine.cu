@@ -216,6 +216,11 @@ int bsi_dit_forward(const bsi_dit* e, float* out, const float* mu, bsi_rowref in
                     int32_t cond_row0, int32_t cond_sample_rows, int32_t cond_step_rows, const int32_t* step_ptr, int32_t B,
                     void* workspace, int64_t workspace_bytes, void* stream) {
     BSI_CHECK_ARG(e && out && mu && in_scale.base && cond && workspace && B > 0 && cond_rows > 0, "bsi_dit_forward: bad arguments");
+    // the host-known part of the conditioning row index must stay inside the table (the step part, read on the device, is the
+    // caller's contract: *step_ptr * cond_step_rows + that index < cond_rows)
+    BSI_CHECK_ARG(cond_row0 >= 0 && cond_sample_rows >= 0 && cond_step_rows >= 0 &&
+                      (int64_t)cond_row0 + (int64_t)(B - 1) * cond_sample_rows < cond_rows,
+                  "%s: conditioning rows [%d + b*%d, b < %d] exceed the table of %d rows", "bsi_dit_forward", cond_row0, cond_sample_rows, B, cond_rows);
     if (bsi_dit_missing_params(e) != 0) {
         set_error("bsi_dit_forward: %d parameters not set", bsi_dit_missing_params(e));
         return BSI_ERR_NOT_READY;

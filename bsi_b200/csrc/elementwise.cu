@@ -62,6 +62,11 @@ __device__ __forceinline__ float mul_rn(float a, float b) { return __fmul_rn(a, 
 __device__ __forceinline__ float addcmul_rn(float a, float b, float c) { return __fmaf_rn(b, c, a); }  // torch.addcmul: one FMA (CPU and CUDA)
 __device__ __forceinline__ float add_mul_sep(float a, float b, float c) { return __fadd_rn(a, __fmul_rn(b, c)); }  // a + b*c as two eager ops
 
+// by-value key, or the {seed, sample_base} pair a replayed graph reads from device memory
+__device__ __forceinline__ bsi_noise resolve_noise(bsi_noise nz) {
+    if (nz.key_ptr) nz.seed = nz.key_ptr[0], nz.sample_base = nz.key_ptr[1];
+    return nz;
+}
 __device__ __forceinline__ float4 noise4(const bsi_noise& nz, int step, int64_t sample, int64_t quad, int64_t D) {
     if (nz.eps) return ld4_stream(nz.eps + sample * D + quad * 4);
     return philox_normal4(nz.seed, nz.sample_base + (uint64_t)sample, (uint32_t)(nz.draw + step), (uint32_t)quad);
@@ -70,7 +75,8 @@ __device__ __forceinline__ float4 noise4(const bsi_noise& nz, int step, int64_t 
 // ------------------------------------------------------------------ sampler init (bsi/bsi.py:325-327)
 // bytes/elem: 4 written (+4 read when noise is injected)
 __global__ void __launch_bounds__(kThreads) k_sample_init(float* __restrict__ mu, const float* __restrict__ sigma0_ptr,
-                                                          bsi_noise nz, int64_t n, int64_t D) {
+                                                          bsi_noise nz_arg, int64_t n, int64_t D) {
+    const bsi_noise nz = resolve_noise(nz_arg);
     const float s0 = sigma0_ptr[0];
     const int64_t qpr = D >> 2, total = n * qpr;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -85,8 +91,9 @@ __global__ void __launch_bounds__(kThreads) k_sample_init(float* __restrict__ mu
 template <bool kPrecond>
 __global__ void __launch_bounds__(kThreads)
     k_step_fused(float* __restrict__ mu, const float* __restrict__ f, const float* __restrict__ coef,
-                 const int32_t* __restrict__ step_ptr, int32_t step_arg, bsi_noise nz, float* __restrict__ x_hat_out,
+                 const int32_t* __restrict__ step_ptr, int32_t step_arg, bsi_noise nz_arg, float* __restrict__ x_hat_out,
                  float* __restrict__ y_out, int64_t n, int64_t D) {
+    const bsi_noise nz = resolve_noise(nz_arg);
     const int step = step_ptr ? *step_ptr : step_arg;
     const float* c = coef + (int64_t)step * 8;
     const float c_skip = c[0], c_out = c[1], sigma = c[2], alpha = c[3], lam = c[4], lam_next = c[5];
@@ -145,7 +152,8 @@ __global__ void __launch_bounds__(kThreads) k_scale_rows(float* __restrict__ out
 // bytes/elem: read x 4 (L2-resident across the n replicas) + write mu 4 (+4 model_in, +4 injected eps)
 __global__ void __launch_bounds__(kThreads)
     k_q_sample(float* __restrict__ mu, float* __restrict__ model_in, const float* __restrict__ x, const float* __restrict__ gamma,
-               const float* __restrict__ sigma, const float* __restrict__ c_in, bsi_noise nz, int64_t R, int64_t B, int64_t D) {
+               const float* __restrict__ sigma, const float* __restrict__ c_in, bsi_noise nz_arg, int64_t R, int64_t B, int64_t D) {
+    const bsi_noise nz = resolve_noise(nz_arg);
     const int64_t qpr = D >> 2, total = R * qpr;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         int64_t r = i / qpr, q = i - r * qpr, off = r * D + q * 4;
@@ -266,7 +274,7 @@ using namespace bsi;
 
 extern "C" {
 
-int bsi_abi_version(void) { return 1; }
+int bsi_abi_version(void) { return 2; }
 long long bsi_launch_counter(void) { return g_launches.load(std::memory_order_relaxed); }
 const char* bsi_last_error(void) { return g_err; }
 int bsi_device_arch(void) {

@@ -232,6 +232,11 @@ int bsi_unet_forward(const bsi_unet* e, float* out, const float* mu, bsi_rowref 
                      int32_t cond_sample_rows, int32_t cond_step_rows, const int32_t* step_ptr, int32_t B, void* workspace, int64_t workspace_bytes,
                      void* stream) {
     BSI_CHECK_ARG(e && out && mu && in_scale.base && cond && workspace && B > 0 && cond_rows > 0, "bsi_unet_forward: bad arguments");
+    // the host-known part of the conditioning row index must stay inside the table (the step part, read on the device, is the
+    // caller's contract: *step_ptr * cond_step_rows + that index < cond_rows)
+    BSI_CHECK_ARG(cond_row0 >= 0 && cond_sample_rows >= 0 && cond_step_rows >= 0 &&
+                      (int64_t)cond_row0 + (int64_t)(B - 1) * cond_sample_rows < cond_rows,
+                  "%s: conditioning rows [%d + b*%d, b < %d] exceed the table of %d rows", "bsi_unet_forward", cond_row0, cond_sample_rows, B, cond_rows);
     if (bsi_unet_missing_params(e) != 0) {
         set_error("bsi_unet_forward: %d parameters not set", bsi_unet_missing_params(e));
         return BSI_ERR_NOT_READY;

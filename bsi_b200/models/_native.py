@@ -48,17 +48,20 @@ class NativeDenoiser(nn.Module):
         yield from self.state_dict(keep_vars=True).items()
 
     def _signature(self):
-        """(address, version) of every packed tensor; a change triggers re-packing.
+        """(address, version, arena generation) of every packed tensor; a change triggers re-packing.
 
-        Tensors created under torch.inference_mode() carry no version counter: for those only a new
-        allocation is detected and in-place updates need an explicit `repack()`."""
+        The native optimizer / EMA kernels (bsi_b200/optim.py) write parameters through raw pointers, which torch's version
+        counters do not see: parameters adopted by a ``FlatArena`` therefore also carry the arena's generation counter, which
+        every native write bumps.  Tensors created under torch.inference_mode() carry no version counter: for those only a
+        new allocation is detected and in-place updates need an explicit `repack()`."""
         sig = []
         for _, p in self._named_tensors():
             try:
                 version = p._version
             except RuntimeError:
                 version = -1
-            sig.append((p.data_ptr(), version))
+            arena = getattr(p, "_bsi_arena", None)
+            sig.append((p.data_ptr(), version, arena[0].generation if arena is not None else 0))
         return tuple(sig)
 
     def _ensure_packed(self, device):
@@ -125,6 +128,17 @@ class NativeDenoiser(nn.Module):
         """f(in_scale[b] * mu[b], t[b]); the scaling is fused into the operand builder."""
         self._check_input(mu)
         dev, B = mu.device, mu.shape[0]
+        t = t.reshape(-1)
+        if t.numel() == 1 and B != 1:  # one time for the whole batch: the reference's modulate() broadcasts it (bsi/models/dit.py:50-55)
+            t = t.expand(B)
+        if t.numel() != B:
+            raise ValueError(f"t has {t.numel()} elements for a batch of {B}")
+        if in_scale is not None:
+            in_scale = in_scale.reshape(-1)
+            if in_scale.numel() == 1 and B != 1:
+                in_scale = in_scale.expand(B)
+            if in_scale.numel() != B:
+                raise ValueError(f"in_scale has {in_scale.numel()} elements for a batch of {B}")
         with torch.cuda.device(dev):
             eng = self._ensure_packed(dev)
             mu = mu.detach().to(torch.float32).contiguous()
@@ -144,10 +158,17 @@ class NativeDenoiser(nn.Module):
         return self.forward_scaled(mu, t, None)
 
     # ---- k-step sampler with a CUDA graph per step (reference bsi/bsi.py:328-336) ---------------------------
+    _MAX_PLANS = 4
+
     @torch.no_grad()
     def sample_loop(self, n: int, lam0_rsqrt: Tensor, coef: Tensor, c_in: Tensor, t_rows: Tensor, k: int, seed: int, sample_offset: int,
-                    precond: int, use_graph: bool = True) -> Tensor:
-        """Run mu_0 -> ... -> mu_k -> x_hat with in-kernel Philox noise.  coef[k+1,8], c_in[k+1], t_rows[k+1]."""
+                    precond: int, use_graph: bool = True, plans: dict | None = None) -> Tensor:
+        """Run mu_0 -> ... -> mu_k -> x_hat with in-kernel Philox noise.  coef[k+1,8], c_in[k+1], t_rows[k+1].
+
+        The captured graph of one step (denoiser forward + fused update + counter increment) only refers to buffers owned by
+        its plan (belief state, step tables, Philox key, step counter) and to this denoiser's arena / conditioning table /
+        workspace, so a plan is reused by every later call with the same (n, k): the call refreshes the tables, the key and
+        the counter and replays.  `plans` is the caller's cache (``BSI._plans``, cleared by ``set_model``)."""
         dev, lib = coef.device, L.load()
         D = self.data_shape[0] * self.data_shape[1] * self.data_shape[2]
         forward = self._fn("forward")
@@ -156,37 +177,55 @@ class NativeDenoiser(nn.Module):
             cond = self._conditioning(eng, t_rows, "cond_sampler")
             ws_bytes = self._fn("workspace_bytes")(eng, n)
             ws = self._buffer("workspace", ws_bytes, dev)
-            mu = torch.empty((n, *self.data_shape), dtype=torch.float32, device=dev)
-            f = torch.empty_like(mu)
-            step = torch.zeros(1, dtype=torch.int32, device=dev)
-            ones = torch.ones(1, dtype=torch.float32, device=dev)
-            scale_ref = L.rowref(c_in, 0, 1) if precond else L.rowref(ones, 0, 0)
+            # a plan is valid for these buffers only (they are re-allocated when a larger request comes along)
+            key = (n, k, precond, dev.index, id(self), self._arena.data_ptr(), cond.data_ptr(), ws.data_ptr())
+            plan = plans.get(key) if plans is not None else None
+            if plan is None:
+                plan = {
+                    "mu": torch.empty((n, *self.data_shape), dtype=torch.float32, device=dev), "f": None,
+                    "step": torch.zeros(1, dtype=torch.int32, device=dev), "coef": torch.empty_like(coef), "c_in": torch.empty_like(c_in),
+                    "key": torch.zeros(2, dtype=torch.int64, device=dev), "ones": torch.ones(1, dtype=torch.float32, device=dev), "graph": None,
+                }
+                plan["f"] = torch.empty_like(plan["mu"])
+                if plans is not None:
+                    while len(plans) >= self._MAX_PLANS:
+                        plans.pop(next(iter(plans)))
+                    plans[key] = plan
+            mu, f, step, key_buf = plan["mu"], plan["f"], plan["step"], plan["key"]
+            plan["coef"].copy_(coef), plan["c_in"].copy_(c_in)
+            step.zero_()
+            # {seed, sample_base} as two's-complement int64 (the kernels read them as uint64)
+            to_i64 = lambda v: (v & 0xFFFFFFFFFFFFFFFF) - (1 << 64) if (v & 0xFFFFFFFFFFFFFFFF) >= (1 << 63) else (v & 0xFFFFFFFFFFFFFFFF)
+            key_buf.copy_(torch.tensor([to_i64(int(seed)), to_i64(int(sample_offset))], dtype=torch.int64), non_blocking=False)
+            scale_ref = L.rowref(plan["c_in"], 0, 1) if precond else L.rowref(plan["ones"], 0, 0)
 
             def enqueue_forward():
                 L.check(
                     forward(eng, f.data_ptr(), mu.data_ptr(), scale_ref, cond.data_ptr(), k + 1, 0, 0, 1, step.data_ptr(), n,
-                            ws.data_ptr(), ws_bytes, L.stream_ptr(dev)),
+                            ws.data_ptr(), ws_bytes, L.stream_ptr(dev)),  # the current stream: the capture stream while capturing
                     self._api + "forward",
                 )
 
             def enqueue_step():
                 enqueue_forward()
                 L.check(
-                    lib.bsi_step_fused(mu.data_ptr(), f.data_ptr(), coef.data_ptr(), step.data_ptr(), 0, precond,
-                                       L.noise(seed=seed, sample_base=sample_offset, draw=1), None, None, n, D, L.stream_ptr(dev)),
+                    lib.bsi_step_fused(mu.data_ptr(), f.data_ptr(), plan["coef"].data_ptr(), step.data_ptr(), 0, precond,
+                                       L.noise(draw=1, key=key_buf), None, None, n, D, L.stream_ptr(dev)),
                     "bsi_step_fused",
                 )
                 L.check(lib.bsi_step_advance(step.data_ptr(), L.stream_ptr(dev)), "bsi_step_advance")
 
-            L.check(lib.bsi_sample_init(mu.data_ptr(), lam0_rsqrt.data_ptr(), L.noise(seed=seed, sample_base=sample_offset, draw=0), n, D,
-                                        L.stream_ptr(dev)), "bsi_sample_init")
+            L.check(lib.bsi_sample_init(mu.data_ptr(), lam0_rsqrt.data_ptr(), L.noise(draw=0, key=key_buf), n, D, L.stream_ptr(dev)),
+                    "bsi_sample_init")
             if use_graph and k > 1:
-                enqueue_forward()  # eager warm-up: first-launch attribute setup happens outside capture; idempotent
-                graph = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(graph):
-                    enqueue_step()
+                if plan["graph"] is None:
+                    enqueue_forward()  # eager warm-up: first-launch attribute setup happens outside capture; idempotent
+                    graph = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(graph):
+                        enqueue_step()
+                    plan["graph"] = graph
                 for _ in range(k):
-                    graph.replay()
+                    plan["graph"].replay()
             else:
                 for _ in range(k):
                     enqueue_step()
@@ -194,10 +233,10 @@ class NativeDenoiser(nn.Module):
             enqueue_forward()
             self.last_sampler_state = {"mu": mu, "step": step}
             if not precond:
-                return f
+                return f.clone()
             x_hat = torch.empty_like(mu)
             L.check(
-                lib.bsi_edm_combine(x_hat.data_ptr(), mu.data_ptr(), f.data_ptr(), L.rowref(coef, 0, 8, 0), L.rowref(coef, 0, 8, 1),
+                lib.bsi_edm_combine(x_hat.data_ptr(), mu.data_ptr(), f.data_ptr(), L.rowref(plan["coef"], 0, 8, 0), L.rowref(plan["coef"], 0, 8, 1),
                                     step.data_ptr(), n, D, L.stream_ptr(dev)),
                 "bsi_edm_combine",
             )

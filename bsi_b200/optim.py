@@ -54,6 +54,9 @@ class FlatArena:
             off += (s.numel() + _ALIGN - 1) // _ALIGN * _ALIGN
         self.numel = max(off, _ALIGN)
         self.flat = torch.zeros(self.numel, dtype=torch.float32, device=device)
+        # bumped by every native kernel that writes the arena through raw pointers (torch's version counters do not see those
+        # writes): NativeDenoiser._signature() includes it, so the packed bf16 weights are rebuilt before the next evaluation
+        self.generation = 0
 
     def view(self, i: int) -> Tensor:
         n = self.shapes[i].numel()
@@ -170,6 +173,7 @@ class EMA(nn.Module):
             ema, online = self._arenas()
             L.check(L.load().bsi_ema_update(L.ptr(ema.flat), L.ptr(online.flat), online.numel, weight, mode, L.stream_ptr(online.flat.device)),
                     "bsi_ema_update")
+            ema.generation += 1
         if mode == 1:  # copy_params_from_model_to_ema also copies the buffers (ema_pytorch.py:273-284)
             for b_ema, b in zip(self.ema_model.buffers(), self.model.buffers()):
                 b_ema.copy_(b)
@@ -339,6 +343,9 @@ class AdamW(torch.optim.Optimizer):
             max_norm=float(self.max_grad_norm) if clip else 0.0, grad_scale=float(self._grad_scale), ema_weight=float(weight), ema_mode=int(mode), zero_grad=1,
         )
         L.check(self._lib.bsi_adamw_ema_step(ctypes.byref(a), st), "bsi_adamw_ema_step")
+        self._p.generation += 1  # the kernel rewrote the parameters (and the EMA weights) behind torch's back
+        if self._ema is not None and mode != 0:
+            self._ema_arena.generation += 1
         self._last_scale, self._grad_scale = self._grad_scale, 1.0
         self._clean_version = self._g.flat._version  # the kernel left the gradients zeroed; autograd accumulation bumps the counter
         for p in self._params:

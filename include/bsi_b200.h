@@ -63,6 +63,8 @@ typedef struct bsi_noise {
     uint64_t seed;         /* Philox key */
     uint64_t sample_base;  /* global index of local sample 0 (multi-GPU sharding invariance) */
     int32_t draw;          /* draw index; the kernel adds *step_ptr when step_ptr != NULL */
+    const uint64_t* key_ptr; /* optional device pointer to {seed, sample_base}: overrides the two by-value fields, so a captured
+                              * CUDA graph can be replayed with a new key without re-capture (NULL = use the fields above) */
 } bsi_noise;
 
 /* mu0 = rsqrt(lambda_0) * eps  (bsi/bsi.py:325-327).  sigma0 = rsqrt(lambda[0]) read from sigma0_ptr[0]. */

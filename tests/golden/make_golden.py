@@ -288,6 +288,84 @@ def gen_optim():
     save("optim.pt", out)
 
 
+# ---------------------------------------------------------------- G. the BASELINE.json sizes at full depth (B = 2..4)
+def gen_full():
+    """DiT-L/4 x24, DiT-L/2 x24 and the 32-level U-Net of BASELINE.json configs 2-4 through the real reference in fp32:
+    forwards, one teacher-forced sampler step and elbo(x[4], 1, 2) with the drawn noise and lambda grid stored, so the GPU
+    tests can inject exactly what the reference consumed (RNG order of bsi/bsi.py:224-226,283-284,430-434)."""
+    out = {}
+    with torch.inference_mode():
+        spec64 = O.DiTSpec((3, 64, 64), 4, 1024, 24, 16)
+        m64, _ = make_ref_dit(spec64)
+        mu = 1.5 * H.det_uniform("full.dit64.mu", (2, *spec64.data_shape))
+        t = torch.tensor([0.3, 0.9])
+        out["dit64"] = dict(y=m64(mu, t))
+        print("dit64 forward done", flush=True)
+
+        bsi = ref_bsi.BSI(m64, data_shape=spec64.data_shape, k=256, discretization=ref_bsi.Discretization.image_8bit(), **HYPER)
+        x = H.det_images("full.x", 4, spec64.data_shape, seed=2)
+        seed = 41
+        e, b, ex = bsi.elbo(x, 1, 2, torch.Generator().manual_seed(seed))
+        g = torch.Generator().manual_seed(seed)  # the same draws again, in the reference's order
+        eps_r = torch.randn((1, 4, *spec64.data_shape), generator=g)
+        off = torch.rand((), generator=g)
+        perm = torch.randperm(8, generator=g)
+        eps_m = torch.randn((2, 4, *spec64.data_shape), generator=g)
+        lam = bsi.p_lambda.icdf(torch.remainder((perm / 9).view(2, 4) + off, 1))
+        # the replayed draws reproduce the reference's result bit for bit
+        l_m = O.inf_measure_loss(lambda a, b_: m64(a, b_), O.make_consts(1e-2, 1e6, 2e6), x, lam, eps_m)
+        assert torch.allclose(l_m, ex["l_measure"], rtol=1e-5), (l_m, ex["l_measure"])
+        out["elbo64"] = dict(seed=seed, elbo=e, bpd=b, l_recon=ex["l_recon"], l_measure=ex["l_measure"], eps_r=eps_r, offset=off, perm=perm,
+                             eps_m=eps_m, lam=lam)
+        print("elbo64 done", b.tolist(), flush=True)
+
+        # one teacher-forced sampler step in the middle of the k = 256 schedule (bsi/bsi.py:331-335)
+        tt = bsi.default_schedule
+        lam_t = bsi.p_lambda.icdf(tt)
+        alpha = lam_t.diff()
+        steps = [1, 128, 255]
+        xs = H.det_images("full.step.x", 2, spec64.data_shape, seed=3)
+        rec = dict(steps=torch.tensor(steps), x_hat=[], mu_next=[])
+        for i in steps:
+            mu_i = bsi._sample_q_mu_lambda(xs, lam_t[i].expand(2), torch.Generator().manual_seed(100 + i))
+            eps = H.det_uniform(f"full.step.eps{i}", (2, *spec64.data_shape)) * 1.7
+            x_hat = bsi._predict_x(mu_i, tt[i].repeat(2))
+            y = x_hat + torch.rsqrt(alpha[i]) * eps
+            mu_next = (alpha[i] * y + lam_t[i] * mu_i) / lam_t[i + 1]
+            rec["x_hat"].append(x_hat), rec["mu_next"].append(mu_next)
+            rec.setdefault("mu", []).append(mu_i)
+        out["step64"] = {k_: (torch.stack(v) if isinstance(v, list) else v) for k_, v in rec.items()}
+        print("step64 done", flush=True)
+        del m64, bsi
+
+        spec32 = O.DiTSpec((3, 32, 32), 2, 1024, 24, 16)
+        m32, _ = make_ref_dit(spec32)
+        mu = 1.5 * H.det_uniform("full.dit32.mu", (2, *spec32.data_shape))
+        out["dit32"] = dict(y=m32(mu, t))
+        del m32
+        print("dit32 forward done", flush=True)
+
+        us = O.UNetSpec((3, 32, 32), dim=128, levels=32)
+        pe = ref_pos.NyquistPositionalEmbedding(us.pos_size, us.pos_rate)
+        mu_ = ref_unet.DenoisingVDMUNet(us.data_shape, pe, "silu", us.dim, us.levels, us.pos_mult, n_attention_heads=1, dropout=0.1,
+                                        fourier_features=ref_nn.FourierFeatures(n_min=6, n_max=8))
+        load_into(mu_, H.det_state_dict(H.unet_shapes(us), seed=1))
+        mu = 1.5 * H.det_uniform("full.unet.mu", (2, *us.data_shape))
+        out["unet32"] = dict(y=mu_(mu, torch.tensor([0.2, 0.95])))
+        xu = H.det_images("full.unet.x", 4, us.data_shape, seed=2)
+        ub = ref_bsi.BSI(mu_, data_shape=us.data_shape, k=256, discretization=ref_bsi.Discretization.image_8bit(), **HYPER)
+        e, b, ex = ub.elbo(xu, 1, 2, torch.Generator().manual_seed(43))
+        g = torch.Generator().manual_seed(43)
+        eps_r = torch.randn((1, 4, *us.data_shape), generator=g)
+        off = torch.rand((), generator=g)
+        perm = torch.randperm(8, generator=g)
+        eps_m = torch.randn((2, 4, *us.data_shape), generator=g)
+        out["elbo_unet32"] = dict(seed=43, elbo=e, bpd=b, l_recon=ex["l_recon"], l_measure=ex["l_measure"], eps_r=eps_r, offset=off, perm=perm,
+                                  eps_m=eps_m, lam=ub.p_lambda.icdf(torch.remainder((perm / 9).view(2, 4) + off, 1)))
+        print("unet done", b.tolist(), flush=True)
+    save("full.pt", out)
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1:
         for name in sys.argv[1:]:
@@ -299,3 +377,5 @@ if __name__ == "__main__":
     gen_dit()
     gen_unet()
     gen_embed()
+    gen_optim()
+    gen_full()

@@ -27,12 +27,12 @@ def test_library_builds_and_exports_header_symbols():
 def test_ctypes_binding_covers_header():
     assert sorted(L.SIGNATURES) == declared_symbols()
     lib = L.load()
-    assert lib.bsi_abi_version() == 1
+    assert lib.bsi_abi_version() == 2
     assert isinstance(lib.bsi_last_error(), bytes)
 
 
 def test_structs_match_header_layout():
-    assert ctypes.sizeof(L.RowRef) == 16 and ctypes.sizeof(L.Noise) == 32
+    assert ctypes.sizeof(L.RowRef) == 16 and ctypes.sizeof(L.Noise) == 40 and L.Noise.key_ptr.offset == 32
     assert ctypes.sizeof(L.DitConfig) == 36
     assert L.GemmArgs.gate.offset % 8 == 0 and ctypes.sizeof(L.GemmArgs) % 8 == 0
 

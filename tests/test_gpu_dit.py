@@ -255,3 +255,57 @@ def test_ema_wrapper_takes_the_native_sampler():
     with torch.inference_mode():
         via_ema = ema_bsi.sample(4, seed=9)
     assert torch.equal(direct, via_ema)
+
+
+def test_sample_equals_last_prediction_of_sample_history_under_philox():
+    """The reference's sample() and sample_history()[1][-1] agree for one generator state (bsi/bsi.py:312-373); with in-kernel Philox
+    the eager history loop must use the same counters (draw 1 + step) as the captured graph."""
+    bsi, m, sd, spec = make_bsi(k=4, noise="philox")
+    with torch.inference_mode():
+        a = bsi.sample(2, torch.Generator().manual_seed(3))
+        mus, xs, ys = bsi.sample_history(2, torch.Generator().manual_seed(3))
+        sync()
+    assert torch.equal(a, xs[-1]), "sample() and sample_history() consumed different noise"
+
+
+def test_sampler_graph_is_cached_and_rekeyed_per_call():
+    """One captured graph per (n, k): later calls refresh the step tables, the Philox key and the counter and replay."""
+    bsi, m, sd, spec = make_bsi(k=6, noise="philox")
+    with torch.inference_mode():
+        a = bsi.sample(3, seed=5)
+        graph = next(iter(bsi._plans.values()))["graph"]
+        b = bsi.sample(3, seed=6)
+        a2 = bsi.sample(3, seed=5)
+        shard = bsi.sample(3, seed=5, sample_offset=1)  # same plan, other sample_base
+        tt = torch.sin(torch.linspace(0, 1, 7, device=dev()) * torch.pi / 2) ** 2
+        c = bsi.sample(3, seed=5, t=tt)  # same k, other schedule: tables refreshed, no re-capture
+        c_eager = m.sample_loop(3, *_loop_args(bsi, tt), 5, 0, 1, use_graph=False)
+        sync()
+        assert len(bsi._plans) == 1 and next(iter(bsi._plans.values()))["graph"] is graph
+        assert torch.equal(a, a2) and not torch.equal(a, b)
+        assert torch.equal(shard[:2], a[1:]), "sample_base read from the key buffer"
+        assert torch.equal(c, c_eager) and not torch.equal(c, a)
+        bsi.sample(2, seed=5)
+        assert len(bsi._plans) == 2
+    bsi.set_model(m)
+    assert len(bsi._plans) == 0
+
+
+def _loop_args(bsi, t):
+    k, lam, coef, c_in, t_rows = bsi._step_table(t)
+    return torch.rsqrt(lam[:1]).contiguous(), coef, c_in, t_rows, k
+
+
+def test_forward_rejects_mismatched_time_rows():
+    spec = SPECS["small64"]
+    m, sd = build(spec)
+    mu = H.det_uniform("tr.mu", (3, *spec.data_shape)).to(dev())
+    with torch.inference_mode():
+        with pytest.raises(ValueError, match="batch of 3"):
+            m(mu, torch.tensor([0.2, 0.7], device=dev()))
+        with pytest.raises(ValueError):
+            m.forward_scaled(mu, torch.full((3,), 0.5, device=dev()), torch.ones(2, device=dev()))
+        one = m(mu, torch.tensor([0.4], device=dev()))  # a single time broadcasts over the batch, like the reference's modulate()
+        full = m(mu, torch.full((3,), 0.4, device=dev()))
+        sync()
+    assert torch.equal(one, full)

@@ -1,0 +1,162 @@
+"""Parity at the real BASELINE.json sizes: DiT-L/4 x24, DiT-L/2 x24 and the 32-level U-Net against fp32 outputs of the
+REAL reference (tests/golden/full.pt, written by tests/golden/make_golden.py::gen_full), at B = 2..4 so the fixtures stay small.
+
+Checked, with the tolerances of BASELINE.json's north_star:
+  * denoiser forward (bf16 tensor-core operands, fp32 accumulation / residual stream) vs the fp32 reference: relative L2,
+  * one teacher-forced sampler step at three points of the k = 256 schedule: mu' within 1e-3 relative (bf16 tier),
+  * elbo(x[4], 1, 2) with the reference's own noise draws and lambda grid injected (ReplayNoise): per-sample |dbpd| <= 1e-3.
+The measured deviations are appended to gpurun_out/full_depth_parity.jsonl (copied to profiles/ per round).
+"""
+
+import json
+import os
+
+import pytest
+import torch
+
+import helpers as H
+from gpu_util import OUT_DIR, dev, sync
+from bsi_b200 import BSI, Discretization
+from bsi_b200 import _lib as L
+from bsi_b200.bsi import ReplayNoise
+from bsi_b200.models import DenoisingDiT, DenoisingVDMUNet, NyquistPositionalEmbedding
+from bsi_b200.nn import FourierFeatures
+
+O = H.O
+pytestmark = pytest.mark.gpu
+HYPER = dict(lambda_0=1e-2, alpha_M=1e6, alpha_R=2e6, preconditioning="edm")
+SPEC64 = O.DiTSpec((3, 64, 64), 4, 1024, 24, 16)
+SPEC32 = O.DiTSpec((3, 32, 32), 2, 1024, 24, 16)
+USPEC = O.UNetSpec((3, 32, 32), dim=128, levels=32)
+
+_SD_CACHE: dict = {}
+
+
+def _state_dict(shapes):
+    """det_state_dict with a per-(name, shape) cache: the two DiT-L variants share all 24 blocks (33 s of numpy Philox)."""
+    todo = {k: v for k, v in shapes.items() if (k, tuple(v)) not in _SD_CACHE}
+    for k, v in H.det_state_dict(todo, seed=1).items():
+        _SD_CACHE[(k, tuple(shapes[k]))] = v
+    return {k: _SD_CACHE[(k, tuple(v))] for k, v in shapes.items()}
+
+
+def _log(**rec):
+    os.makedirs(OUT_DIR, exist_ok=True)
+    with open(os.path.join(OUT_DIR, "full_depth_parity.jsonl"), "a") as fh:
+        fh.write(json.dumps(rec) + "\n")
+
+
+def _dit(spec):
+    m = DenoisingDiT(spec.data_shape, spec.patch, spec.dim, spec.depth, spec.heads, dropout=0.05, fourier_features=FourierFeatures(n_min=6, n_max=8))
+    m.load_state_dict(_state_dict(H.dit_shapes(spec)))
+    return m.to(dev()).eval().requires_grad_(False)
+
+
+@pytest.fixture(scope="module")
+def dit64():
+    return _dit(SPEC64)
+
+
+@pytest.fixture(scope="module")
+def golden():
+    return H.load_golden("full.pt")
+
+
+def _rel_l2(a, b):
+    a, b = a.detach().float().cpu(), b.detach().float().cpu()
+    return float((a - b).norm() / b.norm())
+
+
+# forward of a 24-block bf16 engine vs the fp32 reference: every GEMM output carries ~2^-9 relative rounding of its bf16 operands;
+# measured 3-5e-3 (see profiles/full_depth_parity_r02.jsonl).  The bound is 2x that, far below the 2e-2 of the bf16-vs-bf16 checks.
+FORWARD_REL_L2 = 1e-2
+
+
+def test_dit_l4_depth24_forward_vs_fp32_reference(dit64, golden):
+    mu = 1.5 * H.det_uniform("full.dit64.mu", (2, *SPEC64.data_shape))
+    t = torch.tensor([0.3, 0.9])
+    with torch.inference_mode():
+        y = dit64(mu.to(dev()), t.to(dev()))
+        sync()
+    rel = _rel_l2(y, golden["dit64"]["y"])
+    err = float((y.cpu() - golden["dit64"]["y"]).abs().max() / golden["dit64"]["y"].abs().max())
+    _log(test="dit64_forward", rel_l2=rel, max_abs_over_max=err)
+    assert rel < FORWARD_REL_L2, f"DiT-L/4 x24 forward: relative L2 {rel} vs the fp32 reference"
+
+
+def test_dit_l4_depth24_teacher_forced_steps(dit64, golden):
+    """mu' of one sampler step from the reference's mu_i (k = 256 schedule, steps 1 / 128 / 255): 1e-3 relative (bf16 tier)."""
+    g = golden["step64"]
+    bsi = BSI(dit64, data_shape=SPEC64.data_shape, k=256, discretization=Discretization.image_8bit(), **HYPER).to(dev())
+    k, lam, coef, c_in, t_rows = bsi._step_table(bsi.default_schedule)
+    xs = H.det_images("full.step.x", 2, SPEC64.data_shape, seed=3)  # noqa: F841  (documents what mu_i was drawn around)
+    with torch.inference_mode():
+        for j, i in enumerate(g["steps"].tolist()):
+            mu = g["mu"][j].to(dev())
+            eps = (H.det_uniform(f"full.step.eps{i}", (2, *SPEC64.data_shape)) * 1.7).to(dev())
+            x_hat = bsi._predict_x(mu, t_rows[i].expand(2))
+            f = dit64.forward_scaled(mu, t_rows[i].expand(2), c_in[i].expand(2))
+            mu_next = mu.clone()
+            L.check(L.load().bsi_step_fused(L.ptr(mu_next), L.ptr(f), L.ptr(coef), None, i, 1, L.noise(eps=eps), None, None, 2, 12288, L.stream_ptr()))
+            sync()
+            ref = g["mu_next"][j]
+            rel = float((mu_next.cpu() - ref).abs().max() / ref.abs().max())
+            xerr = float((x_hat.cpu() - g["x_hat"][j]).abs().max())
+            _log(test="dit64_teacher_forced", step=i, mu_next_rel=rel, x_hat_max_abs=xerr, c_out=float(coef[i, 1]))
+            assert rel < 1e-3, f"mu' at step {i}: relative error {rel} (bf16 tier tolerance 1e-3)"
+            # x_hat = c_skip*mu + c_out*f: the denoiser's bf16 error enters scaled by c_out (1 at t = 0 falling to 1e-3 at t = 1)
+            assert xerr < 2e-2 * float(coef[i, 1]) * float(g["x_hat"][j].abs().max()) + 1e-5, f"x_hat at step {i}: max abs err {xerr}"
+
+
+def _elbo_parity(bsi, x, g, tag):
+    draws = [g["eps_r"], g["offset"], g["perm"], g["eps_m"]]
+    replay = ReplayNoise(draws)
+    with torch.inference_mode():
+        e, b, ex = bsi.elbo(x.to(dev()), 1, 2, replay)
+        sync()
+    assert replay.remaining == 0
+    dbpd = (b.cpu() - g["bpd"]).abs()
+    rec = dict(test=tag, bpd=b.cpu().tolist(), bpd_ref=g["bpd"].tolist(), dbpd_max=float(dbpd.max()),
+               l_recon_rel=float(((ex["l_recon"].cpu() - g["l_recon"]).abs() / g["l_recon"].abs().clamp_min(1.0)).max()),
+               l_measure_rel=float(((ex["l_measure"].cpu() - g["l_measure"]).abs() / g["l_measure"].abs()).max()))
+    _log(**rec)
+    assert float(dbpd.max()) <= 1e-3, f"{tag}: bits-per-dim {b.cpu().tolist()} vs reference {g['bpd'].tolist()} (north_star: within 1e-3)"
+    return rec
+
+
+def test_dit_l4_depth24_elbo_bpd_with_replayed_reference_noise(dit64, golden):
+    bsi = BSI(dit64, data_shape=SPEC64.data_shape, k=256, discretization=Discretization.image_8bit(), **HYPER).to(dev())
+    x = H.det_images("full.x", 4, SPEC64.data_shape, seed=2)
+    g = golden["elbo64"]
+    # the lambda grid rebuilt from the replayed offset / permutation equals the reference's (CUDA exp vs CPU exp: <= 1 ulp)
+    lam = bsi._sample_lambda(2, 4, ReplayNoise([g["offset"], g["perm"]]))
+    torch.testing.assert_close(lam.cpu(), g["lam"], rtol=3e-6, atol=0)
+    _elbo_parity(bsi, x, g, "dit64_elbo")
+
+
+def test_dit_l2_depth24_forward_vs_fp32_reference(golden):
+    m = _dit(SPEC32)
+    mu = 1.5 * H.det_uniform("full.dit32.mu", (2, *SPEC32.data_shape))
+    with torch.inference_mode():
+        y = m(mu.to(dev()), torch.tensor([0.3, 0.9], device=dev()))
+        sync()
+    rel = _rel_l2(y, golden["dit32"]["y"])
+    _log(test="dit32_forward", rel_l2=rel)
+    assert rel < FORWARD_REL_L2, f"DiT-L/2 x24 forward: relative L2 {rel} vs the fp32 reference"
+
+
+def test_unet_32_levels_forward_and_elbo_vs_fp32_reference(golden):
+    m = DenoisingVDMUNet(USPEC.data_shape, NyquistPositionalEmbedding(32, 100), "silu", 128, 32, 4, n_attention_heads=1, dropout=0.1,
+                         fourier_features=FourierFeatures(n_min=6, n_max=8))
+    m.load_state_dict(_state_dict(H.unet_shapes(USPEC)))
+    m = m.to(dev()).eval().requires_grad_(False)
+    mu = 1.5 * H.det_uniform("full.unet.mu", (2, *USPEC.data_shape))
+    with torch.inference_mode():
+        y = m(mu.to(dev()), torch.tensor([0.2, 0.95], device=dev()))
+        sync()
+    rel = _rel_l2(y, golden["unet32"]["y"])
+    _log(test="unet32_forward", rel_l2=rel)
+    # 66 residual blocks of bf16 convolutions behind GroupNorm: measured ~6e-3
+    assert rel < 1.5e-2, f"U-Net x32 forward: relative L2 {rel} vs the fp32 reference"
+    bsi = BSI(m, data_shape=USPEC.data_shape, k=256, discretization=Discretization.image_8bit(), **HYPER).to(dev())
+    _elbo_parity(bsi, H.det_images("full.unet.x", 4, USPEC.data_shape, seed=2), golden["elbo_unet32"], "unet32_elbo")

@@ -196,3 +196,40 @@ def test_training_step_through_bsi_train_loss():
             report(f"iteration {it} param {i}", p, side.params[i], RTOL, ATOL)
             report(f"iteration {it} ema {i}", list(ema.ema_model.parameters())[i], side.ema[i], RTOL, ATOL)
     assert ema.step == 3 and ema.initted and float(opt.state[params[0]]["step"]) == 3
+
+
+def test_evaluation_after_native_step_sees_the_new_weights():
+    """The fused optimizer / EMA kernels write parameters through raw pointers (no torch version bump): the packed bf16 arena of
+    the native denoiser must still be rebuilt, for the online model and for the EMA copy (validation during training)."""
+    from test_gpu_dit import SPECS, build
+
+    spec = SPECS["small64"]
+    m, sd = build(spec)
+    mu = H.det_uniform("st.mu", (2, *spec.data_shape)).to(dev())
+    t = torch.tensor([0.3, 0.8], device=dev())
+    m.requires_grad_(True)
+    ema = NO.create_ema(m, beta=0.9, update_after_step=0, update_every=1).to(dev())
+    opt = NO.AdamW(m.parameters(), lr=5e-2, weight_decay=0.0, max_grad_norm=None)
+    opt.attach_ema(ema)
+    with torch.no_grad():
+        y0 = m(mu, t).clone()
+        e0 = ema.ema_model(mu, t).clone()  # packs the EMA copy's arena as well
+    for it in range(3):  # step 1 copies (mode 1, buffer copy_ bumps versions); steps 2-3 lerp through the kernel only
+        for i, p in enumerate(m.parameters()):
+            p.grad.copy_(H.det_uniform(f"st.g{i}.{it}", tuple(p.shape)).to(dev()))
+        opt.step()
+        ema.update()
+    with torch.no_grad():
+        y1 = m(mu, t)
+        e1 = ema.ema_model(mu, t)
+        sync()
+    new_sd = {k: v.detach().float().cpu() for k, v in m.state_dict().items()}
+    ema_sd = {k: v.detach().float().cpu() for k, v in ema.ema_model.state_dict().items()}
+    O = H.O
+    ref1 = O.dit_forward(new_sd, spec, mu.cpu(), t.cpu())
+    refe = O.dit_forward(ema_sd, spec, mu.cpu(), t.cpu())
+    rel = lambda a, b: float((a.cpu() - b).norm() / b.norm())
+    assert rel(y0, ref1) > 5e-2, "the optimizer steps were meant to move the output"
+    assert rel(y1, ref1) < 1.5e-2, f"online model evaluated with stale packed weights: {rel(y1, ref1)}"
+    assert rel(e1, refe) < 1.5e-2, f"EMA model evaluated with stale packed weights: {rel(e1, refe)}"
+    assert rel(e0, refe) > 1e-2

@@ -88,6 +88,33 @@ def test_error_behaviour_without_gpu():
         m.eval().requires_grad_(False)(torch.zeros(1, 3, 64, 64), torch.zeros(1))
 
 
+def test_transposed_lambda_grid_is_rejected_instead_of_read_out_of_bounds():
+    """low_discrepancy_sampling=False draws the reference's [batch, n_samples] grid (bsi/bsi.py:441-445): the kernels index rows
+    as (sample, data point), so anything but n_samples == batch must raise before a launch (it used to read out of bounds)."""
+    bsi = BSI(torch.nn.Identity(), data_shape=(3, 32, 32), k=8, low_discrepancy_sampling=False, **HYPER)
+    x = H.det_images("tl.x", 4, (3, 32, 32))
+    with pytest.raises(ValueError, match="transposed"):
+        bsi.train_loss(x)
+    with pytest.raises(ValueError, match="transposed"):
+        bsi.inf_measurement_loss(x, 3)
+    ld = BSI(torch.nn.Identity(), data_shape=(3, 32, 32), k=8, **HYPER)
+    with pytest.raises((ValueError, BsiNativeError)):  # lambda not ending in the batch axis
+        ld._sample_q_mu_lambda(x.cuda() if torch.cuda.is_available() else x, torch.ones(3))
+
+
+def test_replay_noise_hands_out_recorded_draws_in_order():
+    from bsi_b200.bsi import ReplayNoise
+
+    bsi = BSI(torch.nn.Identity(), data_shape=(3, 32, 32), k=8, **HYPER)
+    off, perm = torch.tensor(0.25), torch.tensor([3, 1, 0, 2, 5, 4])
+    lam = bsi._sample_lambda(2, 3, ReplayNoise([off, perm]))
+    assert torch.equal(lam, O.lam_of_t(O.make_consts(1e-2, 1e6, 2e6), O.ld_times(2, 3, off, perm)))
+    with pytest.raises(RuntimeError, match="shape"):
+        bsi._sample_lambda(2, 3, ReplayNoise([off, perm[:4]]))
+    with pytest.raises(RuntimeError, match="exhausted"):
+        bsi._sample_lambda(2, 3, ReplayNoise([off]))
+
+
 def test_dit_state_dict_layout_and_buffers():
     spec = O.DiTSpec((3, 64, 64), 4, 128, 2, 2)
     m = DenoisingDiT(spec.data_shape, spec.patch, spec.dim, spec.depth, spec.heads, dropout=0.05, fourier_features=FourierFeatures(n_min=6, n_max=8, name="fourier"), name="dit")
@@ -170,7 +197,8 @@ def test_reference_checkpoint_ingestion():
     ckpt = {
         "state_dict": {**{"model." + k: v for k, v in sd.items()}, **{"ema_model.ema_model." + k: v for k, v in ema.items()}, "ema_model.step": torch.tensor(5)},
         "config": {
-            "data": {"name": "imagenet32"},
+            # resolved config/data/imagenet32.yaml as ConfigInCheckpoint stores it (bsi/lightning/callbacks.py:15-16)
+            "data": {"_target_": "bsi.data.imagenet.ImageNetDataModule", "name": "imagenet32", "root": "data/imagenet32", "n": 32},
             "task": {
                 "bsi": {"_target_": "bsi.bsi.BSI", "lambda_0": 1e-2, "alpha_M": 1e6, "alpha_R": 2e6, "k": 50, "preconditioning": "edm", "low_discrepancy_sampling": True},
                 "model": {"_target_": "bsi.models.dit.DenoisingDiT", "name": "DiT", "patch_size": 2, "dim": 128, "depth": 1, "heads": 2, "dropout": None,
@@ -182,6 +210,12 @@ def test_reference_checkpoint_ingestion():
     assert torch.equal(denoiser_state_dict(ckpt, "ema")["dit.patch_encoder.bias"], ema["dit.patch_encoder.bias"])
     bsi, model = from_reference_checkpoint(ckpt, which="ema", device="cpu")
     assert bsi.k == 50 and bsi.data_shape == (3, 32, 32) and torch.equal(model.state_dict()["dit.patch_encoder.bias"], ema["dit.patch_encoder.bias"])
+    from bsi_b200.checkpoint import _data_shape
+
+    assert _data_shape({"data": {"_target_": "bsi.data.imagenet.ImageNetDataModule", "name": "imagenet64", "n": 64}}) == (3, 64, 64)
+    assert _data_shape({"data": {"_target_": "bsi.data.cifar10.CIFAR10DataModule", "name": "cifar10", "width": 32, "height": 32}}) == (3, 32, 32)
+    with pytest.raises(KeyError):
+        _data_shape({"data": {"_target_": "somewhere.Else", "name": "set64"}})  # no guessing from substrings of the name
     unet = build_denoiser({"_target_": "bsi.models.vdm_unet.DenoisingVDMUNet", "name": "unet", "actfn": "silu", "dim": 128, "levels": 1, "dropout": 0.1,
                            "pos_emb_mult": 4, "downsampling_attention": False, "n_attention_heads": 1, "padding_mode": "zeros",
                            "pos_emb": {"name": "nyquist", "size": 32, "expected_rate": 100}, "fourier_features": {"n_min": 6, "n_max": 8}}, (3, 32, 32))

@@ -199,6 +199,27 @@ def test_unet_forward_golden():
     torch.testing.assert_close(y, H.load_golden("unet.pt")["y"], rtol=1e-4, atol=2e-5)
 
 
+def test_full_depth_goldens_pin_the_oracle_at_the_baseline_sizes():
+    """The oracle's functional DiT-L/4 x24 and 32-level U-Net against the REAL reference's fp32 outputs (tests/golden/full.pt)."""
+    g = H.load_golden("full.pt")
+    us = O.UNetSpec((3, 32, 32), dim=128, levels=32)
+    sd = H.det_state_dict(H.unet_shapes(us), seed=1)
+    with torch.inference_mode():
+        y = O.unet_forward(sd, us, 1.5 * H.det_uniform("full.unet.mu", (2, 3, 32, 32)), torch.tensor([0.2, 0.95]))
+    assert float((y - g["unet32"]["y"]).norm() / g["unet32"]["y"].norm()) < 1e-4
+    spec = O.DiTSpec((3, 64, 64), 4, 1024, 24, 16)
+    sd = H.det_state_dict(H.dit_shapes(spec), seed=1)
+    with torch.inference_mode():
+        y = O.dit_forward(sd, spec, 1.5 * H.det_uniform("full.dit64.mu", (2, 3, 64, 64)), torch.tensor([0.3, 0.9]))
+    assert float((y - g["dit64"]["y"]).norm() / g["dit64"]["y"].norm()) < 1e-4
+    # the stored lambda grid is the one the replayed offset / permutation give (RNG order of bsi/bsi.py:430-440)
+    e = g["elbo64"]
+    c = O.make_consts(1e-2, 1e6, 2e6)
+    assert torch.equal(O.lam_of_t(c, O.ld_times(2, 4, e["offset"], e["perm"])), e["lam"])
+    e2, b2, _ = O.combine_elbo(e["l_recon"], e["l_measure"], 12288)
+    assert torch.allclose(b2, e["bpd"], rtol=1e-6)
+
+
 def test_embed_golden():
     g = H.load_golden("embed.pt")
     t = torch.tensor([0.0, 1 / 256, 0.5, 1.0])
