@@ -329,8 +329,13 @@ class BSI(nn.Module):
         return x_hat
 
     # ---- forward process (reference bsi/bsi.py:405-445) --------------------------------------
-    def _sample_q_mu_lambda(self, x: Tensor, lambda_: Tensor, generator=None, *, _c_in: Tensor | None = None, _seed=None, _draw=0):
-        """mu ~ q(mu | x, lambda) for lambda of shape [..., batch]; returns [..., batch, *data_shape]."""
+    def _sample_q_mu_lambda(self, x: Tensor, lambda_: Tensor, generator=None, *, _c_in: Tensor | None = None, _seed=None, _draw=0,
+                            _shard: tuple[int, int] | None = None):
+        """mu ~ q(mu | x, lambda) for lambda of shape [..., batch]; returns [..., batch, *data_shape].
+
+        _shard = (start, batch_total): `x` / `lambda_` are the columns [start, start + len(x)) of a batch of `batch_total` data
+        points evaluated on another rank layout; noise is keyed by the row index of the FULL [..., batch_total] problem (or the
+        full tensor is drawn and sliced in the injected-noise modes), so every shard reproduces the single-GPU values."""
         dev = self._require_cuda()
         x = _cuda_f32(x, "x")
         B, D = x.shape[0], self._numel
@@ -349,18 +354,31 @@ class BSI(nn.Module):
         if R == 0:  # empty batch: nothing to draw (torch.randn of an empty shape consumes no random numbers either)
             mu = torch.empty((*lambda_.shape, *self.data_shape), **self.tensor_args)
             return (mu, torch.empty_like(mu)) if _c_in is not None else mu
-        nz, _keep = self._noise((*lambda_.shape, *self.data_shape), generator, _draw, 0, _seed)
         mu = torch.empty((*lambda_.shape, *self.data_shape), **self.tensor_args)
         model_in = torch.empty_like(mu) if _c_in is not None else None
         c_in = _c_in.contiguous() if _c_in is not None else None
+        lib, st = L.load(), L.stream_ptr(dev)
+        if _shard is None or (_shard[0] == 0 and _shard[1] == B):
+            nz, _keep = self._noise((*lambda_.shape, *self.data_shape), generator, _draw, 0, _seed)
+            with torch.cuda.device(dev):
+                L.check(lib.bsi_q_sample(L.ptr(mu), L.ptr(model_in), L.ptr(x), L.ptr(gamma), L.ptr(sigma), L.ptr(c_in), nz, R, B, D, st), "bsi_q_sample")
+            return (mu, model_in) if _c_in is not None else mu
+        # a column shard of the [..., batch_total] problem: one launch per leading row, keyed by the full problem's row index
+        start, total = _shard
+        lead = R // B
+        eps_full = None
+        if not self._philox(generator):
+            eps_full = _randn((*lambda_.shape[:-1], total, *self.data_shape), generator, **self.tensor_args).reshape(lead, total, D)
+        off4 = lambda t, i: None if t is None else t.data_ptr() + 4 * i
         with torch.cuda.device(dev):
-            L.check(
-                L.load().bsi_q_sample(
-                    L.ptr(mu), L.ptr(model_in), L.ptr(x), L.ptr(gamma), L.ptr(sigma), L.ptr(c_in),
-                    nz, R, B, D, L.stream_ptr(dev),
-                ),
-                "bsi_q_sample",
-            )  # fmt: skip
+            for i in range(lead):
+                if eps_full is not None:
+                    eps_i = eps_full[i, start : start + B].contiguous()
+                    nz = L.noise(eps=eps_i)
+                else:
+                    nz = L.noise(seed=_seed, sample_base=i * total + start, draw=_draw)
+                L.check(lib.bsi_q_sample(off4(mu, i * B * D), off4(model_in, i * B * D), L.ptr(x), off4(gamma, i * B), off4(sigma, i * B), off4(c_in, i * B),
+                                         nz, B, B, D, st), "bsi_q_sample")
         return (mu, model_in) if _c_in is not None else mu
 
     def _sample_lambda(self, n_samples: int, batch_size: int, generator=None) -> Tensor:
@@ -382,7 +400,7 @@ class BSI(nn.Module):
         return self.p_lambda.icdf(t)
 
     # ---- losses (reference bsi/bsi.py:152-310) ------------------------------------------------
-    def _errors(self, x: Tensor, lambda_: Tensor, t_flat: Tensor, generator, draw: int) -> Tensor:
+    def _errors(self, x: Tensor, lambda_: Tensor, t_flat: Tensor, generator, draw: int, _shard=None) -> Tensor:
         """sum_d (x - x_hat)^2 for mu ~ q(.|x, lambda_[n,B]) and the model evaluated at t_flat -> [n,B]."""
         self._check_precond()
         if lambda_.ndim != 2 or lambda_.shape[1] != len(x) or t_flat.numel() != lambda_.numel():
@@ -396,16 +414,16 @@ class BSI(nn.Module):
             return _cuda_f32(x, "x").new_zeros((n, 0))
         if self.preconditioning == "edm":
             c_skip, c_out, c_in = self._edm_preconditioning(t_flat)
-            mu, model_in = self._sample_q_mu_lambda(x, lambda_, generator, _c_in=c_in, _draw=draw)
+            mu, model_in = self._sample_q_mu_lambda(x, lambda_, generator, _c_in=c_in, _draw=draw, _shard=_shard)
         else:
-            mu = self._sample_q_mu_lambda(x, lambda_, generator, _draw=draw)
+            mu = self._sample_q_mu_lambda(x, lambda_, generator, _draw=draw, _shard=_shard)
             model_in, c_skip, c_out = mu, torch.zeros_like(t_flat), torch.ones_like(t_flat)
         mu_f, in_f = mu.flatten(end_dim=1), model_in.flatten(end_dim=1)
         f = _cuda_f32(self.model(in_f, t_flat), "denoiser output")
         err = _SquaredError.apply(f, _cuda_f32(x, "x"), mu_f, c_skip.contiguous(), c_out.contiguous(), B)
         return err.reshape(n, B)
 
-    def reconstruction_loss(self, x: Tensor, n_samples: int, generator=None) -> Tensor:
+    def reconstruction_loss(self, x: Tensor, n_samples: int, generator=None, *, _shard=None) -> Tensor:
         self._check_precond()
         dev = self._require_cuda()
         x = _cuda_f32(x, "x")
@@ -416,9 +434,9 @@ class BSI(nn.Module):
         t_one = x.new_ones(n_samples * B)
         if self.preconditioning == "edm":
             c_skip, c_out, c_in = self._edm_preconditioning(t_one)
-            mu, model_in = self._sample_q_mu_lambda(x, lam_M, generator, _c_in=c_in, _draw=0)
+            mu, model_in = self._sample_q_mu_lambda(x, lam_M, generator, _c_in=c_in, _draw=0, _shard=_shard)
         else:
-            mu = self._sample_q_mu_lambda(x, lam_M, generator, _draw=0)
+            mu = self._sample_q_mu_lambda(x, lam_M, generator, _draw=0, _shard=_shard)
             model_in, c_skip, c_out = mu, torch.zeros_like(t_one), torch.ones_like(t_one)
         f = _cuda_f32(self.model(model_in.flatten(end_dim=1), t_one).detach(), "denoiser output")
         mu_f = mu.flatten(end_dim=1)
@@ -442,23 +460,33 @@ class BSI(nn.Module):
             )  # fmt: skip
         return out.reshape(n_samples, B)
 
-    def inf_measurement_loss(self, x: Tensor, n_samples: int, generator=None) -> Tensor:
-        lambda_ = self._sample_lambda(n_samples, len(x), generator)
+    def _shard_columns(self, grid: Tensor, x: Tensor, _shard) -> Tensor:
+        """Columns of this shard out of a [n, batch_total] grid drawn for the whole batch (draw once, slice)."""
+        if _shard is None:
+            return grid
+        start, total = _shard
+        assert grid.shape[1] == total and start + len(x) <= total
+        return grid[:, start : start + len(x)].contiguous()
+
+    def inf_measurement_loss(self, x: Tensor, n_samples: int, generator=None, *, _shard=None) -> Tensor:
+        lambda_ = self._shard_columns(self._sample_lambda(n_samples, _shard[1] if _shard else len(x), generator), x, _shard)
         t = self.p_lambda.cdf(lambda_).flatten(end_dim=1)
-        err = self._errors(x, lambda_, t, generator, draw=1)
+        err = self._errors(x, lambda_, t, generator, draw=1, _shard=_shard)
         return 0.5 * self.p_lambda.reciprocal_pdf(lambda_) * err
 
-    def finite_measurement_loss(self, x: Tensor, n_samples: int, generator=None, *, t: Tensor | None = None) -> Tensor:
+    def finite_measurement_loss(self, x: Tensor, n_samples: int, generator=None, *, t: Tensor | None = None, _shard=None) -> Tensor:
         if t is None:
             t = self.default_schedule
         lambda_ = self.p_lambda.icdf(t)
         alpha = lambda_.diff()
         k = len(alpha)
+        total = _shard[1] if _shard else len(x)
         if isinstance(generator, ReplayNoise):
-            i = generator.take((n_samples, len(x)), x.device)
+            i = generator.take((n_samples, total), x.device)
         else:
-            i = torch.randint(0, k, (n_samples, len(x)), device=x.device, generator=generator)
-        err = self._errors(x, lambda_[i], t[i].flatten(end_dim=1), generator, draw=1)
+            i = torch.randint(0, k, (n_samples, total), device=x.device, generator=generator)
+        i = self._shard_columns(i, x, _shard)
+        err = self._errors(x, lambda_[i], t[i].flatten(end_dim=1), generator, draw=1, _shard=_shard)
         return (0.5 * k) * alpha[i] * err
 
     def _assemble_elbo(self, l_recon: Tensor, l_measure: Tensor, estimate_var: bool):
@@ -471,15 +499,20 @@ class BSI(nn.Module):
             extra["bpd_var"] = (to_bpd**2) * var
         return elbo, to_bpd * elbo, extra
 
-    def elbo(self, x: Tensor, n_recon_samples: int, n_measure_samples: int, generator=None, *, estimate_var: bool = False):
-        """Monte-Carlo estimate of the infinite-step ELBO: returns (elbo[B], bpd[B], extra)."""
-        l_recon = self.reconstruction_loss(x, n_recon_samples, generator)
-        l_measure = self.inf_measurement_loss(x, n_measure_samples, generator)
+    def elbo(self, x: Tensor, n_recon_samples: int, n_measure_samples: int, generator=None, *, estimate_var: bool = False, _shard=None):
+        """Monte-Carlo estimate of the infinite-step ELBO: returns (elbo[B], bpd[B], extra).
+
+        _shard = (start, batch_total) (extension, used by bsi_b200.distributed.sharded_elbo): `x` is a slice of a larger batch;
+        all random draws are made for the whole batch from `generator` and sliced, so the slice's result equals the corresponding
+        entries of the single-GPU call with the same generator state."""
+        l_recon = self.reconstruction_loss(x, n_recon_samples, generator, _shard=_shard)
+        l_measure = self.inf_measurement_loss(x, n_measure_samples, generator, _shard=_shard)
         return self._assemble_elbo(l_recon, l_measure, estimate_var)
 
-    def finite_elbo(self, x: Tensor, n_recon_samples: int, n_measure_samples: int, generator=None, *, t: Tensor | None = None, estimate_var: bool = False):
-        l_recon = self.reconstruction_loss(x, n_recon_samples, generator)
-        l_measure = self.finite_measurement_loss(x, n_measure_samples, generator, t=t)
+    def finite_elbo(self, x: Tensor, n_recon_samples: int, n_measure_samples: int, generator=None, *, t: Tensor | None = None, estimate_var: bool = False,
+                    _shard=None):
+        l_recon = self.reconstruction_loss(x, n_recon_samples, generator, _shard=_shard)
+        l_measure = self.finite_measurement_loss(x, n_measure_samples, generator, t=t, _shard=_shard)
         return self._assemble_elbo(l_recon, l_measure, estimate_var)
 
     def train_loss(self, x: Tensor, generator=None) -> Tensor:

@@ -72,18 +72,32 @@ __device__ __forceinline__ float4 noise4(const bsi_noise& nz, int step, int64_t 
     return philox_normal4(nz.seed, nz.sample_base + (uint64_t)sample, (uint32_t)(nz.draw + step), (uint32_t)quad);
 }
 
+// Row kernels below use a 2-D grid: blockIdx.x = sample / row, blockIdx.y = chunk of 256 float4 quads inside the row, so there is no
+// 64-bit division per element (the first version spent as many instructions on `i / qpr` and `r % B` as on Philox).
+struct RowGrid {
+    dim3 grid;
+};
+static inline RowGrid row_grid(int64_t rows, int64_t D) {
+    const int64_t qpr = D >> 2;
+    RowGrid g;
+    g.grid = dim3((unsigned)rows, (unsigned)((qpr + kThreads - 1) / kThreads), 1);
+    return g;
+}
+#define BSI_CHECK_ROW_GRID(rows, D)                                                                                   \
+    BSI_CHECK_ARG((rows) <= 0x7fffffffLL && (((D) >> 2) + kThreads - 1) / kThreads <= 65535, "row grid out of range: %lld rows of %lld", \
+                  (long long)(rows), (long long)(D))
+
 // ------------------------------------------------------------------ sampler init (bsi/bsi.py:325-327)
 // bytes/elem: 4 written (+4 read when noise is injected)
 __global__ void __launch_bounds__(kThreads) k_sample_init(float* __restrict__ mu, const float* __restrict__ sigma0_ptr,
                                                           bsi_noise nz_arg, int64_t n, int64_t D) {
     const bsi_noise nz = resolve_noise(nz_arg);
     const float s0 = sigma0_ptr[0];
-    const int64_t qpr = D >> 2, total = n * qpr;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        int64_t s = i / qpr, q = i - s * qpr;
-        float4 e = noise4(nz, 0, s, q, D);
-        st4(mu + s * D + q * 4, make_float4(s0 * e.x, s0 * e.y, s0 * e.z, s0 * e.w));
-    }
+    const int64_t s = blockIdx.x;
+    const int q = blockIdx.y * kThreads + threadIdx.x;
+    if (q >= (int)(D >> 2)) return;
+    float4 e = noise4(nz, 0, s, q, D);
+    st4(mu + s * D + q * 4, make_float4(s0 * e.x, s0 * e.y, s0 * e.z, s0 * e.w));
 }
 
 // ------------------------------------------------------------------ fused sampler step (bsi/bsi.py:331-335, 381-386)
@@ -93,30 +107,29 @@ __global__ void __launch_bounds__(kThreads)
     k_step_fused(float* __restrict__ mu, const float* __restrict__ f, const float* __restrict__ coef,
                  const int32_t* __restrict__ step_ptr, int32_t step_arg, bsi_noise nz_arg, float* __restrict__ x_hat_out,
                  float* __restrict__ y_out, int64_t n, int64_t D) {
+    const int q = blockIdx.y * kThreads + threadIdx.x;
+    if (q >= (int)(D >> 2)) return;
+    const int64_t s = blockIdx.x, off = s * D + (int64_t)q * 4;
+    // the two streaming loads are issued before the (long) Philox chain so that their latency hides under it
+    const float4 m = ld4(mu + off);
+    const float4 fo = ld4_stream(f + off);
     const bsi_noise nz = resolve_noise(nz_arg);
     const int step = step_ptr ? *step_ptr : step_arg;
     const float* c = coef + (int64_t)step * 8;
     const float c_skip = c[0], c_out = c[1], sigma = c[2], alpha = c[3], lam = c[4], lam_next = c[5];
-    const int64_t qpr = D >> 2, total = n * qpr;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        int64_t s = i / qpr, q = i - s * qpr;
-        int64_t off = s * D + q * 4;
-        float4 m = ld4(mu + off);
-        float4 fo = ld4_stream(f + off);
-        float4 e = noise4(nz, step, s, q, D);
-        float mv[4] = {m.x, m.y, m.z, m.w}, fv[4] = {fo.x, fo.y, fo.z, fo.w}, ev[4] = {e.x, e.y, e.z, e.w};
-        float xh[4], yv[4], out[4];
+    const float4 e = noise4(nz, step, s, q, D);
+    const float mv[4] = {m.x, m.y, m.z, m.w}, fv[4] = {fo.x, fo.y, fo.z, fo.w}, ev[4] = {e.x, e.y, e.z, e.w};
+    float xh[4], yv[4], out[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            // x_hat = addcmul(c_skip*mu, c_out, f); y = x_hat + rsqrt(alpha)*eps; mu' = (alpha*y + lam*mu)/lam_next
-            xh[j] = kPrecond ? addcmul_rn(mul_rn(c_skip, mv[j]), c_out, fv[j]) : fv[j];
-            yv[j] = add_mul_sep(xh[j], sigma, ev[j]);
-            out[j] = __fdiv_rn(__fadd_rn(mul_rn(alpha, yv[j]), mul_rn(lam, mv[j])), lam_next);
-        }
-        st4(mu + off, make_float4(out[0], out[1], out[2], out[3]));
-        if (x_hat_out) st4(x_hat_out + off, make_float4(xh[0], xh[1], xh[2], xh[3]));
-        if (y_out) st4(y_out + off, make_float4(yv[0], yv[1], yv[2], yv[3]));
+    for (int j = 0; j < 4; ++j) {
+        // x_hat = addcmul(c_skip*mu, c_out, f); y = x_hat + rsqrt(alpha)*eps; mu' = (alpha*y + lam*mu)/lam_next
+        xh[j] = kPrecond ? addcmul_rn(mul_rn(c_skip, mv[j]), c_out, fv[j]) : fv[j];
+        yv[j] = add_mul_sep(xh[j], sigma, ev[j]);
+        out[j] = __fdiv_rn(__fadd_rn(mul_rn(alpha, yv[j]), mul_rn(lam, mv[j])), lam_next);
     }
+    st4(mu + off, make_float4(out[0], out[1], out[2], out[3]));
+    if (x_hat_out) st4(x_hat_out + off, make_float4(xh[0], xh[1], xh[2], xh[3]));
+    if (y_out) st4(y_out + off, make_float4(yv[0], yv[1], yv[2], yv[3]));
 }
 
 __global__ void k_step_advance(int32_t* step_ptr) { *step_ptr += 1; }
@@ -126,26 +139,24 @@ __global__ void k_step_advance(int32_t* step_ptr) { *step_ptr += 1; }
 __global__ void __launch_bounds__(kThreads)
     k_edm_combine(float* __restrict__ x_hat, const float* __restrict__ mu, const float* __restrict__ f, bsi_rowref c_skip,
                   bsi_rowref c_out, const int32_t* __restrict__ step_ptr, int64_t n, int64_t D) {
+    const int q = blockIdx.y * kThreads + threadIdx.x;
+    if (q >= (int)(D >> 2)) return;
+    const int64_t s = blockIdx.x, off = s * D + (int64_t)q * 4;
     const int step = step_ptr ? *step_ptr : 0;
-    const int64_t qpr = D >> 2, total = n * qpr;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        int64_t s = i / qpr, q = i - s * qpr, off = s * D + q * 4;
-        float cs = rowref_at(c_skip, s, step), co = rowref_at(c_out, s, step);
-        float4 m = ld4_stream(mu + off), fo = ld4_stream(f + off);
-        st4(x_hat + off, make_float4(addcmul_rn(mul_rn(cs, m.x), co, fo.x), addcmul_rn(mul_rn(cs, m.y), co, fo.y),
-                                     addcmul_rn(mul_rn(cs, m.z), co, fo.z), addcmul_rn(mul_rn(cs, m.w), co, fo.w)));
-    }
+    const float cs = rowref_at(c_skip, s, step), co = rowref_at(c_out, s, step);
+    const float4 m = ld4_stream(mu + off), fo = ld4_stream(f + off);
+    st4(x_hat + off, make_float4(addcmul_rn(mul_rn(cs, m.x), co, fo.x), addcmul_rn(mul_rn(cs, m.y), co, fo.y),
+                                 addcmul_rn(mul_rn(cs, m.z), co, fo.z), addcmul_rn(mul_rn(cs, m.w), co, fo.w)));
 }
 __global__ void __launch_bounds__(kThreads) k_scale_rows(float* __restrict__ out, const float* __restrict__ in, bsi_rowref sc,
                                                          const int32_t* __restrict__ step_ptr, int64_t n, int64_t D) {
+    const int q = blockIdx.y * kThreads + threadIdx.x;
+    if (q >= (int)(D >> 2)) return;
+    const int64_t s = blockIdx.x, off = s * D + (int64_t)q * 4;
     const int step = step_ptr ? *step_ptr : 0;
-    const int64_t qpr = D >> 2, total = n * qpr;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        int64_t s = i / qpr, q = i - s * qpr, off = s * D + q * 4;
-        float c = rowref_at(sc, s, step);
-        float4 m = ld4_stream(in + off);
-        st4(out + off, make_float4(c * m.x, c * m.y, c * m.z, c * m.w));
-    }
+    const float c = rowref_at(sc, s, step);
+    const float4 m = ld4_stream(in + off);
+    st4(out + off, make_float4(c * m.x, c * m.y, c * m.z, c * m.w));
 }
 
 // ------------------------------------------------------------------ q(mu|x,lambda) (bsi/bsi.py:405-420)
@@ -153,22 +164,21 @@ __global__ void __launch_bounds__(kThreads) k_scale_rows(float* __restrict__ out
 __global__ void __launch_bounds__(kThreads)
     k_q_sample(float* __restrict__ mu, float* __restrict__ model_in, const float* __restrict__ x, const float* __restrict__ gamma,
                const float* __restrict__ sigma, const float* __restrict__ c_in, bsi_noise nz_arg, int64_t R, int64_t B, int64_t D) {
+    const int q = blockIdx.y * kThreads + threadIdx.x;
+    if (q >= (int)(D >> 2)) return;
+    const uint32_t r32 = blockIdx.x;
+    const int64_t r = r32, b = r32 % (uint32_t)B, off = r * D + (int64_t)q * 4;
+    const float4 xv = ld4(x + b * D + (int64_t)q * 4);
     const bsi_noise nz = resolve_noise(nz_arg);
-    const int64_t qpr = D >> 2, total = R * qpr;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        int64_t r = i / qpr, q = i - r * qpr, off = r * D + q * 4;
-        int64_t b = r % B;
-        float g = gamma[r], sg = sigma[r];
-        float4 xv = ld4(x + b * D + q * 4);
-        float4 e = noise4(nz, 0, r, q, D);
-        // addcmul(gamma*x, sigma, eps)
-        float4 m = make_float4(addcmul_rn(mul_rn(g, xv.x), sg, e.x), addcmul_rn(mul_rn(g, xv.y), sg, e.y),
-                               addcmul_rn(mul_rn(g, xv.z), sg, e.z), addcmul_rn(mul_rn(g, xv.w), sg, e.w));
-        st4(mu + off, m);
-        if (model_in) {
-            float ci = c_in[r];
-            st4(model_in + off, make_float4(ci * m.x, ci * m.y, ci * m.z, ci * m.w));
-        }
+    const float g = gamma[r], sg = sigma[r];
+    const float4 e = noise4(nz, 0, r, q, D);
+    // addcmul(gamma*x, sigma, eps)
+    const float4 m = make_float4(addcmul_rn(mul_rn(g, xv.x), sg, e.x), addcmul_rn(mul_rn(g, xv.y), sg, e.y),
+                                 addcmul_rn(mul_rn(g, xv.z), sg, e.z), addcmul_rn(mul_rn(g, xv.w), sg, e.w));
+    st4(mu + off, m);
+    if (model_in) {
+        const float ci = c_in[r];
+        st4(model_in + off, make_float4(ci * m.x, ci * m.y, ci * m.z, ci * m.w));
     }
 }
 
@@ -258,6 +268,62 @@ __global__ void __launch_bounds__(kThreads)
         }
     }
 }
+// Tiled variant (patch*patch divides 256): a CTA builds the operand rows of 256 / p^2 consecutive tokens in shared memory -- one
+// thread per pixel -- and writes them back as one contiguous block with 16-byte stores (the rows of consecutive tokens are
+// adjacent in A, pitch padding included, so there is no separate zero-fill launch).  The per-pixel version above issues 21
+// scattered 2-byte stores per thread and six range-reducing sinf calls per channel value (0.39 TB/s, profiles r01).
+// Fourier features: sin(2 pi 2^n v) = sinpi(2^(n+1) v), whose argument reduction is exact, evaluated once for n_min; the higher
+// octaves follow by the double-angle identities, the pi/2-shifted partner is the cosine.  This is the exact-math value; the
+// reference's fp32 angle arithmetic (fp32(2 pi 2^n) * v, rounded at magnitude ~2.4e3) deviates from it by <= 3e-4, a seventh of
+// the bf16 rounding step the operand is stored with.
+__global__ void __launch_bounds__(kThreads)
+    k_patch_operand_tiled(__nv_bfloat16* __restrict__ A, const float* __restrict__ mu, bsi_rowref scale, const int32_t* __restrict__ step_ptr,
+                          int total_tokens, int C, int H, int W, int p, int n_min, int nfreq, int lda) {
+    extern __shared__ __align__(16) uint8_t s_raw[];
+    __nv_bfloat16* tile = reinterpret_cast<__nv_bfloat16*>(s_raw);
+    const int step = step_ptr ? *step_ptr : 0;
+    const int pp = p * p, tok_per_cta = kThreads / pp;
+    const int cin = C * (1 + 2 * nfreq), cols = pp * cin;
+    const int gw = W / p, T = (H / p) * gw, HW = H * W;
+    const int tok0 = blockIdx.x * tok_per_cta;
+    const int tl = threadIdx.x / pp, within = threadIdx.x - tl * pp;
+    const int token = tok0 + tl;
+    // zero the pitch padding of this CTA's rows (columns [cols, lda))
+    for (int i = threadIdx.x; i < tok_per_cta * (lda - cols); i += kThreads) {
+        const int r = i / (lda - cols);
+        tile[r * lda + cols + (i - r * (lda - cols))] = __float2bfloat16(0.0f);
+    }
+    if (token < total_tokens) {
+        const int b = token / T, tok = token - b * T;
+        const int gy = tok / gw, gx = tok - gy * gw;
+        const int py = within / p, px = within - py * p;
+        const int pix = (gy * p + py) * W + gx * p + px;
+        const float sc = rowref_at(scale, b, step);
+        __nv_bfloat16* dst = tile + tl * lda + within * cin;
+        for (int c = 0; c < C; ++c) {
+            const float v = sc * mu[((int64_t)b * C + c) * HW + pix];
+            dst[c] = __float2bfloat16(v);
+            if (nfreq > 0) {
+                float sn, cs;
+                sincospif(ldexpf(v, n_min + 1), &sn, &cs);
+                __nv_bfloat16* o = dst + C + c * 2 * nfreq;
+                for (int f = 0; f < nfreq; ++f) {
+                    o[2 * f] = __float2bfloat16(sn);
+                    o[2 * f + 1] = __float2bfloat16(cs);
+                    const float s2 = 2.0f * sn * cs, c2 = (cs - sn) * (cs + sn);
+                    sn = s2, cs = c2;
+                }
+            }
+        }
+    }
+    __syncthreads();
+    // rows [tok0, tok0 + tok_per_cta) of A are one contiguous block of tok_per_cta * lda bf16 (lda % 8 == 0: 16-byte rows)
+    const int rows = min(tok_per_cta, total_tokens - tok0);
+    const int vecs = rows * lda / 8;
+    uint4* gdst = reinterpret_cast<uint4*>(A + (int64_t)tok0 * lda);
+    const uint4* ssrc = reinterpret_cast<const uint4*>(tile);
+    for (int i = threadIdx.x; i < vecs; i += kThreads) gdst[i] = ssrc[i];
+}
 // zero the pitch padding of the operand (columns [cols, lda)) once per allocation
 __global__ void __launch_bounds__(kThreads) k_zero_pad(__nv_bfloat16* __restrict__ A, int64_t rows, int cols, int lda) {
     const int pad = lda - cols;
@@ -290,7 +356,8 @@ int bsi_device_arch(void) {
 int bsi_sample_init(float* mu, const float* sigma0_ptr, bsi_noise noise, int64_t n, int64_t D, void* stream) {
     BSI_CHECK_ARG(mu && sigma0_ptr && n > 0, "bsi_sample_init: null pointer or empty batch");
     BSI_REQUIRE_VEC4(D);
-    k_sample_init<<<grid_for(n * D / 4), kThreads, 0, (cudaStream_t)stream>>>(mu, sigma0_ptr, noise, n, D);
+    BSI_CHECK_ROW_GRID(n, D);
+    k_sample_init<<<row_grid(n, D).grid, kThreads, 0, (cudaStream_t)stream>>>(mu, sigma0_ptr, noise, n, D);
     BSI_LAUNCH_OK("k_sample_init");
     return BSI_OK;
 }
@@ -299,7 +366,8 @@ int bsi_step_fused(float* mu, const float* f, const float* coef, const int32_t* 
                    bsi_noise noise, float* x_hat_out, float* y_out, int64_t n, int64_t D, void* stream) {
     BSI_CHECK_ARG(mu && f && coef && n > 0, "bsi_step_fused: null pointer or empty batch");
     BSI_REQUIRE_VEC4(D);
-    int grid = grid_for(n * D / 4);
+    BSI_CHECK_ROW_GRID(n, D);
+    const dim3 grid = row_grid(n, D).grid;
     if (precond)
         k_step_fused<true><<<grid, kThreads, 0, (cudaStream_t)stream>>>(mu, f, coef, step_ptr, step, noise, x_hat_out, y_out, n, D);
     else
@@ -319,7 +387,8 @@ int bsi_edm_combine(float* x_hat, const float* mu, const float* f, bsi_rowref c_
                     int64_t n, int64_t D, void* stream) {
     BSI_CHECK_ARG(x_hat && mu && f && c_skip.base && c_out.base && n > 0, "bsi_edm_combine: null pointer or empty batch");
     BSI_REQUIRE_VEC4(D);
-    k_edm_combine<<<grid_for(n * D / 4), kThreads, 0, (cudaStream_t)stream>>>(x_hat, mu, f, c_skip, c_out, step_ptr, n, D);
+    BSI_CHECK_ROW_GRID(n, D);
+    k_edm_combine<<<row_grid(n, D).grid, kThreads, 0, (cudaStream_t)stream>>>(x_hat, mu, f, c_skip, c_out, step_ptr, n, D);
     BSI_LAUNCH_OK("k_edm_combine");
     return BSI_OK;
 }
@@ -327,7 +396,8 @@ int bsi_edm_combine(float* x_hat, const float* mu, const float* f, bsi_rowref c_
 int bsi_scale_rows(float* out, const float* in, bsi_rowref scale, const int32_t* step_ptr, int64_t n, int64_t D, void* stream) {
     BSI_CHECK_ARG(out && in && scale.base && n > 0, "bsi_scale_rows: null pointer or empty batch");
     BSI_REQUIRE_VEC4(D);
-    k_scale_rows<<<grid_for(n * D / 4), kThreads, 0, (cudaStream_t)stream>>>(out, in, scale, step_ptr, n, D);
+    BSI_CHECK_ROW_GRID(n, D);
+    k_scale_rows<<<row_grid(n, D).grid, kThreads, 0, (cudaStream_t)stream>>>(out, in, scale, step_ptr, n, D);
     BSI_LAUNCH_OK("k_scale_rows");
     return BSI_OK;
 }
@@ -337,7 +407,9 @@ int bsi_q_sample(float* mu, float* model_in, const float* x, const float* gamma,
     BSI_CHECK_ARG(mu && x && gamma && sigma && R > 0 && B > 0, "bsi_q_sample: null pointer or empty batch");
     BSI_CHECK_ARG(!model_in || c_in, "bsi_q_sample: model_in requested without c_in");
     BSI_REQUIRE_VEC4(D);
-    k_q_sample<<<grid_for(R * D / 4), kThreads, 0, (cudaStream_t)stream>>>(mu, model_in, x, gamma, sigma, c_in, noise, R, B, D);
+    BSI_CHECK_ROW_GRID(R, D);
+    BSI_CHECK_ARG(B <= 0x7fffffffLL, "bsi_q_sample: batch too large");
+    k_q_sample<<<row_grid(R, D).grid, kThreads, 0, (cudaStream_t)stream>>>(mu, model_in, x, gamma, sigma, c_in, noise, R, B, D);
     BSI_LAUNCH_OK("k_q_sample");
     return BSI_OK;
 }
@@ -384,6 +456,16 @@ int bsi_dit_patch_operand(void* A_bf16, const float* mu, bsi_rowref scale, const
     int nfreq = n_max >= n_min ? n_max - n_min + 1 : 0;
     int cols = patch * patch * C * (1 + 2 * nfreq);
     BSI_CHECK_ARG(lda >= cols, "operand pitch %d < %d", lda, cols);
+    const int pp = patch * patch;
+    if (256 % pp == 0 && lda % 8 == 0 && (reinterpret_cast<uintptr_t>(A_bf16) & 15) == 0 && (int64_t)B * H * Wd < 0x7fffffffLL &&
+        (kThreads / pp) * lda * 2 <= 48 * 1024) {
+        const int total_tokens = B * (H / patch) * (Wd / patch), tok_per_cta = kThreads / pp;
+        const int smem = tok_per_cta * lda * 2;
+        k_patch_operand_tiled<<<(total_tokens + tok_per_cta - 1) / tok_per_cta, kThreads, smem, (cudaStream_t)stream>>>(
+            (__nv_bfloat16*)A_bf16, mu, scale, step_ptr, total_tokens, C, H, Wd, patch, n_min, nfreq, lda);
+        BSI_LAUNCH_OK("k_patch_operand_tiled");
+        return BSI_OK;
+    }
     if (lda > cols) {
         int64_t rows = (int64_t)B * (H / patch) * (Wd / patch);
         k_zero_pad<<<grid_for(rows * (lda - cols)), kThreads, 0, (cudaStream_t)stream>>>((__nv_bfloat16*)A_bf16, rows, cols, lda);

@@ -37,11 +37,13 @@ __device__ __forceinline__ int bucket_of_r(float x, float lo_edge, float dx, int
     return min(max(i, 0), k - 1);
 }
 
-__device__ __forceinline__ float normal_cdf(float v, float loc, float inv_scale) {
-    // torch.distributions.Normal.cdf: 0.5 * (1 + erf((v - loc) * scale.reciprocal() / sqrt(2)))
-    float z = __fdiv_rn(__fmul_rn(__fsub_rn(v, loc), inv_scale), 1.4142135623730951f);
-    return __fmul_rn(0.5f, __fadd_rn(1.0f, erff(z)));
+// torch.distributions.Normal.cdf: 0.5 * (1 + erf((v - loc) * scale.reciprocal() / sqrt(2))), split in its two halves
+__device__ __forceinline__ float cdf_arg(float v, float loc, float inv_scale) {
+    return __fdiv_rn(__fmul_rn(__fsub_rn(v, loc), inv_scale), 1.4142135623730951f);
 }
+__device__ __forceinline__ float cdf_of_erf(float e) { return __fmul_rn(0.5f, __fadd_rn(1.0f, e)); }
+// |z| >= 4: erfc(4) = 1.5e-8 is a quarter of the fp32 spacing below 1, so erff(z) is exactly +-1 and the cdf exactly 0 or 1
+constexpr float kErfSaturated = 4.0f;
 
 __global__ void __launch_bounds__(kRThreads)
     k_recon_reduce(float* __restrict__ out, const float* __restrict__ x, const float* __restrict__ mu, const float* __restrict__ f,
@@ -67,8 +69,15 @@ __global__ void __launch_bounds__(kRThreads)
         for (int j = 0; j < 4; ++j) {
             float xh = combine(has_mu, cs, co, ms[j], fs[j]);
             int idx = bucket_of_r(xs[j], lo_edge, dx, k);
-            float left = idx == 0 ? 0.0f : normal_cdf(s_edges[idx], xh, inv_scale);
-            float right = idx == k - 1 ? 1.0f : normal_cdf(s_edges[idx + 1], xh, inv_scale);
+            // The bin is 11 sigma wide (image_8bit with alpha_R = 2e6), so at most one of its two edges lies within the 4 sqrt(2)
+            // sigma of x_hat where erf is not saturated -- except in a thin sliver around the bin centre.  One erff per element
+            // serves whichever edge needs it; the other cdf is the exact constant.  Same values as evaluating both.
+            const float zl = cdf_arg(s_edges[idx], xh, inv_scale), zr = cdf_arg(s_edges[idx + 1], xh, inv_scale);
+            const bool nl = idx != 0 && fabsf(zl) < kErfSaturated, nr = idx != k - 1 && fabsf(zr) < kErfSaturated;
+            const float e = erff(nl ? zl : zr);
+            float left = idx == 0 ? 0.0f : (nl ? cdf_of_erf(e) : (zl < 0.0f ? 0.0f : 1.0f));
+            float right = idx == k - 1 ? 1.0f : (nr ? cdf_of_erf(e) : (zr < 0.0f ? 0.0f : 1.0f));
+            if (nl && nr) right = cdf_of_erf(erff(zr));  // both edges unsaturated (x_hat within 0.08 sigma-units of the centre)
             acc -= logf(fmaxf(__fsub_rn(right, left), 1e-20f));
         }
     }
@@ -108,22 +117,23 @@ __global__ void __launch_bounds__(kRThreads)
     k_sqerr_backward(float* __restrict__ grad_f, const float* __restrict__ w, const float* __restrict__ x,
                      const float* __restrict__ mu, const float* __restrict__ f, const float* __restrict__ c_skip,
                      const float* __restrict__ c_out, int64_t R, int64_t B, int64_t D) {
-    const int64_t qpr = D >> 2, total = R * qpr;
+    // blockIdx.x = row, blockIdx.y = chunk of 256 quads: no 64-bit division per element
+    const int q = blockIdx.y * kRThreads + threadIdx.x;
+    if (q >= (int)(D >> 2)) return;
+    const uint32_t r32 = blockIdx.x;
+    const int64_t r = r32, b = r32 % (uint32_t)B;
     const bool has_mu = mu != nullptr;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        int64_t r = i / qpr, q = i - r * qpr, b = r % B;
-        const float cs = has_mu ? c_skip[r] : 0.0f, co = has_mu ? c_out[r] : 1.0f;
-        const float g = -2.0f * w[r] * co;
-        float4 xv = *reinterpret_cast<const float4*>(x + b * D + q * 4);
-        float4 fv = __ldcs(reinterpret_cast<const float4*>(f + r * D) + q);
-        float4 mv = has_mu ? __ldcs(reinterpret_cast<const float4*>(mu + r * D) + q) : make_float4(0, 0, 0, 0);
-        float4 o;
-        o.x = g * (xv.x - combine(has_mu, cs, co, mv.x, fv.x));
-        o.y = g * (xv.y - combine(has_mu, cs, co, mv.y, fv.y));
-        o.z = g * (xv.z - combine(has_mu, cs, co, mv.z, fv.z));
-        o.w = g * (xv.w - combine(has_mu, cs, co, mv.w, fv.w));
-        *reinterpret_cast<float4*>(grad_f + r * D + q * 4) = o;
-    }
+    const float cs = has_mu ? c_skip[r] : 0.0f, co = has_mu ? c_out[r] : 1.0f;
+    const float g = -2.0f * w[r] * co;
+    float4 xv = *reinterpret_cast<const float4*>(x + b * D + (int64_t)q * 4);
+    float4 fv = __ldcs(reinterpret_cast<const float4*>(f + r * D) + q);
+    float4 mv = has_mu ? __ldcs(reinterpret_cast<const float4*>(mu + r * D) + q) : make_float4(0, 0, 0, 0);
+    float4 o;
+    o.x = g * (xv.x - combine(has_mu, cs, co, mv.x, fv.x));
+    o.y = g * (xv.y - combine(has_mu, cs, co, mv.y, fv.y));
+    o.z = g * (xv.z - combine(has_mu, cs, co, mv.z, fv.z));
+    o.w = g * (xv.w - combine(has_mu, cs, co, mv.w, fv.w));
+    *reinterpret_cast<float4*>(grad_f + r * D + (int64_t)q * 4) = o;
 }
 
 }  // namespace bsi
@@ -162,9 +172,9 @@ int bsi_sqerr_backward(float* grad_f, const float* w, const float* x, const floa
     BSI_CHECK_ARG(grad_f && w && x && f && R > 0 && B > 0, "bsi_sqerr_backward: null pointer or empty batch");
     BSI_CHECK_ARG(!mu || (c_skip && c_out), "bsi_sqerr_backward: mu given without c_skip/c_out");
     BSI_CHECK_ARG(D > 0 && D % 4 == 0, "data numel per sample (%lld) must be a positive multiple of 4", (long long)D);
-    int64_t need = (R * D / 4 + kRThreads - 1) / kRThreads, cap = (int64_t)sm_count() * 8;
-    k_sqerr_backward<<<(unsigned)(need < cap ? need : cap), kRThreads, 0, (cudaStream_t)stream>>>(grad_f, w, x, mu, f, c_skip, c_out,
-                                                                                                R, B, D);
+    const int64_t chunks = ((D >> 2) + kRThreads - 1) / kRThreads;
+    BSI_CHECK_ARG(R <= 0x7fffffffLL && B <= 0x7fffffffLL && chunks <= 65535, "bsi_sqerr_backward: shape out of range");
+    k_sqerr_backward<<<dim3((unsigned)R, (unsigned)chunks), kRThreads, 0, (cudaStream_t)stream>>>(grad_f, w, x, mu, f, c_skip, c_out, R, B, D);
     BSI_LAUNCH_OK("k_sqerr_backward");
     return BSI_OK;
 }

@@ -44,11 +44,23 @@ def sharded_sample(bsi, n_total: int, seed: int, *, t=None, gather: bool = True,
     return gather_rows(local, n_total, group) if gather else local
 
 
-def sharded_elbo(bsi, x_full: torch.Tensor, n_recon: int, n_measure: int, seed: int, *, group=None):
-    """ELBO of a batch sharded on the data axis; every rank returns the full (elbo[B], bpd[B])."""
+def sharded_elbo(bsi, x_full: torch.Tensor, n_recon: int, n_measure: int, seed: int, *, estimate_var: bool = False, group=None):
+    """``bsi.elbo(x_full, n_recon, n_measure, Generator(seed))`` with the data points split over the ranks.
+
+    Every rank seeds the same generator, so the Philox keys, the low-discrepancy offset and the permutation over all
+    ``n_measure * B`` grid points (bsi/bsi.py:422-440) are drawn ONCE for the whole batch and each rank keeps its columns; the
+    noise of row (replica, data point) is keyed by its index in the full problem.  The gathered result therefore equals the
+    single-GPU call entry by entry for any world size; the only communication is the final all_gather of ``[n, B]`` losses.
+    Returns (elbo[B], bpd[B], extra) like ``BSI.elbo``."""
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     world = dist.get_world_size(group) if dist.is_initialized() else 1
-    start, count = shard_range(len(x_full), rank, world)
-    gen = torch.Generator(device=x_full.device).manual_seed(seed + rank)
-    elbo, bpd, _ = bsi.elbo(x_full[start : start + count], n_recon, n_measure, gen)
-    return gather_rows(elbo, len(x_full), group), gather_rows(bpd, len(x_full), group)
+    B = len(x_full)
+    start, count = shard_range(B, rank, world)
+    gen = torch.Generator(device=x_full.device).manual_seed(seed)
+    x_local = x_full[start : start + count]
+    l_recon = bsi.reconstruction_loss(x_local, n_recon, gen, _shard=(start, B))
+    l_measure = bsi.inf_measurement_loss(x_local, n_measure, gen, _shard=(start, B))
+    # [n, B_local] -> gather along the data axis
+    l_recon = gather_rows(l_recon.t().contiguous(), B, group).t().contiguous()
+    l_measure = gather_rows(l_measure.t().contiguous(), B, group).t().contiguous()
+    return bsi._assemble_elbo(l_recon, l_measure, estimate_var)

@@ -185,3 +185,29 @@ def test_edge_cases_empty_single_and_ragged_batches():
     odd = BSI(model, data_shape=(1, 5, 5), k=4, discretization=Discretization.image_8bit(), **HYPER).to(dev())
     with torch.inference_mode(), pytest.raises((BsiNativeError, RuntimeError), match="multiple of 4"):
         odd.sample(2, torch.Generator(device=dev()).manual_seed(1))
+
+
+@pytest.mark.parametrize("noise", ["philox", "torch"])
+def test_elbo_is_invariant_to_how_the_batch_is_sharded(noise):
+    """the low-discrepancy grid (offset + permutation over n_m * B points, bsi/bsi.py:422-440) and the noise are drawn
+    once for the whole batch and sliced, so a column shard evaluated alone (as a rank of bsi_b200.distributed.sharded_elbo would)
+    reproduces the corresponding entries of the single-GPU call bit for bit -- for ragged splits and for finite_elbo too."""
+    bsi, sd = make(k=16, noise=noise)
+    B = 7
+    x = H.det_images("shard.x", B, (3, 32, 32), seed=4).to(dev())
+    gen = lambda: torch.Generator(device=dev()).manual_seed(77)
+    with torch.inference_mode():
+        e, b, ex = bsi.elbo(x, 2, 3, gen(), estimate_var=True)
+        fe, fb, fex = bsi.finite_elbo(x, 1, 3, gen())
+        for splits in ([(0, 4), (4, 3)], [(0, 3), (3, 2), (5, 2)], [(0, 7)]):
+            parts = [bsi.elbo(x[a : a + c], 2, 3, gen(), _shard=(a, B)) for a, c in splits]
+            assert torch.equal(torch.cat([p[2]["l_recon"] for p in parts], dim=1), ex["l_recon"])
+            assert torch.equal(torch.cat([p[2]["l_measure"] for p in parts], dim=1), ex["l_measure"])
+            assert torch.equal(torch.cat([p[1] for p in parts]), b)
+            fparts = [bsi.finite_elbo(x[a : a + c], 1, 3, gen(), _shard=(a, B)) for a, c in splits]
+            assert torch.equal(torch.cat([p[2]["l_measure"] for p in fparts], dim=1), fex["l_measure"])
+        # without a process group sharded_elbo is the single-GPU call
+        from bsi_b200.distributed import sharded_elbo
+
+        e2, b2, ex2 = sharded_elbo(bsi, x, 2, 3, 77, estimate_var=True)
+        assert torch.equal(b2, b) and torch.equal(ex2["bpd_var"], ex["bpd_var"])

@@ -187,6 +187,22 @@ def test_gather_rows_gloo_world2():
     assert res[0] == res[1] == [float(i) for i in range(7)]
 
 
+def test_sharded_lambda_grid_is_a_column_slice_of_the_single_gpu_grid():
+    """Host logic of sharded_elbo: every rank draws offset + permutation for the WHOLE batch from the same seed and
+    keeps its columns; the concatenation over any world size is the single-GPU grid (reference bsi/bsi.py:422-440)."""
+    bsi = BSI(torch.nn.Identity(), data_shape=(3, 32, 32), k=8, **HYPER)
+    B, n = 11, 3
+    full = bsi._sample_lambda(n, B, torch.Generator().manual_seed(5))
+    for world in (1, 2, 3, 4, 16):
+        cols = []
+        for rank in range(world):
+            start, count = shard_range(B, rank, world)
+            x_local = torch.zeros(count, 3, 32, 32)
+            grid = bsi._sample_lambda(n, B, torch.Generator().manual_seed(5))
+            cols.append(bsi._shard_columns(grid, x_local, (start, B)))
+        assert torch.equal(torch.cat(cols, dim=1), full)
+
+
 def test_reference_checkpoint_ingestion():
     """A Lightning checkpoint of the reference (state_dict keys model.* / ema_model.ema_model.*, config under "config") loads unchanged."""
     from bsi_b200.checkpoint import build_denoiser, denoiser_state_dict, from_reference_checkpoint
