@@ -230,11 +230,11 @@ def hbm_kernel_rooflines(dev, peak_gbs: float, n: int = 256, n_measure: int = 10
     one = torch.ones(1, device=dev)
     xm = torch.empty(n * T, 1024, dtype=torch.bfloat16, device=dev)
     xs = torch.randn(n * T, 1024, device=dev, generator=g)
-    none = L.RowRef(None, 0, 0)
+    mod = torch.rand(2, 1024, device=dev, generator=g) * 0.1  # one shift / scale row shared by all samples
     cases = [
         ("k_step_fused", n * D * 12, lambda: lib.bsi_step_fused(L.ptr(mu_s), L.ptr(f_s), L.ptr(coef), None, 1, 1, L.noise(seed=3, draw=1), None, None, n, D, st)),
         ("k_patch_operand_tiled", n * D * 4 + n * T * lda * 2, lambda: lib.bsi_dit_patch_operand(L.ptr(A), L.ptr(mu_s), L.rowref(one, 0), None, n, shape[0], shape[1], shape[2], patch, 6, 8, lda, st)),
-        ("k_layernorm_mod", n * T * 1024 * 6, lambda: lib.bsi_layernorm_mod_bf16(L.ptr(xm), L.ptr(xs), none, none, None, None, None, T, n * T, 1024, 1e-5, st)),
+        ("k_layernorm_mod", n * T * 1024 * 6, lambda: lib.bsi_layernorm_mod_bf16(L.ptr(xm), L.ptr(xs), L.rowref(mod, 0, 0, 0), L.rowref(mod, 0, 0, 1024), None, None, None, T, n * T, 1024, 1e-5, st)),
         ("k_sqerr_reduce", R * D * 8, lambda: lib.bsi_sqerr_reduce(L.ptr(out), L.ptr(x), L.ptr(mu), L.ptr(f), L.ptr(cs), L.ptr(co), R, n, D, st)),
         ("k_recon_reduce", R * D * 8, lambda: lib.bsi_recon_reduce(L.ptr(out), L.ptr(x), L.ptr(mu), L.ptr(f), L.ptr(cs), L.ptr(co), L.ptr(edges), 256, -1 - 1 / 255, 2 / 255,
                                                                    1414.2135, R, n, D, st)),

@@ -3,6 +3,8 @@
 // weights live in a caller-provided arena (bf16 matrices + fp32 vectors, packed from the reference
 // state_dict by key), activations in a caller-provided workspace.  Every call only enqueues
 // kernels on the given stream, so a whole sampler step can be captured in a CUDA graph.
+#include <cstdlib>
+#include <cstring>
 #include <map>
 #include <string>
 #include <vector>
@@ -234,6 +236,10 @@ int bsi_dit_forward(const bsi_dit* e, float* out, const float* mu, bsi_rowref in
     const int d = c.dim, T = e->T, M = B * T;
     cudaStream_t st = (cudaStream_t)stream;
     int rc;
+    // BSI_DEBUG_SKIP=ln|attn|ln,attn: timing experiments only (wrong results) -- which share of a step is a kernel family worth
+    // under the power cap?  (profiles/skip_experiment_r02.txt)
+    static const char* dbg = getenv("BSI_DEBUG_SKIP");
+    const bool skip_ln = dbg && strstr(dbg, "ln"), skip_attn = dbg && strstr(dbg, "attn");
 #define BSI_TRY(call) \
     if ((rc = (call)) != BSI_OK) return rc
 
@@ -256,15 +262,15 @@ int bsi_dit_forward(const bsi_dit* e, float* out, const float* mu, bsi_rowref in
         bsi_gemm_args g{};
         g.rows_per_sample = T, g.step_ptr = step_ptr;
         // attention branch: x += gate_msa * to_out(attn(to_qkv(modulate(norm(x), shift_msa, scale_msa))))   (dit.py:93-97)
-        BSI_TRY(bsi_layernorm_mod_bf16(w.xm, w.x, part(0), part(1), step_ptr, nullptr, nullptr, T, M, d, 1e-5f, st));
+        if (!skip_ln) BSI_TRY(bsi_layernorm_mod_bf16(w.xm, w.x, part(0), part(1), step_ptr, nullptr, nullptr, T, M, d, 1e-5f, st));
         BSI_TRY(gemm(w.xm, d, e->ptr<void>(e->blk(l, "attn.to_qkv.weight")), d, w.qkv, 3 * d, e->ptr<float>(e->blk(l, "attn.to_qkv.bias")), M,
                      3 * d, d, BSI_EPI_BIAS_BF16, st));
-        BSI_TRY(bsi_attention_bf16(w.att, w.qkv, B, T, c.heads, d / c.heads, st));
+        if (!skip_attn) BSI_TRY(bsi_attention_bf16(w.att, w.qkv, B, T, c.heads, d / c.heads, st));
         g.gate = part(2);
         BSI_TRY(gemm(w.att, d, e->ptr<void>(e->blk(l, "attn.to_out.weight")), d, w.x, d, e->ptr<float>(e->blk(l, "attn.to_out.bias")), M, d, d,
                      BSI_EPI_GATE_RESID_F32, st, &g));
         // MLP branch: x += gate_mlp * mlp(modulate(norm(x), shift_mlp, scale_mlp))                          (dit.py:98-102)
-        BSI_TRY(bsi_layernorm_mod_bf16(w.xm, w.x, part(3), part(4), step_ptr, nullptr, nullptr, T, M, d, 1e-5f, st));
+        if (!skip_ln) BSI_TRY(bsi_layernorm_mod_bf16(w.xm, w.x, part(3), part(4), step_ptr, nullptr, nullptr, T, M, d, 1e-5f, st));
         BSI_TRY(gemm(w.xm, d, e->ptr<void>(e->blk(l, "mlp.0.weight")), d, w.h, 4 * d, e->ptr<float>(e->blk(l, "mlp.0.bias")), M, 4 * d, d,
                      BSI_EPI_BIAS_GELU_BF16, st));
         g.gate = part(5);
