@@ -12,7 +12,9 @@ import os
 import torch
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libbsi_b200.so")
+# BSI_B200_LIB selects an experimental build of the same library (kernel A/B runs: `python -m bsi_b200.build --variant NAME -DFLAG`
+# writes libbsi_b200_NAME.so next to the product library); unset = the product library
+LIB_PATH = os.environ.get("BSI_B200_LIB") or os.path.join(_PKG, "libbsi_b200.so")
 
 
 class RowRef(C.Structure):

@@ -279,9 +279,9 @@ __device__ __forceinline__ float ex2_poly(float t) {
 }
 
 // cycles per phase of softmax warp 0, summed over items and CTAs (BSI_ATT_VARIANT=9: timing build of the kernel)
-__device__ unsigned long long g_att_phase[8];
+__device__ unsigned long long g_att_phase[16];  // [0,6): softmax warp 0; [8,14): control warp
 
-template <bool LSE, int POLY, bool TIMING = false>
+template <bool LSE, int POLY, bool TIMING = false, bool SPIN = false>
 __global__ void __launch_bounds__(att2::kThreads, 2)
     k_attention_tc2(const __grid_constant__ CUtensorMap map_qkv, const __grid_constant__ CUtensorMap map_out, const int dim, const int heads,
                     const int total_items, const float scale_log2, float* __restrict__ lse) {
@@ -302,6 +302,10 @@ __global__ void __launch_bounds__(att2::kThreads, 2)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_qk + 7);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    auto bwait = [](uint64_t* bar, uint32_t parity) {
+        if constexpr (SPIN) ptx::mbar_wait_spin(bar, parity);
+        else ptx::mbar_wait(bar, parity);
+    };
     if (warp == kSoftmaxWarps) {
         if (lane == 0) {
             ptx::prefetch_tensormap(&map_qkv);
@@ -358,32 +362,49 @@ __global__ void __launch_bounds__(att2::kThreads, 2)
                 load_v(blockIdx.x);
             }
             int it = 0;
+            long long cphase[6] = {0, 0, 0, 0, 0, 0}, cc = 0;
+            auto ctick = [&](int i) {
+                if constexpr (TIMING) {
+                    const long long now = clock64();
+                    cphase[i] += now - cc;
+                    cc = now;
+                }
+            };
+            if constexpr (TIMING) cc = clock64();
             for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++it) {
                 const uint32_t ph = it & 1;
                 const int next = item + gridDim.x;
-                ptx::mbar_wait(bar_qk, ph);
-                ptx::mbar_wait(bar_ofree, ph ^ 1);
+                bwait(bar_qk, ph);
+                bwait(bar_ofree, ph ^ 1);
                 ptx::tc_fence_after();
+                ctick(0);  // waiting for Q/K and for O to be read out
 #pragma unroll
                 for (int k = 0; k < HD / 16; ++k) ptx::umma_bf16_ss<1>(tmem, dq + 2 * k, dk + 2 * k, idesc_s, k != 0 ? 1u : 0u);
                 ptx::umma_commit<1>(bar_s);
-                ptx::mbar_wait(bar_s, ph);
+                bwait(bar_s, ph);
+                ctick(1);  // S = Q K^T issue -> completion
                 if (next < total_items) load_qk(next);
                 // O = P V in two halves: keys [0,128) as soon as their probabilities are written, keys [128,256) after the rest
-                ptx::mbar_wait(bar_v, ph);
-                ptx::mbar_wait(bar_p0, ph);
+                bwait(bar_v, ph);
+                bwait(bar_p0, ph);
                 ptx::tc_fence_after();
+                ctick(2);  // waiting for the first half of P
 #pragma unroll
                 for (int k = 0; k < 8; ++k)
                     ptx::umma_bf16_ts(tmem + kOCol, tmem + 8 * k, ptx::umma_desc_mn_sw128(v0 + k * 2048, 8192, 1024), idesc_o, k != 0 ? 1u : 0u);
-                ptx::mbar_wait(bar_p1, ph);
+                bwait(bar_p1, ph);
                 ptx::tc_fence_after();
+                ctick(3);  // first P V half issued; waiting for the second half of P
 #pragma unroll
                 for (int k = 8; k < 16; ++k)
                     ptx::umma_bf16_ts(tmem + kOCol, tmem + 128 + 8 * (k - 8), ptx::umma_desc_mn_sw128(v0 + k * 2048, 8192, 1024), idesc_o, 1u);
                 ptx::umma_commit<1>(bar_o);
-                ptx::mbar_wait(bar_o, ph);
+                bwait(bar_o, ph);
+                ctick(4);  // second P V half issue -> completion
                 if (next < total_items) load_v(next);
+            }
+            if constexpr (TIMING) {
+                for (int i = 0; i < 5; ++i) atomicAdd(&g_att_phase[8 + i], (unsigned long long)cphase[i]);
             }
         }
     } else {
@@ -405,7 +426,7 @@ __global__ void __launch_bounds__(att2::kThreads, 2)
             const uint32_t ph = it & 1;
             int qblk, h, row0;
             coords(item, qblk, h, row0);
-            ptx::mbar_wait(bar_s, ph);
+            bwait(bar_s, ph);
             ptx::tc_fence_after();
             tick(0);  // waiting for S
 
@@ -452,7 +473,7 @@ __global__ void __launch_bounds__(att2::kThreads, 2)
 
             tick(2);  // pass 2
             // ---- O / sum -> bf16 -> this warp's 32 x 128 B staging tile -> TMA store
-            ptx::mbar_wait(bar_o, ph);
+            bwait(bar_o, ph);
             ptx::tc_fence_after();
             tick(3);  // waiting for O
             uint32_t o[2][32];
@@ -502,28 +523,30 @@ __global__ void __launch_bounds__(att2::kThreads, 2)
     }
 }
 
-template <bool LSE, int POLY, bool TIMING = false>
+template <bool LSE, int POLY, bool TIMING = false, bool SPIN = false>
 static int launch_attention2(const CUtensorMap& mq, const CUtensorMap& mo, int dim, int heads, int total, float scale_log2, float* lse, cudaStream_t stream) {
     using namespace att2;
-    BSI_ENSURE_SMEM((k_attention_tc2<LSE, POLY, TIMING>), kSmem);
+    BSI_ENSURE_SMEM((k_attention_tc2<LSE, POLY, TIMING, SPIN>), kSmem);
     const int resident = 2 * sm_count();
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(total < resident ? total : resident), cfg.blockDim = dim3(kThreads), cfg.dynamicSmemBytes = kSmem, cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     fill_pdl_attr(&attr[0]);
     cfg.attrs = attr, cfg.numAttrs = use_pdl() ? 1 : 0;
-    BSI_CUDA_OK(cudaLaunchKernelEx(&cfg, k_attention_tc2<LSE, POLY, TIMING>, mq, mo, dim, heads, total, scale_log2, lse));
+    BSI_CUDA_OK(cudaLaunchKernelEx(&cfg, k_attention_tc2<LSE, POLY, TIMING, SPIN>, mq, mo, dim, heads, total, scale_log2, lse));
     BSI_LAUNCH_OK("k_attention_tc2");
     return BSI_OK;
 }
 
-// 0 = first design (8 softmax warps), 1..3 = second design with 0 / 2 / 4 of every 8 exponentials on the FMA pipe
+// 0 = first design (8 softmax warps), 1..3 = second design with 0 / 2 / 4 of every 8 exponentials on the FMA pipe, 4 = second design
+// with polling mbarrier waits, 5 / 9 = timing builds (bsi_attention_debug_phases)
 static int attention_variant() {
     static int v = -1;
     if (v < 0) {
         const char* e = getenv("BSI_ATT_VARIANT");
-        v = e ? atoi(e) : 0;
-        if ((v < 0 || v > 3) && v != 9) v = 0;
+        v = e ? atoi(e) : 1;  // measured on B200 at B = 256: design 1 139 us, design 2 118 us (torch SDPA 118 us); FMA-pipe exponentials
+                              // (2, 3) and polling barrier waits (4) are slower or equal -- profiles/attention_r02.jsonl
+        if ((v < 0 || v > 5) && v != 9) v = 0;
     }
     return v;
 }
@@ -539,6 +562,9 @@ int attention_tcgen05(void* out_bf16, const void* qkv_bf16, int B, int heads, fl
     if (const int variant = attention_variant()) {
         rc = make_tile_map(&mo, out_bf16, 2, (int64_t)B * T, dim, dim, 1, 0, 32);  // one store per warp: boxes of 32 rows
         if (rc != BSI_OK) return rc;
+        if (variant == 4) return lse ? launch_attention2<true, 0, false, true>(mq, mo, dim, heads, total, scale_log2, lse, stream)
+                                     : launch_attention2<false, 0, false, true>(mq, mo, dim, heads, total, scale_log2, nullptr, stream);
+        if (variant == 5) return launch_attention2<false, 0, true, true>(mq, mo, dim, heads, total, scale_log2, nullptr, stream);
         if (lse) {
             if (variant == 1) return launch_attention2<true, 0>(mq, mo, dim, heads, total, scale_log2, lse, stream);
             if (variant == 2) return launch_attention2<true, 2>(mq, mo, dim, heads, total, scale_log2, lse, stream);
@@ -567,12 +593,13 @@ int attention_tcgen05(void* out_bf16, const void* qkv_bf16, int B, int heads, fl
 
 }  // namespace bsi
 
-// Development aid: cycles per phase {wait S, pass 1, pass 2, wait O, epilogue, items} accumulated by the timing build of the kernel
+// Development aid: cycles per phase {wait S, pass 1, pass 2, wait O, epilogue, items, -, -} of softmax warp 0 and {wait Q/K + O free,
+// S latency, wait P half 1, wait P half 2, P V tail latency} of the control warp at [8, 13), accumulated by the timing build of the kernel
 // (BSI_ATT_VARIANT=9) since the last call; resets the counters.
 extern "C" int bsi_attention_debug_phases(unsigned long long* out6) {
     BSI_CHECK_ARG(out6, "bsi_attention_debug_phases: null pointer");
-    unsigned long long zero[8] = {0};
-    BSI_CUDA_OK(cudaMemcpyFromSymbol(out6, bsi::g_att_phase, 6 * sizeof(unsigned long long)));
+    unsigned long long zero[16] = {0};
+    BSI_CUDA_OK(cudaMemcpyFromSymbol(out6, bsi::g_att_phase, 14 * sizeof(unsigned long long)));
     BSI_CUDA_OK(cudaMemcpyToSymbol(bsi::g_att_phase, zero, sizeof(zero)));
     return BSI_OK;
 }

@@ -40,6 +40,17 @@ __host__ __device__ constexpr int epi_kind(int epi) {
                                          : KIND_F32;
 }
 
+// pipeline-depth experiments (python -m bsi_b200.build --variant NAME -DBSI_EXP_...): defaults are the product configuration
+#ifndef BSI_EXP_PLAIN_STAGES
+#define BSI_EXP_PLAIN_STAGES 5
+#endif
+#ifndef BSI_EXP_HEAVY_STAGES
+#define BSI_EXP_HEAVY_STAGES 4
+#endif
+#ifndef BSI_EXP_HEAVY_BUFS
+#define BSI_EXP_HEAVY_BUFS 2
+#endif
+
 constexpr int kReuseMaxW = 32;  // widest image row for which a convolution's A box (128 + 2W pixels) fits the stage
 
 template <int EPI, int CG, int BN, bool CONV = false>
@@ -61,13 +72,13 @@ struct Cfg {
     // (16 warps, one 64-column block each, measured no faster than 8: the GELU epilogue is bound by the fp32 pipe, not by latency)
     static constexpr int kEpiWarps = kHeavy ? 8 : 4;
     static constexpr int kGroups = kEpiWarps / 4;                                   // groups of 4 warps, each owning BN / kGroups columns
-    static constexpr int kBufsPerGroup = kHeavy ? (kGroups == 4 ? 1 : 2) : 2;      // staging tiles per group (KIND_BF16)
+    static constexpr int kBufsPerGroup = kHeavy ? (kGroups == 4 ? 1 : BSI_EXP_HEAVY_BUFS) : 2;  // staging tiles per group (KIND_BF16)
     static constexpr int kThreads = 128 + 32 * kEpiWarps;
-    static constexpr int kEpiBufs = (kKind == KIND_RMW || kHeavy) ? 4 : (kKind == KIND_SCATTER ? 0 : 2);
+    static constexpr int kEpiBufs = kKind == KIND_RMW ? 4 : kHeavy ? kGroups * kBufsPerGroup : (kKind == KIND_SCATTER ? 0 : 2);
     static constexpr int kVecBytes = 2 * 3 * BN * 4;  // bias, gate/scale and shift slices of the tile, double-buffered by tile parity
     static constexpr int kStages = kRowReuse ? (232448 - 1280 - kVecBytes - kEpiBufs * kEpiBufBytes) / kStageBytes
                                    : BN == 128 ? (CG == 2 ? 6 : 4)
-                                               : (CG == 2 ? ((kKind == KIND_RMW || kHeavy) ? 4 : 5) : 3);
+                                               : (CG == 2 ? (kKind == KIND_RMW ? 4 : kHeavy ? BSI_EXP_HEAVY_STAGES : BSI_EXP_PLAIN_STAGES) : 3);
     static_assert(kStages >= 2, "pipeline needs two stages");
     static constexpr int kSmemBytes = kStages * kStageBytes + kEpiBufs * kEpiBufBytes + kVecBytes + 1024 /*align*/ + 256 /*barriers*/;
     static_assert(kSmemBytes <= 232448, "exceeds the 227 KB of shared memory per CTA");

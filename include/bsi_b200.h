@@ -209,9 +209,10 @@ int bsi_layernorm_mod_bf16(void* out_bf16, const float* x, bsi_rowref shift, bsi
 int bsi_attention_bf16(void* out_bf16, const void* qkv_bf16, int32_t B, int32_t T, int32_t heads, int32_t head_dim, void* stream);
 /* Test hook: T = 256 runs the tcgen05 kernel (scores in TMEM); 1 forces the warp-level mma.sync kernel used for other T. */
 int bsi_attention_force_legacy(int32_t on);
-/* Development aid: cycles per phase {wait S, pass 1, pass 2, wait O, epilogue, items} of the tcgen05 attention kernel's timing
- * build (environment BSI_ATT_VARIANT=9), summed over CTAs since the last call. */
-int bsi_attention_debug_phases(unsigned long long* out6);
+/* Development aid: cycles per phase of the tcgen05 attention kernel's timing build (environment BSI_ATT_VARIANT=9), summed over
+ * CTAs since the last call: out14[0..5] = softmax warp 0 {wait S, pass 1, pass 2, wait O, epilogue, items},
+ * out14[8..12] = control warp {wait Q/K + O free, S latency, wait P half 1, wait P half 2, P V tail latency}. */
+int bsi_attention_debug_phases(unsigned long long* out14);
 
 /* Backward of bsi_attention_bf16 on the same packed layouts (autograd of dit.py:36-47): dqkv bf16 [B*T][3*dim] from the saved qkv,
  * the saved forward output and the upstream gradient dout bf16 [B*T][dim].  lse_ws / dsum_ws: B*heads*T floats of scratch each

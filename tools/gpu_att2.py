@@ -46,15 +46,16 @@ rel = float((o[: 8 * 256].float() - ref).norm() / ref.norm())
 lse_ref = torch.logsumexp(q[:8].float() @ k[:8].float().transpose(-1, -2) / 8.0, dim=-1) * 1.4426950408889634
 lse_err = float((lse.reshape(B, 16, 256)[:8] - lse_ref).abs().max())
 fl = 4.0 * B * 16 * 256 * 256 * 64
-if os.environ.get("BSI_ATT_VARIANT") == "9":
+if os.environ.get("BSI_ATT_VARIANT") in ("9", "5"):
     import ctypes
 
-    buf = (ctypes.c_ulonglong * 6)()
+    buf = (ctypes.c_ulonglong * 14)()
     lib.bsi_attention_debug_phases(buf)
     L.check(lib.bsi_attention_bf16(o.data_ptr(), qkv.data_ptr(), B, 256, 16, 64, st))
     torch.cuda.synchronize()
     lib.bsi_attention_debug_phases(buf)
     items = max(1, buf[5])
-    print(json.dumps(dict(phases_clk_per_item=dict(zip(["wait_S", "pass1", "pass2", "wait_O", "epilogue"], [round(buf[i] / items, 1) for i in range(5)])), items=items)))
+    print(json.dumps(dict(phases_clk_per_item=dict(zip(["wait_S", "pass1", "pass2", "wait_O", "epilogue"], [round(buf[i] / items, 1) for i in range(5)])),
+                          control_clk_per_item=dict(zip(["wait_qk_ofree", "S_latency", "wait_P0", "wait_P1", "PV_tail"], [round(buf[8 + i] / items, 1) for i in range(5)])), items=items)))
 print(json.dumps(dict(variant=os.environ.get("BSI_ATT_VARIANT", "0"), B=B, us=ms * 1e3, us_lse=ms_lse * 1e3, tflops=fl / ms / 1e9, sdpa_us=ms_sdpa * 1e3, max_abs_err=err,
                       rel_l2=rel, lse_max_err=lse_err)), flush=True)
