@@ -46,7 +46,7 @@ class ConvArgs(C.Structure):
         ("X1", C.c_void_p), ("X2", C.c_void_p), ("W", C.c_void_p), ("Y", C.c_void_p), ("bias", C.c_void_p), ("resid", C.c_void_p),
         ("B", C.c_int32), ("H", C.c_int32), ("Wd", C.c_int32), ("C1", C.c_int32), ("C2", C.c_int32), ("N", C.c_int32),
         ("taps", C.c_int32), ("ldc", C.c_int32), ("epilogue", C.c_int32),
-        ("scale", RowRef), ("shift", RowRef), ("step_ptr", C.c_void_p),
+        ("scale", RowRef), ("shift", RowRef), ("step_ptr", C.c_void_p), ("gn_partial", C.c_void_p),
     ]  # fmt: skip
 
 
@@ -116,6 +116,7 @@ SIGNATURES = {
     "bsi_sqerr_backward": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _vp]),
     "bsi_gemm_bf16": (C.c_int, [C.POINTER(GemmArgs), _vp]),
     "bsi_conv_bf16": (C.c_int, [C.POINTER(ConvArgs), _vp]),
+    "bsi_groupnorm_apply_bf16": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _f32, _i32, _vp]),
     "bsi_gemm_force_cta_group": (C.c_int, [_i32]),
     "bsi_cast_bf16": (C.c_int, [_vp, _vp, _i64, _i64, _i64, _vp]),
     "bsi_layernorm_mod_bf16": (C.c_int, [_vp, _vp, RowRef, RowRef, _vp, _vp, _vp, _i32, _i64, _i32, _f32, _vp]),

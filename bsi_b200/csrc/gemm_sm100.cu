@@ -44,11 +44,13 @@ __host__ __device__ constexpr int epi_kind(int epi) {
 #ifndef BSI_EXP_PLAIN_STAGES
 #define BSI_EXP_PLAIN_STAGES 5
 #endif
+// GELU / SiLU epilogues: 5 pipeline stages with one staging tile per warp group beat 4 stages with two (MLP-1 shape, M = 65536,
+// back-to-back under the power cap: 484 vs 496-500 us, profiles/gemm_ab_r02.jsonl); plain epilogue: 5 vs 4 stages is within 1 %
 #ifndef BSI_EXP_HEAVY_STAGES
-#define BSI_EXP_HEAVY_STAGES 4
+#define BSI_EXP_HEAVY_STAGES 5
 #endif
 #ifndef BSI_EXP_HEAVY_BUFS
-#define BSI_EXP_HEAVY_BUFS 2
+#define BSI_EXP_HEAVY_BUFS 1
 #endif
 
 constexpr int kReuseMaxW = 32;  // widest image row for which a convolution's A box (128 + 2W pixels) fits the stage
@@ -76,11 +78,14 @@ struct Cfg {
     static constexpr int kThreads = 128 + 32 * kEpiWarps;
     static constexpr int kEpiBufs = kKind == KIND_RMW ? 4 : kHeavy ? kGroups * kBufsPerGroup : (kKind == KIND_SCATTER ? 0 : 2);
     static constexpr int kVecBytes = 2 * 3 * BN * 4;  // bias, gate/scale and shift slices of the tile, double-buffered by tile parity
-    static constexpr int kStages = kRowReuse ? (232448 - 1280 - kVecBytes - kEpiBufs * kEpiBufBytes) / kStageBytes
+    static constexpr int kStages = kRowReuse ? (232448 - 1280 - 1024 /*kGnBytes*/ - kVecBytes - kEpiBufs * kEpiBufBytes) / kStageBytes
                                    : BN == 128 ? (CG == 2 ? 6 : 4)
                                                : (CG == 2 ? (kKind == KIND_RMW ? 4 : kHeavy ? BSI_EXP_HEAVY_STAGES : BSI_EXP_PLAIN_STAGES) : 3);
     static_assert(kStages >= 2, "pipeline needs two stages");
-    static constexpr int kSmemBytes = kStages * kStageBytes + kEpiBufs * kEpiBufBytes + kVecBytes + 1024 /*align*/ + 256 /*barriers*/;
+    // GroupNorm partial sums of a convolution's fp32 output (U-Net residual stream): [4 warps][32 groups][sum, sum of squares]
+    static constexpr bool kGnStats = CONV && BN == 128 && kKind == KIND_RMW;
+    static constexpr int kGnBytes = kGnStats ? 4 * 64 * 4 : 0;
+    static constexpr int kSmemBytes = kStages * kStageBytes + kEpiBufs * kEpiBufBytes + kVecBytes + 1024 /*align*/ + 256 /*barriers*/ + kGnBytes;
     static_assert(kSmemBytes <= 232448, "exceeds the 227 KB of shared memory per CTA");
 };
 
@@ -95,6 +100,7 @@ struct EpiParams {
     int rows_per_sample;
     const float* pos;
     int patch, grid_w, channels;
+    float* gn_partial;  // CONV, N = 128, GATE_RESID: [M / 128][32][2] per-tile GroupNorm sums of the fp32 output (NULL = off)
 };
 
 // Implicit-GEMM 3x3 / 1x1 convolution over NHWC activations: the A tile of k-block (tap, channel block) is a 4-D TMA box
@@ -118,6 +124,35 @@ __device__ __forceinline__ float gelu_tanh(float x) {
     return fmaf(hx, t, hx);
 }
 __device__ __forceinline__ float silu(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
+
+// Sum 16 per-lane values over the 32 lanes of a warp with 16 shuffles (each step halves the values a lane keeps); returns the total
+// of value (lane >> 1), held by both lanes of the pair.  Fixed order: deterministic.
+__device__ __forceinline__ float warp_reduce16(float (&v)[16], int lane) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const bool hi = lane & 16;
+        const float send = hi ? v[i] : v[i + 8], keep = hi ? v[i + 8] : v[i];
+        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const bool hi = lane & 8;
+        const float send = hi ? v[i] : v[i + 4], keep = hi ? v[i + 4] : v[i];
+        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const bool hi = lane & 4;
+        const float send = hi ? v[i] : v[i + 2], keep = hi ? v[i + 2] : v[i];
+        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    }
+    {
+        const bool hi = lane & 2;
+        const float send = hi ? v[0] : v[1], keep = hi ? v[1] : v[0];
+        v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+    }
+    return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
+}
 
 // named barrier of one group of 4 epilogue warps (group 0 or 1)
 __device__ __forceinline__ void epi_bar(int group = 0) { asm volatile("bar.sync %0, 128;" ::"r"(group + 1) : "memory"); }
@@ -150,6 +185,7 @@ __global__ void __launch_bounds__(Cfg<EPI, CG, BN, CONV>::kThreads, 1)
     uint64_t* tmem_empty = tmem_full + 2;
     uint64_t* c_full = tmem_empty + 2;  // residual chunk landed (KIND_RMW), one per staging buffer
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(c_full + 4);
+    float* s_gn = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full_bar) + 256);  // [4][64], only when C::kGnStats
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int total_tiles = batch * m_tiles * n_tiles;
@@ -441,6 +477,7 @@ __global__ void __launch_bounds__(Cfg<EPI, CG, BN, CONV>::kThreads, 1)
                         }
                         ptx::mbar_wait(&c_full[g & 3], (g >> 2) & 1);
                         const uint32_t sb = buf0 + (g & 3) * kEpiBufBytes;
+                        float gn[16];  // C::kGnStats: (sum, sum of squares) of this row's 8 four-channel groups of the chunk
 #pragma unroll
                         for (int c = 0; c < 8; ++c) {
                             const uint32_t addr = sb + swz(et, c);
@@ -452,6 +489,16 @@ __global__ void __launch_bounds__(Cfg<EPI, CG, BN, CONV>::kThreads, 1)
                             x4.z = fmaf(gt[2], __uint_as_float(a[h][c * 4 + 2]) + bs[2], x4.z);
                             x4.w = fmaf(gt[3], __uint_as_float(a[h][c * 4 + 3]) + bs[3], x4.w);
                             st_shared_v4(addr, __float_as_uint(x4.x), __float_as_uint(x4.y), __float_as_uint(x4.z), __float_as_uint(x4.w));
+                            if constexpr (C::kGnStats) {
+                                gn[2 * c] = (x4.x + x4.y) + (x4.z + x4.w);
+                                gn[2 * c + 1] = fmaf(x4.x, x4.x, x4.y * x4.y) + fmaf(x4.z, x4.z, x4.w * x4.w);
+                            }
+                        }
+                        if constexpr (C::kGnStats) {
+                            if (ep.gn_partial) {  // uniform branch
+                                const float tot = warp_reduce16(gn, lane);
+                                if ((lane & 1) == 0) s_gn[q * 64 + cidx * 16 + (lane >> 1)] = tot;
+                            }
                         }
                         ptx::fence_proxy_async();
                         epi_bar();
@@ -480,6 +527,15 @@ __global__ void __launch_bounds__(Cfg<EPI, CG, BN, CONV>::kThreads, 1)
                                 }
                             }
                         }
+                    }
+                }
+            }
+            if constexpr (C::kGnStats) {
+                if (ep.gn_partial) {
+                    // all four warps have written their 64 partial sums of this tile (the last chunk's epi_bar above orders them)
+                    if (et < 64) {
+                        const float t = (s_gn[et] + s_gn[64 + et]) + (s_gn[128 + et] + s_gn[192 + et]);
+                        ep.gn_partial[(long long)(row_base / BM) * 64 + et] = t;
                     }
                 }
             }
@@ -698,6 +754,7 @@ extern "C" int bsi_gemm_bf16(const bsi_gemm_args* a, void* stream) {
     ep.stride_c = a->stride_c, ep.stride_bias = a->stride_bias;
     ep.gate = a->gate, ep.shift = bsi_rowref{}, ep.step_ptr = a->step_ptr, ep.rows_per_sample = a->rows_per_sample > 0 ? a->rows_per_sample : 1;
     ep.pos = a->pos, ep.patch = a->patch, ep.grid_w = a->grid_w, ep.channels = a->channels;
+    ep.gn_partial = nullptr;
     int rc = check_common(p, a->epilogue);
     if (rc != BSI_OK) return rc;
     if (a->epilogue == BSI_EPI_GATE_RESID_F32) BSI_CHECK_ARG(a->gate.base, "bsi_gemm_bf16: GATE_RESID needs a gate");
@@ -735,6 +792,10 @@ extern "C" int bsi_conv_bf16(const bsi_conv_args* a, void* stream) {
     ep.C = a->Y, ep.bias = a->bias, ep.M = p.M, ep.N = p.N, ep.ldc = a->ldc, ep.stride_c = 0, ep.stride_bias = 0;
     ep.gate = a->scale, ep.shift = a->shift, ep.step_ptr = a->step_ptr, ep.rows_per_sample = a->H * a->Wd;
     ep.pos = nullptr, ep.patch = ep.grid_w = ep.channels = 0;
+    ep.gn_partial = a->gn_partial;
+    if (a->gn_partial)
+        BSI_CHECK_ARG(a->epilogue == BSI_EPI_GATE_RESID_F32 && a->N == 128 && (a->H * a->Wd) % BM == 0,
+                      "bsi_conv_bf16: GroupNorm partial sums need the GATE_RESID epilogue, N = 128 and H*W %% 128 == 0");
     int rc = check_common(p, a->epilogue);
     if (rc != BSI_OK) return rc;
     if (a->epilogue == BSI_EPI_MOD_SILU_BF16) BSI_CHECK_ARG(a->scale.base && a->shift.base, "bsi_conv_bf16: MOD_SILU needs scale and shift");

@@ -3,6 +3,7 @@
 // Activations are NHWC; every 3x3 / 1x1 convolution is an implicit GEMM on tcgen05 (bsi_conv_bf16), the channel concat of the
 // up path is a two-source K loop, the residual adds are the GEMM's fp32 read-modify-write epilogue (gate = 1), and the skip
 // tensors are simply the outputs of the down blocks (no copies).  Like the DiT engine it owns no device memory.
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -63,6 +64,7 @@ static void add_conv(bsi_unet* e, const std::string& key, int n, int cin, int ta
 struct UWork {
     __nv_bfloat16 *in_op, *act1, *act2, *raw1, *raw2, *h, *qkv, *att;
     float *stream, *bufA, *bufB;  // stream: (L+1) x [P][d]
+    float *gn_stream, *gn_A, *gn_B;  // GroupNorm partial sums [P/128][64] of stream[i], bufA, bufB (written by the producing convolution)
     int64_t bytes;
 };
 static UWork carve_unet(const bsi_unet* e, int B, uint8_t* base) {
@@ -81,6 +83,8 @@ static UWork carve_unet(const bsi_unet* e, int B, uint8_t* base) {
     w.qkv = (__nv_bfloat16*)take(P * 3 * d * 2), w.att = (__nv_bfloat16*)take(P * d * 2);
     w.stream = (float*)take((int64_t)(e->L + 1) * P * d * 4);
     w.bufA = (float*)take(P * d * 4), w.bufB = (float*)take(P * d * 4);
+    const int64_t gnb = P / 128 * 64 * 4;
+    w.gn_stream = (float*)take((int64_t)(e->L + 1) * gnb), w.gn_A = (float*)take(gnb), w.gn_B = (float*)take(gnb);
     w.bytes = off;
     return w;
 }
@@ -254,12 +258,26 @@ int bsi_unet_forward(const bsi_unet* e, float* out, const float* mu, bsi_rowref 
     if ((rc = (call)) != BSI_OK) return rc
 
     auto conv = [&](const void* x1, int c1, const void* x2, int c2, const std::string& wkey, const std::string& bkey, int taps, int N, void* y, int ldc,
-                    int epi, const float* resid, bsi_rowref scale, bsi_rowref shift) {
+                    int epi, const float* resid, bsi_rowref scale, bsi_rowref shift, float* gn_out = nullptr) {
         bsi_conv_args a{};
         a.X1 = x1, a.X2 = x2, a.W = e->ptr<void>(wkey), a.Y = y, a.bias = e->ptr<float>(bkey), a.resid = resid;
         a.B = B, a.H = c.height, a.Wd = c.width, a.C1 = c1, a.C2 = c2, a.N = N, a.taps = taps, a.ldc = ldc, a.epilogue = epi;
-        a.scale = scale, a.shift = shift, a.step_ptr = step_ptr;
+        a.scale = scale, a.shift = shift, a.step_ptr = step_ptr, a.gn_partial = gn_out;
         return bsi_conv_bf16(&a, stream);
+    };
+    // GroupNorm statistics of a residual-stream tensor: left behind by the convolution that wrote it (gn != NULL), else computed by
+    // the stand-alone cluster kernel (only the encode convolution's output, which has a plain bias epilogue)
+    static const bool gn_from_epilogue = [] { const char* v = getenv("BSI_GN_EPILOGUE"); return !(v && v[0] == '0'); }();
+    auto gn_of = [&](const float* x) -> float* {
+        if (!gn_from_epilogue) return nullptr;
+        if (x == w.bufA) return w.gn_A;
+        if (x == w.bufB) return w.gn_B;
+        const int64_t i = (x - w.stream) / (P * d);
+        return i >= 1 && i <= L ? w.gn_stream + i * (P / 128 * 64) : nullptr;  // stream[0] is the encode output
+    };
+    auto groupnorm = [&](__nv_bfloat16* act, __nv_bfloat16* raw, const float* x, const float* gam, const float* bet, int cpg, int silu) {
+        if (float* st = gn_of(x)) return bsi_groupnorm_apply_bf16(act, raw, x, st, gam, bet, B, HW, d, cpg, 1e-5f, silu, stream);
+        return bsi_groupnorm_act_bf16(act, raw, x, gam, bet, B, HW, d, cpg, 1e-5f, silu, stream);
     };
     auto modref = [&](int blk, int part) {
         bsi_rowref r;
@@ -274,18 +292,18 @@ int bsi_unet_forward(const bsi_unet* e, float* out, const float* mu, bsi_rowref 
         const float* gam = e->ptr<float>(p + ".layers.0.weight");
         const float* bet = e->ptr<float>(p + ".layers.0.bias");
         if (!skip) {
-            U_TRY(bsi_groupnorm_act_bf16(w.act1, nullptr, x, gam, bet, B, HW, d, d / 32, 1e-5f, 1, stream));
+            U_TRY(groupnorm(w.act1, nullptr, x, gam, bet, d / 32, 1));
             U_TRY(conv(w.act1, d, nullptr, 0, p + ".layers.2.weight", p + ".layers.2.bias", 9, d, w.h, d, BSI_EPI_MOD_SILU_BF16, nullptr, modref(blk, 0),
                        modref(blk, 1)));
-            return conv(w.h, d, nullptr, 0, p + ".conv2.weight", p + ".conv2.bias", 9, d, y, d, BSI_EPI_GATE_RESID_F32, x, none, none);
+            return conv(w.h, d, nullptr, 0, p + ".conv2.weight", p + ".conv2.bias", 9, d, y, d, BSI_EPI_GATE_RESID_F32, x, none, none, gn_of(y));
         }
         // up path: the input is cat(x, skip) (simplified_unet.py:46); GroupNorm(32, 2d) splits into 16 groups per source
-        U_TRY(bsi_groupnorm_act_bf16(w.act1, w.raw1, x, gam, bet, B, HW, d, 2 * d / 32, 1e-5f, 1, stream));
-        U_TRY(bsi_groupnorm_act_bf16(w.act2, w.raw2, skip, gam + d, bet + d, B, HW, d, 2 * d / 32, 1e-5f, 1, stream));
+        U_TRY(groupnorm(w.act1, w.raw1, x, gam, bet, 2 * d / 32, 1));
+        U_TRY(groupnorm(w.act2, w.raw2, skip, gam + d, bet + d, 2 * d / 32, 1));
         U_TRY(conv(w.act1, d, w.act2, d, p + ".layers.2.weight", p + ".layers.2.bias", 9, d, w.h, d, BSI_EPI_MOD_SILU_BF16, nullptr, modref(blk, 0),
                    modref(blk, 1)));
         U_TRY(conv(w.raw1, d, w.raw2, d, p + ".skip.weight", p + ".skip.bias", 1, d, y, d, BSI_EPI_BIAS_F32, nullptr, none, none));
-        return conv(w.h, d, nullptr, 0, p + ".conv2.weight", p + ".conv2.bias", 9, d, y, d, BSI_EPI_GATE_RESID_F32, y, none, none);
+        return conv(w.h, d, nullptr, 0, p + ".conv2.weight", p + ".conv2.bias", 9, d, y, d, BSI_EPI_GATE_RESID_F32, y, none, none, gn_of(y));
     };
 
     U_TRY(bsi_unet_input_bf16(w.in_op, mu, in_scale, step_ptr, B, c.channels, HW, c.fourier_n_min, c.fourier_n_max, e->cin_pad, stream));
@@ -295,10 +313,10 @@ int bsi_unet_forward(const bsi_unet* e, float* out, const float* mu, bsi_rowref 
     U_TRY(resblock(L, w.stream + (int64_t)L * P * d, nullptr, w.bufA));
     {
         const std::string a = "u_net.center_block.1.fn";
-        U_TRY(bsi_groupnorm_act_bf16(w.act1, nullptr, w.bufA, e->ptr<float>(a + ".0.weight"), e->ptr<float>(a + ".0.bias"), B, HW, d, d / 32, 1e-5f, 0, stream));
+        U_TRY(groupnorm(w.act1, nullptr, w.bufA, e->ptr<float>(a + ".0.weight"), e->ptr<float>(a + ".0.bias"), d / 32, 0));
         U_TRY(conv(w.act1, d, nullptr, 0, a + ".1.to_qkv.weight", a + ".1.to_qkv.bias", 9, 3 * d, w.qkv, 3 * d, BSI_EPI_BIAS_BF16, nullptr, none, none));
         U_TRY(bsi_attention_d128_bf16(w.att, w.qkv, B, HW, stream));
-        U_TRY(conv(w.att, d, nullptr, 0, a + ".1.to_out.weight", a + ".1.to_out.bias", 9, d, w.bufB, d, BSI_EPI_GATE_RESID_F32, w.bufA, none, none));
+        U_TRY(conv(w.att, d, nullptr, 0, a + ".1.to_out.weight", a + ".1.to_out.bias", 9, d, w.bufB, d, BSI_EPI_GATE_RESID_F32, w.bufA, none, none, gn_of(w.bufB)));
     }
     U_TRY(resblock(L + 1, w.bufB, nullptr, w.bufA));
     float* cur = w.bufA;

@@ -161,6 +161,61 @@ __global__ void __launch_bounds__(kGnClusterThreads, 3)
     }
 }
 
+// GroupNorm + SiLU from PRE-COMPUTED statistics: the convolution that produced x has left, per 128-pixel tile, the sums and sums of
+// squares of every group of 4 channels (bsi_conv_args.gn_partial).  What remains is a pure streaming pass -- 4 B read, 2 (or 4) B
+// written per element, no cluster, no shared-memory staging, no second look at x: every CTA first folds its image's
+// HW/128 x 64 partial sums (fp64, fixed order: deterministic) into per-channel mean / rstd, then normalises a 64-pixel strip.
+// cpg = 4 (GroupNorm(32, 128)) or 8 (one source of GroupNorm(32, 256) over cat(x, skip): adjacent 4-channel groups are merged).
+constexpr int kGnApplyThreads = 256, kGnApplyPixels = 64;
+__global__ void __launch_bounds__(kGnApplyThreads)
+    k_groupnorm_apply(__nv_bfloat16* __restrict__ act, __nv_bfloat16* __restrict__ raw, const float* __restrict__ x, const float* __restrict__ partial,
+                      const float* __restrict__ gamma, const float* __restrict__ beta, int HW, int cpg, float eps, int apply_silu) {
+    constexpr int C = 128;
+    __shared__ float s_mean[C], s_rstd[C];
+    const int img = blockIdx.y, strip = blockIdx.x, tiles = HW / 128;
+    if (threadIdx.x < 32) {
+        const int g4 = threadIdx.x;  // 4-channel group
+        double a = 0.0, b = 0.0;
+        const float* pp = partial + (size_t)img * tiles * 64;
+        if (cpg == 4) {
+            for (int t = 0; t < tiles; ++t) a += pp[t * 64 + 2 * g4], b += pp[t * 64 + 2 * g4 + 1];
+        } else {  // cpg == 8: groups (g4 & ~1) and (g4 | 1) form one group
+            const int g0 = g4 & ~1;
+            for (int t = 0; t < tiles; ++t)
+                a += (double)pp[t * 64 + 2 * g0] + (double)pp[t * 64 + 2 * g0 + 2], b += (double)pp[t * 64 + 2 * g0 + 1] + (double)pp[t * 64 + 2 * g0 + 3];
+        }
+        const double n = (double)HW * cpg, mean = a / n;
+        const double var = fmax(b / n - mean * mean, 0.0);
+        const float rstd = rsqrtf((float)var + eps);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) s_mean[g4 * 4 + j] = (float)mean, s_rstd[g4 * 4 + j] = rstd;
+    }
+    __syncthreads();
+    const int cq = threadIdx.x & 31, ps = threadIdx.x >> 5;  // 32 channel quads x 8 pixel stripes
+    const float4 g4v = *reinterpret_cast<const float4*>(gamma + cq * 4), b4v = *reinterpret_cast<const float4*>(beta + cq * 4);
+    const float m[4] = {s_mean[cq * 4], s_mean[cq * 4 + 1], s_mean[cq * 4 + 2], s_mean[cq * 4 + 3]};
+    const float r[4] = {s_rstd[cq * 4], s_rstd[cq * 4 + 1], s_rstd[cq * 4 + 2], s_rstd[cq * 4 + 3]};
+    // fold the affine into one FMA per element: y = x * (rstd*gamma) + (beta - mean*rstd*gamma) ... kept as the reference's op order
+    const float g[4] = {g4v.x, g4v.y, g4v.z, g4v.w}, be[4] = {b4v.x, b4v.y, b4v.z, b4v.w};
+    const size_t base = ((size_t)img * HW + (size_t)strip * kGnApplyPixels) * C;
+    float4 v[kGnApplyPixels / 8];
+#pragma unroll
+    for (int i = 0; i < kGnApplyPixels / 8; ++i) v[i] = __ldcs(reinterpret_cast<const float4*>(x + base + (size_t)(ps + 8 * i) * C + cq * 4));
+#pragma unroll
+    for (int i = 0; i < kGnApplyPixels / 8; ++i) {
+        const float in[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+        float y[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float t = fmaf((in[j] - m[j]) * r[j], g[j], be[j]);
+            y[j] = apply_silu ? __fdividef(t, 1.0f + __expf(-t)) : t;
+        }
+        const size_t off = base + (size_t)(ps + 8 * i) * C + cq * 4;
+        *reinterpret_cast<uint2*>(act + off) = make_uint2(pack_bf16(y[0], y[1]), pack_bf16(y[2], y[3]));
+        if (raw) *reinterpret_cast<uint2*>(raw + off) = make_uint2(pack_bf16(in[0], in[1]), pack_bf16(in[2], in[3]));
+    }
+}
+
 // ------------------------------------------------------------------ U-Net input operand   (vdm_unet.py:95-98, fourier_features.py:24-36)
 // bf16 NHWC [B][H][W][Cpad]: channels [0,C) = scale*mu, then for each channel (n, {sin,cos}) Fourier features, zero padding up to Cpad.
 __global__ void __launch_bounds__(256) k_unet_input(__nv_bfloat16* __restrict__ out, const float* __restrict__ mu, bsi_rowref scale,
@@ -396,6 +451,18 @@ int bsi_groupnorm_act_bf16(void* act_bf16, void* raw_bf16, const float* x, const
     k_groupnorm_act<<<B, kGnThreads, smem, (cudaStream_t)stream>>>((__nv_bfloat16*)act_bf16, (__nv_bfloat16*)raw_bf16, x, gamma, beta, HW, C,
                                                                   channels_per_group, eps, apply_silu);
     BSI_LAUNCH_OK("k_groupnorm_act");
+    return BSI_OK;
+}
+
+int bsi_groupnorm_apply_bf16(void* act_bf16, void* raw_bf16, const float* x, const float* partial, const float* gamma, const float* beta, int32_t B,
+                             int32_t HW, int32_t C, int32_t channels_per_group, float eps, int32_t apply_silu, void* stream) {
+    BSI_CHECK_ARG(act_bf16 && x && partial && gamma && beta && B > 0 && HW > 0, "bsi_groupnorm_apply_bf16: bad arguments");
+    BSI_CHECK_ARG(C == 128 && (channels_per_group == 4 || channels_per_group == 8) && HW % 128 == 0 && B <= 65535,
+                  "bsi_groupnorm_apply_bf16: implemented for C = 128, groups of 4 or 8 channels, H*W %% 128 == 0 (got C=%d cpg=%d HW=%d)", C,
+                  channels_per_group, HW);
+    k_groupnorm_apply<<<dim3(HW / kGnApplyPixels, B), kGnApplyThreads, 0, (cudaStream_t)stream>>>((__nv_bfloat16*)act_bf16, (__nv_bfloat16*)raw_bf16, x, partial,
+                                                                                                 gamma, beta, HW, channels_per_group, eps, apply_silu);
+    BSI_LAUNCH_OK("k_groupnorm_apply");
     return BSI_OK;
 }
 

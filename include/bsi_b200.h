@@ -181,6 +181,9 @@ typedef struct bsi_conv_args {
     bsi_rowref scale;    /* MOD_SILU: scale; GATE_RESID: gate (per image) */
     bsi_rowref shift;    /* MOD_SILU: shift */
     const int32_t* step_ptr;
+    float* gn_partial;   /* optional (GATE_RESID, N = 128): [B*H*W / 128][32][2] sums and sums of squares of the fp32 output over each
+                          * 128-pixel tile and each group of 4 channels -- the GroupNorm statistics of the NEXT layer for free
+                          * (nn.GroupNorm(32, .), vdm_unet.py:52; consumed by bsi_groupnorm_apply_bf16) */
 } bsi_conv_args;
 
 int bsi_conv_bf16(const bsi_conv_args* args, void* stream);
@@ -299,6 +302,10 @@ int bsi_dit_peek(const bsi_dit* e, int32_t what, float* out, int32_t B, const vo
  * x fp32 [B][HW][C]; groups of `channels_per_group` consecutive channels; raw_bf16 (optional) receives bf16(x). */
 int bsi_groupnorm_act_bf16(void* act_bf16, void* raw_bf16, const float* x, const float* gamma, const float* beta, int32_t B, int32_t HW, int32_t C,
                            int32_t channels_per_group, float eps, int32_t apply_silu, void* stream);
+/* The same from statistics the producing convolution left behind (bsi_conv_args.gn_partial: [B*HW/128][32][2]): one streaming pass,
+ * x is read once.  C = 128; channels_per_group = 4, or 8 for one 128-channel source of GroupNorm(32, 256) over cat(x, skip). */
+int bsi_groupnorm_apply_bf16(void* act_bf16, void* raw_bf16, const float* x, const float* partial, const float* gamma, const float* beta, int32_t B,
+                             int32_t HW, int32_t C, int32_t channels_per_group, float eps, int32_t apply_silu, void* stream);
 /* bf16 NHWC [B][HW][cpad] = cat(scale*mu, fourier(scale*mu)) zero-padded to cpad channels (vdm_unet.py:95-98); mu fp32 NCHW. */
 int bsi_unet_input_bf16(void* out_bf16, const float* mu, bsi_rowref scale, const int32_t* step_ptr, int32_t B, int32_t C, int32_t HW, int32_t n_min,
                         int32_t n_max, int32_t cpad, void* stream);

@@ -35,7 +35,7 @@ def pack_weight(w, cpad=None):
     return out
 
 
-def conv(x1, w_packed, y, bias, epi, taps, x2=None, resid=None, scale=None, shift=None):
+def conv(x1, w_packed, y, bias, epi, taps, x2=None, resid=None, scale=None, shift=None, gn_partial=None):
     a = L.ConvArgs()
     B, Hh, Ww, C1 = x1.shape
     a.X1, a.X2, a.W, a.Y, a.bias, a.resid = L.ptr(x1), L.ptr(x2), L.ptr(w_packed), L.ptr(y), L.ptr(bias), L.ptr(resid)
@@ -43,6 +43,7 @@ def conv(x1, w_packed, y, bias, epi, taps, x2=None, resid=None, scale=None, shif
     a.scale = scale if scale is not None else L.RowRef(None, 0, 0)
     a.shift = shift if shift is not None else L.RowRef(None, 0, 0)
     a.step_ptr = None
+    a.gn_partial = L.ptr(gn_partial)
     call("bsi_conv_bf16", ctypes.byref(a), L.stream_ptr())
     sync()
 
@@ -115,6 +116,42 @@ def test_conv3x3_other_image_widths(Hh, Ww, cg):
         y = torch.full((B * Hh * Ww, N), float("nan"), device=dev())
         conv(x, pack_weight(w), y, bias, L.EPI_BIAS_F32, 9)
         report(f"conv3x3 W={Ww} cg{cg}", y, ref_conv(x, w, bias, 1), 2e-3, 2e-3)
+    finally:
+        call("bsi_gemm_force_cta_group", 0)
+
+
+@pytest.mark.parametrize("cg", [2, 1])
+def test_groupnorm_statistics_from_the_conv_epilogue(cg):
+    """The residual-stream convolution leaves per-tile (sum, sum of squares) of every 4-channel group behind; GroupNorm + SiLU from
+    those statistics (one streaming pass) must equal torch's GroupNorm of the tensor the convolution wrote, for groups of 4 and 8."""
+    call("bsi_gemm_force_cta_group", cg)
+    try:
+        B, Hh, Ww, C, N = 3, 32, 32, 128, 128
+        x = rnd("gs.x", (B, Hh, Ww, C)).bfloat16()
+        w = rnd("gs.w", (N, C, 3, 3), 1 / math.sqrt(9 * C))
+        bias = rnd("gs.b", (N,), 0.1)
+        r0 = rnd("gs.r", (B * Hh * Ww, N), 2.0) + 0.3
+        y = torch.zeros_like(r0)
+        part = torch.full((B * Hh * Ww // 128, 32, 2), float("nan"), device=dev())
+        conv(x, pack_weight(w), y, bias, L.EPI_GATE_RESID_F32, 9, resid=r0, gn_partial=part)
+        report(f"conv output with statistics cg{cg}", y, r0 + ref_conv(x, w, bias, 1), 2e-3, 2e-3)
+        tiles = y.reshape(-1, 128, 32, 4)  # [tile][pixel][group][channel]
+        report("per-tile group sums", part[..., 0], tiles.sum(dim=(1, 3)), 1e-4, 1e-3)
+        report("per-tile group sums of squares", part[..., 1], (tiles * tiles).sum(dim=(1, 3)), 1e-4, 1e-3)
+        gamma, beta = rnd("gs.g", (C,)) + 1, rnd("gs.be", (C,), 0.2)
+        yb = y.reshape(B, Hh * Ww, C)
+        for cpg, silu in ((4, 1), (8, 1), (4, 0)):
+            act = torch.zeros((B, Hh * Ww, C), dtype=torch.bfloat16, device=dev())
+            raw = torch.zeros_like(act)
+            call("bsi_groupnorm_apply_bf16", L.ptr(act), L.ptr(raw), L.ptr(y), L.ptr(part), L.ptr(gamma), L.ptr(beta), B, Hh * Ww, C, cpg, 1e-5, silu, L.stream_ptr())
+            old = torch.zeros_like(act)
+            call("bsi_groupnorm_act_bf16", L.ptr(old), None, L.ptr(y), L.ptr(gamma), L.ptr(beta), B, Hh * Ww, C, cpg, 1e-5, silu, L.stream_ptr())
+            sync()
+            ref = F.group_norm(yb.permute(0, 2, 1), C // cpg, gamma, beta, 1e-5).permute(0, 2, 1)
+            ref = F.silu(ref) if silu else ref
+            report(f"groupnorm from epilogue statistics cpg={cpg} silu={silu}", act, ref, 1e-2, 1e-2)
+            report("agrees with the stand-alone kernel", act, old, 1e-2, 4e-3)
+            report("raw bf16 copy", raw, yb, 4e-3, 4e-3)
     finally:
         call("bsi_gemm_force_cta_group", 0)
 
