@@ -38,6 +38,7 @@ class GemmArgs(C.Structure):
         ("rows_per_sample", C.c_int32),
         ("pos", C.c_void_p),
         ("patch", C.c_int32), ("grid_w", C.c_int32), ("channels", C.c_int32),
+        ("aux", C.c_void_p),
     ]  # fmt: skip
 
 
@@ -74,7 +75,8 @@ class AdamWArgs(C.Structure):
     ]  # fmt: skip
 
 
-EPI_BIAS_BF16, EPI_BIAS_GELU_BF16, EPI_BIAS_SILU_BF16, EPI_BIAS_F32, EPI_GATE_RESID_F32, EPI_POS_F32, EPI_UNPATCH_F32, EPI_MOD_SILU_BF16 = range(8)
+(EPI_BIAS_BF16, EPI_BIAS_GELU_BF16, EPI_BIAS_SILU_BF16, EPI_BIAS_F32, EPI_GATE_RESID_F32, EPI_POS_F32, EPI_UNPATCH_F32, EPI_MOD_SILU_BF16,
+ EPI_BIAS_GELU_DUAL_BF16, EPI_MUL_GELU_GRAD_BF16) = range(10)
 
 _vp, _i32, _i64, _f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
 

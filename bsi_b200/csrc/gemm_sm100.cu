@@ -32,9 +32,11 @@ constexpr int kTmemCols = 512;
 constexpr int kABytes = BM * BK * 2;
 constexpr int kEpiBufBytes = BM * 128;  // staging tile: 128 rows x 128 B (64 bf16 or 32 fp32 columns)
 
-enum EpiKind { KIND_BF16 = 0, KIND_F32 = 1, KIND_RMW = 2, KIND_SCATTER = 3 };
+// KIND_AUX16: bf16 output combined with a bf16 auxiliary tile of the same geometry that arrives by TMA (GELU' of the saved pre-activation)
+enum EpiKind { KIND_BF16 = 0, KIND_F32 = 1, KIND_RMW = 2, KIND_SCATTER = 3, KIND_AUX16 = 4 };
 __host__ __device__ constexpr int epi_kind(int epi) {
-    return (epi <= BSI_EPI_BIAS_SILU_BF16 || epi == BSI_EPI_MOD_SILU_BF16) ? KIND_BF16
+    return epi == BSI_EPI_MUL_GELU_GRAD_BF16 ? KIND_AUX16
+           : (epi <= BSI_EPI_BIAS_SILU_BF16 || epi == BSI_EPI_MOD_SILU_BF16 || epi == BSI_EPI_BIAS_GELU_DUAL_BF16) ? KIND_BF16
            : epi == BSI_EPI_GATE_RESID_F32 ? KIND_RMW
            : epi == BSI_EPI_UNPATCH_F32  ? KIND_SCATTER
                                          : KIND_F32;
@@ -70,17 +72,18 @@ struct Cfg {
     // bf16 epilogues (bias / GELU / SiLU / modulation) are ALU-bound with one warp per scheduler (ncu: 25 % issue utilisation,
     // tensor pipe 63 % on the GELU shape): they get 8 epilogue warps, two per TMEM lane quarter, each pair splitting the columns
     // (the plain bias epilogue keeps 4 warps and the fifth pipeline stage: it already holds the tensor pipe at 87 %)
-    static constexpr bool kHeavy = EPI == BSI_EPI_BIAS_GELU_BF16 || EPI == BSI_EPI_BIAS_SILU_BF16 || EPI == BSI_EPI_MOD_SILU_BF16;
+    static constexpr bool kDual = EPI == BSI_EPI_BIAS_GELU_DUAL_BF16;  // two bf16 outputs per tile: one staging tile each
+    static constexpr bool kHeavy = EPI == BSI_EPI_BIAS_GELU_BF16 || EPI == BSI_EPI_BIAS_SILU_BF16 || EPI == BSI_EPI_MOD_SILU_BF16 || kDual;
     // (16 warps, one 64-column block each, measured no faster than 8: the GELU epilogue is bound by the fp32 pipe, not by latency)
     static constexpr int kEpiWarps = kHeavy ? 8 : 4;
     static constexpr int kGroups = kEpiWarps / 4;                                   // groups of 4 warps, each owning BN / kGroups columns
-    static constexpr int kBufsPerGroup = kHeavy ? (kGroups == 4 ? 1 : BSI_EXP_HEAVY_BUFS) : 2;  // staging tiles per group (KIND_BF16)
+    static constexpr int kBufsPerGroup = kDual ? 2 : kHeavy ? (kGroups == 4 ? 1 : BSI_EXP_HEAVY_BUFS) : 2;  // staging tiles per group (KIND_BF16)
     static constexpr int kThreads = 128 + 32 * kEpiWarps;
-    static constexpr int kEpiBufs = kKind == KIND_RMW ? 4 : kHeavy ? kGroups * kBufsPerGroup : (kKind == KIND_SCATTER ? 0 : 2);
+    static constexpr int kEpiBufs = (kKind == KIND_RMW || kKind == KIND_AUX16) ? 4 : kHeavy ? kGroups * kBufsPerGroup : (kKind == KIND_SCATTER ? 0 : 2);
     static constexpr int kVecBytes = 2 * 3 * BN * 4;  // bias, gate/scale and shift slices of the tile, double-buffered by tile parity
     static constexpr int kStages = kRowReuse ? (232448 - 1280 - 1024 /*kGnBytes*/ - kVecBytes - kEpiBufs * kEpiBufBytes) / kStageBytes
                                    : BN == 128 ? (CG == 2 ? 6 : 4)
-                                               : (CG == 2 ? (kKind == KIND_RMW ? 4 : kHeavy ? BSI_EXP_HEAVY_STAGES : BSI_EXP_PLAIN_STAGES) : 3);
+                                               : (CG == 2 ? ((kKind == KIND_RMW || kKind == KIND_AUX16 || kDual) ? 4 : kHeavy ? BSI_EXP_HEAVY_STAGES : BSI_EXP_PLAIN_STAGES) : 3);
     static_assert(kStages >= 2, "pipeline needs two stages");
     // GroupNorm partial sums of a convolution's fp32 output (U-Net residual stream): [4 warps][32 groups][sum, sum of squares]
     static constexpr bool kGnStats = CONV && BN == 128 && kKind == KIND_RMW;
@@ -124,6 +127,23 @@ __device__ __forceinline__ float gelu_tanh(float x) {
     return fmaf(hx, t, hx);
 }
 __device__ __forceinline__ float silu(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float gelu_tanh_grad(float x) {
+    // d/dx gelu_tanh(x) = 0.5 (1 + t) + 0.5 x (1 - t^2) u'(x),  t = tanh(u), u = sqrt(2/pi) (x + 0.044715 x^3)
+    const float x2 = x * x;
+    const float u = x * fmaf(x2, 0.7978845608028654f * 0.044715f, 0.7978845608028654f);
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(u));
+    const float du = fmaf(x2, 3.0f * 0.044715f * 0.7978845608028654f, 0.7978845608028654f);
+    const float hx = 0.5f * x;
+    return fmaf(hx * fmaf(-t, t, 1.0f), du, fmaf(0.5f, t, 0.5f));
+}
+__device__ __forceinline__ float bf16_lo(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf16_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
+__device__ __forceinline__ uint4 ld_shared_u4(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+    return v;
+}
 
 // Sum 16 per-lane values over the 32 lanes of a warp with 16 shuffles (each step halves the values a lane keeps); returns the total
 // of value (lane >> 1), held by both lanes of the pair.  Fixed order: deterministic.
@@ -327,7 +347,8 @@ __global__ void __launch_bounds__(Cfg<EPI, CG, BN, CONV>::kThreads, 1)
         // et: epilogue thread; er = row inside the CTA tile (TMEM lane); hf = column half handled by this warp (8-warp epilogues)
         const int q = warp & 3, et = threadIdx.x - 128, er = et & 127, hf = et >> 7;
         constexpr int kBatches = (BN / 64) / C::kGroups;  // 64-column batches per warp
-        constexpr int kChunks = BN / 32;  // 32-column chunks of a tile (KIND_RMW / KIND_F32)
+        constexpr int kChunkCols = kKind == KIND_AUX16 ? 64 : 32;  // columns per 128-byte staging row: 32 fp32 or 64 bf16
+        constexpr int kChunks = BN / kChunkCols;  // chunks of a tile (KIND_RMW / KIND_F32 / KIND_AUX16)
         const int step = ep.step_ptr ? *ep.step_ptr : 0;
         const uint32_t buf0 = ptx::smem_u32(epi_buf);
         const int my_tiles = worker < total_tiles ? (total_tiles - worker + num_workers - 1) / num_workers : 0;
@@ -338,9 +359,9 @@ __global__ void __launch_bounds__(Cfg<EPI, CG, BN, CONV>::kThreads, 1)
             const int tile = worker + (g / kChunks) * num_workers, c = g % kChunks;
             const int n_t = tile % n_tiles, m_t = (tile / n_tiles) % m_tiles, b = tile / (n_tiles * m_tiles);
             ptx::mbar_arrive_expect_tx(&c_full[g & 3], kEpiBufBytes);
-            ptx::tma_load_3d(epi_buf + (g & 3) * kEpiBufBytes, &map_r, &c_full[g & 3], n_t * BN + c * 32, (m_t * CG + cta_rank) * BM, b);
+            ptx::tma_load_3d(epi_buf + (g & 3) * kEpiBufBytes, &map_r, &c_full[g & 3], n_t * BN + c * kChunkCols, (m_t * CG + cta_rank) * BM, b);
         };
-        if constexpr (kKind == KIND_RMW) {
+        if constexpr (kKind == KIND_RMW || kKind == KIND_AUX16) {
             if (et == 0) {
                 issue_residual_load(0);
                 issue_residual_load(1);
@@ -401,7 +422,36 @@ __global__ void __launch_bounds__(Cfg<EPI, CG, BN, CONV>::kThreads, 1)
                 }
                 const uint32_t(&a)[2][32] = acc[jl & 1];
 
-                if constexpr (kKind == KIND_BF16) {
+                if constexpr (kKind == KIND_BF16 && C::kDual) {
+                    // ---- 64 columns -> pre-activation tile (aux) and GELU tile (C), one staging tile and one TMA store each
+                    const int sbuf = hf * 2;
+                    const uint32_t sb_pre = buf0 + sbuf * kEpiBufBytes, sb_act = sb_pre + kEpiBufBytes;
+                    if (er == 0) ptx::tma_store_wait_read<0>();  // both tiles of the previous batch have been read by their stores
+                    epi_bar(hf);
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            uint32_t pw[4], gw[4];
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                const int col = jb * 64 + h * 32 + c * 8 + 2 * i;
+                                const uint32_t pk = pack_bf16(__uint_as_float(a[h][c * 8 + 2 * i]) + s_bias[col], __uint_as_float(a[h][c * 8 + 2 * i + 1]) + s_bias[col + 1]);
+                                pw[i] = pk;  // the activation is taken of the ROUNDED pre-activation: what the backward differentiates
+                                gw[i] = pack_bf16(gelu_tanh(bf16_lo(pk)), gelu_tanh(bf16_hi(pk)));
+                            }
+                            st_shared_v4(sb_pre + swz(er, h * 4 + c), pw[0], pw[1], pw[2], pw[3]);
+                            st_shared_v4(sb_act + swz(er, h * 4 + c), gw[0], gw[1], gw[2], gw[3]);
+                        }
+                    }
+                    ptx::fence_proxy_async();
+                    epi_bar(hf);
+                    if (er == 0) {
+                        ptx::tma_store_3d(&map_c, epi_buf + (sbuf + 1) * kEpiBufBytes, n_base + jb * 64, row_base, b);
+                        ptx::tma_store_3d(&map_r, epi_buf + sbuf * kEpiBufBytes, n_base + jb * 64, row_base, b);
+                        ptx::tma_store_commit();
+                    }
+                } else if constexpr (kKind == KIND_BF16) {
                     // ---- 64 bf16 columns -> one 128 x 128 B staging tile -> TMA store
                     const int sbuf = hf * C::kBufsPerGroup + (jl % C::kBufsPerGroup);  // staging tiles of this warp group
                     const uint32_t sb = buf0 + sbuf * kEpiBufBytes;
@@ -506,6 +556,37 @@ __global__ void __launch_bounds__(Cfg<EPI, CG, BN, CONV>::kThreads, 1)
                             ptx::tma_store_3d(&map_c, epi_buf + (g & 3) * kEpiBufBytes, n_base + cidx * 32, row_base, b);
                             ptx::tma_store_commit();
                         }
+                    }
+                } else if constexpr (kKind == KIND_AUX16) {
+                    // ---- out = (acc + bias) * gelu'(pre): the pre-activation chunk (64 bf16 columns) arrives by TMA two chunks ahead, is
+                    //      replaced in place by the product and goes out by TMA store
+                    const int g = it * kChunks + jb;
+                    if (et == 0) {
+                        ptx::tma_store_wait_read<1>();
+                        issue_residual_load(g + 2);
+                    }
+                    ptx::mbar_wait(&c_full[g & 3], (g >> 2) & 1);
+                    const uint32_t sb = buf0 + (g & 3) * kEpiBufBytes;
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        const uint32_t addr = sb + swz(et, c);
+                        const uint4 p4 = ld_shared_u4(addr);
+                        const uint32_t pw[4] = {p4.x, p4.y, p4.z, p4.w};
+                        uint32_t ow[4];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const int col = jb * 64 + c * 8 + 2 * i;
+                            const float v0 = __uint_as_float(a[c >> 2][(c & 3) * 8 + 2 * i]) + s_bias[col];
+                            const float v1 = __uint_as_float(a[c >> 2][(c & 3) * 8 + 2 * i + 1]) + s_bias[col + 1];
+                            ow[i] = pack_bf16(v0 * gelu_tanh_grad(bf16_lo(pw[i])), v1 * gelu_tanh_grad(bf16_hi(pw[i])));
+                        }
+                        st_shared_v4(addr, ow[0], ow[1], ow[2], ow[3]);
+                    }
+                    ptx::fence_proxy_async();
+                    epi_bar();
+                    if (et == 0) {
+                        ptx::tma_store_3d(&map_c, epi_buf + (g & 3) * kEpiBufBytes, n_base + jb * 64, row_base, b);
+                        ptx::tma_store_commit();
                     }
                 } else {
                     // ---- KIND_SCATTER: b (nh nw) (ph pw c) -> b c (nh ph) (nw pw)   (bsi/models/dit.py:166-172); N = p*p*c is tiny
@@ -636,6 +717,7 @@ struct Problem {
     const void *A = nullptr, *A2 = nullptr, *W = nullptr;
     void* C = nullptr;
     const float* resid = nullptr;  // RMW residual source (fp32, same geometry as C); nullptr = C itself
+    const void* aux = nullptr;     // bf16 second output (GELU_DUAL) / auxiliary input (MUL_GELU_GRAD), geometry of C
     int M = 0, N = 0, K = 0, lda = 0, ldw = 0, ldc = 0, batch = 1, a_shared = 0;
     int64_t stride_a = 0, stride_w = 0, stride_c = 0;
     // convolution geometry (conv == true): A/A2 are NHWC [B][H][W][C1|C2]
@@ -671,7 +753,7 @@ static int launch_gemm(const Problem& p, cudaStream_t stream) {
     rc = make_tile_map(&mw, p.W, 2, p.N, p.K, p.ldw, p.batch, p.stride_w, C::kBRows);
     if (rc != BSI_OK) return rc;
     if (C::kKind != KIND_SCATTER) {
-        rc = make_tile_map(&mc, p.C, C::kKind == KIND_BF16 ? 2 : 4, p.M, p.N, p.ldc, p.batch, p.stride_c, BM);
+        rc = make_tile_map(&mc, p.C, (C::kKind == KIND_BF16 || C::kKind == KIND_AUX16) ? 2 : 4, p.M, p.N, p.ldc, p.batch, p.stride_c, BM);
         if (rc != BSI_OK) return rc;
     } else {
         mc = ma;  // unused by the scatter epilogue
@@ -679,6 +761,10 @@ static int launch_gemm(const Problem& p, cudaStream_t stream) {
     mr = mc;
     if (C::kKind == KIND_RMW && p.resid && p.resid != p.C) {
         rc = make_tile_map(&mr, p.resid, 4, p.M, p.N, p.ldc, p.batch, p.stride_c, BM);
+        if (rc != BSI_OK) return rc;
+    }
+    if (C::kDual || C::kKind == KIND_AUX16) {
+        rc = make_tile_map(&mr, p.aux, 2, p.M, p.N, p.ldc, p.batch, p.stride_c, BM);
         if (rc != BSI_OK) return rc;
     }
     const int m_tiles = (p.M + BM * CG - 1) / (BM * CG), n_tiles = (p.N + BN - 1) / BN;
@@ -725,7 +811,7 @@ static int dispatch_cta_group(const Problem& p, cudaStream_t stream) {
 static int check_common(const Problem& p, int epilogue) {
     BSI_CHECK_ARG(p.M > 0 && p.N > 0 && p.K > 0 && p.batch >= 1, "gemm: bad shape M=%d N=%d K=%d batch=%d", p.M, p.N, p.K, p.batch);
     BSI_CHECK_ARG(p.N % (epilogue == BSI_EPI_UNPATCH_F32 ? 4 : 8) == 0, "gemm: N=%d must be a multiple of 8 (4 for UNPATCH)", p.N);
-    const bool f32_out = epi_kind(epilogue) != KIND_BF16;
+    const bool f32_out = epi_kind(epilogue) != KIND_BF16 && epi_kind(epilogue) != KIND_AUX16;
     if (epilogue != BSI_EPI_UNPATCH_F32) {
         BSI_CHECK_ARG(p.ldc >= p.N && p.ldc % (f32_out ? 4 : 8) == 0, "gemm: ldc=%d invalid for N=%d", p.ldc, p.N);
         BSI_CHECK_ARG((reinterpret_cast<uintptr_t>(p.C) & 15) == 0, "gemm: C must be 16-byte aligned");
@@ -743,12 +829,18 @@ using namespace bsi;
 extern "C" int bsi_gemm_bf16(const bsi_gemm_args* a, void* stream) {
     BSI_CHECK_ARG(a && a->A && a->W && a->C, "bsi_gemm_bf16: null operand");
     BSI_CHECK_ARG(a->lda >= a->K && a->ldw >= a->K, "bsi_gemm_bf16: pitch smaller than K");
-    BSI_CHECK_ARG(a->epilogue >= BSI_EPI_BIAS_BF16 && a->epilogue <= BSI_EPI_UNPATCH_F32, "bsi_gemm_bf16: unknown epilogue %d", a->epilogue);
+    BSI_CHECK_ARG((a->epilogue >= BSI_EPI_BIAS_BF16 && a->epilogue <= BSI_EPI_UNPATCH_F32) || a->epilogue == BSI_EPI_BIAS_GELU_DUAL_BF16 ||
+                      a->epilogue == BSI_EPI_MUL_GELU_GRAD_BF16,
+                  "bsi_gemm_bf16: unknown epilogue %d", a->epilogue);
+    if (a->epilogue == BSI_EPI_BIAS_GELU_DUAL_BF16 || a->epilogue == BSI_EPI_MUL_GELU_GRAD_BF16)
+        BSI_CHECK_ARG(a->aux && (reinterpret_cast<uintptr_t>(a->aux) & 15) == 0 && a->batch <= 1 && a->M > BM,
+                      "bsi_gemm_bf16: epilogue %d needs a 16-byte aligned aux tensor, batch 1 and M > 128 (CTA-pair kernel)", a->epilogue);
     Problem p;
     p.A = a->A, p.W = a->W, p.C = a->C;
     p.M = a->M, p.N = a->N, p.K = a->K, p.lda = a->lda, p.ldw = a->ldw, p.ldc = a->ldc, p.batch = a->batch;
     p.stride_a = a->stride_a, p.stride_w = a->stride_w, p.stride_c = a->stride_c;
     p.a_shared = (a->batch > 1 && a->stride_a == 0) ? 1 : 0;
+    p.aux = a->aux;
     EpiParams& ep = p.ep;
     ep.C = a->C, ep.bias = a->bias, ep.M = a->M, ep.N = a->N, ep.ldc = a->ldc;
     ep.stride_c = a->stride_c, ep.stride_bias = a->stride_bias;
@@ -773,6 +865,9 @@ extern "C" int bsi_gemm_bf16(const bsi_gemm_args* a, void* stream) {
         case BSI_EPI_BIAS_F32: return dispatch_cta_group<BSI_EPI_BIAS_F32, false>(p, st);
         case BSI_EPI_GATE_RESID_F32: return dispatch_cta_group<BSI_EPI_GATE_RESID_F32, false>(p, st);
         case BSI_EPI_POS_F32: return dispatch_cta_group<BSI_EPI_POS_F32, false>(p, st);
+        // training epilogues: CTA-pair kernel only (M > 128 is checked above; the single-CTA variant is not instantiated)
+        case BSI_EPI_BIAS_GELU_DUAL_BF16: return launch_gemm<BSI_EPI_BIAS_GELU_DUAL_BF16, 2, false, 256>(p, st);
+        case BSI_EPI_MUL_GELU_GRAD_BF16: return launch_gemm<BSI_EPI_MUL_GELU_GRAD_BF16, 2, false, 256>(p, st);
         default: return dispatch_cta_group<BSI_EPI_UNPATCH_F32, false>(p, st);
     }
 }

@@ -22,6 +22,7 @@ mask (csrc/common.cuh ``dropout_keep``), which the backward kernels regenerate.
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import torch
 from torch import Tensor
@@ -29,6 +30,8 @@ from torch import Tensor
 from .. import _lib as L
 
 _LN_ROWS_PER_CTA = 32
+# A/B switch for measurements: 0 keeps GELU forward / backward as separate elementwise kernels (the round-1 path)
+_FUSED_GELU = os.environ.get("BSI_TRAIN_FUSED_GELU", "1") != "0"
 
 
 def _st(dev):
@@ -56,8 +59,9 @@ def _pad_rows(t: Tensor, n: int) -> Tensor:
     return out
 
 
-def _gemm(A: Tensor, W: Tensor, out: Tensor, bias: Tensor, epi: int, *, pos: Tensor | None = None, rows_per_sample: int = 0) -> None:
-    """out[M][N] = epilogue(A[M][K] @ W[N][K]^T + bias); A, W bf16 row-major (pitch = last stride-1 dimension)."""
+def _gemm(A: Tensor, W: Tensor, out: Tensor, bias: Tensor, epi: int, *, pos: Tensor | None = None, rows_per_sample: int = 0, aux: Tensor | None = None) -> None:
+    """out[M][N] = epilogue(A[M][K] @ W[N][K]^T + bias); A, W bf16 row-major (pitch = last stride-1 dimension).
+    aux: bf16 [M][N] second output (EPI_BIAS_GELU_DUAL_BF16) or saved pre-activation input (EPI_MUL_GELU_GRAD_BF16)."""
     a = L.GemmArgs()
     a.A, a.W, a.C, a.bias = A.data_ptr(), W.data_ptr(), out.data_ptr(), bias.data_ptr()
     a.M, a.N, a.K = A.shape[0], W.shape[0], A.shape[1]
@@ -69,6 +73,7 @@ def _gemm(A: Tensor, W: Tensor, out: Tensor, bias: Tensor, epi: int, *, pos: Ten
     a.step_ptr, a.rows_per_sample = None, rows_per_sample
     a.pos = pos.data_ptr() if pos is not None else None
     a.patch = a.grid_w = a.channels = 0
+    a.aux = aux.data_ptr() if aux is not None else None
     L.check(L.load().bsi_gemm_bf16(C.byref(a), _st(A.device)), "bsi_gemm_bf16")
 
 
@@ -179,9 +184,12 @@ class DiTTrainFunction(torch.autograd.Function):
                 _gemm(att, bf(w_o), br1, b_o.detach().float(), L.EPI_BIAS_BF16)
                 x_mid, a2 = gate_ln(x, br1, ref(2), ref(3), ref(4), drop_site=(drop_p, _layer_seed(drop_seed, 2 * l + 1)))
                 pre = torch.empty((M, 4 * D), dtype=torch.bfloat16, device=dev)
-                _gemm(a2, bf(w_1), pre, b_1.detach().float(), L.EPI_BIAS_BF16)
                 h = torch.empty_like(pre)
-                L.check(lib.bsi_gelu_bf16(h.data_ptr(), pre.data_ptr(), pre.numel(), _st(dev)), "bsi_gelu_bf16")
+                if _FUSED_GELU and M > 128:  # one GEMM writes the pre-activation (kept for the backward) and its GELU from the same accumulator tile
+                    _gemm(a2, bf(w_1), h, b_1.detach().float(), L.EPI_BIAS_GELU_DUAL_BF16, aux=pre)
+                else:
+                    _gemm(a2, bf(w_1), pre, b_1.detach().float(), L.EPI_BIAS_BF16)
+                    L.check(lib.bsi_gelu_bf16(h.data_ptr(), pre.data_ptr(), pre.numel(), _st(dev)), "bsi_gelu_bf16")
                 br2 = torch.empty((M, D), dtype=torch.bfloat16, device=dev)
                 _gemm(h, bf(w_2), br2, b_2.detach().float(), L.EPI_BIAS_BF16)
                 saved.append((x_in, a1, qkv, att, br1, x_mid, a2, pre, h, br2, lse))
@@ -284,8 +292,11 @@ class DiTTrainFunction(torch.autograd.Function):
                 dm[:, 5 * D :] = dgate
                 g_w2, g_b2 = emit_w(w_2, dbr, h), emit_b(b_2, dbias.sum(0))
                 dh = torch.empty((M, 4 * D), dtype=torch.bfloat16, device=dev)
-                _gemm(dbr, wt_2, dh, zeros(4 * D), L.EPI_BIAS_BF16)
-                L.check(lib.bsi_gelu_backward_bf16(dh.data_ptr(), dh.data_ptr(), pre.data_ptr(), dh.numel(), _st(dev)), "bsi_gelu_backward_bf16")
+                if _FUSED_GELU and M > 128:  # d(pre) = (dbr W2) * gelu'(pre): the derivative is applied in the data-gradient GEMM's epilogue
+                    _gemm(dbr, wt_2, dh, zeros(4 * D), L.EPI_MUL_GELU_GRAD_BF16, aux=pre)
+                else:
+                    _gemm(dbr, wt_2, dh, zeros(4 * D), L.EPI_BIAS_BF16)
+                    L.check(lib.bsi_gelu_backward_bf16(dh.data_ptr(), dh.data_ptr(), pre.data_ptr(), dh.numel(), _st(dev)), "bsi_gelu_backward_bf16")
                 g_w1, g_b1 = emit_w(w_1, dh, a2), emit_b(b_1, colsum(dh))
                 _gemm(dh, wt_1, da, zeros(D), L.EPI_BIAS_BF16)
                 dsc, dsh = part(_ln_mod_backward(dx, da, x_mid, ref(4), T, drop=(drop_p, _layer_seed(drop_seed, 2 * l + 1))))

@@ -137,7 +137,11 @@ typedef enum bsi_epilogue {
     BSI_EPI_GATE_RESID_F32 = 4,  /* out_f32 += gate[row] * (acc + bias)     (dit.py:93-102) */
     BSI_EPI_POS_F32 = 5,         /* out_f32  = acc + bias + pos[m % T]      (dit.py:178)    */
     BSI_EPI_UNPATCH_F32 = 6,     /* out_f32[b,c,y,x] = acc + bias, unpatchified (dit.py:166-172) */
-    BSI_EPI_MOD_SILU_BF16 = 7    /* out_bf16 = silu(shift[b] + (1+scale[b])*(acc+bias))  (residual_block.py:19-21,45-46); conv only */
+    BSI_EPI_MOD_SILU_BF16 = 7,   /* out_bf16 = silu(shift[b] + (1+scale[b])*(acc+bias))  (residual_block.py:19-21,45-46); conv only */
+    /* training path (autograd of dit.py:71-76): the MLP's first Linear keeps its pre-activation for the backward ... */
+    BSI_EPI_BIAS_GELU_DUAL_BF16 = 8, /* aux_bf16 = p = bf16(acc + bias);  out_bf16 = gelu_tanh(p)                       */
+    /* ... and the data-gradient GEMM of the second Linear applies GELU' while the tile is on chip */
+    BSI_EPI_MUL_GELU_GRAD_BF16 = 9   /* out_bf16 = (acc + bias) * gelu_tanh'(aux_bf16[m][n])                            */
 } bsi_epilogue;
 
 typedef struct bsi_gemm_args {
@@ -156,6 +160,7 @@ typedef struct bsi_gemm_args {
     int32_t rows_per_sample; /* tokens per sample T (GATE_RESID, POS, UNPATCH) */
     const float* pos;        /* POS: [T][N] fp32 */
     int32_t patch, grid_w, channels; /* UNPATCH: patch size p, patches per row, output channels; N = p*p*channels */
+    void* aux;               /* GELU_DUAL: second output (pre-activation); MUL_GELU_GRAD: pre-activation input; bf16 [M][ldc], batch 1 */
 } bsi_gemm_args;
 
 int bsi_gemm_bf16(const bsi_gemm_args* args, void* stream);

@@ -40,6 +40,7 @@ def gemm(A, W, C, bias, epi, **kw):
     a.rows_per_sample = kw.get("rows_per_sample", 0)
     a.pos = kw.get("pos", None)
     a.patch, a.grid_w, a.channels = kw.get("patch", 0), kw.get("grid_w", 0), kw.get("channels", 0)
+    a.aux = L.ptr(kw.get("aux", None))
     import ctypes
 
     call("bsi_gemm_bf16", ctypes.byref(a), L.stream_ptr())
@@ -74,6 +75,34 @@ def test_gemm_bf16_epilogues():
     C = torch.zeros((M, N), dtype=torch.bfloat16, device=dev())
     gemm(A, W, C, None, L.EPI_BIAS_BF16)
     report("gemm no bias", C, A.float() @ W.float().T, 1e-2, 4e-3)
+
+
+@pytest.mark.parametrize("M,N,K", [(512, 768, 256), (1000, 4096, 1024), (32768, 1024, 512)])
+def test_gemm_training_epilogues_gelu_dual_and_gelu_grad(M, N, K):
+    """Training path of the MLP (autograd of dit.py:71-76): the first Linear writes its bf16 pre-activation AND gelu of that rounded
+    value from one accumulator tile; the data-gradient GEMM multiplies by gelu'(pre) in its epilogue.  Ragged M covers the TMA
+    clipping of both outputs / the auxiliary load."""
+    A = rnd(f"t.a{M}", (M, K)).bfloat16()
+    W = rnd(f"t.w{M}", (N, K), 2 / math.sqrt(K)).bfloat16()
+    bias = rnd(f"t.b{M}", (N,), 0.1)
+    pre_ref = (A.float() @ W.float().T + bias).bfloat16()
+    act = torch.full((M, N), float("nan"), dtype=torch.bfloat16, device=dev())
+    pre = torch.full((M, N), float("nan"), dtype=torch.bfloat16, device=dev())
+    gemm(A, W, act, bias, L.EPI_BIAS_GELU_DUAL_BF16, aux=pre)
+    report("dual: pre-activation", pre, pre_ref, 1e-2, 4e-3)
+    report("dual: gelu of the stored pre-activation", act, F.gelu(pre.float(), approximate="tanh"), 1e-2, 2e-3)
+    # backward: dpre = (dY W2) * gelu'(pre), against autograd of F.gelu on the stored pre-activation
+    dY = rnd(f"t.dy{M}", (M, K)).bfloat16()
+    x = pre.float().requires_grad_(True)
+    up = dY.float() @ W.float().T
+    (F.gelu(x, approximate="tanh") * up).sum().backward()
+    dpre = torch.full((M, N), float("nan"), dtype=torch.bfloat16, device=dev())
+    gemm(dY, W, dpre, None, L.EPI_MUL_GELU_GRAD_BF16, aux=pre)
+    report("gelu-grad epilogue", dpre, x.grad, 2e-2, 1e-2 * float(up.abs().mean()))
+    rel = float((dpre.float() - x.grad).norm() / x.grad.norm())
+    assert rel < 5e-3, f"relative L2 error {rel}"
+    with pytest.raises(L.BsiNativeError):
+        gemm(A[:128], W, act[:128], bias, L.EPI_BIAS_GELU_DUAL_BF16, aux=pre[:128])  # single-CTA variant is not built: fails loudly
 
 
 def test_gemm_gate_residual_pos_unpatch():
