@@ -125,6 +125,7 @@ SIGNATURES = {
     "bsi_attention_bf16": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _vp]),
     "bsi_attention_force_legacy": (C.c_int, [_i32]),
     "bsi_attention_debug_phases": (C.c_int, [_vp]),
+    "bsi_attention_backward_debug_phases": (C.c_int, [_vp]),
     "bsi_dit_patch_operand": (C.c_int, [_vp, _vp, RowRef, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
     "bsi_time_embed": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i32, _vp]),
     "bsi_dit_create": (C.c_int, [C.POINTER(DitConfig), C.POINTER(_vp)]),

@@ -7,6 +7,8 @@
 //                       lse[B][H][T] together with D), pass 2 recomputes P per 64-key chunk, forms dS and accumulates dQ += dS K.
 //   k_attention_bwd_kv  CTA = 128 key rows: per 64-query chunk S^T = K Q^T, P^T, dP^T = V dO^T, dS^T, and dV += P^T dO, dK += dS^T Q.
 // S and dP are computed twice (8 instead of 5 products); the library flash-attention backward this replaces also recomputes S.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace bsi {
@@ -287,6 +289,9 @@ __global__ void __launch_bounds__(ab::kThreads, 1)
     store_rows(dv, 1.0f, sV, r0, lane, dst + 2 * dim, ld);
 }
 
+int attention_backward_tcgen05(void* dqkv_bf16, const float* lse, float* dsum, const void* qkv_bf16, const void* out_bf16, const void* dout_bf16, int B,
+                               int heads, float drop_p, uint32_t drop_seed, cudaStream_t stream);  // attention_bwd_sm100.cu
+
 }  // namespace bsi
 
 using namespace bsi;
@@ -302,6 +307,10 @@ extern "C" int bsi_attention_backward_bf16(void* dqkv_bf16, float* lse_ws, float
         set_error("bsi_attention_backward_bf16: only head_dim=64 and T in {128,256,384,512} are implemented (got head_dim=%d T=%d)", head_dim, T);
         return BSI_ERR_UNSUPPORTED;
     }
+    // T = 256 with the forward's saved statistics: the tcgen05 kernel (BSI_ATT_BWD_VARIANT=0 keeps the mma.sync row-owner kernels)
+    static const bool use_tc = [] { const char* e = getenv("BSI_ATT_BWD_VARIANT"); return !(e && e[0] == '0'); }();
+    if (use_tc && T == 256 && lse_valid)
+        return attention_backward_tcgen05(dqkv_bf16, lse_ws, dsum_ws, qkv_bf16, out_bf16, dout_bf16, B, heads, drop_p, drop_seed, (cudaStream_t)stream);
     const int dim = heads * head_dim;
     const float scale = 1.0f / sqrtf((float)head_dim), scale_log2 = 1.4426950408889634f * scale;
     dim3 grid(T / ab::kRows, heads, B);

@@ -1,0 +1,387 @@
+// Backward of the DiT attention on tcgen05 (autograd of bsi/models/dit.py:36-47), T = 256 tokens, head dim 64, training path.
+//   qkv [B*T][3*dim] bf16, dout [B*T][dim] bf16, lse2[B][H][T] (log2-sum-exp saved by the forward), dsum[B][H][T] = rowsum(dO o O)
+//   ->  dqkv [B*T][3*dim] bf16
+// With P = exp2(scale*log2e * Q K^T - lse2), M = dropout mask / (1 - p):
+//   dV = (P o M)^T dO,   dS = P o (M o (dO V^T) - D),   dQ = scale * dS K,   dK = scale * dS^T Q.
+// Everything is formed TRANSPOSED (rows = keys), so that every thread owns one key row and the per-query constants (lse2, D) are
+// per-column -- there is no row reduction and no exchange between threads in this kernel at all:
+//   S^T  = K Q^T  and  dP^T = V dO^T   UMMA 128x128x16, both operands K-major from smem          -> TMEM [0,128) and [128,256)
+//   softmax warps: P^T (bf16) back into TMEM over columns already read; dS^T (bf16) into a 128B-swizzled smem tile
+//   dV  += P^T  dO    A = P^T from TMEM,           B = dO rows (MN-major smem)                    -> TMEM [256,320)
+//   dK  += dS^T Q     A = the dS^T tile, K-major,  B = Q rows  (MN-major smem)                    -> TMEM [320,384)
+//   dQ  += dS   K     A = the SAME tile read MN-major (its 128-byte lines are the query axis), B = K rows (MN-major)
+//                                                                                                  -> TMEM [384,448) / [448,512)
+// One work item = one (sample, head); four steps (key half x query half) of 128 x 128 scores each; dV / dK leave after each key
+// half, dQ at the end.  One CTA per SM (the whole TMEM), 8 softmax warps + 1 control warp (TMA loads and all MMAs).
+// Replaces the two mma.sync row-owner kernels of attention_bwd.cu, which recompute S and dP twice (17 % of a training step).
+#include <cuda.h>
+
+#include <cstdlib>
+
+#include "common.cuh"
+#include "ptx_sm100.cuh"
+
+namespace bsi {
+
+int make_tile_map(CUtensorMap* map, const void* base, int esize, int64_t rows, int64_t cols, int64_t ld, int64_t batch, int64_t batch_stride,
+                  int box_rows);
+
+namespace abt {
+constexpr int T = 256, HD = 64, HALF = 128;
+constexpr int kSoftmaxWarps = 8, kThreads = 32 * (kSoftmaxWarps + 1);
+constexpr int kTile = HALF * 128;  // 128 rows x 128 B = 16 KB
+constexpr int kStage = 32 * 128;  // one warp's read-out tile: 32 rows x 128 B
+constexpr int kSmem = 10 * kTile /*Q, K, V, dO: 2 tiles each; dS^T: 2 blocks*/ + kSoftmaxWarps * kStage + 2 * 2 * T * 4 /*lse2, D: double-buffered*/ +
+                      1024 /*align*/ + 128 /*barriers*/;
+constexpr uint32_t kColS = 0, kColDP = 128, kColDV = 256, kColDK = 320, kColDQ = 384;
+}  // namespace abt
+
+__device__ __forceinline__ float ex2_approx_ftz(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// D[b][h][t] = sum_c dO[b,t,h,c] * O[b,t,h,c]: one thread per (token, head), 2 x 128 B contiguous
+__global__ void __launch_bounds__(256) k_attention_dsum(float* __restrict__ dsum, const __nv_bfloat16* __restrict__ out, const __nv_bfloat16* __restrict__ dout,
+                                                        int64_t rows, int T, int heads) {
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= rows * heads) return;
+    const int64_t row = i / heads;
+    const int h = (int)(i - row * heads);
+    const uint4* o = reinterpret_cast<const uint4*>(out + (row * heads + h) * 64);
+    const uint4* d = reinterpret_cast<const uint4*>(dout + (row * heads + h) * 64);
+    float acc = 0.0f;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        const uint4 a = o[c], g = d[c];
+        const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, gw[4] = {g.x, g.y, g.z, g.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            acc = fmaf(__uint_as_float(aw[j] << 16), __uint_as_float(gw[j] << 16), acc);
+            acc = fmaf(__uint_as_float(aw[j] & 0xffff0000u), __uint_as_float(gw[j] & 0xffff0000u), acc);
+        }
+    }
+    const int64_t b = row / T;
+    dsum[(b * heads + h) * T + (row - b * T)] = acc;
+}
+
+// timing build (BSI_ATT_BWD_VARIANT=9): cycles of softmax warp 0 {wait S/dP, softmax math, wait accumulators, read-out} and of the
+// control warp {wait inputs, wait P, wait read-out, wait tile release} summed over items and CTAs; [15] = items
+__device__ unsigned long long g_attbwd_phase[16];
+
+template <bool DROP, bool TIMING = false>
+__global__ void __launch_bounds__(abt::kThreads, 1)
+    k_attention_bwd_tc(const __grid_constant__ CUtensorMap map_qkv, const __grid_constant__ CUtensorMap map_do, const __grid_constant__ CUtensorMap map_dqkv,
+                       const float* __restrict__ lse, const float* __restrict__ dsum, const int dim, const int heads, const int total_items,
+                       const float scale_log2, const float scale, const uint32_t drop_thresh, const uint32_t drop_seed, const float drop_inv) {
+    using namespace abt;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sQ = smem;                  // [256 queries][128 B], two 128-row TMA boxes
+    uint8_t* sK = smem + 2 * kTile;
+    uint8_t* sV = smem + 4 * kTile;
+    uint8_t* sdO = smem + 6 * kTile;
+    uint8_t* sDS = smem + 8 * kTile;     // dS^T of the current step: [2 blocks of 64 queries][128 keys][128 B], 128B-swizzled
+    uint8_t* sStage = smem + 10 * kTile;  // [8 warps][32 rows][128 B]: read-out tiles, stored by TMA
+    float* sL = reinterpret_cast<float*>(sStage + kSoftmaxWarps * kStage);  // [2][T]
+    float* sD = sL + 2 * T;                                   // [2][T]
+    uint64_t* bar_in = reinterpret_cast<uint64_t*>(sD + 2 * T);  // first halves of Q, K, V, dO have landed (all that step 0 needs)
+    uint64_t* bar_in2 = bar_in + 7;      // second halves
+    uint64_t* bar_s = bar_in + 1;        // S^T and dP^T of the step are complete
+    uint64_t* bar_p = bar_in + 2;        // P^T (TMEM) and dS^T (smem) of the step are written
+    uint64_t* bar_step = bar_in + 3;     // the step's accumulating MMAs have retired (P^T columns and the dS^T tile are free)
+    uint64_t* bar_acc = bar_in + 4;      // dV, dK of a key half (and, the second time, dQ) are complete
+    uint64_t* bar_accfree = bar_in + 5;  // ... and have been read out
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_in + 8);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == kSoftmaxWarps) {
+        if (lane == 0) {
+            ptx::prefetch_tensormap(&map_qkv);
+            ptx::prefetch_tensormap(&map_do);
+            ptx::prefetch_tensormap(&map_dqkv);
+            ptx::mbar_init(bar_in, 1);
+            ptx::mbar_init(bar_in2, 1);
+            ptx::mbar_init(bar_s, 1);
+            ptx::mbar_init(bar_p, kSoftmaxWarps);
+            ptx::mbar_init(bar_step, 1);
+            ptx::mbar_init(bar_acc, 1);
+            ptx::mbar_init(bar_accfree, kSoftmaxWarps);
+            ptx::fence_mbar_init();
+        }
+        __syncwarp();
+        ptx::tmem_alloc<1>(tmem_slot, 512);
+        ptx::tmem_relinquish<1>();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == kSoftmaxWarps) {
+        if (lane == 0) {
+            // The first halves of the four operands are dead after step 2 (key half 1 x query half 0) and are exactly what the next
+            // item's step 0 needs: they are refilled before step 3 runs; the second halves follow when the item's last MMA has retired.
+            auto load_half = [&](int item, int half) {
+                const int h = item % heads, row0 = (item / heads) * T;
+                uint64_t* bar = half ? bar_in2 : bar_in;
+                ptx::mbar_arrive_expect_tx(bar, 4 * kTile);
+                ptx::tma_load_3d(sQ + half * kTile, &map_qkv, bar, h * HD, row0 + half * HALF, 0);
+                ptx::tma_load_3d(sK + half * kTile, &map_qkv, bar, dim + h * HD, row0 + half * HALF, 0);
+                ptx::tma_load_3d(sV + half * kTile, &map_qkv, bar, 2 * dim + h * HD, row0 + half * HALF, 0);
+                ptx::tma_load_3d(sdO + half * kTile, &map_do, bar, h * HD, row0 + half * HALF, 0);
+            };
+            constexpr uint32_t idesc_s = ptx::umma_idesc_bf16(HALF, HALF);          // S^T, dP^T: K-major x K-major
+            constexpr uint32_t idesc_kv = ptx::umma_idesc_bf16(HALF, HD, 0, 1);     // dV, dK: A K-major (TMEM / smem), B MN-major
+            constexpr uint32_t idesc_q = ptx::umma_idesc_bf16(HALF, HD, 1, 1);      // dQ: A MN-major (the dS^T tile), B MN-major
+            const uint32_t q0 = ptx::smem_u32(sQ), k0 = ptx::smem_u32(sK), v0 = ptx::smem_u32(sV), o0 = ptx::smem_u32(sdO), ds0 = ptx::smem_u32(sDS);
+            if ((int)blockIdx.x < total_items) load_half(blockIdx.x, 0), load_half(blockIdx.x, 1);
+            int it = 0;
+            long long cph[4] = {0, 0, 0, 0}, cc = 0;
+            auto ctick = [&](int i) {
+                if constexpr (TIMING) {
+                    const long long now = clock64();
+                    cph[i] += now - cc;
+                    cc = now;
+                }
+            };
+            if constexpr (TIMING) cc = clock64();
+            for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++it) {
+                const int next = item + gridDim.x;
+#pragma unroll 1
+                for (int step = 0; step < 4; ++step) {
+                    const int kh = step >> 1, qh = step & 1;
+                    ctick(3);
+                    if (step == 0) ptx::mbar_wait(bar_in, it & 1);
+                    if (step == 1) ptx::mbar_wait(bar_in2, it & 1);
+                    ptx::tc_fence_after();
+                    ctick(0);
+                    {
+                        const uint64_t dk = ptx::umma_desc_k_sw128(k0 + kh * kTile), dq = ptx::umma_desc_k_sw128(q0 + qh * kTile);
+                        const uint64_t dv = ptx::umma_desc_k_sw128(v0 + kh * kTile), dd = ptx::umma_desc_k_sw128(o0 + qh * kTile);
+#pragma unroll
+                        for (int k = 0; k < HD / 16; ++k) ptx::umma_bf16_ss<1>(tmem + kColS, dk + 2 * k, dq + 2 * k, idesc_s, k != 0 ? 1u : 0u);
+#pragma unroll
+                        for (int k = 0; k < HD / 16; ++k) ptx::umma_bf16_ss<1>(tmem + kColDP, dv + 2 * k, dd + 2 * k, idesc_s, k != 0 ? 1u : 0u);
+                        ptx::umma_commit<1>(bar_s);
+                    }
+                    ptx::mbar_wait(bar_p, step & 1);
+                    ctick(1);
+                    if (qh == 0) ptx::mbar_wait(bar_accfree, (kh & 1) ^ 1);  // the previous key half's dV / dK (and dQ) have been read out
+                    ptx::tc_fence_after();
+                    ctick(2);
+                    // dV[kh] += P^T dO[qh]: 16 queries per k-step = 8 packed TMEM columns; queries [0,64) at [0,32), [64,128) at [64,96)
+#pragma unroll
+                    for (int k = 0; k < 8; ++k)
+                        ptx::umma_bf16_ts(tmem + kColDV, tmem + kColS + (k < 4 ? 8 * k : 64 + 8 * (k - 4)),
+                                          ptx::umma_desc_mn_sw128(o0 + qh * kTile + k * 2048, 8192, 1024), idesc_kv, (qh | k) != 0 ? 1u : 0u);
+                    // dK[kh] += dS^T Q[qh]: the dS^T tile as a K-major A operand (two 64-query blocks of four k-steps)
+#pragma unroll
+                    for (int k = 0; k < 8; ++k)
+                        ptx::umma_bf16_ss<1>(tmem + kColDK, ptx::umma_desc_k_sw128(ds0 + (k >> 2) * kTile) + 2 * (k & 3),
+                                             ptx::umma_desc_mn_sw128(q0 + qh * kTile + k * 2048, 8192, 1024), idesc_kv, (qh | k) != 0 ? 1u : 0u);
+                    // dQ[qh] += dS K[kh]: the same tile read MN-major (M = 128 queries = two 64-wide blocks kTile apart; 16 keys per k-step)
+#pragma unroll
+                    for (int k = 0; k < 8; ++k)
+                        ptx::umma_bf16_ss<1>(tmem + kColDQ + qh * HD, ptx::umma_desc_mn_sw128(ds0 + k * 2048, kTile, 1024),
+                                             ptx::umma_desc_mn_sw128(k0 + kh * kTile + k * 2048, 8192, 1024), idesc_q, (kh | k) != 0 ? 1u : 0u);
+                    if (qh == 1) ptx::umma_commit<1>(bar_acc);
+                    // The next step's S^T / dP^T MMAs overwrite the P^T columns the MMAs above read: tcgen05.mma operations of one
+                    // thread execute in issue order, so no wait is needed for that.  Refilling operand tiles is different (TMA, the
+                    // async proxy): wait for the MMAs that read them.
+                    if (step >= 2 && next < total_items) {
+                        ptx::umma_commit<1>(bar_step);
+                        ptx::mbar_wait(bar_step, step & 1);
+                        load_half(next, step == 2 ? 0 : 1);
+                    }
+                }
+            }
+            if constexpr (TIMING) {
+                for (int i = 0; i < 4; ++i) atomicAdd(&g_attbwd_phase[8 + i], (unsigned long long)cph[i]);
+            }
+        }
+    } else {
+        const int q = warp & 3, hf = warp >> 2;
+        const int kr = q * 32 + lane;  // key row inside the half == TMEM lane
+        const uint32_t trow = tmem + (static_cast<uint32_t>(q * 32) << 16);
+        const uint32_t ds_row = ptx::smem_u32(sDS) + hf * kTile + kr * 128;  // this thread's 128-byte line of the block of queries [64 hf, +64)
+        const int tid = threadIdx.x;
+        int it = 0;
+        long long sph[4] = {0, 0, 0, 0}, sc = 0;
+        auto tick = [&](int i) {
+            if constexpr (TIMING) {
+                const long long now = clock64();
+                sph[i] += now - sc;
+                sc = now;
+            }
+        };
+        if constexpr (TIMING) sc = clock64();
+        for (int item = blockIdx.x; item < total_items; item += gridDim.x, ++it) {
+            const int h = item % heads, b = item / heads;
+            const size_t row0 = (size_t)b * T;
+            // per-query constants of this (sample, head), double-buffered by item parity
+            float* L = sL + (it & 1) * T;
+            float* D = sD + (it & 1) * T;
+            L[tid] = lse[((size_t)b * heads + h) * T + tid];
+            D[tid] = dsum[((size_t)b * heads + h) * T + tid];
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            const uint32_t sd = DROP ? mix32(drop_seed ^ ((uint32_t)(b * heads + h) * 0x9E3779B9u)) : 0u;
+#pragma unroll 1
+            for (int step = 0; step < 4; ++step) {
+                const int kh = step >> 1, qh = step & 1;
+                const uint32_t key = (uint32_t)(kh * HALF + kr);
+                ptx::mbar_wait(bar_s, step & 1);
+                ptx::tc_fence_after();
+                tick(0);
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    uint32_t s[32], dp[32];
+                    ptx::tmem_ld_32x32b_x32(trow + kColS + hf * 64 + c * 32, s);
+                    ptx::tmem_ld_32x32b_x32(trow + kColDP + hf * 64 + c * 32, dp);
+                    ptx::tmem_ld_wait();
+                    const int qc0 = qh * HALF + hf * 64 + c * 32;  // first query column of the chunk
+                    uint32_t pp[16], dsp[16];
+#pragma unroll
+                    for (int j4 = 0; j4 < 8; ++j4) {
+                        const float4 l4 = *reinterpret_cast<const float4*>(L + qc0 + 4 * j4), d4 = *reinterpret_cast<const float4*>(D + qc0 + 4 * j4);
+                        const float lv[4] = {l4.x, l4.y, l4.z, l4.w}, dv[4] = {d4.x, d4.y, d4.z, d4.w};
+                        float pv[4], gv[4];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const int j = 4 * j4 + i;
+                            const float p = ex2_approx_ftz(fmaf(__uint_as_float(s[j]), scale_log2, -lv[i]));
+                            float m = 1.0f;
+                            if constexpr (DROP) m = dropout_keep(sd, (uint32_t)(qc0 + j) * T + key, drop_thresh) ? drop_inv : 0.0f;
+                            gv[i] = p * fmaf(__uint_as_float(dp[j]), m, -dv[i]);  // dS^T
+                            pv[i] = p * m;                                        // dropped probabilities (dV)
+                        }
+                        pp[2 * j4] = pack_bf16(pv[0], pv[1]), pp[2 * j4 + 1] = pack_bf16(pv[2], pv[3]);
+                        dsp[2 * j4] = pack_bf16(gv[0], gv[1]), dsp[2 * j4 + 1] = pack_bf16(gv[2], gv[3]);
+                    }
+                    // P^T chunk: 16 packed columns over score columns this warp has already consumed
+                    ptx::tmem_st_32x32b_x16(trow + kColS + hf * 64 + c * 16, pp);
+                    // dS^T chunk: 32 queries = 64 B = four 16-byte chunks of this thread's line, 128B-swizzled
+#pragma unroll
+                    for (int ch = 0; ch < 4; ++ch) {
+                        const uint32_t addr = ds_row + (((c * 4 + ch) ^ (kr & 7)) << 4);
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(dsp[4 * ch]), "r"(dsp[4 * ch + 1]), "r"(dsp[4 * ch + 2]),
+                                     "r"(dsp[4 * ch + 3])
+                                     : "memory");
+                    }
+                }
+                ptx::tmem_st_wait();
+                ptx::tc_fence_before();
+                ptx::fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(bar_p);
+                tick(1);
+
+                if (qh == 1) {
+                    // ---- dK (warps with hf = 0) / dV (hf = 1) of this key half, and after the last step dQ: 64 channels = one 128-byte line
+                    ptx::mbar_wait(bar_acc, kh & 1);
+                    ptx::tc_fence_after();
+                    tick(2);
+                    // 64 accumulator columns of this warp's 32 rows -> bf16 -> the warp's swizzled staging tile -> one TMA store
+                    // (per-thread 16-byte global stores of 128-byte rows 6 KB apart took 2 000 clk per tile)
+                    const uint32_t stage = ptx::smem_u32(sStage + warp * kStage);
+                    auto store_rows = [&](uint32_t col, float sc, int gcol, int grow) {
+                        uint32_t o[2][32];
+                        ptx::tmem_ld_32x32b_x32(trow + col, o[0]);
+                        ptx::tmem_ld_32x32b_x32(trow + col + 32, o[1]);
+                        ptx::tmem_ld_wait();
+                        if (lane == 0) ptx::tma_store_wait_read<0>();  // this warp's previous store has drained the staging tile
+                        __syncwarp();
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) {
+                            const uint32_t* oc = o[c >> 2] + (c & 3) * 8;
+                            const uint32_t addr = stage + (uint32_t)(lane * 128 + ((c ^ (lane & 7)) << 4));
+                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pack_bf16(__uint_as_float(oc[0]) * sc, __uint_as_float(oc[1]) * sc)),
+                                         "r"(pack_bf16(__uint_as_float(oc[2]) * sc, __uint_as_float(oc[3]) * sc)),
+                                         "r"(pack_bf16(__uint_as_float(oc[4]) * sc, __uint_as_float(oc[5]) * sc)),
+                                         "r"(pack_bf16(__uint_as_float(oc[6]) * sc, __uint_as_float(oc[7]) * sc))
+                                         : "memory");
+                        }
+                        ptx::fence_proxy_async();
+                        __syncwarp();
+                        if (lane == 0) {
+                            ptx::tma_store_3d(&map_dqkv, sStage + warp * kStage, gcol, grow, 0);
+                            ptx::tma_store_commit();
+                        }
+                    };
+                    const int krow = (int)row0 + kh * HALF + q * 32;
+                    if (hf == 0) store_rows(kColDK, scale, dim + h * HD, krow);
+                    else store_rows(kColDV, 1.0f, 2 * dim + h * HD, krow);
+                    if (kh == 1) store_rows(kColDQ + hf * HD, scale, h * HD, (int)row0 + hf * HALF + q * 32);
+                    ptx::tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) ptx::mbar_arrive(bar_accfree);
+                    tick(3);
+                }
+            }
+        }
+        if (lane == 0) ptx::tma_store_wait_all<0>();  // every staged tile has reached global memory
+        if constexpr (TIMING) {
+            if (threadIdx.x == 0) {
+                for (int i = 0; i < 4; ++i) atomicAdd(&g_attbwd_phase[i], (unsigned long long)sph[i]);
+                atomicAdd(&g_attbwd_phase[15], (unsigned long long)it);
+            }
+        }
+    }
+
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == kSoftmaxWarps) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc<1>(tmem, 512);
+    }
+}
+
+int attention_backward_tcgen05(void* dqkv_bf16, const float* lse, float* dsum, const void* qkv_bf16, const void* out_bf16, const void* dout_bf16, int B,
+                               int heads, float drop_p, uint32_t drop_seed, cudaStream_t stream) {
+    using namespace abt;
+    const int dim = heads * HD;
+    const int64_t rows = (int64_t)B * T;
+    k_attention_dsum<<<(unsigned)((rows * heads + 255) / 256), 256, 0, stream>>>(dsum, (const __nv_bfloat16*)out_bf16, (const __nv_bfloat16*)dout_bf16, rows, T,
+                                                                               heads);
+    BSI_LAUNCH_OK("k_attention_dsum");
+    CUtensorMap mq, md;
+    int rc = make_tile_map(&mq, qkv_bf16, 2, rows, 3 * dim, 3 * dim, 1, 0, HALF);
+    if (rc != BSI_OK) return rc;
+    rc = make_tile_map(&md, dout_bf16, 2, rows, dim, dim, 1, 0, HALF);
+    if (rc != BSI_OK) return rc;
+    CUtensorMap mg;
+    rc = make_tile_map(&mg, dqkv_bf16, 2, rows, 3 * dim, 3 * dim, 1, 0, 32);  // read-out: one 32-row box per warp
+    if (rc != BSI_OK) return rc;
+    const float scale = 1.0f / sqrtf((float)HD), scale_log2 = 1.4426950408889634f * scale;
+    const uint32_t thresh = dropout_thresh(drop_p);
+    const float drop_inv = drop_p > 0.0f ? 1.0f / (1.0f - drop_p) : 1.0f;
+    const int total = B * heads;
+    const int grid = total < sm_count() ? total : sm_count();
+    static const bool timing = [] { const char* e = getenv("BSI_ATT_BWD_VARIANT"); return e && e[0] == '9'; }();
+    if (timing) {
+        BSI_ENSURE_SMEM((k_attention_bwd_tc<false, true>), kSmem);
+        k_attention_bwd_tc<false, true><<<grid, kThreads, kSmem, stream>>>(mq, md, mg, lse, dsum, dim, heads, total, scale_log2, scale, 0u, 0u,
+                                                                         1.0f);
+    } else if (thresh) {
+        BSI_ENSURE_SMEM(k_attention_bwd_tc<true>, kSmem);
+        k_attention_bwd_tc<true><<<grid, kThreads, kSmem, stream>>>(mq, md, mg, lse, dsum, dim, heads, total, scale_log2, scale, thresh,
+                                                                   drop_seed, drop_inv);
+    } else {
+        BSI_ENSURE_SMEM(k_attention_bwd_tc<false>, kSmem);
+        k_attention_bwd_tc<false><<<grid, kThreads, kSmem, stream>>>(mq, md, mg, lse, dsum, dim, heads, total, scale_log2, scale, 0u, 0u, 1.0f);
+    }
+    BSI_LAUNCH_OK("k_attention_bwd_tc");
+    return BSI_OK;
+}
+
+}  // namespace bsi
+
+// Development aid: phase counters of the timing build (BSI_ATT_BWD_VARIANT=9) since the last call; resets them.
+extern "C" int bsi_attention_backward_debug_phases(unsigned long long* out16) {
+    BSI_CHECK_ARG(out16, "bsi_attention_backward_debug_phases: null pointer");
+    unsigned long long zero[16] = {0};
+    BSI_CUDA_OK(cudaMemcpyFromSymbol(out16, bsi::g_attbwd_phase, sizeof(zero)));
+    BSI_CUDA_OK(cudaMemcpyToSymbol(bsi::g_attbwd_phase, zero, sizeof(zero)));
+    return BSI_OK;
+}

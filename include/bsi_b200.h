@@ -221,6 +221,9 @@ int bsi_attention_force_legacy(int32_t on);
  * CTAs since the last call: out14[0..5] = softmax warp 0 {wait S, pass 1, pass 2, wait O, epilogue, items},
  * out14[8..12] = control warp {wait Q/K + O free, S latency, wait P half 1, wait P half 2, P V tail latency}. */
 int bsi_attention_debug_phases(unsigned long long* out14);
+/* Same for the tcgen05 attention backward (BSI_ATT_BWD_VARIANT=9): out16[0..3] = softmax warp 0 {wait S/dP, softmax math, wait
+ * accumulators, read-out}, out16[8..11] = control warp {wait inputs, wait P, wait read-out, rest}, out16[15] = items. */
+int bsi_attention_backward_debug_phases(unsigned long long* out16);
 
 /* Backward of bsi_attention_bf16 on the same packed layouts (autograd of dit.py:36-47): dqkv bf16 [B*T][3*dim] from the saved qkv,
  * the saved forward output and the upstream gradient dout bf16 [B*T][dim].  lse_ws / dsum_ws: B*heads*T floats of scratch each

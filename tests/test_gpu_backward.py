@@ -322,3 +322,37 @@ def test_shared_memory_opt_in_is_never_lowered_by_another_entry_point():
             assert torch.isfinite(out.float()).all()
     finally:
         call("bsi_attention_force_legacy", 0)
+
+
+@pytest.mark.parametrize("B,heads,p", [(2, 2, 0.0), (10, 16, 0.0), (3, 4, 0.1)], ids=["small", "two_items_per_cta", "dropout"])
+def test_attention_backward_tcgen05_vs_autograd(B, heads, p):
+    """The tcgen05 backward (T = 256, statistics saved by the forward; attention_bwd_sm100.cu) against torch autograd, with the
+    dropout mask restated in Python; 160 (sample, head) items make some CTAs loop over two items."""
+    T, hd, dim, seed = 256, 64, heads * 64, 20261017
+    qkv = rnd(f"tb.qkv{B}", (B * T, 3 * dim), 2.0).bfloat16()
+    dout = rnd(f"tb.do{B}", (B * T, dim)).bfloat16()
+    out = torch.zeros((B * T, dim), dtype=torch.bfloat16, device=dev())
+    lse = torch.zeros(B * heads * T, device=dev())
+    if p > 0:
+        call("bsi_attention_dropout_bf16", L.ptr(out), L.ptr(lse), L.ptr(qkv), B, T, heads, hd, p, seed, L.stream_ptr())
+    else:
+        call("bsi_attention_lse_bf16", L.ptr(out), L.ptr(lse), L.ptr(qkv), B, T, heads, hd, L.stream_ptr())
+    dqkv = torch.full((B * T, 3 * dim), float("nan"), dtype=torch.bfloat16, device=dev())
+    dsum = torch.zeros(B * heads * T, device=dev())
+    call("bsi_attention_backward_bf16", L.ptr(dqkv), L.ptr(lse), L.ptr(dsum), L.ptr(qkv), L.ptr(out), L.ptr(dout), B, T, heads, hd, p, seed, 1, L.stream_ptr())
+    sync()
+    q, k, v = (t.detach().requires_grad_(True) for t in qkv.float().reshape(B, T, 3, heads, hd).permute(2, 0, 3, 1, 4))
+    prob = torch.softmax(q @ k.transpose(-1, -2) / 8.0, dim=-1)
+    if p > 0:
+        prob = prob * H.attention_dropout_mask(seed, B, heads, T, p).to(dev()) / (1 - p)
+    o = prob @ v
+    o.backward(dout.float().reshape(B, T, heads, hd).permute(0, 2, 1, 3))
+    ref = torch.stack((q.grad, k.grad, v.grad)).permute(1, 3, 0, 2, 4).reshape(B * T, 3 * dim)
+    d_ref = (dout.float() * out.float()).reshape(B, T, heads, hd).sum(-1).permute(0, 2, 1)
+    report("D = rowsum(dO o O)", dsum.reshape(B, heads, T), d_ref, 1e-5, 1e-5)
+    assert torch.isfinite(dqkv.float()).all()
+    for name, sl in (("dq", slice(0, dim)), ("dk", slice(dim, 2 * dim)), ("dv", slice(2 * dim, 3 * dim))):
+        got, want = dqkv[:, sl].float(), ref[:, sl]
+        rel = float((got - want).norm() / want.norm())
+        assert rel < 1.5e-2, f"{name}: relative L2 error {rel}"
+        report(name, got, want, 5e-2, 2e-2 * float(want.abs().max()))
