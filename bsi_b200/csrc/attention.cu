@@ -183,7 +183,9 @@ __global__ void __launch_bounds__(kAttThreads, 2)
     }
 }
 
-int attention_tcgen05(void* out_bf16, const void* qkv_bf16, int B, int heads, float* lse, cudaStream_t stream);  // attention_sm100.cu
+int attention_tcgen05(void* out_bf16, const void* qkv_bf16, int B, int heads, float* lse, cudaStream_t stream, float drop_p = 0.0f,
+                      uint32_t drop_seed = 0);  // attention_sm100.cu
+bool attention_tcgen05_has_dropout();  // the second design of the kernel is selected (the first one has no dropout variant)
 static int g_force_legacy_attention = 0;
 
 }  // namespace bsi
@@ -242,6 +244,8 @@ extern "C" int bsi_attention_dropout_bf16(void* out_bf16, float* lse_out, const 
         set_error("bsi_attention_dropout_bf16: only head_dim=64 and T in {128,256,384,512} are implemented (got head_dim=%d T=%d)", head_dim, T);
         return BSI_ERR_UNSUPPORTED;
     }
+    if (T == 256 && !g_force_legacy_attention && lse_out && attention_tcgen05_has_dropout())
+        return attention_tcgen05(out_bf16, qkv_bf16, B, heads, lse_out, (cudaStream_t)stream, drop_p, drop_seed);
     const int dim = heads * head_dim;
     const int smem = (kQRows + 2 * T) * 128;
     BSI_ENSURE_SMEM(k_attention_mma<true>, smem);

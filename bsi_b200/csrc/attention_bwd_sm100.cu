@@ -42,19 +42,16 @@ __device__ __forceinline__ float ex2_approx_ftz(float x) {
     return y;
 }
 
-// D[b][h][t] = sum_c dO[b,t,h,c] * O[b,t,h,c]: one thread per (token, head), 2 x 128 B contiguous
+// D[b][h][t] = sum_c dO[b,t,h,c] * O[b,t,h,c].  A group of 8 lanes owns one (token, head): 8 x 16 B = its 128-byte line of each tensor,
+// so a warp reads four consecutive heads of one token (512 contiguous bytes per tensor); 3 shuffles finish the dot product.
 __global__ void __launch_bounds__(256) k_attention_dsum(float* __restrict__ dsum, const __nv_bfloat16* __restrict__ out, const __nv_bfloat16* __restrict__ dout,
                                                         int64_t rows, int T, int heads) {
-    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
-    if (i >= rows * heads) return;
-    const int64_t row = i / heads;
-    const int h = (int)(i - row * heads);
-    const uint4* o = reinterpret_cast<const uint4*>(out + (row * heads + h) * 64);
-    const uint4* d = reinterpret_cast<const uint4*>(dout + (row * heads + h) * 64);
+    const int64_t i = ((int64_t)blockIdx.x * 256 + threadIdx.x) >> 3;  // (token, head) index
+    const int part = threadIdx.x & 7;
     float acc = 0.0f;
-#pragma unroll
-    for (int c = 0; c < 8; ++c) {
-        const uint4 a = o[c], g = d[c];
+    const bool live = i < rows * heads;
+    if (live) {
+        const uint4 a = reinterpret_cast<const uint4*>(out + i * 64)[part], g = reinterpret_cast<const uint4*>(dout + i * 64)[part];
         const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, gw[4] = {g.x, g.y, g.z, g.w};
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -62,8 +59,15 @@ __global__ void __launch_bounds__(256) k_attention_dsum(float* __restrict__ dsum
             acc = fmaf(__uint_as_float(aw[j] & 0xffff0000u), __uint_as_float(gw[j] & 0xffff0000u), acc);
         }
     }
-    const int64_t b = row / T;
-    dsum[(b * heads + h) * T + (row - b * T)] = acc;
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+    if (live && part == 0) {
+        const int64_t row = i / heads;
+        const int h = (int)(i - row * heads);
+        const int64_t b = row / T;
+        dsum[(b * heads + h) * T + (row - b * T)] = acc;
+    }
 }
 
 // timing build (BSI_ATT_BWD_VARIANT=9): cycles of softmax warp 0 {wait S/dP, softmax math, wait accumulators, read-out} and of the
@@ -342,7 +346,7 @@ int attention_backward_tcgen05(void* dqkv_bf16, const float* lse, float* dsum, c
     using namespace abt;
     const int dim = heads * HD;
     const int64_t rows = (int64_t)B * T;
-    k_attention_dsum<<<(unsigned)((rows * heads + 255) / 256), 256, 0, stream>>>(dsum, (const __nv_bfloat16*)out_bf16, (const __nv_bfloat16*)dout_bf16, rows, T,
+    k_attention_dsum<<<(unsigned)((rows * heads * 8 + 255) / 256), 256, 0, stream>>>(dsum, (const __nv_bfloat16*)out_bf16, (const __nv_bfloat16*)dout_bf16, rows, T,
                                                                                heads);
     BSI_LAUNCH_OK("k_attention_dsum");
     CUtensorMap mq, md;

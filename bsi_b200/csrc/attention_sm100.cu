@@ -281,10 +281,13 @@ __device__ __forceinline__ float ex2_poly(float t) {
 // cycles per phase of softmax warp 0, summed over items and CTAs (BSI_ATT_VARIANT=9: timing build of the kernel)
 __device__ unsigned long long g_att_phase[16];  // [0,6): softmax warp 0; [8,14): control warp
 
-template <bool LSE, int POLY, bool TIMING = false, bool SPIN = false>
+// DROP: attention dropout of the training path (F.scaled_dot_product_attention(dropout_p), dit.py:43-44): the softmax is normalised by
+// the full row sum, the probabilities that enter P V carry the stateless mask of common.cuh (same mask as the backward kernels).
+template <bool LSE, int POLY, bool TIMING = false, bool SPIN = false, bool DROP = false>
 __global__ void __launch_bounds__(att2::kThreads, 2)
     k_attention_tc2(const __grid_constant__ CUtensorMap map_qkv, const __grid_constant__ CUtensorMap map_out, const int dim, const int heads,
-                    const int total_items, const float scale_log2, float* __restrict__ lse) {
+                    const int total_items, const float scale_log2, float* __restrict__ lse, const uint32_t drop_thresh, const uint32_t drop_seed,
+                    const float drop_inv) {
     using namespace att2;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -442,6 +445,8 @@ __global__ void __launch_bounds__(att2::kThreads, 2)
                 for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(s[c & 1][j]));
             }
             const float moff = mx * scale_log2;
+            const uint32_t drop_sd = DROP ? mix32(drop_seed ^ ((uint32_t)(item >> 1) * 0x9E3779B9u)) : 0u;  // (sample, head) stream
+            const uint32_t drop_q = (uint32_t)(qblk * QB + r) * T;
             tick(1);  // pass 1
 
             // ---- pass 2: p = exp2(s*scale - max*scale), row sum, P -> TMEM as packed bf16 over score columns already consumed:
@@ -457,9 +462,14 @@ __global__ void __launch_bounds__(att2::kThreads, 2)
                     const float t0 = fmaf(__uint_as_float(s[c & 1][2 * j]), scale_log2, -moff);
                     const float t1 = fmaf(__uint_as_float(s[c & 1][2 * j + 1]), scale_log2, -moff);
                     // POLY of every 8 scores take the FMA-pipe exponential
-                    const float p0 = ((2 * j) & 7) < POLY ? ex2_poly(t0) : ex2_approx(t0);
-                    const float p1 = ((2 * j + 1) & 7) < POLY ? ex2_poly(t1) : ex2_approx(t1);
+                    float p0 = ((2 * j) & 7) < POLY ? ex2_poly(t0) : ex2_approx(t0);
+                    float p1 = ((2 * j + 1) & 7) < POLY ? ex2_poly(t1) : ex2_approx(t1);
                     sum += p0 + p1;
+                    if constexpr (DROP) {
+                        const uint32_t idx = drop_q + (uint32_t)(c * 32 + 2 * j);  // query * T + key
+                        p0 = dropout_keep(drop_sd, idx, drop_thresh) ? p0 * drop_inv : 0.0f;
+                        p1 = dropout_keep(drop_sd, idx + 1, drop_thresh) ? p1 * drop_inv : 0.0f;
+                    }
                     p[j] = pack_bf16(p0, p1);
                 }
                 ptx::tmem_st_32x32b_x16(trow + (c < 4 ? c * 16 : 128 + (c - 4) * 16), p);
@@ -523,17 +533,18 @@ __global__ void __launch_bounds__(att2::kThreads, 2)
     }
 }
 
-template <bool LSE, int POLY, bool TIMING = false, bool SPIN = false>
-static int launch_attention2(const CUtensorMap& mq, const CUtensorMap& mo, int dim, int heads, int total, float scale_log2, float* lse, cudaStream_t stream) {
+template <bool LSE, int POLY, bool TIMING = false, bool SPIN = false, bool DROP = false>
+static int launch_attention2(const CUtensorMap& mq, const CUtensorMap& mo, int dim, int heads, int total, float scale_log2, float* lse, cudaStream_t stream,
+                             uint32_t drop_thresh = 0, uint32_t drop_seed = 0, float drop_inv = 1.0f) {
     using namespace att2;
-    BSI_ENSURE_SMEM((k_attention_tc2<LSE, POLY, TIMING, SPIN>), kSmem);
+    BSI_ENSURE_SMEM((k_attention_tc2<LSE, POLY, TIMING, SPIN, DROP>), kSmem);
     const int resident = 2 * sm_count();
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(total < resident ? total : resident), cfg.blockDim = dim3(kThreads), cfg.dynamicSmemBytes = kSmem, cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     fill_pdl_attr(&attr[0]);
     cfg.attrs = attr, cfg.numAttrs = use_pdl() ? 1 : 0;
-    BSI_CUDA_OK(cudaLaunchKernelEx(&cfg, k_attention_tc2<LSE, POLY, TIMING, SPIN>, mq, mo, dim, heads, total, scale_log2, lse));
+    BSI_CUDA_OK(cudaLaunchKernelEx(&cfg, k_attention_tc2<LSE, POLY, TIMING, SPIN, DROP>, mq, mo, dim, heads, total, scale_log2, lse, drop_thresh, drop_seed, drop_inv));
     BSI_LAUNCH_OK("k_attention_tc2");
     return BSI_OK;
 }
@@ -551,7 +562,9 @@ static int attention_variant() {
     return v;
 }
 
-int attention_tcgen05(void* out_bf16, const void* qkv_bf16, int B, int heads, float* lse, cudaStream_t stream) {
+bool attention_tcgen05_has_dropout() { return attention_variant() == 1; }
+
+int attention_tcgen05(void* out_bf16, const void* qkv_bf16, int B, int heads, float* lse, cudaStream_t stream, float drop_p, uint32_t drop_seed) {
     using namespace att;
     const int dim = heads * HD;
     CUtensorMap mq, mo;
@@ -562,6 +575,9 @@ int attention_tcgen05(void* out_bf16, const void* qkv_bf16, int B, int heads, fl
     if (const int variant = attention_variant()) {
         rc = make_tile_map(&mo, out_bf16, 2, (int64_t)B * T, dim, dim, 1, 0, 32);  // one store per warp: boxes of 32 rows
         if (rc != BSI_OK) return rc;
+        if (drop_p > 0.0f)
+            return launch_attention2<true, 0, false, false, true>(mq, mo, dim, heads, total, scale_log2, lse, stream, dropout_thresh(drop_p), drop_seed,
+                                                                  1.0f / (1.0f - drop_p));
         if (variant == 4) return lse ? launch_attention2<true, 0, false, true>(mq, mo, dim, heads, total, scale_log2, lse, stream)
                                      : launch_attention2<false, 0, false, true>(mq, mo, dim, heads, total, scale_log2, nullptr, stream);
         if (variant == 5) return launch_attention2<false, 0, true, true>(mq, mo, dim, heads, total, scale_log2, nullptr, stream);

@@ -75,7 +75,8 @@ struct Cfg {
     static constexpr bool kDual = EPI == BSI_EPI_BIAS_GELU_DUAL_BF16;  // two bf16 outputs per tile: one staging tile each
     static constexpr bool kHeavy = EPI == BSI_EPI_BIAS_GELU_BF16 || EPI == BSI_EPI_BIAS_SILU_BF16 || EPI == BSI_EPI_MOD_SILU_BF16 || kDual;
     // (16 warps, one 64-column block each, measured no faster than 8: the GELU epilogue is bound by the fp32 pipe, not by latency)
-    static constexpr int kEpiWarps = kHeavy ? 8 : 4;
+    // (the GELU' epilogue of the training path is the heaviest of all -- ~20 instructions per element: 8 warps as well)
+    static constexpr int kEpiWarps = (kHeavy || epi_kind(EPI) == KIND_AUX16) ? 8 : 4;
     static constexpr int kGroups = kEpiWarps / 4;                                   // groups of 4 warps, each owning BN / kGroups columns
     static constexpr int kBufsPerGroup = kDual ? 2 : kHeavy ? (kGroups == 4 ? 1 : BSI_EXP_HEAVY_BUFS) : 2;  // staging tiles per group (KIND_BF16)
     static constexpr int kThreads = 128 + 32 * kEpiWarps;
@@ -361,11 +362,24 @@ __global__ void __launch_bounds__(Cfg<EPI, CG, BN, CONV>::kThreads, 1)
             ptx::mbar_arrive_expect_tx(&c_full[g & 3], kEpiBufBytes);
             ptx::tma_load_3d(epi_buf + (g & 3) * kEpiBufBytes, &map_r, &c_full[g & 3], n_t * BN + c * kChunkCols, (m_t * CG + cta_rank) * BM, b);
         };
-        if constexpr (kKind == KIND_RMW || kKind == KIND_AUX16) {
+        if constexpr (kKind == KIND_RMW) {
             if (et == 0) {
                 issue_residual_load(0);
                 issue_residual_load(1);
             }
+        }
+        // KIND_AUX16: each group of 4 warps (hf) owns two of the tile's four 64-column chunks and two staging tiles; gl is the group's
+        // running chunk index, its auxiliary tile goes to staging tile hf*2 + (gl & 1)
+        auto issue_aux_load = [&](int gl) {
+            if (gl >= my_tiles * 2) return;
+            const int tile = worker + (gl >> 1) * num_workers, c = hf * 2 + (gl & 1);
+            const int n_t = tile % n_tiles, m_t = (tile / n_tiles) % m_tiles, b = tile / (n_tiles * m_tiles);
+            uint64_t* bar = &c_full[hf * 2 + (gl & 1)];
+            ptx::mbar_arrive_expect_tx(bar, kEpiBufBytes);
+            ptx::tma_load_3d(epi_buf + (hf * 2 + (gl & 1)) * kEpiBufBytes, &map_r, bar, n_t * BN + c * 64, (m_t * CG + cta_rank) * BM, b);
+        };
+        if constexpr (kKind == KIND_AUX16) {
+            if (er == 0) issue_aux_load(0);
         }
 
         int it = 0;
@@ -558,18 +572,18 @@ __global__ void __launch_bounds__(Cfg<EPI, CG, BN, CONV>::kThreads, 1)
                         }
                     }
                 } else if constexpr (kKind == KIND_AUX16) {
-                    // ---- out = (acc + bias) * gelu'(pre): the pre-activation chunk (64 bf16 columns) arrives by TMA two chunks ahead, is
-                    //      replaced in place by the product and goes out by TMA store
-                    const int g = it * kChunks + jb;
-                    if (et == 0) {
-                        ptx::tma_store_wait_read<1>();
-                        issue_residual_load(g + 2);
+                    // ---- out = (acc + bias) * gelu'(pre): the group's pre-activation chunk (64 bf16 columns) arrives by TMA one chunk ahead,
+                    //      is replaced in place by the product and goes out by TMA store
+                    const int gl = it * 2 + jl, sbuf = hf * 2 + (gl & 1);
+                    if (er == 0) {
+                        ptx::tma_store_wait_read<0>();  // the other staging tile of this group has been read by the previous chunk's store
+                        issue_aux_load(gl + 1);
                     }
-                    ptx::mbar_wait(&c_full[g & 3], (g >> 2) & 1);
-                    const uint32_t sb = buf0 + (g & 3) * kEpiBufBytes;
+                    ptx::mbar_wait(&c_full[sbuf], (gl >> 1) & 1);
+                    const uint32_t sb = buf0 + sbuf * kEpiBufBytes;
 #pragma unroll
                     for (int c = 0; c < 8; ++c) {
-                        const uint32_t addr = sb + swz(et, c);
+                        const uint32_t addr = sb + swz(er, c);
                         const uint4 p4 = ld_shared_u4(addr);
                         const uint32_t pw[4] = {p4.x, p4.y, p4.z, p4.w};
                         uint32_t ow[4];
@@ -583,9 +597,9 @@ __global__ void __launch_bounds__(Cfg<EPI, CG, BN, CONV>::kThreads, 1)
                         st_shared_v4(addr, ow[0], ow[1], ow[2], ow[3]);
                     }
                     ptx::fence_proxy_async();
-                    epi_bar();
-                    if (et == 0) {
-                        ptx::tma_store_3d(&map_c, epi_buf + (g & 3) * kEpiBufBytes, n_base + jb * 64, row_base, b);
+                    epi_bar(hf);
+                    if (er == 0) {
+                        ptx::tma_store_3d(&map_c, epi_buf + sbuf * kEpiBufBytes, n_base + jb * 64, row_base, b);
                         ptx::tma_store_commit();
                     }
                 } else {
