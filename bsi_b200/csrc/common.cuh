@@ -121,6 +121,10 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
     return c;
 }
 // Four N(0,1) values for (seed, global sample, draw, element-quad): Box-Muller on (r0,r1) and (r2,r3).
+// The transcendental part uses the SFU approximations (lg2 / sqrt / sin / cos .approx): with the library versions the generator
+// costs ~230 instructions per quad and every kernel that draws noise is instruction-bound (ncu r02: k_q_sample 77 % issue-active at
+// 0.34 of the HBM roof).  Absolute error of a sample <= 4e-5 (only where |z| < 0.01, from lg2.approx near 1), typically 1e-6:
+// far below what any statistic of the sampler resolves; the oracle's fp64 restatement agrees to 1e-4 (tests/test_gpu_elementwise.py).
 __device__ __forceinline__ float4 philox_normal4(uint64_t seed, uint64_t sample, uint32_t draw, uint32_t quad) {
     uint4 r = philox4x32_10(make_uint4(quad, draw, (uint32_t)sample, (uint32_t)(sample >> 32)),
                             make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
@@ -128,10 +132,12 @@ __device__ __forceinline__ float4 philox_normal4(uint64_t seed, uint64_t sample,
     float u0 = ((float)r.x + 0.5f) * k2m32, u1 = ((float)r.y + 0.5f) * k2m32;
     float u2 = ((float)r.z + 0.5f) * k2m32, u3 = ((float)r.w + 0.5f) * k2m32;
     // (float)r can round up to 2^32 -> u = 1 -> log = 0: fine (radius 0).  u > 0 always.
-    float rad0 = sqrtf(-2.0f * logf(u0)), rad1 = sqrtf(-2.0f * logf(u2));
-    float s0, c0, s1, c1;
-    sincospif(2.0f * u1, &s0, &c0);
-    sincospif(2.0f * u3, &s1, &c1);
+    float rad0, rad1;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rad0) : "f"(-2.0f * __logf(u0)));
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rad1) : "f"(-2.0f * __logf(u2)));
+    // angle 2 pi u in [0, 2 pi): evaluate at x = 2 pi u - pi in [-pi, pi), where sin/cos.approx are accurate to 2^-21; sin(x + pi) = -sin x
+    const float x0 = fmaf(6.283185307179586f, u1, -3.141592653589793f), x1 = fmaf(6.283185307179586f, u3, -3.141592653589793f);
+    const float s0 = -__sinf(x0), c0 = -__cosf(x0), s1 = -__sinf(x1), c1 = -__cosf(x1);
     return make_float4(rad0 * c0, rad0 * s0, rad1 * c1, rad1 * s1);
 }
 

@@ -182,6 +182,73 @@ __global__ void __launch_bounds__(kThreads)
     }
 }
 
+// ------------------------------------------------------------------ scalar variants of the row kernels
+// Data shapes whose element count is not a multiple of 4 (the reference accepts any data_shape): rows are not 16-byte aligned, so
+// these kernels use 4-byte accesses, one element per thread.  Element e still takes component e & 3 of Philox quad e >> 2, i.e. the
+// noise of an element does not depend on which variant runs.  Same arithmetic (rounding points) as the vector kernels.
+__device__ __forceinline__ float noise1(const bsi_noise& nz, int step, int64_t sample, int e, int64_t D) {
+    if (nz.eps) return __ldcs(nz.eps + sample * D + e);
+    const float4 v = philox_normal4(nz.seed, nz.sample_base + (uint64_t)sample, (uint32_t)(nz.draw + step), (uint32_t)(e >> 2));
+    const int c = e & 3;
+    return c == 0 ? v.x : c == 1 ? v.y : c == 2 ? v.z : v.w;
+}
+static inline dim3 row_grid_scalar(int64_t rows, int64_t D) { return dim3((unsigned)rows, (unsigned)((D + kThreads - 1) / kThreads), 1); }
+#define BSI_CHECK_ROW_GRID_SCALAR(rows, D) \
+    BSI_CHECK_ARG((D) > 0 && (rows) <= 0x7fffffffLL && ((D) + kThreads - 1) / kThreads <= 65535, "row grid out of range: %lld rows of %lld", (long long)(rows), (long long)(D))
+
+__global__ void __launch_bounds__(kThreads) k_sample_init_s(float* __restrict__ mu, const float* __restrict__ sigma0_ptr, bsi_noise nz_arg, int64_t D) {
+    const int e = blockIdx.y * kThreads + threadIdx.x;
+    if (e >= D) return;
+    const bsi_noise nz = resolve_noise(nz_arg);
+    const int64_t s = blockIdx.x;
+    mu[s * D + e] = sigma0_ptr[0] * noise1(nz, 0, s, e, D);
+}
+template <bool kPrecond>
+__global__ void __launch_bounds__(kThreads)
+    k_step_fused_s(float* __restrict__ mu, const float* __restrict__ f, const float* __restrict__ coef, const int32_t* __restrict__ step_ptr, int32_t step_arg,
+                   bsi_noise nz_arg, float* __restrict__ x_hat_out, float* __restrict__ y_out, int64_t D) {
+    const int e = blockIdx.y * kThreads + threadIdx.x;
+    if (e >= D) return;
+    const int64_t s = blockIdx.x, off = s * D + e;
+    const bsi_noise nz = resolve_noise(nz_arg);
+    const int step = step_ptr ? *step_ptr : step_arg;
+    const float* c = coef + (int64_t)step * 8;
+    const float m = mu[off], fo = f[off], eps = noise1(nz, step, s, e, D);
+    const float xh = kPrecond ? addcmul_rn(mul_rn(c[0], m), c[1], fo) : fo;
+    const float y = add_mul_sep(xh, c[2], eps);
+    mu[off] = __fdiv_rn(__fadd_rn(mul_rn(c[3], y), mul_rn(c[4], m)), c[5]);
+    if (x_hat_out) x_hat_out[off] = xh;
+    if (y_out) y_out[off] = y;
+}
+__global__ void __launch_bounds__(kThreads)
+    k_edm_combine_s(float* __restrict__ x_hat, const float* __restrict__ mu, const float* __restrict__ f, bsi_rowref c_skip, bsi_rowref c_out,
+                    const int32_t* __restrict__ step_ptr, int64_t D) {
+    const int e = blockIdx.y * kThreads + threadIdx.x;
+    if (e >= D) return;
+    const int64_t s = blockIdx.x, off = s * D + e;
+    const int step = step_ptr ? *step_ptr : 0;
+    x_hat[off] = addcmul_rn(mul_rn(rowref_at(c_skip, s, step), mu[off]), rowref_at(c_out, s, step), f[off]);
+}
+__global__ void __launch_bounds__(kThreads) k_scale_rows_s(float* __restrict__ out, const float* __restrict__ in, bsi_rowref sc, const int32_t* __restrict__ step_ptr,
+                                                           int64_t D) {
+    const int e = blockIdx.y * kThreads + threadIdx.x;
+    if (e >= D) return;
+    const int64_t s = blockIdx.x, off = s * D + e;
+    out[off] = rowref_at(sc, s, step_ptr ? *step_ptr : 0) * in[off];
+}
+__global__ void __launch_bounds__(kThreads)
+    k_q_sample_s(float* __restrict__ mu, float* __restrict__ model_in, const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ sigma,
+                 const float* __restrict__ c_in, bsi_noise nz_arg, int64_t B, int64_t D) {
+    const int e = blockIdx.y * kThreads + threadIdx.x;
+    if (e >= D) return;
+    const uint32_t r32 = blockIdx.x;
+    const int64_t r = r32, b = r32 % (uint32_t)B, off = r * D + e;
+    const bsi_noise nz = resolve_noise(nz_arg);
+    const float m = addcmul_rn(mul_rn(gamma[r], x[b * D + e]), sigma[r], noise1(nz, 0, r, e, D));
+    mu[off] = m;
+    if (model_in) model_in[off] = c_in[r] * m;
+}
+
 // ------------------------------------------------------------------ bucketize (bsi/bsi.py:32-35)
 __device__ __forceinline__ int bucket_of(float x, float lo_edge, float dx, int k) {
     // fp32 subtract, true division, truncation toward zero, clamp — same op order as the reference.
@@ -351,11 +418,19 @@ int bsi_device_arch(void) {
     return major * 10 + minor;
 }
 
-#define BSI_REQUIRE_VEC4(D) BSI_CHECK_ARG((D) > 0 && ((D) % 4) == 0, "data numel per sample (%lld) must be a positive multiple of 4", (long long)(D))
+#define BSI_REQUIRE_VEC4(D) BSI_CHECK_ARG((D) > 0, "data numel per sample (%lld) must be positive", (long long)(D))
+// element counts that are not a multiple of 4 take the scalar kernels
+#define BSI_SCALAR_PATH(D) (((D) & 3) != 0)
 
 int bsi_sample_init(float* mu, const float* sigma0_ptr, bsi_noise noise, int64_t n, int64_t D, void* stream) {
     BSI_CHECK_ARG(mu && sigma0_ptr && n > 0, "bsi_sample_init: null pointer or empty batch");
     BSI_REQUIRE_VEC4(D);
+    if (BSI_SCALAR_PATH(D)) {
+        BSI_CHECK_ROW_GRID_SCALAR(n, D);
+        k_sample_init_s<<<row_grid_scalar(n, D), kThreads, 0, (cudaStream_t)stream>>>(mu, sigma0_ptr, noise, D);
+        BSI_LAUNCH_OK("k_sample_init_s");
+        return BSI_OK;
+    }
     BSI_CHECK_ROW_GRID(n, D);
     k_sample_init<<<row_grid(n, D).grid, kThreads, 0, (cudaStream_t)stream>>>(mu, sigma0_ptr, noise, n, D);
     BSI_LAUNCH_OK("k_sample_init");
@@ -366,6 +441,15 @@ int bsi_step_fused(float* mu, const float* f, const float* coef, const int32_t* 
                    bsi_noise noise, float* x_hat_out, float* y_out, int64_t n, int64_t D, void* stream) {
     BSI_CHECK_ARG(mu && f && coef && n > 0, "bsi_step_fused: null pointer or empty batch");
     BSI_REQUIRE_VEC4(D);
+    if (BSI_SCALAR_PATH(D)) {
+        BSI_CHECK_ROW_GRID_SCALAR(n, D);
+        if (precond)
+            k_step_fused_s<true><<<row_grid_scalar(n, D), kThreads, 0, (cudaStream_t)stream>>>(mu, f, coef, step_ptr, step, noise, x_hat_out, y_out, D);
+        else
+            k_step_fused_s<false><<<row_grid_scalar(n, D), kThreads, 0, (cudaStream_t)stream>>>(mu, f, coef, step_ptr, step, noise, x_hat_out, y_out, D);
+        BSI_LAUNCH_OK("k_step_fused_s");
+        return BSI_OK;
+    }
     BSI_CHECK_ROW_GRID(n, D);
     const dim3 grid = row_grid(n, D).grid;
     if (precond)
@@ -387,6 +471,12 @@ int bsi_edm_combine(float* x_hat, const float* mu, const float* f, bsi_rowref c_
                     int64_t n, int64_t D, void* stream) {
     BSI_CHECK_ARG(x_hat && mu && f && c_skip.base && c_out.base && n > 0, "bsi_edm_combine: null pointer or empty batch");
     BSI_REQUIRE_VEC4(D);
+    if (BSI_SCALAR_PATH(D)) {
+        BSI_CHECK_ROW_GRID_SCALAR(n, D);
+        k_edm_combine_s<<<row_grid_scalar(n, D), kThreads, 0, (cudaStream_t)stream>>>(x_hat, mu, f, c_skip, c_out, step_ptr, D);
+        BSI_LAUNCH_OK("k_edm_combine_s");
+        return BSI_OK;
+    }
     BSI_CHECK_ROW_GRID(n, D);
     k_edm_combine<<<row_grid(n, D).grid, kThreads, 0, (cudaStream_t)stream>>>(x_hat, mu, f, c_skip, c_out, step_ptr, n, D);
     BSI_LAUNCH_OK("k_edm_combine");
@@ -396,6 +486,12 @@ int bsi_edm_combine(float* x_hat, const float* mu, const float* f, bsi_rowref c_
 int bsi_scale_rows(float* out, const float* in, bsi_rowref scale, const int32_t* step_ptr, int64_t n, int64_t D, void* stream) {
     BSI_CHECK_ARG(out && in && scale.base && n > 0, "bsi_scale_rows: null pointer or empty batch");
     BSI_REQUIRE_VEC4(D);
+    if (BSI_SCALAR_PATH(D)) {
+        BSI_CHECK_ROW_GRID_SCALAR(n, D);
+        k_scale_rows_s<<<row_grid_scalar(n, D), kThreads, 0, (cudaStream_t)stream>>>(out, in, scale, step_ptr, D);
+        BSI_LAUNCH_OK("k_scale_rows_s");
+        return BSI_OK;
+    }
     BSI_CHECK_ROW_GRID(n, D);
     k_scale_rows<<<row_grid(n, D).grid, kThreads, 0, (cudaStream_t)stream>>>(out, in, scale, step_ptr, n, D);
     BSI_LAUNCH_OK("k_scale_rows");
@@ -407,8 +503,14 @@ int bsi_q_sample(float* mu, float* model_in, const float* x, const float* gamma,
     BSI_CHECK_ARG(mu && x && gamma && sigma && R > 0 && B > 0, "bsi_q_sample: null pointer or empty batch");
     BSI_CHECK_ARG(!model_in || c_in, "bsi_q_sample: model_in requested without c_in");
     BSI_REQUIRE_VEC4(D);
-    BSI_CHECK_ROW_GRID(R, D);
     BSI_CHECK_ARG(B <= 0x7fffffffLL, "bsi_q_sample: batch too large");
+    if (BSI_SCALAR_PATH(D)) {
+        BSI_CHECK_ROW_GRID_SCALAR(R, D);
+        k_q_sample_s<<<row_grid_scalar(R, D), kThreads, 0, (cudaStream_t)stream>>>(mu, model_in, x, gamma, sigma, c_in, noise, B, D);
+        BSI_LAUNCH_OK("k_q_sample_s");
+        return BSI_OK;
+    }
+    BSI_CHECK_ROW_GRID(R, D);
     k_q_sample<<<row_grid(R, D).grid, kThreads, 0, (cudaStream_t)stream>>>(mu, model_in, x, gamma, sigma, c_in, noise, R, B, D);
     BSI_LAUNCH_OK("k_q_sample");
     return BSI_OK;

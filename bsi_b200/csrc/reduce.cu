@@ -45,6 +45,7 @@ __device__ __forceinline__ float cdf_of_erf(float e) { return __fmul_rn(0.5f, __
 // |z| >= 4: erfc(4) = 1.5e-8 is a quarter of the fp32 spacing below 1, so erff(z) is exactly +-1 and the cdf exactly 0 or 1
 constexpr float kErfSaturated = 4.0f;
 
+template <bool VEC>
 __global__ void __launch_bounds__(kRThreads)
     k_recon_reduce(float* __restrict__ out, const float* __restrict__ x, const float* __restrict__ mu, const float* __restrict__ f,
                    const float* __restrict__ c_skip, const float* __restrict__ c_out, const float* __restrict__ edges, int k,
@@ -60,13 +61,19 @@ __global__ void __launch_bounds__(kRThreads)
     const float4* m4 = has_mu ? reinterpret_cast<const float4*>(mu + r * D) : nullptr;
     const float4* f4 = reinterpret_cast<const float4*>(f + r * D);
     float acc = 0.0f;
-    for (int64_t q = threadIdx.x; q < (D >> 2); q += blockDim.x) {
-        float4 xv = x4[q];
-        float4 fv = __ldcs(f4 + q);
-        float4 mv = has_mu ? __ldcs(m4 + q) : make_float4(0, 0, 0, 0);
-        float xs[4] = {xv.x, xv.y, xv.z, xv.w}, fs[4] = {fv.x, fv.y, fv.z, fv.w}, ms[4] = {mv.x, mv.y, mv.z, mv.w};
+    // VEC: four elements per 16-byte access; otherwise (element count not a multiple of 4: rows are not 16-byte aligned) one
+    const int64_t items = VEC ? (D >> 2) : D;
+    for (int64_t q = threadIdx.x; q < items; q += blockDim.x) {
+        float xs[4], fs[4], ms[4] = {0.f, 0.f, 0.f, 0.f};
+        if constexpr (VEC) {
+            const float4 xv = x4[q], fv = __ldcs(f4 + q), mv = has_mu ? __ldcs(m4 + q) : make_float4(0, 0, 0, 0);
+            xs[0] = xv.x, xs[1] = xv.y, xs[2] = xv.z, xs[3] = xv.w, fs[0] = fv.x, fs[1] = fv.y, fs[2] = fv.z, fs[3] = fv.w;
+            ms[0] = mv.x, ms[1] = mv.y, ms[2] = mv.z, ms[3] = mv.w;
+        } else {
+            xs[0] = x[b * D + q], fs[0] = f[r * D + q], ms[0] = has_mu ? mu[r * D + q] : 0.0f;
+        }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < (VEC ? 4 : 1); ++j) {
             float xh = combine(has_mu, cs, co, ms[j], fs[j]);
             int idx = bucket_of_r(xs[j], lo_edge, dx, k);
             // The bin is 11 sigma wide (image_8bit with alpha_R = 2e6), so at most one of its two edges lies within the 4 sqrt(2)
@@ -85,6 +92,7 @@ __global__ void __launch_bounds__(kRThreads)
     if (threadIdx.x == 0) out[r] = total;
 }
 
+template <bool VEC>
 __global__ void __launch_bounds__(kRThreads)
     k_sqerr_reduce(float* __restrict__ out, const float* __restrict__ x, const float* __restrict__ mu, const float* __restrict__ f,
                    const float* __restrict__ c_skip, const float* __restrict__ c_out, int64_t B, int64_t D) {
@@ -96,14 +104,21 @@ __global__ void __launch_bounds__(kRThreads)
     const float4* m4 = has_mu ? reinterpret_cast<const float4*>(mu + r * D) : nullptr;
     const float4* f4 = reinterpret_cast<const float4*>(f + r * D);
     float acc = 0.0f;
-    for (int64_t q = threadIdx.x; q < (D >> 2); q += blockDim.x) {
-        float4 xv = x4[q];
-        float4 fv = __ldcs(f4 + q);
-        float4 mv = has_mu ? __ldcs(m4 + q) : make_float4(0, 0, 0, 0);
-        float xs[4] = {xv.x, xv.y, xv.z, xv.w}, fs[4] = {fv.x, fv.y, fv.z, fv.w}, ms[4] = {mv.x, mv.y, mv.z, mv.w};
+    if constexpr (VEC) {
+        for (int64_t q = threadIdx.x; q < (D >> 2); q += blockDim.x) {
+            float4 xv = x4[q];
+            float4 fv = __ldcs(f4 + q);
+            float4 mv = has_mu ? __ldcs(m4 + q) : make_float4(0, 0, 0, 0);
+            float xs[4] = {xv.x, xv.y, xv.z, xv.w}, fs[4] = {fv.x, fv.y, fv.z, fv.w}, ms[4] = {mv.x, mv.y, mv.z, mv.w};
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            float d = __fsub_rn(xs[j], combine(has_mu, cs, co, ms[j], fs[j]));
+            for (int j = 0; j < 4; ++j) {
+                float d = __fsub_rn(xs[j], combine(has_mu, cs, co, ms[j], fs[j]));
+                acc = fmaf(d, d, acc);
+            }
+        }
+    } else {
+        for (int64_t e = threadIdx.x; e < D; e += blockDim.x) {
+            float d = __fsub_rn(x[b * D + e], combine(has_mu, cs, co, has_mu ? mu[r * D + e] : 0.0f, f[r * D + e]));
             acc = fmaf(d, d, acc);
         }
     }
@@ -113,6 +128,19 @@ __global__ void __launch_bounds__(kRThreads)
 
 // d/df of  w[r] * sum_d (x - (c_skip*mu + c_out*f))^2  =  -2 * w[r] * c_out[r] * (x - x_hat)
 // (autograd of bsi/bsi.py:309-310 w.r.t. the denoiser output).  16 B/elem.
+// scalar variant for element counts that are not a multiple of 4
+__global__ void __launch_bounds__(kRThreads)
+    k_sqerr_backward_s(float* __restrict__ grad_f, const float* __restrict__ w, const float* __restrict__ x, const float* __restrict__ mu,
+                       const float* __restrict__ f, const float* __restrict__ c_skip, const float* __restrict__ c_out, int64_t B, int64_t D) {
+    const int e = blockIdx.y * kRThreads + threadIdx.x;
+    if (e >= D) return;
+    const uint32_t r32 = blockIdx.x;
+    const int64_t r = r32, b = r32 % (uint32_t)B;
+    const bool has_mu = mu != nullptr;
+    const float cs = has_mu ? c_skip[r] : 0.0f, co = has_mu ? c_out[r] : 1.0f;
+    grad_f[r * D + e] = -2.0f * w[r] * co * (x[b * D + e] - combine(has_mu, cs, co, has_mu ? mu[r * D + e] : 0.0f, f[r * D + e]));
+}
+
 __global__ void __launch_bounds__(kRThreads)
     k_sqerr_backward(float* __restrict__ grad_f, const float* __restrict__ w, const float* __restrict__ x,
                      const float* __restrict__ mu, const float* __restrict__ f, const float* __restrict__ c_skip,
@@ -148,10 +176,14 @@ int bsi_recon_reduce(float* out, const float* x, const float* mu, const float* f
     BSI_CHECK_ARG(out && x && f && edges && R > 0 && B > 0, "bsi_recon_reduce: null pointer or empty batch");
     BSI_CHECK_ARG(!mu || (c_skip && c_out), "bsi_recon_reduce: mu given without c_skip/c_out");
     BSI_CHECK_ARG(k >= 2 && k <= 1024, "bsi_recon_reduce: k=%d outside [2,1024]", k);
-    BSI_CHECK_ARG(D > 0 && D % 4 == 0, "data numel per sample (%lld) must be a positive multiple of 4", (long long)D);
+    BSI_CHECK_ARG(D > 0, "data numel per sample (%lld) must be positive", (long long)D);
     BSI_CHECK_ARG(R <= 0x7fffffff, "too many rows");
-    k_recon_reduce<<<(unsigned)R, kRThreads, (k + 1) * sizeof(float), (cudaStream_t)stream>>>(out, x, mu, f, c_skip, c_out, edges,
-                                                                                             k, lo_edge, dx, inv_scale, B, D);
+    if (D % 4 == 0)
+        k_recon_reduce<true><<<(unsigned)R, kRThreads, (k + 1) * sizeof(float), (cudaStream_t)stream>>>(out, x, mu, f, c_skip, c_out, edges, k, lo_edge, dx,
+                                                                                                       inv_scale, B, D);
+    else
+        k_recon_reduce<false><<<(unsigned)R, kRThreads, (k + 1) * sizeof(float), (cudaStream_t)stream>>>(out, x, mu, f, c_skip, c_out, edges, k, lo_edge, dx,
+                                                                                                        inv_scale, B, D);
     BSI_LAUNCH_OK("k_recon_reduce");
     return BSI_OK;
 }
@@ -160,9 +192,10 @@ int bsi_sqerr_reduce(float* out, const float* x, const float* mu, const float* f
                      int64_t R, int64_t B, int64_t D, void* stream) {
     BSI_CHECK_ARG(out && x && f && R > 0 && B > 0, "bsi_sqerr_reduce: null pointer or empty batch");
     BSI_CHECK_ARG(!mu || (c_skip && c_out), "bsi_sqerr_reduce: mu given without c_skip/c_out");
-    BSI_CHECK_ARG(D > 0 && D % 4 == 0, "data numel per sample (%lld) must be a positive multiple of 4", (long long)D);
+    BSI_CHECK_ARG(D > 0, "data numel per sample (%lld) must be positive", (long long)D);
     BSI_CHECK_ARG(R <= 0x7fffffff, "too many rows");
-    k_sqerr_reduce<<<(unsigned)R, kRThreads, 0, (cudaStream_t)stream>>>(out, x, mu, f, c_skip, c_out, B, D);
+    if (D % 4 == 0) k_sqerr_reduce<true><<<(unsigned)R, kRThreads, 0, (cudaStream_t)stream>>>(out, x, mu, f, c_skip, c_out, B, D);
+    else k_sqerr_reduce<false><<<(unsigned)R, kRThreads, 0, (cudaStream_t)stream>>>(out, x, mu, f, c_skip, c_out, B, D);
     BSI_LAUNCH_OK("k_sqerr_reduce");
     return BSI_OK;
 }
@@ -171,7 +204,14 @@ int bsi_sqerr_backward(float* grad_f, const float* w, const float* x, const floa
                        const float* c_out, int64_t R, int64_t B, int64_t D, void* stream) {
     BSI_CHECK_ARG(grad_f && w && x && f && R > 0 && B > 0, "bsi_sqerr_backward: null pointer or empty batch");
     BSI_CHECK_ARG(!mu || (c_skip && c_out), "bsi_sqerr_backward: mu given without c_skip/c_out");
-    BSI_CHECK_ARG(D > 0 && D % 4 == 0, "data numel per sample (%lld) must be a positive multiple of 4", (long long)D);
+    BSI_CHECK_ARG(D > 0, "data numel per sample (%lld) must be positive", (long long)D);
+    if (D % 4 != 0) {
+        const int64_t chunks_s = (D + kRThreads - 1) / kRThreads;
+        BSI_CHECK_ARG(R <= 0x7fffffffLL && B <= 0x7fffffffLL && chunks_s <= 65535, "bsi_sqerr_backward: shape out of range");
+        k_sqerr_backward_s<<<dim3((unsigned)R, (unsigned)chunks_s), kRThreads, 0, (cudaStream_t)stream>>>(grad_f, w, x, mu, f, c_skip, c_out, B, D);
+        BSI_LAUNCH_OK("k_sqerr_backward_s");
+        return BSI_OK;
+    }
     const int64_t chunks = ((D >> 2) + kRThreads - 1) / kRThreads;
     BSI_CHECK_ARG(R <= 0x7fffffffLL && B <= 0x7fffffffLL && chunks <= 65535, "bsi_sqerr_backward: shape out of range");
     k_sqerr_backward<<<dim3((unsigned)R, (unsigned)chunks), kRThreads, 0, (cudaStream_t)stream>>>(grad_f, w, x, mu, f, c_skip, c_out, R, B, D);

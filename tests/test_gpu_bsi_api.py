@@ -181,10 +181,11 @@ def test_edge_cases_empty_single_and_ragged_batches():
     one, _ = make(k=1)
     with torch.inference_mode():
         assert torch.isfinite(one.sample(2, torch.Generator(device=dev()).manual_seed(3))).all()
-    model = torch.nn.Identity()
-    odd = BSI(model, data_shape=(1, 5, 5), k=4, discretization=Discretization.image_8bit(), **HYPER).to(dev())
-    with torch.inference_mode(), pytest.raises((BsiNativeError, RuntimeError), match="multiple of 4"):
-        odd.sample(2, torch.Generator(device=dev()).manual_seed(1))
+    # element counts that are not a multiple of 4 are served by the scalar kernels (test_data_shapes_not_divisible_by_four_...)
+    odd = BSI(lambda mu, t: 0.5 * mu, data_shape=(1, 5, 5), k=4, discretization=Discretization.image_8bit(), **HYPER).to(dev())
+    with torch.inference_mode():
+        s_odd = odd.sample(2, torch.Generator(device=dev()).manual_seed(1))
+    assert s_odd.shape == (2, 1, 5, 5) and torch.isfinite(s_odd).all()
 
 
 @pytest.mark.parametrize("noise", ["philox", "torch"])
@@ -211,3 +212,55 @@ def test_elbo_is_invariant_to_how_the_batch_is_sharded(noise):
 
         e2, b2, ex2 = sharded_elbo(bsi, x, 2, 3, 77, estimate_var=True)
         assert torch.equal(b2, b) and torch.equal(ex2["bpd_var"], ex["bpd_var"])
+
+
+def test_data_shapes_not_divisible_by_four_take_the_scalar_kernels():
+    """The reference accepts any data_shape; 3 x 5 x 5 = 75 elements per sample leaves rows unaligned for 16-byte accesses, so every
+    row kernel has a scalar variant.  Sampler (free running, config-1 model), ELBO and train_loss gradient vs the oracle; Philox noise of
+    an element is the same whichever variant draws it."""
+    shape = (3, 5, 5)
+    model = ToyModel()
+    sd = H.det_state_dict(H.TOY_SHAPES, seed=1, bf16_exact=False)
+    model.load_state_dict(sd)
+    bsi = BSI(model.to(dev()), data_shape=shape, k=32, discretization=Discretization.image_8bit(), **HYPER).to(dev())
+    bsi.noise_source = "torch"
+    f = lambda mu, t: O.toy_conv_forward(sd, mu, t)
+    with torch.inference_mode():
+        out = bsi.sample(6, torch.Generator(device=dev()).manual_seed(7))
+        gen = torch.Generator(device=dev()).manual_seed(7)
+        eps = torch.stack([torch.randn((6, *shape), device=dev(), generator=gen) for _ in range(33)]).cpu()
+        ref = O.sample_with_noise(f, C32, torch.linspace(0.0, 1.0, 33), eps)
+    report("odd shape: sample (free running)", out, ref, 1e-5, 1e-5)
+    x = H.det_images("odd.x", 5, shape, seed=2)
+    with torch.inference_mode():
+        e, b, ex = bsi.elbo(x.to(dev()), 2, 3, torch.Generator(device=dev()).manual_seed(4))
+        gen = torch.Generator(device=dev()).manual_seed(4)
+        eps_r = torch.randn((2, 5, *shape), device=dev(), generator=gen).cpu()
+        off, perm = torch.rand((), device=dev(), generator=gen).cpu(), torch.randperm(15, device=dev(), generator=gen).cpu()
+        eps_m = torch.randn((3, 5, *shape), device=dev(), generator=gen).cpu()
+        l_r = O.recon_loss(f, C32, x, 2, eps_r, O.GRID_8BIT)
+        l_m = O.inf_measure_loss(f, C32, x, O.lam_of_t(C32, O.ld_times(3, 5, off, perm)), eps_m)
+    report("odd shape: l_recon", ex["l_recon"], l_r, 1e-4, 1e-2)
+    report("odd shape: l_measure", ex["l_measure"], l_m, 1e-4, 1e-3)
+    # gradient of the training loss through the scalar backward kernel
+    gen = torch.Generator(device=dev()).manual_seed(9)
+    loss = bsi.train_loss(x.to(dev()), gen).mean()
+    grads = torch.autograd.grad(loss, list(bsi.model.parameters()))
+    gen = torch.Generator(device=dev()).manual_seed(9)
+    off, perm = torch.rand((), device=dev(), generator=gen).cpu(), torch.randperm(5, device=dev(), generator=gen).cpu()
+    eps = torch.randn((1, 5, *shape), device=dev(), generator=gen).cpu()[0]
+    w, bias = sd["layer.weight"].clone().requires_grad_(True), sd["layer.bias"].clone().requires_grad_(True)
+    ref_loss = O.train_loss_with(lambda mu, t: O.toy_conv_forward({"layer.weight": w, "layer.bias": bias}, mu, t), C32, x,
+                                 O.lam_of_t(C32, O.ld_times(1, 5, off, perm))[0], eps).mean()
+    gw, gb = torch.autograd.grad(ref_loss, [w, bias])
+    report("odd shape: train_loss", loss.detach().reshape(1), ref_loss.detach().reshape(1), 1e-4, 1e-5)
+    report("odd shape: dL/dw", grads[0], gw, 1e-3, 1e-4 * float(gw.abs().max()))
+    # in-kernel Philox: element e of a row is component e & 3 of quad e >> 2 -- the scalar kernel draws what the vector kernel would
+    from bsi_b200 import _lib as L
+
+    n, D = 3, 75
+    mu = torch.empty(n, D, device=dev())
+    s0 = torch.ones(1, device=dev())
+    L.check(L.load().bsi_sample_init(L.ptr(mu), L.ptr(s0), L.noise(seed=11, sample_base=2, draw=0), n, D, L.stream_ptr()))
+    sync()
+    report("odd shape: philox", mu, torch.from_numpy(O.philox_normal(11, 2, n, D, 0)), 1e-4, 1e-4)

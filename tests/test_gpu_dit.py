@@ -56,7 +56,7 @@ def test_dit_forward_vs_golden_and_oracle(name):
     scale = float(g["y"].abs().max())
     report(f"{name} forward vs reference golden", y, g["y"], 3e-2, 2e-2 * scale)
     rel = float((y.cpu() - g["y"]).norm() / g["y"].norm())
-    assert rel < 1e-2, f"relative L2 error {rel} of the bf16 engine vs the fp32 reference"
+    assert rel < 4e-3, f"relative L2 error {rel} of the bf16 engine vs the fp32 reference (measured 1.5-2.0e-3)"
 
 
 def test_forward_scaled_and_batch_sizes():

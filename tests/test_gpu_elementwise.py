@@ -260,7 +260,8 @@ def test_recon_and_sqerr_reduce_vs_oracle_and_golden():
 def test_abi_rejects_bad_arguments():
     lib = L.load()
     t = torch.zeros(8, device=dev())
-    assert lib.bsi_step_fused(L.ptr(t), L.ptr(t), L.ptr(t), None, 0, 1, L.noise(eps=t), None, None, 1, 6, L.stream_ptr()) == -1
-    assert b"multiple of 4" in lib.bsi_last_error()
+    assert lib.bsi_step_fused(L.ptr(t), L.ptr(t), L.ptr(t), None, 0, 1, L.noise(eps=t), None, None, 1, 0, L.stream_ptr()) == -1
+    assert b"must be positive" in lib.bsi_last_error()
+    assert lib.bsi_step_fused(L.ptr(t), None, L.ptr(t), None, 0, 1, L.noise(eps=t), None, None, 1, 8, L.stream_ptr()) == -1
     assert lib.bsi_bucketize(L.ptr(t), None, None, 0.0, 1.0, 4, 8, L.stream_ptr()) == -1
     assert lib.bsi_device_arch() == 100

@@ -68,8 +68,9 @@ def _rel_l2(a, b):
 
 
 # forward of a 24-block bf16 engine vs the fp32 reference: every GEMM output carries ~2^-9 relative rounding of its bf16 operands;
-# measured 3-5e-3 (see profiles/full_depth_parity_r02.jsonl).  The bound is 2x that, far below the 2e-2 of the bf16-vs-bf16 checks.
-FORWARD_REL_L2 = 1e-2
+# measured 1.9e-3 for both DiT-L variants (profiles/full_depth_parity_r02.jsonl).  The bound is 2x that, a fifth of the 2e-2 that the
+# bf16-vs-bf16 comparisons of tests/test_gpu_reference_speed.py use.
+FORWARD_REL_L2 = 4e-3
 
 
 def test_dit_l4_depth24_forward_vs_fp32_reference(dit64, golden):
@@ -156,7 +157,7 @@ def test_unet_32_levels_forward_and_elbo_vs_fp32_reference(golden):
         sync()
     rel = _rel_l2(y, golden["unet32"]["y"])
     _log(test="unet32_forward", rel_l2=rel)
-    # 66 residual blocks of bf16 convolutions behind GroupNorm: measured ~6e-3
-    assert rel < 1.5e-2, f"U-Net x32 forward: relative L2 {rel} vs the fp32 reference"
+    # 66 residual blocks of bf16 convolutions behind GroupNorm: measured 2.5e-3
+    assert rel < 5e-3, f"U-Net x32 forward: relative L2 {rel} vs the fp32 reference"
     bsi = BSI(m, data_shape=USPEC.data_shape, k=256, discretization=Discretization.image_8bit(), **HYPER).to(dev())
     _elbo_parity(bsi, H.det_images("full.unet.x", 4, USPEC.data_shape, seed=2), golden["elbo_unet32"], "unet32_elbo")
