@@ -55,7 +55,7 @@ class DitConfig(C.Structure):
     _fields_ = [
         ("channels", C.c_int32), ("height", C.c_int32), ("width", C.c_int32),
         ("patch", C.c_int32), ("dim", C.c_int32), ("depth", C.c_int32), ("heads", C.c_int32),
-        ("fourier_n_min", C.c_int32), ("fourier_n_max", C.c_int32),
+        ("fourier_n_min", C.c_int32), ("fourier_n_max", C.c_int32), ("exact", C.c_int32),
     ]  # fmt: skip
 
 
@@ -123,6 +123,10 @@ SIGNATURES = {
     "bsi_cast_bf16": (C.c_int, [_vp, _vp, _i64, _i64, _i64, _vp]),
     "bsi_layernorm_mod_bf16": (C.c_int, [_vp, _vp, RowRef, RowRef, _vp, _vp, _vp, _i32, _i64, _i32, _f32, _vp]),
     "bsi_attention_bf16": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _vp]),
+    "bsi_split3_bf16": (C.c_int, [_vp, _vp, _i64, _i32, _i64, _i32, _i32, _i32, _vp]),
+    "bsi_attention_f32": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _vp]),
+    "bsi_layernorm_mod_f32": (C.c_int, [_vp, _vp, RowRef, RowRef, _vp, _vp, _vp, _i32, _i64, _i32, _f32, _vp]),
+    "bsi_dit_patch_operand_f32": (C.c_int, [_vp, _vp, RowRef, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
     "bsi_attention_force_legacy": (C.c_int, [_i32]),
     "bsi_attention_debug_phases": (C.c_int, [_vp]),
     "bsi_attention_backward_debug_phases": (C.c_int, [_vp]),

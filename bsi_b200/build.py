@@ -12,7 +12,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 OBJ = os.path.join(PKG, "csrc", "_obj")
 LIB = os.path.join(PKG, "libbsi_b200.so")
-SOURCES = ["elementwise.cu", "reduce.cu", "layernorm.cu", "attention.cu", "attention_sm100.cu", "gemm_sm100.cu", "dit_engine.cu", "unet_kernels.cu", "unet_engine.cu", "optim.cu", "wgrad_sm100.cu", "train_kernels.cu", "attention_bwd.cu", "attention_bwd_sm100.cu"]
+SOURCES = ["elementwise.cu", "reduce.cu", "layernorm.cu", "attention.cu", "attention_sm100.cu", "gemm_sm100.cu", "dit_engine.cu", "unet_kernels.cu", "unet_engine.cu", "optim.cu", "wgrad_sm100.cu", "train_kernels.cu", "attention_bwd.cu", "attention_bwd_sm100.cu", "exact_kernels.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
     "-Xcompiler", "-fPIC,-O2", "--expt-relaxed-constexpr",

@@ -40,22 +40,27 @@ struct bsi_dit {
 
 namespace bsi {
 
+// In the fp32-accurate mode (cfg.exact) a matrix row holds three bf16 blocks [hi | hi | lo] of pitch ld each (exact_kernels.cu).
 static void add_slot(bsi_dit* e, const std::string& key, int64_t rows, int64_t cols, bool bf16, int64_t ld = 0) {
     ParamSlot s;
     s.rows = rows, s.cols = cols, s.bf16 = bf16, s.ld = bf16 ? (ld ? ld : cols) : cols;
     s.offset = e->param_bytes;
-    e->param_bytes = align_up(e->param_bytes + rows * s.ld * (bf16 ? 2 : 4), 256);
+    const int64_t terms = (bf16 && e->cfg.exact) ? 3 : 1;
+    e->param_bytes = align_up(e->param_bytes + rows * s.ld * terms * (bf16 ? 2 : 4), 256);
     e->slots[key] = s;
 }
 
 struct Workspace {
     __nv_bfloat16 *a_patch, *xm, *qkv, *att, *h;
     float* x;
+    // fp32-accurate mode: fp32 activations (f_*) and their three-term bf16 splits (s_*)
+    float *f_a, *f_qkv, *f_h;
+    __nv_bfloat16 *s_a, *s_h;
     int64_t bytes;
 };
 static Workspace carve(const bsi_dit* e, int B, uint8_t* base) {
     const int64_t M = (int64_t)B * e->T, d = e->cfg.dim;
-    Workspace w;
+    Workspace w{};
     int64_t off = 0;
     auto take = [&](int64_t bytes) {
         uint8_t* p = base ? base + off : nullptr;
@@ -63,6 +68,16 @@ static Workspace carve(const bsi_dit* e, int B, uint8_t* base) {
         return p;
     };
     w.x = reinterpret_cast<float*>(take(M * d * 4));
+    if (e->cfg.exact) {
+        const int64_t wide = e->ldp > d ? e->ldp : d;
+        w.f_a = reinterpret_cast<float*>(take(M * wide * 4));              // patch operand / LayerNorm output / attention output
+        w.f_qkv = reinterpret_cast<float*>(take(M * 3 * d * 4));
+        w.f_h = reinterpret_cast<float*>(take(M * 4 * d * 4));             // MLP pre-activation
+        w.s_a = reinterpret_cast<__nv_bfloat16*>(take(M * 3 * wide * 2));  // split of f_a
+        w.s_h = reinterpret_cast<__nv_bfloat16*>(take(M * 12 * d * 2));    // split of gelu(f_h)
+        w.bytes = off;
+        return w;
+    }
     w.a_patch = reinterpret_cast<__nv_bfloat16*>(take(M * e->ldp * 2));
     w.xm = reinterpret_cast<__nv_bfloat16*>(take(M * d * 2));
     w.qkv = reinterpret_cast<__nv_bfloat16*>(take(M * 3 * d * 2));
@@ -147,6 +162,8 @@ int64_t bsi_dit_cond_bytes(const bsi_dit* e, int32_t rows) {
 int64_t bsi_dit_cond_scratch_bytes(const bsi_dit* e, int32_t rows) {
     if (!e || rows <= 0) return 0;
     const int64_t d = e->cfg.dim, L = e->cfg.depth;
+    if (e->cfg.exact)  // fp32 embedding, its split, fp32 hidden layer of all blocks, its split
+        return align_up(rows * d * 4, 1024) + align_up(rows * 3 * d * 2, 1024) + align_up(rows * L * d * 4, 1024) + align_up(rows * L * 3 * d * 2, 1024);
     return align_up(rows * d * 2, 1024) + align_up(rows * L * d * 2, 1024);
 }
 
@@ -167,7 +184,10 @@ int bsi_dit_set_param(bsi_dit* e, const char* key, const float* src, int64_t num
     ParamSlot& s = it->second;
     BSI_CHECK_ARG(numel == s.rows * s.cols, "bsi_dit_set_param: '%s' has %lld elements, expected %lld", key, (long long)numel,
                   (long long)(s.rows * s.cols));
-    if (s.bf16) {
+    if (s.bf16 && e->cfg.exact) {
+        int rc = bsi_split3_bf16(e->arena + s.offset, src, s.rows, (int32_t)s.cols, s.cols, (int32_t)s.ld, /*weight layout*/ 1, 0, stream);
+        if (rc != BSI_OK) return rc;
+    } else if (s.bf16) {
         int rc = bsi_cast_bf16(e->arena + s.offset, src, s.rows, s.cols, s.ld, stream);
         if (rc != BSI_OK) return rc;
     } else {
@@ -197,6 +217,31 @@ int bsi_dit_conditioning(const bsi_dit* e, float* cond, const float* t, int32_t 
     }
     const int d = e->cfg.dim, L = e->cfg.depth;
     cudaStream_t st = (cudaStream_t)stream;
+    if (e->cfg.exact) {
+        // same chain with every operand split into three bf16 terms (exact_kernels.cu): fp32-level accuracy from the tensor cores
+        uint8_t* sp = reinterpret_cast<uint8_t*>(scratch);
+        float* c32 = reinterpret_cast<float*>(sp);
+        sp += align_up((int64_t)rows * d * 4, 1024);
+        auto* c3 = reinterpret_cast<__nv_bfloat16*>(sp);
+        sp += align_up((int64_t)rows * 3 * d * 2, 1024);
+        float* h32 = reinterpret_cast<float*>(sp);
+        sp += align_up((int64_t)rows * L * d * 4, 1024);
+        auto* h3 = reinterpret_cast<__nv_bfloat16*>(sp);
+        int rc = bsi_time_embed(nullptr, c32, t, e->ptr<float>("dit.t_embedding.scale"), e->ptr<float>("dit.t_embedding.bias"), rows, d, st);
+        if (rc != BSI_OK) return rc;
+        if ((rc = bsi_split3_bf16(c3, c32, rows, d, d, d, 0, 0, st)) != BSI_OK) return rc;
+        // the first adaLN Linear of all layers is one stacked [L*d][3d] matrix (slots are contiguous: d rows of 3d each per layer)
+        rc = gemm(c3, 3 * d, e->ptr<void>(e->blk(0, "adaLN_modulation.0.weight")), 3 * d, h32, L * d, e->ptr<float>(e->blk(0, "adaLN_modulation.0.bias")), rows,
+                  L * d, 3 * d, BSI_EPI_BIAS_F32, st);
+        if (rc != BSI_OK) return rc;
+        // SiLU + split, viewed as [rows * L][d] -> [rows * L][3d]
+        if ((rc = bsi_split3_bf16(h3, h32, (int64_t)rows * L, d, d, d, 0, /*silu*/ 2, st)) != BSI_OK) return rc;
+        bsi_gemm_args x{};
+        x.batch = L;
+        x.stride_a = 3 * d, x.stride_w = (int64_t)6 * d * 3 * d, x.stride_c = (int64_t)rows * 6 * d, x.stride_bias = 6 * d;
+        return gemm(h3, L * 3 * d, e->ptr<void>(e->blk(0, "adaLN_modulation.2.weight")), 3 * d, cond, 6 * d, e->ptr<float>(e->blk(0, "adaLN_modulation.2.bias")),
+                    rows, 6 * d, 3 * d, BSI_EPI_BIAS_F32, st, &x);
+    }
     auto* c16 = reinterpret_cast<__nv_bfloat16*>(scratch);
     auto* h16 = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<uint8_t*>(scratch) + align_up((int64_t)rows * d * 2, 1024));
     // c = t_embedding(t)                                                   (dit.py:177)
@@ -243,6 +288,53 @@ int bsi_dit_forward(const bsi_dit* e, float* out, const float* mu, bsi_rowref in
 #define BSI_TRY(call) \
     if ((rc = (call)) != BSI_OK) return rc
 
+    if (c.exact) {
+        // ---- fp32-accurate mode: fp32 activations, three-term bf16 splits as GEMM operands (K three times as long), fp32 attention
+        const int P3 = 3 * e->ldp, d3 = 3 * d;
+        BSI_TRY(bsi_dit_patch_operand_f32(w.f_a, mu, in_scale, step_ptr, B, c.channels, c.height, c.width, c.patch, c.fourier_n_min, c.fourier_n_max, e->P, st));
+        BSI_TRY(bsi_split3_bf16(w.s_a, w.f_a, M, e->P, e->P, e->ldp, 0, 0, st));
+        {
+            bsi_gemm_args x{};
+            x.rows_per_sample = T, x.pos = e->ptr<float>("dit.patch_pos_embedding");
+            BSI_TRY(gemm(w.s_a, P3, e->ptr<void>("dit.patch_encoder.weight"), P3, w.x, d, e->ptr<float>("dit.patch_encoder.bias"), M, d, P3, BSI_EPI_POS_F32, st, &x));
+        }
+        for (int l = 0; l < c.depth; ++l) {
+            const float* cl = cond + ((int64_t)l * cond_rows + cond_row0) * 6 * d;
+            auto part = [&](int p) {
+                bsi_rowref r;
+                r.base = cl + (int64_t)p * d, r.sample_stride = cond_sample_rows * 6 * d, r.step_stride = cond_step_rows * 6 * d;
+                return r;
+            };
+            bsi_gemm_args g{};
+            g.rows_per_sample = T, g.step_ptr = step_ptr;
+            BSI_TRY(bsi_layernorm_mod_f32(w.f_a, w.x, part(0), part(1), step_ptr, nullptr, nullptr, T, M, d, 1e-5f, st));
+            BSI_TRY(bsi_split3_bf16(w.s_a, w.f_a, M, d, d, d, 0, 0, st));
+            BSI_TRY(gemm(w.s_a, d3, e->ptr<void>(e->blk(l, "attn.to_qkv.weight")), d3, w.f_qkv, 3 * d, e->ptr<float>(e->blk(l, "attn.to_qkv.bias")), M, 3 * d, d3,
+                         BSI_EPI_BIAS_F32, st));
+            BSI_TRY(bsi_attention_f32(w.f_a, w.f_qkv, B, T, c.heads, d / c.heads, st));
+            BSI_TRY(bsi_split3_bf16(w.s_a, w.f_a, M, d, d, d, 0, 0, st));
+            g.gate = part(2);
+            BSI_TRY(gemm(w.s_a, d3, e->ptr<void>(e->blk(l, "attn.to_out.weight")), d3, w.x, d, e->ptr<float>(e->blk(l, "attn.to_out.bias")), M, d, d3,
+                         BSI_EPI_GATE_RESID_F32, st, &g));
+            BSI_TRY(bsi_layernorm_mod_f32(w.f_a, w.x, part(3), part(4), step_ptr, nullptr, nullptr, T, M, d, 1e-5f, st));
+            BSI_TRY(bsi_split3_bf16(w.s_a, w.f_a, M, d, d, d, 0, 0, st));
+            BSI_TRY(gemm(w.s_a, d3, e->ptr<void>(e->blk(l, "mlp.0.weight")), d3, w.f_h, 4 * d, e->ptr<float>(e->blk(l, "mlp.0.bias")), M, 4 * d, d3, BSI_EPI_BIAS_F32,
+                         st));
+            BSI_TRY(bsi_split3_bf16(w.s_h, w.f_h, M, 4 * d, 4 * d, 4 * d, 0, /*gelu*/ 1, st));
+            g.gate = part(5);
+            BSI_TRY(gemm(w.s_h, 12 * d, e->ptr<void>(e->blk(l, "mlp.2.weight")), 12 * d, w.x, d, e->ptr<float>(e->blk(l, "mlp.2.bias")), M, d, 12 * d,
+                         BSI_EPI_GATE_RESID_F32, st, &g));
+        }
+        bsi_rowref none{};
+        BSI_TRY(bsi_layernorm_mod_f32(w.f_a, w.x, none, none, nullptr, e->ptr<float>("dit.patch_decoder.0.weight"), e->ptr<float>("dit.patch_decoder.0.bias"), T, M, d,
+                                      1e-5f, st));
+        BSI_TRY(bsi_split3_bf16(w.s_a, w.f_a, M, d, d, d, 0, 0, st));
+        bsi_gemm_args x{};
+        x.rows_per_sample = T, x.patch = c.patch, x.grid_w = e->gw, x.channels = c.channels;
+        BSI_TRY(gemm(w.s_a, d3, e->ptr<void>("dit.patch_decoder.1.weight"), d3, out, e->nout, e->ptr<float>("dit.patch_decoder.1.bias"), M, e->nout, d3,
+                     BSI_EPI_UNPATCH_F32, st, &x));
+        return BSI_OK;
+    }
     // patchify + Fourier features + c_in scaling -> bf16 operand; then patch_encoder + positional table
     BSI_TRY(bsi_dit_patch_operand(w.a_patch, mu, in_scale, step_ptr, B, c.channels, c.height, c.width, c.patch, c.fourier_n_min,
                                   c.fourier_n_max, e->ldp, st));

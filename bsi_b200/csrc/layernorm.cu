@@ -8,9 +8,9 @@ namespace bsi {
 
 constexpr int kLnThreads = 256;
 
-template <int NV>  // NV float4 per lane: dim = 128 * NV
+template <int NV, bool F32OUT = false>  // NV float4 per lane: dim = 128 * NV; F32OUT: fp32 output (the fp32-accurate mode, exact_kernels.cu)
 __global__ void __launch_bounds__(kLnThreads, 2)
-    k_layernorm_mod(__nv_bfloat16* __restrict__ out, const float* __restrict__ x, bsi_rowref shift, bsi_rowref scale,
+    k_layernorm_mod(void* __restrict__ out_raw, const float* __restrict__ x, bsi_rowref shift, bsi_rowref scale,
                     const int32_t* __restrict__ step_ptr, const float* __restrict__ gamma, const float* __restrict__ beta,
                     int rows_per_sample, int64_t M, float eps, uint32_t drop_thresh, uint32_t drop_seed, float drop_inv) {
     constexpr int dim = 128 * NV;
@@ -45,7 +45,8 @@ __global__ void __launch_bounds__(kLnThreads, 2)
             p_add = reinterpret_cast<const float4*>(rowref_ptr(shift, sample, step));
         }
         const float one = gamma ? 0.0f : 1.0f;  // modulate uses (1 + scale)
-        uint2* o = reinterpret_cast<uint2*>(out + row * dim);
+        uint2* o = reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(out_raw) + row * dim);
+        float4* o32 = reinterpret_cast<float4*>(reinterpret_cast<float*>(out_raw) + row * dim);
 #pragma unroll
         for (int i = 0; i < NV; ++i) {
             float4 m = p_mul[lane + 32 * i], a = p_add[lane + 32 * i];
@@ -60,7 +61,8 @@ __global__ void __launch_bounds__(kLnThreads, 2)
                 y2 = dropout_keep(drop_seed, e + 2, drop_thresh) ? y2 * drop_inv : 0.0f;
                 y3 = dropout_keep(drop_seed, e + 3, drop_thresh) ? y3 * drop_inv : 0.0f;
             }
-            o[lane + 32 * i] = make_uint2(pack_bf16(y0, y1), pack_bf16(y2, y3));
+            if constexpr (F32OUT) o32[lane + 32 * i] = make_float4(y0, y1, y2, y3);
+            else o[lane + 32 * i] = make_uint2(pack_bf16(y0, y1), pack_bf16(y2, y3));
         }
     }
 }
@@ -71,7 +73,7 @@ using namespace bsi;
 
 static int layernorm_mod_launch(void* out_bf16, const float* x, bsi_rowref shift, bsi_rowref scale, const int32_t* step_ptr, const float* gamma,
                                 const float* beta, int32_t rows_per_sample, int64_t M, int32_t dim, float eps, float drop_p, uint32_t drop_seed,
-                                void* stream) {
+                                void* stream, bool f32_out = false) {
     const uint32_t drop_thresh = dropout_thresh(drop_p);
     const float drop_inv = drop_p > 0.0f ? 1.0f / (1.0f - drop_p) : 1.0f;
     BSI_CHECK_ARG(out_bf16 && x && M > 0, "bsi_layernorm_mod_bf16: null pointer or empty input");
@@ -81,7 +83,7 @@ static int layernorm_mod_launch(void* out_bf16, const float* x, bsi_rowref shift
     int64_t blocks = (M + (kLnThreads / 32) - 1) / (kLnThreads / 32);
     int64_t cap = (int64_t)sm_count() * 8;
     int grid = (int)(blocks < cap ? blocks : cap);
-    auto* o = reinterpret_cast<__nv_bfloat16*>(out_bf16);
+    void* o = out_bf16;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid), cfg.blockDim = dim3(kLnThreads), cfg.dynamicSmemBytes = 0, cfg.stream = (cudaStream_t)stream;
     cudaLaunchAttribute attr[1];
@@ -89,7 +91,10 @@ static int layernorm_mod_launch(void* out_bf16, const float* x, bsi_rowref shift
     cfg.attrs = attr, cfg.numAttrs = use_pdl() ? 1 : 0;
 #define BSI_LN_CASE(NV)                                                                                                         \
     case NV:                                                                                                                    \
-        BSI_CUDA_OK(cudaLaunchKernelEx(&cfg, k_layernorm_mod<NV>, o, x, shift, scale, step_ptr, gamma, beta, rows_per_sample, M, eps, drop_thresh, drop_seed, drop_inv)); \
+        if (f32_out)                                                                                                            \
+            BSI_CUDA_OK(cudaLaunchKernelEx(&cfg, k_layernorm_mod<NV, true>, o, x, shift, scale, step_ptr, gamma, beta, rows_per_sample, M, eps, drop_thresh, drop_seed, drop_inv)); \
+        else                                                                                                                    \
+            BSI_CUDA_OK(cudaLaunchKernelEx(&cfg, k_layernorm_mod<NV, false>, o, x, shift, scale, step_ptr, gamma, beta, rows_per_sample, M, eps, drop_thresh, drop_seed, drop_inv)); \
         break;
     switch (dim / 128) {
         BSI_LN_CASE(1) BSI_LN_CASE(2) BSI_LN_CASE(3) BSI_LN_CASE(4) BSI_LN_CASE(5) BSI_LN_CASE(6) BSI_LN_CASE(7) BSI_LN_CASE(8)
@@ -111,4 +116,10 @@ extern "C" int bsi_layernorm_mod_dropout_bf16(void* out_bf16, const float* x, bs
                                               int32_t dim, float eps, float drop_p, uint32_t drop_seed, void* stream) {
     BSI_CHECK_ARG(drop_p >= 0.0f && drop_p < 1.0f && M * dim < (int64_t)1 << 32, "bsi_layernorm_mod_dropout_bf16: p in [0,1) and M*dim < 2^32 required");
     return layernorm_mod_launch(out_bf16, x, shift, scale, nullptr, nullptr, nullptr, rows_per_sample, M, dim, eps, drop_p, drop_seed, stream);
+}
+
+// fp32 output: the operand of the fp32-accurate mode before it is split into bf16 terms (exact_kernels.cu)
+extern "C" int bsi_layernorm_mod_f32(float* out_f32, const float* x, bsi_rowref shift, bsi_rowref scale, const int32_t* step_ptr, const float* gamma,
+                                     const float* beta, int32_t rows_per_sample, int64_t M, int32_t dim, float eps, void* stream) {
+    return layernorm_mod_launch(out_f32, x, shift, scale, step_ptr, gamma, beta, rows_per_sample, M, dim, eps, 0.0f, 0u, stream, true);
 }

@@ -21,6 +21,7 @@ class NativeDenoiser(nn.Module):
         self._arena = None
         self._packed_sig = None
         self._scratch: dict = {}
+        self._epoch = 0  # bumped whenever the engine or the arena is (re)created: part of the sampler-plan key
 
     def _fn(self, name: str):
         return getattr(L.load(), self._api + name)
@@ -30,7 +31,7 @@ class NativeDenoiser(nn.Module):
         the engine handle, the packed arena, workspaces / CUDA graphs and an attached optimizer sink belong to this instance and
         are rebuilt lazily by the copy's first call."""
         state = self.__dict__.copy()
-        state.update(_engine=None, _arena=None, _packed_sig=None, _scratch={})
+        state.update(_engine=None, _arena=None, _packed_sig=None, _scratch={}, _epoch=0)
         state.pop("_grad_sink", None)
         return state
 
@@ -69,11 +70,13 @@ class NativeDenoiser(nn.Module):
             handle = C.c_void_p()
             L.check(self._fn("create")(C.byref(self._cfg), C.byref(handle)), self._api + "create")
             self._engine = handle
+            self._epoch = getattr(self, "_epoch", 0) + 1
         sig = self._signature()
         if self._arena is None or self._arena.device != device or sig != self._packed_sig:
             nbytes = self._fn("param_bytes")(self._engine)
             if self._arena is None or self._arena.device != device:
                 self._arena = torch.zeros(nbytes + 256, dtype=torch.uint8, device=device)
+                self._epoch = getattr(self, "_epoch", 0) + 1
             base = (self._arena.data_ptr() + 255) // 256 * 256
             st = L.stream_ptr(device)
             L.check(self._fn("bind_params")(self._engine, base, nbytes), self._api + "bind_params")
@@ -178,7 +181,7 @@ class NativeDenoiser(nn.Module):
             ws_bytes = self._fn("workspace_bytes")(eng, n)
             ws = self._buffer("workspace", ws_bytes, dev)
             # a plan is valid for these buffers only (they are re-allocated when a larger request comes along)
-            key = (n, k, precond, dev.index, id(self), self._arena.data_ptr(), cond.data_ptr(), ws.data_ptr())
+            key = (n, k, precond, dev.index, id(self), self._epoch, self._arena.data_ptr(), cond.data_ptr(), ws.data_ptr())
             plan = plans.get(key) if plans is not None else None
             if plan is None:
                 plan = {

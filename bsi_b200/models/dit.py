@@ -81,8 +81,27 @@ class DenoisingDiT(NativeDenoiser):
         self.dit = _DiTParams(self.data_shape[1:], patch_size, in_channels, channels, dim, depth, heads, 4, dropout)
         self._cfg = L.DitConfig(channels, self.data_shape[1], self.data_shape[2], patch_size, dim, depth, heads,
                                 fourier_features.n_min if fourier_features is not None else 0,
-                                fourier_features.n_max if fourier_features is not None else -1)
+                                fourier_features.n_max if fourier_features is not None else -1, 0)
         self._init_native()
+
+    # ---- evaluation precision (extension; the reference evaluates in fp32, bsi/lightning/plugins.py:7-24) ----------------------
+    @property
+    def precision(self) -> str:
+        """"bf16" (default): bf16 tensor-core operands, fp32 accumulation and residual stream.  "fp32": every GEMM operand is split
+        into three bf16 terms and attention runs in fp32 (csrc/exact_kernels.cu) -- fp32-level agreement with the reference
+        (the 1e-5 tier of the trajectory test) at 3-5x the cost.  Inference only; training always uses the bf16 path."""
+        return "fp32" if self._cfg.exact else "bf16"
+
+    def set_precision(self, precision: str) -> "DenoisingDiT":
+        if precision not in ("bf16", "fp32"):
+            raise ValueError(f"precision must be 'bf16' or 'fp32', got {precision!r}")
+        exact = 1 if precision == "fp32" else 0
+        if exact != self._cfg.exact:
+            self._cfg.exact = exact
+            if self._engine:  # arena layout and workspaces differ: rebuild everything on the next call
+                self._fn("destroy")(self._engine)
+            self._engine, self._arena, self._packed_sig, self._scratch = None, None, None, {}
+        return self
 
     def forward_scaled(self, mu: Tensor, t: Tensor, in_scale: Tensor | None) -> Tensor:
         """Inference: the fused engine.  Under autograd with trainable parameters: the differentiable path of

@@ -212,6 +212,19 @@ int bsi_layernorm_mod_bf16(void* out_bf16, const float* x, bsi_rowref shift, bsi
                            const float* gamma, const float* beta, int32_t rows_per_sample, int64_t M, int32_t dim, float eps,
                            void* stream);
 
+/* Building blocks of the fp32-accurate mode (csrc/exact_kernels.cu).
+ * split3: fp32 [rows][cols] (pitch ld_in) -> bf16 [rows][3*block_pitch], x = hi + lo: activation layout [hi | lo | hi] (weight_layout 0) or
+ * weight layout [hi | hi | lo] (1), so that one bf16 GEMM over K = 3*block_pitch forms hi*hi + lo*hi + hi*lo; act: 0 none, 1 GELU-tanh, 2 SiLU
+ * applied before the split.  attention_f32: softmax(Q K^T / sqrt(64)) V on packed fp32 QKV [B*T][3*dim] -> fp32 [B*T][dim] (dit.py:36-47).
+ * layernorm_mod_f32 / patch_operand_f32: fp32-output variants of the operand builders (reference-exact angle arithmetic). */
+int bsi_split3_bf16(void* out_bf16, const float* in, int64_t rows, int32_t cols, int64_t ld_in, int32_t block_pitch, int32_t weight_layout, int32_t act,
+                    void* stream);
+int bsi_attention_f32(float* out, const float* qkv, int32_t B, int32_t T, int32_t heads, int32_t head_dim, void* stream);
+int bsi_layernorm_mod_f32(float* out_f32, const float* x, bsi_rowref shift, bsi_rowref scale, const int32_t* step_ptr, const float* gamma,
+                          const float* beta, int32_t rows_per_sample, int64_t M, int32_t dim, float eps, void* stream);
+int bsi_dit_patch_operand_f32(float* A, const float* mu, bsi_rowref scale, const int32_t* step_ptr, int32_t B, int32_t C, int32_t H, int32_t Wd, int32_t patch,
+                              int32_t n_min, int32_t n_max, int32_t lda, void* stream);
+
 /* Multi-head attention over packed QKV (dit.py:36-47): qkv bf16 [B*T][3*dim] with columns
  * (qkv, head, channel); out bf16 [B*T][dim] with columns (head, channel).  head_dim = 64. */
 int bsi_attention_bf16(void* out_bf16, const void* qkv_bf16, int32_t B, int32_t T, int32_t heads, int32_t head_dim, void* stream);
@@ -265,6 +278,8 @@ typedef struct bsi_dit_config {
     int32_t channels, height, width; /* data_shape */
     int32_t patch, dim, depth, heads;
     int32_t fourier_n_min, fourier_n_max; /* n_max < n_min: no Fourier features */
+    int32_t exact; /* 1: fp32-accurate mode -- every GEMM operand split into three bf16 terms, fp32 attention (reference eval precision,
+                    * bsi/lightning/plugins.py:7-24); 3-5x slower than the bf16 engine.  0: bf16 tensor-core operands */
 } bsi_dit_config;
 
 typedef struct bsi_dit bsi_dit;

@@ -33,7 +33,7 @@ def test_ctypes_binding_covers_header():
 
 def test_structs_match_header_layout():
     assert ctypes.sizeof(L.RowRef) == 16 and ctypes.sizeof(L.Noise) == 40 and L.Noise.key_ptr.offset == 32
-    assert ctypes.sizeof(L.DitConfig) == 36
+    assert ctypes.sizeof(L.DitConfig) == 40
     assert L.GemmArgs.gate.offset % 8 == 0 and ctypes.sizeof(L.GemmArgs) % 8 == 0
 
 

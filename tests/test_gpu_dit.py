@@ -309,3 +309,84 @@ def test_forward_rejects_mismatched_time_rows():
         full = m(mu, torch.full((3,), 0.4, device=dev()))
         sync()
     assert torch.equal(one, full)
+
+
+def test_fp32_accurate_mode_meets_the_fp32_tier():
+    """precision="fp32" (three-term bf16 split GEMMs + fp32 attention, csrc/exact_kernels.cu): the native DiT agrees with the fp32
+    reference at the 1e-5 tier of north_star -- forward, teacher-forced mu' trajectory and bits-per-dim -- and switching back restores
+    the bf16 engine."""
+    bsi, m, sd, spec = make_bsi()
+    g = H.load_golden("dit.pt")
+    mu = 1.5 * H.det_uniform("dit.small64.mu", (2, *spec.data_shape))
+    t = torch.tensor([0.3, 0.9])
+    with torch.inference_mode():
+        y16 = m(mu.to(dev()), t.to(dev())).cpu()
+        assert m.precision == "bf16"
+        m.set_precision("fp32")
+        y32 = m(mu.to(dev()), t.to(dev())).cpu()
+    ref = g["small64"]["y"]
+    rel16, rel32 = float((y16 - ref).norm() / ref.norm()), float((y32 - ref).norm() / ref.norm())
+    assert rel32 < 1e-5 and rel32 < rel16 / 50, f"fp32-accurate forward: relative L2 {rel32} (bf16 engine {rel16})"
+    # teacher-forced trajectory (bsi/bsi.py:331-335) at the fp32 tier
+    tr = g["bsi_small64"]["traj"]
+    tt = torch.linspace(0.0, 1.0, 17)
+    k, lam_d, coef, c_in, t_rows = bsi._step_table(bsi.default_schedule)
+    from bsi_b200 import _lib as L
+
+    with torch.inference_mode():
+        for j, i in enumerate(tr["steps"].tolist()):
+            mu_i = tr["mu"][j].to(dev())
+            x_hat = bsi._predict_x(mu_i, tt[i].expand(2).to(dev()))
+            report(f"fp32 mode: x_hat at step {i}", x_hat, tr["x_hat"][j], 1e-5, 2e-5 * float(tr["x_hat"][j].abs().max()))
+            f = m.forward_scaled(mu_i, tt[i].expand(2).to(dev()), c_in[i].expand(2))
+            mu_next = mu_i.clone()
+            eps_d = tr["eps"][j].to(dev())
+            L.check(L.load().bsi_step_fused(L.ptr(mu_next), L.ptr(f), L.ptr(coef), None, i, 1, L.noise(eps=eps_d), None, None, 2, 12288, L.stream_ptr()))
+            sync()
+            rel = float((mu_next.cpu() - tr["mu_next"][j]).abs().max() / tr["mu_next"][j].abs().max())
+            assert rel < 1e-5, f"fp32 mode: mu' at step {i}: relative error {rel} (fp32 tier tolerance 1e-5)"
+        # sampler graph and ELBO run in this mode as well
+        bsi.noise_source = "philox"
+        s = bsi.sample(2, seed=3)
+        assert torch.isfinite(s).all()
+        m.set_precision("bf16")
+        y16b = m(mu.to(dev()), t.to(dev())).cpu()
+    assert torch.equal(y16, y16b)
+    with pytest.raises(ValueError):
+        m.set_precision("fp16")
+
+
+def test_fp32_mode_building_blocks():
+    """split3: x = hi + lo to 2^-16; fp32 attention vs torch; one split GEMM vs an fp32 matmul."""
+    from bsi_b200 import _lib as L
+    import ctypes
+
+    x = (H.det_uniform("sp.x", (300, 200)) * 3).to(dev())
+    out = torch.full((300, 3 * 208), 7.0, dtype=torch.bfloat16, device=dev())
+    L.check(L.load().bsi_split3_bf16(L.ptr(out), L.ptr(x), 300, 200, 200, 208, 0, 0, L.stream_ptr()))
+    w = (H.det_uniform("sp.w", (64, 200)) / 14).to(dev())
+    wo = torch.zeros((64, 3 * 208), dtype=torch.bfloat16, device=dev())
+    L.check(L.load().bsi_split3_bf16(L.ptr(wo), L.ptr(w), 64, 200, 200, 208, 1, 0, L.stream_ptr()))
+    sync()
+    o = out.float().reshape(300, 3, 208)
+    assert torch.equal(o[:, 0], o[:, 2]) and float(o[:, :, 200:].abs().max()) == 0.0
+    assert float(((o[:, 0, :200] + o[:, 1, :200]) - x).abs().max()) < 3 * 2.0**-16
+    y = torch.full((300, 64), float("nan"), device=dev())
+    a = L.GemmArgs()
+    a.A, a.W, a.C, a.bias = L.ptr(out), L.ptr(wo), L.ptr(y), None
+    a.M, a.N, a.K, a.lda, a.ldw, a.ldc, a.batch = 300, 64, 624, 624, 624, 64, 1
+    a.epilogue, a.gate, a.rows_per_sample = L.EPI_BIAS_F32, L.RowRef(None, 0, 0), 0
+    L.check(L.load().bsi_gemm_bf16(ctypes.byref(a), L.stream_ptr()))
+    sync()
+    ref = x.double() @ w.double().T
+    # hi + lo carries 16 mantissa bits per operand element (2^-17 relative): a K = 200 product agrees to ~5e-6 of the output range,
+    # 500x closer than a plain bf16 GEMM (4e-3)
+    assert float((y.double() - ref).abs().max() / ref.abs().max()) < 1.5e-5
+    B, T, heads = 2, 256, 2
+    qkv = (H.det_uniform("sp.qkv", (B * T, 3 * heads * 64)) * 2).to(dev())
+    att = torch.empty((B * T, heads * 64), device=dev())
+    L.check(L.load().bsi_attention_f32(L.ptr(att), L.ptr(qkv), B, T, heads, 64, L.stream_ptr()))
+    sync()
+    q, k, v = qkv.double().reshape(B, T, 3, heads, 64).permute(2, 0, 3, 1, 4)
+    ref = (torch.softmax(q @ k.transpose(-1, -2) / 8.0, dim=-1) @ v).permute(0, 2, 1, 3).reshape(B * T, heads * 64)
+    report("fp32 attention", att, ref.float(), 1e-5, 2e-6)

@@ -161,3 +161,29 @@ def test_unet_32_levels_forward_and_elbo_vs_fp32_reference(golden):
     assert rel < 5e-3, f"U-Net x32 forward: relative L2 {rel} vs the fp32 reference"
     bsi = BSI(m, data_shape=USPEC.data_shape, k=256, discretization=Discretization.image_8bit(), **HYPER).to(dev())
     _elbo_parity(bsi, H.det_images("full.unet.x", 4, USPEC.data_shape, seed=2), golden["elbo_unet32"], "unet32_elbo")
+
+
+def test_dit_l4_depth24_fp32_accurate_mode(dit64, golden):
+    """The fp32-accurate mode at the real depth: forward and bits-per-dim against the fp32 reference (what the bf16 engine reaches to
+    1.9e-3 / 6e-4, this mode reaches to ~1e-5)."""
+    mu = 1.5 * H.det_uniform("full.dit64.mu", (2, *SPEC64.data_shape))
+    try:
+        dit64.set_precision("fp32")
+        with torch.inference_mode():
+            y = dit64(mu.to(dev()), torch.tensor([0.3, 0.9], device=dev()))
+            sync()
+        rel = _rel_l2(y, golden["dit64"]["y"])
+        _log(test="dit64_forward_fp32_mode", rel_l2=rel)
+        assert rel < 2e-5, f"fp32-accurate DiT-L/4 x24 forward: relative L2 {rel}"
+        bsi = BSI(dit64, data_shape=SPEC64.data_shape, k=256, discretization=Discretization.image_8bit(), **HYPER).to(dev())
+        g = golden["elbo64"]
+        replay = ReplayNoise([g["eps_r"], g["offset"], g["perm"], g["eps_m"]])
+        with torch.inference_mode():
+            e, b, ex = bsi.elbo(H.det_images("full.x", 4, SPEC64.data_shape, seed=2).to(dev()), 1, 2, replay)
+            sync()
+        dbpd = float((b.cpu() - g["bpd"]).abs().max())
+        _log(test="dit64_elbo_fp32_mode", bpd=b.cpu().tolist(), dbpd_max=dbpd,
+             l_measure_rel=float(((ex["l_measure"].cpu() - g["l_measure"]).abs() / g["l_measure"].abs()).max()))
+        assert dbpd < 1e-4, f"fp32-accurate mode: bits-per-dim deviate by {dbpd}"
+    finally:
+        dit64.set_precision("bf16")
