@@ -60,6 +60,9 @@ void fill_pdl_attr(cudaLaunchAttribute* attr);
             BSI_CUDA_OK(cudaFuncGetAttributes(&_fa, kernel));                                                     \
             const int _want = (int)(bytes) > _fa.maxDynamicSharedSizeBytes ? (int)(bytes) : _fa.maxDynamicSharedSizeBytes; \
             BSI_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, _want));        \
+            /* every kernel that opts in to large shared memory asks for the same (maximal) L1/shared split: a kernel with a moderate   \
+             * request after a 227 KB one otherwise makes the SMs reconfigure their carve-out (58 us idle per occurrence, r02 timeline) */ \
+            cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);   \
             _done[_dev] = (bytes);                                                                                \
         }                                                                                                         \
     } while (0)
