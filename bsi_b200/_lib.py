@@ -89,6 +89,7 @@ SIGNATURES = {
     "bsi_gate_residual": (C.c_int, [_vp, _vp, _vp, RowRef, _i32, _i64, _i32, _vp]),
     "bsi_gate_residual_layernorm_bf16": (C.c_int, [_vp, _vp, _vp, _vp, RowRef, RowRef, RowRef, _vp, _vp, _i32, _i64, _i32, _f32, _f32, C.c_uint32, _vp]),
     "bsi_gate_residual_backward": (C.c_int, [_vp, _vp, _vp, _vp, _vp, RowRef, _i32, _i32, _i32, _vp]),
+    "bsi_gate_residual_backward_rows": (C.c_int, [_vp, _vp, _vp, _vp, _vp, RowRef, _i32, _i32, _i64, _i32, _vp]),
     "bsi_cast_transpose_bf16": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp]),
     "bsi_colsum_bf16": (C.c_int, [_vp, _vp, _i64, _i32, _i64, _i32, _vp]),
     "bsi_gelu_bf16": (C.c_int, [_vp, _vp, _i64, _vp]),

@@ -359,7 +359,9 @@ __global__ void __launch_bounds__(att2::kThreads, 2)
             constexpr uint32_t idesc_s = ptx::umma_idesc_bf16(QB, T);
             constexpr uint32_t idesc_o = ptx::umma_idesc_bf16(QB, HD, 0, 1);
             const uint64_t dq = ptx::umma_desc_k_sw128(ptx::smem_u32(sQ)), dk = ptx::umma_desc_k_sw128(ptx::smem_u32(sK));
-            const uint32_t v0 = ptx::smem_u32(sV);
+            // the V descriptor of k-step k is this base + k * (2048 >> 4) in its address field: one add per MMA on the issuing thread
+            // (a 128 x 64 x 16 MMA occupies the tensor pipe for ~51 clk, tools/mma_probe.cu; the issue path must stay below that)
+            const uint64_t dv0 = ptx::umma_desc_mn_sw128(ptx::smem_u32(sV), 8192, 1024);
             if ((int)blockIdx.x < total_items) {
                 load_qk(blockIdx.x);
                 load_v(blockIdx.x);
@@ -394,13 +396,13 @@ __global__ void __launch_bounds__(att2::kThreads, 2)
                 ctick(2);  // waiting for the first half of P
 #pragma unroll
                 for (int k = 0; k < 8; ++k)
-                    ptx::umma_bf16_ts(tmem + kOCol, tmem + 8 * k, ptx::umma_desc_mn_sw128(v0 + k * 2048, 8192, 1024), idesc_o, k != 0 ? 1u : 0u);
+                    ptx::umma_bf16_ts(tmem + kOCol, tmem + 8 * k, dv0 + k * 128, idesc_o, k != 0 ? 1u : 0u);
                 bwait(bar_p1, ph);
                 ptx::tc_fence_after();
                 ctick(3);  // first P V half issued; waiting for the second half of P
 #pragma unroll
                 for (int k = 8; k < 16; ++k)
-                    ptx::umma_bf16_ts(tmem + kOCol, tmem + 128 + 8 * (k - 8), ptx::umma_desc_mn_sw128(v0 + k * 2048, 8192, 1024), idesc_o, 1u);
+                    ptx::umma_bf16_ts(tmem + kOCol, tmem + 128 + 8 * (k - 8), dv0 + k * 128, idesc_o, 1u);
                 ptx::umma_commit<1>(bar_o);
                 bwait(bar_o, ph);
                 ctick(4);  // second P V half issue -> completion

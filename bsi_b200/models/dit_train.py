@@ -101,11 +101,13 @@ def _ln_mod(x: Tensor, shift: L.RowRef | None, scale: L.RowRef | None, T: int, g
 
 
 def _ln_mod_backward(dx_io: Tensor, da: Tensor, x: Tensor, scale: L.RowRef | None, T: int, gamma: Tensor | None = None,
-                     drop: tuple[float, int] = (0.0, 0)):
-    """dx_io += dL/dx; returns the per-CTA partial sums [2 (dscale, dshift)][M / 32][D]."""
+                     drop: tuple[float, int] = (0.0, 0), shift_first: bool = False):
+    """dx_io += dL/dx; returns the per-CTA partial sums [2 (dscale, dshift)][M / 32][D] -- (dshift, dscale), the order of the
+    modulation vector's chunks, with ``shift_first``."""
     M, D = x.shape
     parts = torch.empty((2, (M + _LN_ROWS_PER_CTA - 1) // _LN_ROWS_PER_CTA, D), dtype=torch.float32, device=x.device)
-    L.check(L.load().bsi_layernorm_mod_backward(dx_io.data_ptr(), parts[0].data_ptr(), parts[1].data_ptr(), da.data_ptr(), x.data_ptr(),
+    i_scale, i_shift = (1, 0) if shift_first else (0, 1)
+    L.check(L.load().bsi_layernorm_mod_backward(dx_io.data_ptr(), parts[i_scale].data_ptr(), parts[i_shift].data_ptr(), da.data_ptr(), x.data_ptr(),
                                                 scale or L.RowRef(None, 0, 0), L.ptr(gamma), T, _LN_ROWS_PER_CTA, M, D, 1e-5, drop[0], drop[1],
                                                 _st(x.device)),
             "bsi_layernorm_mod_backward")
@@ -234,7 +236,8 @@ class DiTTrainFunction(torch.autograd.Function):
             L.check(lib.bsi_colsum_bf16(parts.data_ptr(), t.data_ptr(), t.shape[0], t.shape[1], t.stride(0), 256, _st(dev)), "bsi_colsum_bf16")
             return parts.sum(0)
 
-        zeros = lambda n: torch.zeros(n, dtype=torch.float32, device=dev)
+        zero_bias = torch.zeros(4 * D, dtype=torch.float32, device=dev)  # the data-gradient GEMMs have no bias: one shared zero vector
+        zeros = lambda n: zero_bias[:n]
         grads: list[Tensor] = []
         sink = getattr(model, "_grad_sink", None)
 
@@ -274,22 +277,36 @@ class DiTTrainFunction(torch.autograd.Function):
             tail = [emit_b(ln_g, dgb[0]), emit_b(ln_b, dgb[1]), g_wdec, g_bdec]
             if sink is not None:
                 sink.grads_ready([ln_g, ln_b, w_dec, b_dec])
-            dmods = torch.empty_like(mods)
+            # d(mods) is collected chunk by chunk, [layer][chunk (shift, scale, gate) x (msa, mlp)][B][D]: the kernels and the partial-sum
+            # reductions write their [B][D] results in place, one permuting copy at the end builds [layer][B][6 D]
+            dparts = torch.empty((depth, 6, B, D), dtype=torch.float32, device=dev)
             block_grads = []
+            rows_ok = T % _LN_ROWS_PER_CTA == 0 and D % 128 == 0 and D <= 1024
+
+            def gate_backward(dbr: Tensor, dgate_out: Tensor, br: Tensor, gate) -> Tensor:
+                """dbr = gate * dx, dgate_out[B][D] = sum_t dx * br; returns partial column sums of dbr (their sum over dim 0 is the bias gradient)."""
+                if not rows_ok:
+                    dbias = torch.empty((B, D), dtype=torch.float32, device=dev)
+                    L.check(lib.bsi_gate_residual_backward(dbr.data_ptr(), dgate_out.data_ptr(), dbias.data_ptr(), dx.data_ptr(), br.data_ptr(), gate, T, B, D,
+                                                           _st(dev)), "bsi_gate_residual_backward")
+                    return dbias
+                parts = torch.empty((2, M // _LN_ROWS_PER_CTA, D), dtype=torch.float32, device=dev)
+                L.check(lib.bsi_gate_residual_backward_rows(dbr.data_ptr(), parts[0].data_ptr(), parts[1].data_ptr(), dx.data_ptr(), br.data_ptr(), gate, T,
+                                                            _LN_ROWS_PER_CTA, M, D, _st(dev)), "bsi_gate_residual_backward_rows")
+                torch.sum(parts[0].view(B, T // _LN_ROWS_PER_CTA, D), 1, out=dgate_out)
+                return parts[1]
+
             for l in reversed(range(depth)):
                 w_qkv, b_qkv, w_o, b_o, w_1, b_1, w_2, b_2 = blocks[l]
                 x_in, a1, qkv, att, br1, x_mid, a2, pre, h, br2, lse = saved[l]
                 wt_qkv, wt_o, wt_1, wt_2 = wt_blocks[l]
-                m, dm = mods[l], dmods[l]
+                m, dm = mods[l], dparts[l]
                 ref = lambda j: L.rowref(m, 6 * D, 0, j * D)
-                part = lambda t: t.reshape(2, B, T // _LN_ROWS_PER_CTA, D).sum(2)  # per-sample (dscale, dshift) from the CTA partials
+                # per-sample (dshift, dscale) from the CTA partials, written into chunks [j, j + 2) of d(mods)
+                part = lambda t, j: torch.sum(t.view(2, B, T // _LN_ROWS_PER_CTA, D), 2, out=dm[j : j + 2])
                 # ---- MLP branch: x_out = x_mid + gate_mlp * (gelu(a2 W1^T + b1) W2^T + b2)
                 dbr = torch.empty((M, D), dtype=torch.bfloat16, device=dev)
-                dgate = torch.empty((B, D), dtype=torch.float32, device=dev)
-                dbias = torch.empty((B, D), dtype=torch.float32, device=dev)
-                L.check(lib.bsi_gate_residual_backward(dbr.data_ptr(), dgate.data_ptr(), dbias.data_ptr(), dx.data_ptr(), br2.data_ptr(), ref(5), T, B, D,
-                                                       _st(dev)), "bsi_gate_residual_backward")
-                dm[:, 5 * D :] = dgate
+                dbias = gate_backward(dbr, dm[5], br2, ref(5))
                 g_w2, g_b2 = emit_w(w_2, dbr, h), emit_b(b_2, dbias.sum(0))
                 dh = torch.empty((M, 4 * D), dtype=torch.bfloat16, device=dev)
                 if _FUSED_GELU and M > 128:  # d(pre) = (dbr W2) * gelu'(pre): the derivative is applied in the data-gradient GEMM's epilogue
@@ -299,20 +316,16 @@ class DiTTrainFunction(torch.autograd.Function):
                     L.check(lib.bsi_gelu_backward_bf16(dh.data_ptr(), dh.data_ptr(), pre.data_ptr(), dh.numel(), _st(dev)), "bsi_gelu_backward_bf16")
                 g_w1, g_b1 = emit_w(w_1, dh, a2), emit_b(b_1, colsum(dh))
                 _gemm(dh, wt_1, da, zeros(D), L.EPI_BIAS_BF16)
-                dsc, dsh = part(_ln_mod_backward(dx, da, x_mid, ref(4), T, drop=(drop_p, _layer_seed(drop_seed, 2 * l + 1))))
-                dm[:, 3 * D : 4 * D], dm[:, 4 * D : 5 * D] = dsh, dsc
+                part(_ln_mod_backward(dx, da, x_mid, ref(4), T, drop=(drop_p, _layer_seed(drop_seed, 2 * l + 1)), shift_first=True), 3)
                 # ---- attention branch: x_mid = x_in + gate_msa * (attn(a1 Wqkv^T + b) Wo^T + b)
-                L.check(lib.bsi_gate_residual_backward(dbr.data_ptr(), dgate.data_ptr(), dbias.data_ptr(), dx.data_ptr(), br1.data_ptr(), ref(2), T, B, D,
-                                                       _st(dev)), "bsi_gate_residual_backward")
-                dm[:, 2 * D : 3 * D] = dgate
+                dbias = gate_backward(dbr, dm[2], br1, ref(2))
                 g_wo, g_bo = emit_w(w_o, dbr, att), emit_b(b_o, dbias.sum(0))
                 datt = torch.empty((M, D), dtype=torch.bfloat16, device=dev)
                 _gemm(dbr, wt_o, datt, zeros(D), L.EPI_BIAS_BF16)
                 dqkv = _attention_backward(qkv, att, datt, B, T, heads, D // heads, (drop_p, _layer_seed(drop_seed, 2 * l)), lse)
                 g_wqkv, g_bqkv = emit_w(w_qkv, dqkv, a1), emit_b(b_qkv, colsum(dqkv))
                 _gemm(dqkv, wt_qkv, da, zeros(D), L.EPI_BIAS_BF16)
-                dsc, dsh = part(_ln_mod_backward(dx, da, x_in, ref(1), T))
-                dm[:, :D], dm[:, D : 2 * D] = dsh, dsc
+                part(_ln_mod_backward(dx, da, x_in, ref(1), T, shift_first=True), 0)
                 block_grads.append([g_wqkv, g_bqkv, g_wo, g_bo, g_w1, g_b1, g_w2, g_b2])
                 if sink is not None:  # this block's eight tensors are final: their all-reduce can overlap the remaining layers
                     sink.grads_ready([w_qkv, b_qkv, w_o, b_o, w_1, b_1, w_2, b_2])
@@ -324,7 +337,8 @@ class DiTTrainFunction(torch.autograd.Function):
             for bg in reversed(block_grads):
                 grads += bg
             grads += tail
-        return (None, None, None, None, dmods.to(ctx.mods_dtype), *grads)
+            dmods = dparts.permute(0, 2, 1, 3).reshape(depth, B, 6 * D).to(ctx.mods_dtype)
+        return (None, None, None, None, dmods, *grads)
 
 
 def _attention_backward(qkv: Tensor, att: Tensor, datt: Tensor, B: int, T: int, heads: int, hd: int, drop: tuple[float, int] = (0.0, 0),

@@ -383,6 +383,11 @@ int bsi_gate_residual_layernorm_bf16(void* out_bf16, float* x_out, const float* 
 /* dbranch = gate * dx (bf16);  dgate[b][d] = sum_t dx[b,t,d] * branch[b,t,d];  dbias_part[b][d] = sum_t dbranch[b,t,d]  (either may be NULL) */
 int bsi_gate_residual_backward(void* dbranch_bf16, float* dgate, float* dbias_part, const float* dx, const void* branch_bf16, bsi_rowref gate,
                                int32_t rows_per_sample, int32_t B, int32_t D, void* stream);
+/* The same with per-CTA partial sums (row-pipelined kernel, D a multiple of 128 up to 1024): a CTA owns rows_per_cta consecutive rows of one sample
+ * (rows_per_cta divides rows_per_sample) and writes row blockIdx of dgate_part / dbias_part, both [ceil(M / rows_per_cta)][D]; the caller adds the
+ * partial rows of a sample (dgate) or all of them (bias gradient of the branch's last Linear). */
+int bsi_gate_residual_backward_rows(void* dbranch_bf16, float* dgate_part, float* dbias_part, const float* dx, const void* branch_bf16, bsi_rowref gate,
+                                    int32_t rows_per_sample, int32_t rows_per_cta, int64_t M, int32_t D, void* stream);
 /* fp32 [rows][cols] -> bf16 copy out[rows][ld_out] and bf16 transposed copy out_t[cols][ld_t] in one pass (either may be NULL;
  * padding beyond cols / rows is left untouched: allocate it zeroed).  The transposed weight is the operand of dX = dY W. */
 int bsi_cast_transpose_bf16(void* out_bf16, void* out_t_bf16, const float* in, int32_t rows, int32_t cols, int32_t ld_out, int32_t ld_t, void* stream);

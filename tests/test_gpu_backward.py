@@ -86,6 +86,15 @@ def test_gate_residual_forward_backward_vs_autograd():
     report("dbranch", dbr, brf.grad, 1e-2, 1e-3)
     report("dgate", dgate, g.grad, 1e-4, 1e-4)
     report("bias gradient of the branch", dbias.sum(0), dbr.float().sum(0), 1e-5, 1e-4)
+    # the row-pipelined kernel (per-CTA partial sums over 32 consecutive rows): same dbranch bit for bit, same sums
+    dbr2 = torch.zeros_like(dbr)
+    parts = torch.zeros((2, M // 32, D), device=dev())
+    call("bsi_gate_residual_backward_rows", L.ptr(dbr2), L.ptr(parts[0]), L.ptr(parts[1]), L.ptr(dx), L.ptr(br), gate, T, 32, M, D, L.stream_ptr())
+    sync()
+    assert torch.equal(dbr2, dbr)
+    report("dgate from row partials", parts[0].view(B, T // 32, D).sum(1), g.grad, 1e-4, 1e-4)
+    report("bias gradient from row partials", parts[1].sum(0), dbr.float().sum(0), 1e-5, 1e-4)
+    assert L.load().bsi_gate_residual_backward_rows(L.ptr(dbr2), L.ptr(parts[0]), L.ptr(parts[1]), L.ptr(dx), L.ptr(br), gate, T, 48, M, D, L.stream_ptr()) != 0
 
 
 def test_colsum_bf16():

@@ -76,3 +76,10 @@ for g, a, b in gaps:
 print("largest idle totals by (kernel before -> kernel after):")
 for (a, b), (n, t) in sorted(by.items(), key=lambda kv: -kv[1][1])[:25]:
     print(f"  {a:44s} -> {b:44s} n={n:4d} total={t / 1e3:7.3f} ms avg={t / n:7.1f} us")
+per = collections.defaultdict(lambda: [0, 0.0])
+for e in ev:
+    per[short(e["name"])][0] += 1
+    per[short(e["name"])][1] += e["dur"]
+print("device time per kernel:")
+for name, (n, t) in sorted(per.items(), key=lambda kv: -kv[1][1])[:28]:
+    print(f"  {name:44s} n={n:4d} total={t / 1e3:8.3f} ms avg={t / n:8.1f} us")
