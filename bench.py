@@ -185,15 +185,16 @@ def run_reference(a):
 
 # ------------------------------------------------------------------------------------------ native arm: side measurements
 def _time_ms(fn, warmup: int, iters: int, flush=None) -> float:
-    """Mean device time of fn() [ms] from CUDA events on the current stream; `flush` (a tensor larger than L2) is rewritten
-    before every timed call so the kernel starts with a cold L2, as it does behind a denoiser forward."""
+    """Mean device time of fn() [ms] from CUDA events on the current stream; `flush` (a tensor larger than L2) is READ before every
+    timed call so the kernel starts with none of its inputs in L2, as it does behind a denoiser forward.  (Round 2 first rewrote the
+    buffer instead: that leaves 126 MB of dirty lines which the timed kernel has to write back -- 8-15 % of a 250 MB kernel's time.)"""
     for _ in range(warmup):
         fn()
     torch.cuda.synchronize()
     total = 0.0
     for _ in range(iters):
         if flush is not None:
-            flush.add_(1.0)
+            flush.sum()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         fn()
@@ -548,7 +549,7 @@ def run_native(a):
             B = a.batch
             el_flops = (1 + 10) * B * (a.cfg["flops"] + 0.352e9) * a.depth / a.cfg["depth"]
             tr_flops = side["gb"] * 3 * (a.cfg["flops"] + 0.352e9) * a.depth / a.cfg["depth"]
-            line["roofline_hbm"] = {"peak_gbs": peak_hbm, "l2": "flushed before every launch", "kernels": side["hbm"]}
+            line["roofline_hbm"] = {"peak_gbs": peak_hbm, "l2": "evicted before every launch (a 384 MB buffer is read: clean lines, no write-backs inside the timed kernel)", "kernels": side["hbm"]}
             line["elbo"] = {
                 "workload": f"{a.config} elbo(x[{B}], n_recon=1, n_measure=10), data points sharded x{world} (strong scaling, final all_gather)",
                 "value": B / el_ms * 1e3, "unit": "data points/s", "ms_per_call": el_ms, "tflops_per_gpu": el_flops / el_ms / 1e9 / world,

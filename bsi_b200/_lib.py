@@ -66,6 +66,11 @@ class UnetConfig(C.Structure):
     ]  # fmt: skip
 
 
+class ReduceJob(C.Structure):
+    _fields_ = [("src", C.c_void_p), ("dst", C.c_void_p), ("groups", C.c_int32), ("rows", C.c_int32), ("D", C.c_int32), ("dst_ld", C.c_int32),
+                ("accumulate", C.c_int32), ("reserved", C.c_int32)]  # fmt: skip
+
+
 class AdamWArgs(C.Structure):
     _fields_ = [
         ("param", C.c_void_p), ("grad", C.c_void_p), ("exp_avg", C.c_void_p), ("exp_avg_sq", C.c_void_p), ("ema", C.c_void_p),
@@ -90,6 +95,7 @@ SIGNATURES = {
     "bsi_gate_residual_layernorm_bf16": (C.c_int, [_vp, _vp, _vp, _vp, RowRef, RowRef, RowRef, _vp, _vp, _i32, _i64, _i32, _f32, _f32, C.c_uint32, _vp]),
     "bsi_gate_residual_backward": (C.c_int, [_vp, _vp, _vp, _vp, _vp, RowRef, _i32, _i32, _i32, _vp]),
     "bsi_gate_residual_backward_rows": (C.c_int, [_vp, _vp, _vp, _vp, _vp, RowRef, _i32, _i32, _i64, _i32, _vp]),
+    "bsi_reduce_rows": (C.c_int, [C.POINTER(ReduceJob), _i32, _vp]),
     "bsi_cast_transpose_bf16": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp]),
     "bsi_colsum_bf16": (C.c_int, [_vp, _vp, _i64, _i32, _i64, _i32, _vp]),
     "bsi_gelu_bf16": (C.c_int, [_vp, _vp, _i64, _vp]),

@@ -568,6 +568,54 @@ __global__ void __launch_bounds__(kLnbWarps * 32, 2)
     }
 }
 
+// ------------------------------------------------------------------ several partial-sum reductions in one launch
+// The row kernels above leave per-CTA partial rows behind ([groups * rows][D]: `rows` partial rows per group).  One launch of this kernel
+// finishes up to kMaxReduceJobs of them: dst[g][:] (+)= sum_r src[g * rows + r][:], rows added in a fixed order (4 interleaved slices, then
+// slice 0..3).  A CTA owns 256 columns of one group of one job; a transformer block's backward needs one launch instead of a dozen
+// torch.sum / add_ calls (each of them a kernel, some with a memset, and a launch gap on the stream).
+constexpr int kMaxReduceJobs = 12;
+struct ReduceJobs {
+    bsi_reduce_job job[kMaxReduceJobs];
+    int cta_begin[kMaxReduceJobs + 1];
+    int n;
+};
+__global__ void __launch_bounds__(kTrThreads) k_reduce_rows(const __grid_constant__ ReduceJobs J) {
+    __shared__ float4 part[4][64];
+    int j = 0;
+    while (j + 1 < J.n && (int)blockIdx.x >= J.cta_begin[j + 1]) ++j;
+    const bsi_reduce_job& jb = J.job[j];
+    const int chunks = (jb.D + 255) / 256;
+    const int local = (int)blockIdx.x - J.cta_begin[j];
+    const int g = local / chunks, chunk = local - g * chunks;
+    const int colq = threadIdx.x & 63, slice = threadIdx.x >> 6;
+    const int col = chunk * 256 + colq * 4;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (col < jb.D) {
+        const float* src = jb.src + ((int64_t)g * jb.rows) * jb.D + col;
+#pragma unroll 4
+        for (int r = slice; r < jb.rows; r += 4) {
+            const float4 v = *reinterpret_cast<const float4*>(src + (int64_t)r * jb.D);
+            acc.x += v.x, acc.y += v.y, acc.z += v.z, acc.w += v.w;
+        }
+    }
+    part[slice][colq] = acc;
+    __syncthreads();
+    if (slice == 0 && col < jb.D) {
+        float4 t = part[0][colq];
+#pragma unroll
+        for (int sl = 1; sl < 4; ++sl) {
+            const float4 v = part[sl][colq];
+            t.x += v.x, t.y += v.y, t.z += v.z, t.w += v.w;
+        }
+        float4* d = reinterpret_cast<float4*>(jb.dst + (int64_t)g * jb.dst_ld + col);
+        if (jb.accumulate) {
+            const float4 o = *d;
+            t.x += o.x, t.y += o.y, t.z += o.z, t.w += o.w;
+        }
+        *d = t;
+    }
+}
+
 // ------------------------------------------------------------------ column sums of a bf16 [M][N] matrix (bias gradients)
 // grid (N / 512, ceil(M / rows_per_cta)): a thread owns two adjacent columns and walks rows_per_cta rows; partial[chunk][N]
 __global__ void __launch_bounds__(kTrThreads) k_colsum_bf16(float* __restrict__ partial, const __nv_bfloat16* __restrict__ a, int64_t M, int N, int64_t ld,
@@ -700,6 +748,27 @@ int bsi_gate_residual_backward_rows(void* dbranch_bf16, float* dgate_part, float
     }
 #undef BSI_GRB_CASE
     BSI_LAUNCH_OK("k_gate_residual_backward_pipe");
+    return BSI_OK;
+}
+
+int bsi_reduce_rows(const bsi_reduce_job* jobs, int32_t n_jobs, void* stream) {
+    BSI_CHECK_ARG(jobs && n_jobs > 0 && n_jobs <= kMaxReduceJobs, "bsi_reduce_rows: between 1 and %d jobs per call (got %d)", kMaxReduceJobs, n_jobs);
+    ReduceJobs J;
+    J.n = n_jobs;
+    int total = 0;
+    for (int i = 0; i < n_jobs; ++i) {
+        const bsi_reduce_job& jb = jobs[i];
+        BSI_CHECK_ARG(jb.src && jb.dst && jb.groups > 0 && jb.rows > 0 && jb.D > 0 && jb.D % 4 == 0 && jb.dst_ld >= jb.D && jb.dst_ld % 4 == 0,
+                      "bsi_reduce_rows: job %d: bad arguments (groups=%d rows=%d D=%d dst_ld=%d; D and dst_ld must be multiples of 4)", i, jb.groups, jb.rows,
+                      jb.D, jb.dst_ld);
+        BSI_CHECK_ARG((reinterpret_cast<uintptr_t>(jb.src) | reinterpret_cast<uintptr_t>(jb.dst)) % 16 == 0, "bsi_reduce_rows: job %d: pointers must be 16-byte aligned", i);
+        J.job[i] = jb;
+        J.cta_begin[i] = total;
+        total += jb.groups * ((jb.D + 255) / 256);
+    }
+    for (int i = n_jobs; i <= kMaxReduceJobs; ++i) J.cta_begin[i] = total;
+    k_reduce_rows<<<total, kTrThreads, 0, (cudaStream_t)stream>>>(J);
+    BSI_LAUNCH_OK("k_reduce_rows");
     return BSI_OK;
 }
 

@@ -114,6 +114,31 @@ def _ln_mod_backward(dx_io: Tensor, da: Tensor, x: Tensor, scale: L.RowRef | Non
     return parts
 
 
+class _ReduceBatch:
+    """Collects partial-sum reductions (csrc/train_kernels.cu k_reduce_rows) and runs them in one launch: dst[g] (+)= sum_r src[g * rows + r].
+    The partial buffers are kept alive until ``flush``."""
+
+    MAX = 12
+
+    def __init__(self, dev):
+        self.dev, self.jobs, self.keep = dev, [], []
+
+    def add(self, src: Tensor, dst: Tensor, groups: int, rows: int, accumulate: bool = False) -> None:
+        D = src.shape[-1]
+        assert src.is_contiguous() and src.dtype == torch.float32 and dst.dtype == torch.float32 and dst.stride(-1) == 1 and src.numel() == groups * rows * D
+        ld = dst.stride(0) if dst.dim() > 1 else D
+        self.jobs.append(L.ReduceJob(src.data_ptr(), dst.data_ptr(), groups, rows, D, ld, int(accumulate), 0))
+        self.keep += [src, dst]
+        if len(self.jobs) == self.MAX:
+            self.flush()
+
+    def flush(self) -> None:
+        if self.jobs:
+            arr = (L.ReduceJob * len(self.jobs))(*self.jobs)
+            L.check(L.load().bsi_reduce_rows(arr, len(self.jobs), _st(self.dev)), "bsi_reduce_rows")
+        self.jobs, self.keep = [], []
+
+
 class DiTTrainFunction(torch.autograd.Function):
     """out = DiT(in_scale * mu; mods, params).  Differentiable w.r.t. ``mods`` [L][B][6*dim] and the parameter list (not mu)."""
 
@@ -229,12 +254,18 @@ class DiTTrainFunction(torch.autograd.Function):
         w_patch, b_patch = next(it), next(it)
         blocks = [tuple(next(it) for _ in range(8)) for _ in range(depth)]
         ln_g, ln_b, w_dec, b_dec = next(it), next(it), next(it), next(it)
+        red = _ReduceBatch(dev)  # the partial-sum reductions of a block run as one launch at the end of the block
+
+        def colsum_parts(t: Tensor) -> Tensor:
+            """per-CTA partial column sums [ceil(M / 256)][N] of a bf16 matrix"""
+            parts = torch.empty(((t.shape[0] + 255) // 256, t.shape[1]), dtype=torch.float32, device=dev)
+            L.check(lib.bsi_colsum_bf16(parts.data_ptr(), t.data_ptr(), t.shape[0], t.shape[1], t.stride(0), 256, _st(dev)), "bsi_colsum_bf16")
+            return parts
+
         def colsum(t: Tensor) -> Tensor:
             if t.dtype != torch.bfloat16:
                 return t.sum(0, dtype=torch.float32)
-            parts = torch.empty(((t.shape[0] + 255) // 256, t.shape[1]), dtype=torch.float32, device=dev)
-            L.check(lib.bsi_colsum_bf16(parts.data_ptr(), t.data_ptr(), t.shape[0], t.shape[1], t.stride(0), 256, _st(dev)), "bsi_colsum_bf16")
-            return parts.sum(0)
+            return colsum_parts(t).sum(0)
 
         zero_bias = torch.zeros(4 * D, dtype=torch.float32, device=dev)  # the data-gradient GEMMs have no bias: one shared zero vector
         zeros = lambda n: zero_bias[:n]
@@ -261,6 +292,18 @@ class DiTTrainFunction(torch.autograd.Function):
             if view is not None:
                 view.add_(g)
                 return None
+            return g
+
+        def emit_b_parts(p: Tensor, parts: Tensor):
+            """Bias gradient = sum of all partial rows: accumulated into the optimizer's arena, or into a fresh tensor for autograd."""
+            view = sink.grad_view(p) if sink is not None else None
+            if parts.shape[-1] % 4 or (view is not None and view.data_ptr() % 16):
+                return emit_b(p, parts.sum(0))
+            if view is not None:
+                red.add(parts, view, 1, parts.shape[0], accumulate=True)
+                return None
+            g = torch.empty(parts.shape[-1], dtype=torch.float32, device=dev)
+            red.add(parts, g, 1, parts.shape[0])
             return g
 
         with torch.cuda.device(dev):
@@ -293,7 +336,7 @@ class DiTTrainFunction(torch.autograd.Function):
                 parts = torch.empty((2, M // _LN_ROWS_PER_CTA, D), dtype=torch.float32, device=dev)
                 L.check(lib.bsi_gate_residual_backward_rows(dbr.data_ptr(), parts[0].data_ptr(), parts[1].data_ptr(), dx.data_ptr(), br.data_ptr(), gate, T,
                                                             _LN_ROWS_PER_CTA, M, D, _st(dev)), "bsi_gate_residual_backward_rows")
-                torch.sum(parts[0].view(B, T // _LN_ROWS_PER_CTA, D), 1, out=dgate_out)
+                red.add(parts[0], dgate_out, B, T // _LN_ROWS_PER_CTA)
                 return parts[1]
 
             for l in reversed(range(depth)):
@@ -303,33 +346,35 @@ class DiTTrainFunction(torch.autograd.Function):
                 m, dm = mods[l], dparts[l]
                 ref = lambda j: L.rowref(m, 6 * D, 0, j * D)
                 # per-sample (dshift, dscale) from the CTA partials, written into chunks [j, j + 2) of d(mods)
-                part = lambda t, j: torch.sum(t.view(2, B, T // _LN_ROWS_PER_CTA, D), 2, out=dm[j : j + 2])
+                part = lambda t, j: red.add(t, dm[j : j + 2].view(2 * B, D), 2 * B, T // _LN_ROWS_PER_CTA)
                 # ---- MLP branch: x_out = x_mid + gate_mlp * (gelu(a2 W1^T + b1) W2^T + b2)
                 dbr = torch.empty((M, D), dtype=torch.bfloat16, device=dev)
                 dbias = gate_backward(dbr, dm[5], br2, ref(5))
-                g_w2, g_b2 = emit_w(w_2, dbr, h), emit_b(b_2, dbias.sum(0))
+                g_w2, g_b2 = emit_w(w_2, dbr, h), emit_b_parts(b_2, dbias)
                 dh = torch.empty((M, 4 * D), dtype=torch.bfloat16, device=dev)
                 if _FUSED_GELU and M > 128:  # d(pre) = (dbr W2) * gelu'(pre): the derivative is applied in the data-gradient GEMM's epilogue
                     _gemm(dbr, wt_2, dh, zeros(4 * D), L.EPI_MUL_GELU_GRAD_BF16, aux=pre)
                 else:
                     _gemm(dbr, wt_2, dh, zeros(4 * D), L.EPI_BIAS_BF16)
                     L.check(lib.bsi_gelu_backward_bf16(dh.data_ptr(), dh.data_ptr(), pre.data_ptr(), dh.numel(), _st(dev)), "bsi_gelu_backward_bf16")
-                g_w1, g_b1 = emit_w(w_1, dh, a2), emit_b(b_1, colsum(dh))
+                g_w1, g_b1 = emit_w(w_1, dh, a2), emit_b_parts(b_1, colsum_parts(dh))
                 _gemm(dh, wt_1, da, zeros(D), L.EPI_BIAS_BF16)
                 part(_ln_mod_backward(dx, da, x_mid, ref(4), T, drop=(drop_p, _layer_seed(drop_seed, 2 * l + 1)), shift_first=True), 3)
                 # ---- attention branch: x_mid = x_in + gate_msa * (attn(a1 Wqkv^T + b) Wo^T + b)
                 dbias = gate_backward(dbr, dm[2], br1, ref(2))
-                g_wo, g_bo = emit_w(w_o, dbr, att), emit_b(b_o, dbias.sum(0))
+                g_wo, g_bo = emit_w(w_o, dbr, att), emit_b_parts(b_o, dbias)
                 datt = torch.empty((M, D), dtype=torch.bfloat16, device=dev)
                 _gemm(dbr, wt_o, datt, zeros(D), L.EPI_BIAS_BF16)
                 dqkv = _attention_backward(qkv, att, datt, B, T, heads, D // heads, (drop_p, _layer_seed(drop_seed, 2 * l)), lse)
-                g_wqkv, g_bqkv = emit_w(w_qkv, dqkv, a1), emit_b(b_qkv, colsum(dqkv))
+                g_wqkv, g_bqkv = emit_w(w_qkv, dqkv, a1), emit_b_parts(b_qkv, colsum_parts(dqkv))
                 _gemm(dqkv, wt_qkv, da, zeros(D), L.EPI_BIAS_BF16)
                 part(_ln_mod_backward(dx, da, x_in, ref(1), T, shift_first=True), 0)
                 block_grads.append([g_wqkv, g_bqkv, g_wo, g_bo, g_w1, g_b1, g_w2, g_b2])
+                red.flush()
                 if sink is not None:  # this block's eight tensors are final: their all-reduce can overlap the remaining layers
                     sink.grads_ready([w_qkv, b_qkv, w_o, b_o, w_1, b_1, w_2, b_2])
                 saved[l] = None  # release this layer's activations
+            red.flush()
             dx16 = dx.to(torch.bfloat16)
             grads = [emit_w(w_patch, dx16, a0, cols=w_patch.shape[1]), emit_b(b_patch, colsum(dx))]
             if sink is not None:
@@ -339,6 +384,65 @@ class DiTTrainFunction(torch.autograd.Function):
             grads += tail
             dmods = dparts.permute(0, 2, 1, 3).reshape(depth, B, 6 * D).to(ctx.mods_dtype)
         return (None, None, None, None, dmods, *grads)
+
+
+class _AdaLNChain(torch.autograd.Function):
+    """mods[l] = Linear_2^l(SiLU(Linear_0^l(cond))) for all blocks at once (dit.py:79-81,90-92) on bf16 tensor cores, like the inference engine's
+    conditioning chain (and the reference under bf16 autocast): two batched matmuls over the stacked adaLN weights instead of 24 x
+    (Linear, SiLU, Linear).  The backward is written out because autograd's generic path costs more than the chain itself: it materialises
+    the stacked weight gradients in fp32 (0.6 GB for DiT-L) and then adds 96 slices into the parameters' gradients.  Here the weight
+    gradients dW^l = dY^l^T X^l go through the weight-gradient GEMM straight into the optimizer's arena when one is attached
+    (TMA reduce-add is the "+="), the bias gradients through one multi-tensor add."""
+
+    @staticmethod
+    def forward(ctx, model, cond: Tensor, *ada: Tensor):
+        nl = len(ada) // 4
+        w0 = torch.stack([ada[4 * l] for l in range(nl)]).to(torch.bfloat16)      # [L, d, d]
+        b0 = torch.stack([ada[4 * l + 1] for l in range(nl)]).to(torch.bfloat16)  # [L, d]
+        w2 = torch.stack([ada[4 * l + 2] for l in range(nl)]).to(torch.bfloat16)  # [L, 6d, d]
+        b2 = torch.stack([ada[4 * l + 3] for l in range(nl)]).to(torch.bfloat16)  # [L, 6d]
+        c16 = cond.to(torch.bfloat16).contiguous()
+        pre = torch.baddbmm(b0[:, None, :], c16[None].expand(nl, -1, -1), w0.transpose(1, 2))  # [L, B, d]
+        h = torch.nn.functional.silu(pre)
+        mods = torch.baddbmm(b2[:, None, :], h, w2.transpose(1, 2))  # [L, B, 6d]
+        ctx.model, ctx.nl = model, nl
+        ctx.params = ada
+        ctx.save_for_backward(c16, pre, h, w0, w2)
+        return mods
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, dmods: Tensor):
+        c16, pre, h, w0, w2 = ctx.saved_tensors
+        nl, ada = ctx.nl, ctx.params
+        sink = getattr(ctx.model, "_grad_sink", None)
+        dm16 = dmods.to(torch.bfloat16).contiguous()
+        db2 = dmods.sum(1, dtype=torch.float32)                 # [L, 6d]
+        dh = torch.bmm(dm16, w2)                                # [L, B, d]
+        sg = torch.sigmoid(pre.float())
+        dpre = dh.float() * (sg * (1.0 + pre.float() * (1.0 - sg)))  # SiLU'
+        dp16 = dpre.to(torch.bfloat16)
+        db0 = dpre.sum(1)                                       # [L, d]
+        dcond = torch.bmm(dp16, w0).sum(0, dtype=torch.float32)  # [B, d]
+        views = [sink.grad_view(p) if sink is not None else None for p in ada]
+        grads: list = [None] * len(ada)
+        direct = all(v is not None for v in views) and h.shape[1] % 8 == 0
+        if direct:
+            for l in range(nl):
+                _wgrad(dp16[l], c16, into=views[4 * l])
+                _wgrad(dm16[l], h[l], into=views[4 * l + 2])
+            torch._foreach_add_([views[4 * l + 1] for l in range(nl)], list(db0.unbind(0)))
+            torch._foreach_add_([views[4 * l + 3] for l in range(nl)], list(db2.unbind(0)))
+        else:
+            dw0 = torch.bmm(dp16.transpose(1, 2), c16[None].expand(nl, -1, -1)).float()
+            dw2 = torch.bmm(dm16.transpose(1, 2), h).float()
+            for l in range(nl):
+                for j, g in enumerate((dw0[l], db0[l], dw2[l], db2[l])):
+                    if views[4 * l + j] is not None:
+                        views[4 * l + j].add_(g)
+                    else:
+                        grads[4 * l + j] = g
+        return (None, dcond, *grads)
 
 
 def _attention_backward(qkv: Tensor, att: Tensor, datt: Tensor, B: int, T: int, heads: int, hd: int, drop: tuple[float, int] = (0.0, 0),
@@ -384,16 +488,8 @@ def forward_train(model, mu: Tensor, t: Tensor, in_scale: Tensor | None, seed: i
     if drop_p > 0 and seed is None:
         seed = int(torch.randint(0, 2**31 - 1, (1,)).item())  # CPU generator: no device synchronisation
     cond = model.dit.t_embedding(t.to(torch.float32))
-    # The conditioning chain (dit.py:79-81,90-92) runs on bf16 tensor cores like the inference engine's (and the reference under bf16
-    # autocast).  All blocks at once: two batched matmuls over the stacked adaLN weights instead of 24 x (Linear, SiLU, Linear) --
-    # ~190 tiny launches less in the forward and ~240 less in the backward, during which the device just waits for the host
-    # (profiles/train_timeline_r02.txt).
-    blocks = model.dit.blocks
-    w0 = torch.stack([blk.adaLN_modulation[0].weight for blk in blocks])  # [L, d, d]
-    b0 = torch.stack([blk.adaLN_modulation[0].bias for blk in blocks])    # [L, d]
-    w2 = torch.stack([blk.adaLN_modulation[2].weight for blk in blocks])  # [L, 6d, d]
-    b2 = torch.stack([blk.adaLN_modulation[2].bias for blk in blocks])    # [L, 6d]
-    with torch.autocast("cuda", dtype=torch.bfloat16):
-        h = torch.nn.functional.silu(torch.baddbmm(b0[:, None, :], cond[None].expand(len(blocks), -1, -1), w0.transpose(1, 2)))
-        mods = torch.baddbmm(b2[:, None, :], h, w2.transpose(1, 2))  # [L, B, 6d]
+    ada = []
+    for blk in model.dit.blocks:
+        ada += [blk.adaLN_modulation[0].weight, blk.adaLN_modulation[0].bias, blk.adaLN_modulation[2].weight, blk.adaLN_modulation[2].bias]
+    mods = _AdaLNChain.apply(model, cond, *ada)  # [L, B, 6d]
     return DiTTrainFunction.apply(model, mu, in_scale, (drop_p, int(seed or 0)), mods, *trainable_parameters(model))

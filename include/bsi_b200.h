@@ -388,6 +388,19 @@ int bsi_gate_residual_backward(void* dbranch_bf16, float* dgate, float* dbias_pa
  * partial rows of a sample (dgate) or all of them (bias gradient of the branch's last Linear). */
 int bsi_gate_residual_backward_rows(void* dbranch_bf16, float* dgate_part, float* dbias_part, const float* dx, const void* branch_bf16, bsi_rowref gate,
                                     int32_t rows_per_sample, int32_t rows_per_cta, int64_t M, int32_t D, void* stream);
+
+/* Finishing pass for per-CTA partial sums (bsi_layernorm_mod_backward, bsi_gate_residual_backward_rows, bsi_colsum_bf16):
+ * dst[g][0..D) (+)= sum over r < rows of src[(g * rows + r)][0..D), for up to 12 independent jobs in ONE launch (fixed summation order).
+ * Replaces the torch.sum / add_ calls on the partial buffers (autograd of bsi/models/dit.py:87-103: d(shift), d(scale), d(gate) per sample,
+ * bias gradients over all rows). */
+typedef struct bsi_reduce_job {
+    const float* src;    /* [groups * rows][D], contiguous, 16-byte aligned */
+    float* dst;          /* [groups] rows of pitch dst_ld */
+    int32_t groups, rows, D, dst_ld;
+    int32_t accumulate;  /* 1: dst += (gradient accumulation into an existing buffer), 0: dst = */
+    int32_t reserved;
+} bsi_reduce_job;
+int bsi_reduce_rows(const bsi_reduce_job* jobs, int32_t n_jobs, void* stream);
 /* fp32 [rows][cols] -> bf16 copy out[rows][ld_out] and bf16 transposed copy out_t[cols][ld_t] in one pass (either may be NULL;
  * padding beyond cols / rows is left untouched: allocate it zeroed).  The transposed weight is the operand of dX = dY W. */
 int bsi_cast_transpose_bf16(void* out_bf16, void* out_t_bf16, const float* in, int32_t rows, int32_t cols, int32_t ld_out, int32_t ld_t, void* stream);

@@ -97,6 +97,29 @@ def test_gate_residual_forward_backward_vs_autograd():
     assert L.load().bsi_gate_residual_backward_rows(L.ptr(dbr2), L.ptr(parts[0]), L.ptr(parts[1]), L.ptr(dx), L.ptr(br), gate, T, 48, M, D, L.stream_ptr()) != 0
 
 
+def test_reduce_rows_several_jobs_in_one_launch():
+    """dst[g] (+)= sum_r src[g * rows + r] for several partial buffers at once (the finishing pass of the row kernels' partial sums)."""
+    a = rnd("rr.a", (6 * 8, 384))       # 6 groups of 8 partial rows -> a strided destination (column block of a wider table)
+    b = rnd("rr.b", (1000, 1024))       # one group: a bias gradient, accumulated into an existing buffer
+    c = rnd("rr.c", (2 * 3, 260))       # D not a multiple of 256
+    tab = torch.zeros((6, 3 * 384), device=dev())
+    acc0 = rnd("rr.acc", (1024,))
+    acc = acc0.clone()
+    out_c = torch.zeros((2, 260), device=dev())
+    jobs = (L.ReduceJob * 3)(L.ReduceJob(L.ptr(a), tab[:, 384:768].data_ptr(), 6, 8, 384, 3 * 384, 0, 0),
+                             L.ReduceJob(L.ptr(b), L.ptr(acc), 1, 1000, 1024, 1024, 1, 0),
+                             L.ReduceJob(L.ptr(c), L.ptr(out_c), 2, 3, 260, 260, 0, 0))
+    L.check(L.load().bsi_reduce_rows(jobs, 3, L.stream_ptr()))
+    sync()
+    report("per-group sums", tab[:, 384:768], a.view(6, 8, 384).sum(1), 1e-6, 1e-5)
+    assert float(tab[:, :384].abs().max()) == 0 and float(tab[:, 768:].abs().max()) == 0
+    report("accumulated column sums", acc, acc0 + b.double().sum(0).float(), 1e-5, 1e-4)
+    report("ragged width", out_c, c.view(2, 3, 260).sum(1), 1e-6, 1e-5)
+    assert L.load().bsi_reduce_rows(jobs, 13, L.stream_ptr()) != 0
+    bad = (L.ReduceJob * 1)(L.ReduceJob(L.ptr(a), L.ptr(out_c), 1, 1, 386, 386, 0, 0))
+    assert L.load().bsi_reduce_rows(bad, 1, L.stream_ptr()) != 0
+
+
 def test_colsum_bf16():
     M, N = 1000, 384
     a = rnd("cs.a", (M, 2 * N)).bfloat16()[:, N:]  # strided view (pitch 2N)
