@@ -469,8 +469,10 @@ __global__ void __launch_bounds__(att2::kThreads, 2)
                     sum += p0 + p1;
                     if constexpr (DROP) {
                         const uint32_t idx = drop_q + (uint32_t)(c * 32 + 2 * j);  // query * T + key
-                        p0 = dropout_keep(drop_sd, idx, drop_thresh) ? p0 * drop_inv : 0.0f;
-                        p1 = dropout_keep(drop_sd, idx + 1, drop_thresh) ? p1 * drop_inv : 0.0f;
+                        bool k0, k1;  // idx is even: one hash serves both keys
+                        dropout_keep_pair(drop_sd, idx, drop_thresh, k0, k1);
+                        p0 = k0 ? p0 * drop_inv : 0.0f;
+                        p1 = k1 ? p1 * drop_inv : 0.0f;
                     }
                     p[j] = pack_bf16(p0, p1);
                 }

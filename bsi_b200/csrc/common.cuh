@@ -93,7 +93,7 @@ __device__ __forceinline__ float warp_max(float v) {
 }
 
 // Counter-based dropout mask (training path): keep element `idx` of the stream keyed by `seed` with probability 1 - p, where
-// thresh = round(p * 2^32).  murmur3's 32-bit finaliser over a Weyl-multiplied index: stateless, so the forward and both backward
+// murmur3's 32-bit finaliser over a Weyl-multiplied index: stateless, so the forward and both backward
 // kernels regenerate the identical mask from (seed, index) instead of storing it (tests/helpers.py restates it in Python).
 __host__ __device__ __forceinline__ uint32_t mix32(uint32_t x) {
     x ^= x >> 16;
@@ -103,8 +103,20 @@ __host__ __device__ __forceinline__ uint32_t mix32(uint32_t x) {
     x ^= x >> 16;
     return x;
 }
-__host__ __device__ __forceinline__ bool dropout_keep(uint32_t seed, uint32_t idx, uint32_t thresh) { return mix32(idx * 0x9E3779B9u + seed) >= thresh; }
-__host__ __device__ __forceinline__ uint32_t dropout_thresh(float p) { return p <= 0.0f ? 0u : (uint32_t)((double)p * 4294967296.0); }
+// 16 random bits per element: elements 2i and 2i + 1 share the hash of pair i (round 2: the mask generation was 40 % of the tcgen05
+// attention forward's instructions; a thread that walks consecutive elements now hashes once per two).  thresh = floor(p * 2^16), i.e. the
+// drop probability is quantised to 1/65536 (p = 0.05 -> 0.04999); the 1 / (1 - p) rescale uses the caller's p.
+__host__ __device__ __forceinline__ uint32_t dropout_bits(uint32_t seed, uint32_t pair) { return mix32(pair * 0x9E3779B9u + seed); }
+__host__ __device__ __forceinline__ bool dropout_keep(uint32_t seed, uint32_t idx, uint32_t thresh) {
+    const uint32_t h = dropout_bits(seed, idx >> 1);
+    return ((idx & 1u) ? (h >> 16) : (h & 0xffffu)) >= thresh;
+}
+// keep decisions of elements idx_even and idx_even + 1 from one hash
+__host__ __device__ __forceinline__ void dropout_keep_pair(uint32_t seed, uint32_t idx_even, uint32_t thresh, bool& k0, bool& k1) {
+    const uint32_t h = dropout_bits(seed, idx_even >> 1);
+    k0 = (h & 0xffffu) >= thresh, k1 = (h >> 16) >= thresh;
+}
+__host__ __device__ __forceinline__ uint32_t dropout_thresh(float p) { return p <= 0.0f ? 0u : (uint32_t)((double)p * 65536.0); }
 
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
     __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);

@@ -59,10 +59,11 @@ __global__ void __launch_bounds__(kLnThreads, 2)
             float y3 = fmaf((v[i].w - mean) * rstd, m.w + one, a.w);
             if (drop_thresh) {  // nn.Dropout on the modulated activations (training, dit.py:101): element index = row * dim + column
                 const uint32_t e = (uint32_t)row * dim + (lane + 32 * i) * 4;
-                y0 = dropout_keep(drop_seed, e, drop_thresh) ? y0 * drop_inv : 0.0f;
-                y1 = dropout_keep(drop_seed, e + 1, drop_thresh) ? y1 * drop_inv : 0.0f;
-                y2 = dropout_keep(drop_seed, e + 2, drop_thresh) ? y2 * drop_inv : 0.0f;
-                y3 = dropout_keep(drop_seed, e + 3, drop_thresh) ? y3 * drop_inv : 0.0f;
+                bool k0, k1, k2, k3;  // e is a multiple of 4: two hashes for four elements
+                dropout_keep_pair(drop_seed, e, drop_thresh, k0, k1);
+                dropout_keep_pair(drop_seed, e + 2, drop_thresh, k2, k3);
+                y0 = k0 ? y0 * drop_inv : 0.0f, y1 = k1 ? y1 * drop_inv : 0.0f;
+                y2 = k2 ? y2 * drop_inv : 0.0f, y3 = k3 ? y3 * drop_inv : 0.0f;
             }
             if constexpr (F32OUT) o32[lane + 32 * i] = make_float4(y0, y1, y2, y3);
             else o[lane + 32 * i] = make_uint2(pack_bf16(y0, y1), pack_bf16(y2, y3));
@@ -152,10 +153,11 @@ __global__ void __launch_bounds__(kLnThreads, 2)
             float y3 = fmaf((v[i].w - mean) * rstd, m[i].w + one, a[i].w);
             if (drop_thresh) {
                 const uint32_t e = (uint32_t)row * dim + (lane + 32 * i) * 4;
-                y0 = dropout_keep(drop_seed, e, drop_thresh) ? y0 * drop_inv : 0.0f;
-                y1 = dropout_keep(drop_seed, e + 1, drop_thresh) ? y1 * drop_inv : 0.0f;
-                y2 = dropout_keep(drop_seed, e + 2, drop_thresh) ? y2 * drop_inv : 0.0f;
-                y3 = dropout_keep(drop_seed, e + 3, drop_thresh) ? y3 * drop_inv : 0.0f;
+                bool k0, k1, k2, k3;  // e is a multiple of 4: two hashes for four elements
+                dropout_keep_pair(drop_seed, e, drop_thresh, k0, k1);
+                dropout_keep_pair(drop_seed, e + 2, drop_thresh, k2, k3);
+                y0 = k0 ? y0 * drop_inv : 0.0f, y1 = k1 ? y1 * drop_inv : 0.0f;
+                y2 = k2 ? y2 * drop_inv : 0.0f, y3 = k3 ? y3 * drop_inv : 0.0f;
             }
             if constexpr (F32OUT) o32[lane + 32 * i] = make_float4(y0, y1, y2, y3);
             else o[lane + 32 * i] = make_uint2(pack_bf16(y0, y1), pack_bf16(y2, y3));

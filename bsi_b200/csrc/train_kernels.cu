@@ -86,10 +86,11 @@ __global__ void __launch_bounds__(kTrThreads, 2)
             float y2 = fmaf((v[i].z - mean) * rstd, m.z + one, a.z), y3 = fmaf((v[i].w - mean) * rstd, m.w + one, a.w);
             if (drop_thresh) {
                 const uint32_t e = (uint32_t)row * dim + (lane + 32 * i) * 4;
-                y0 = dropout_keep(drop_seed, e, drop_thresh) ? y0 * drop_inv : 0.0f;
-                y1 = dropout_keep(drop_seed, e + 1, drop_thresh) ? y1 * drop_inv : 0.0f;
-                y2 = dropout_keep(drop_seed, e + 2, drop_thresh) ? y2 * drop_inv : 0.0f;
-                y3 = dropout_keep(drop_seed, e + 3, drop_thresh) ? y3 * drop_inv : 0.0f;
+                bool k0, k1, k2, k3;  // e is a multiple of 4: two hashes for four elements
+                dropout_keep_pair(drop_seed, e, drop_thresh, k0, k1);
+                dropout_keep_pair(drop_seed, e + 2, drop_thresh, k2, k3);
+                y0 = k0 ? y0 * drop_inv : 0.0f, y1 = k1 ? y1 * drop_inv : 0.0f;
+                y2 = k2 ? y2 * drop_inv : 0.0f, y3 = k3 ? y3 * drop_inv : 0.0f;
             }
             o[lane + 32 * i] = make_uint2(pack_bf16(y0, y1), pack_bf16(y2, y3));
         }
@@ -176,10 +177,11 @@ __global__ void __launch_bounds__(kTrThreads, 2)
             float y2 = fmaf((v[i].z - mean) * rstd, m.z + one, a.z), y3 = fmaf((v[i].w - mean) * rstd, m.w + one, a.w);
             if (drop_thresh) {
                 const uint32_t e = (uint32_t)row * dim + (lane + 32 * i) * 4;
-                y0 = dropout_keep(drop_seed, e, drop_thresh) ? y0 * drop_inv : 0.0f;
-                y1 = dropout_keep(drop_seed, e + 1, drop_thresh) ? y1 * drop_inv : 0.0f;
-                y2 = dropout_keep(drop_seed, e + 2, drop_thresh) ? y2 * drop_inv : 0.0f;
-                y3 = dropout_keep(drop_seed, e + 3, drop_thresh) ? y3 * drop_inv : 0.0f;
+                bool k0, k1, k2, k3;  // e is a multiple of 4: two hashes for four elements
+                dropout_keep_pair(drop_seed, e, drop_thresh, k0, k1);
+                dropout_keep_pair(drop_seed, e + 2, drop_thresh, k2, k3);
+                y0 = k0 ? y0 * drop_inv : 0.0f, y1 = k1 ? y1 * drop_inv : 0.0f;
+                y2 = k2 ? y2 * drop_inv : 0.0f, y3 = k3 ? y3 * drop_inv : 0.0f;
             }
             o[lane + 32 * i] = make_uint2(pack_bf16(y0, y1), pack_bf16(y2, y3));
         }
@@ -382,7 +384,11 @@ __global__ void __launch_bounds__(kTrThreads, 2)  // the per-warp partial sums l
             for (int i = 0; i < NV; ++i) {
                 const uint32_t e = (uint32_t)row * dim + (lane + 32 * i) * 4;
 #pragma unroll
-                for (int j = 0; j < 4; ++j) keep |= (dropout_keep(drop_seed, e + j, drop_thresh) ? 1u : 0u) << (4 * i + j);
+                for (int j = 0; j < 4; j += 2) {  // e is a multiple of 4: one hash per two elements
+                    bool k0, k1;
+                    dropout_keep_pair(drop_seed, e + j, drop_thresh, k0, k1);
+                    keep |= ((k0 ? 1u : 0u) | (k1 ? 2u : 0u)) << (4 * i + j);
+                }
             }
         }
         auto grad_in = [&](int i, float& g0, float& g1, float& g2, float& g3) {
@@ -507,7 +513,11 @@ __global__ void __launch_bounds__(kLnbWarps * 32, 2)
             for (int i = 0; i < NV; ++i) {
                 const uint32_t e = (uint32_t)row * dim + (lane + 32 * i) * 4;
 #pragma unroll
-                for (int j = 0; j < 4; ++j) keep |= (dropout_keep(drop_seed, e + j, drop_thresh) ? 1u : 0u) << (4 * i + j);
+                for (int j = 0; j < 4; j += 2) {  // e is a multiple of 4: one hash per two elements
+                    bool k0, k1;
+                    dropout_keep_pair(drop_seed, e + j, drop_thresh, k0, k1);
+                    keep |= ((k0 ? 1u : 0u) | (k1 ? 2u : 0u)) << (4 * i + j);
+                }
             }
         }
         auto grad_in = [&](int i, float& g0, float& g1, float& g2, float& g3) {
@@ -570,8 +580,8 @@ __global__ void __launch_bounds__(kLnbWarps * 32, 2)
 
 // ------------------------------------------------------------------ several partial-sum reductions in one launch
 // The row kernels above leave per-CTA partial rows behind ([groups * rows][D]: `rows` partial rows per group).  One launch of this kernel
-// finishes up to kMaxReduceJobs of them: dst[g][:] (+)= sum_r src[g * rows + r][:], rows added in a fixed order (4 interleaved slices, then
-// slice 0..3).  A CTA owns 256 columns of one group of one job; a transformer block's backward needs one launch instead of a dozen
+// finishes up to kMaxReduceJobs of them: dst[g][:] (+)= sum_r src[g * rows + r][:], rows added in a fixed order (8 interleaved slices, then
+// slice 0..7).  A CTA owns 128 columns of one group of one job; a transformer block's backward needs one launch instead of a dozen
 // torch.sum / add_ calls (each of them a kernel, some with a memset, and a launch gap on the stream).
 constexpr int kMaxReduceJobs = 12;
 struct ReduceJobs {
@@ -580,20 +590,21 @@ struct ReduceJobs {
     int n;
 };
 __global__ void __launch_bounds__(kTrThreads) k_reduce_rows(const __grid_constant__ ReduceJobs J) {
-    __shared__ float4 part[4][64];
+    constexpr int kSlices = 8, kColq = kTrThreads / kSlices;  // 32 float4 columns (128 floats) x 8 interleaved row slices per CTA
+    __shared__ float4 part[kSlices][kColq];
     int j = 0;
     while (j + 1 < J.n && (int)blockIdx.x >= J.cta_begin[j + 1]) ++j;
     const bsi_reduce_job& jb = J.job[j];
-    const int chunks = (jb.D + 255) / 256;
+    const int chunks = (jb.D + 127) / 128;
     const int local = (int)blockIdx.x - J.cta_begin[j];
     const int g = local / chunks, chunk = local - g * chunks;
-    const int colq = threadIdx.x & 63, slice = threadIdx.x >> 6;
-    const int col = chunk * 256 + colq * 4;
+    const int colq = threadIdx.x & (kColq - 1), slice = threadIdx.x / kColq;
+    const int col = chunk * 128 + colq * 4;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     if (col < jb.D) {
         const float* src = jb.src + ((int64_t)g * jb.rows) * jb.D + col;
-#pragma unroll 4
-        for (int r = slice; r < jb.rows; r += 4) {
+#pragma unroll 8
+        for (int r = slice; r < jb.rows; r += kSlices) {
             const float4 v = *reinterpret_cast<const float4*>(src + (int64_t)r * jb.D);
             acc.x += v.x, acc.y += v.y, acc.z += v.z, acc.w += v.w;
         }
@@ -603,7 +614,7 @@ __global__ void __launch_bounds__(kTrThreads) k_reduce_rows(const __grid_constan
     if (slice == 0 && col < jb.D) {
         float4 t = part[0][colq];
 #pragma unroll
-        for (int sl = 1; sl < 4; ++sl) {
+        for (int sl = 1; sl < kSlices; ++sl) {
             const float4 v = part[sl][colq];
             t.x += v.x, t.y += v.y, t.z += v.z, t.w += v.w;
         }
@@ -764,7 +775,7 @@ int bsi_reduce_rows(const bsi_reduce_job* jobs, int32_t n_jobs, void* stream) {
         BSI_CHECK_ARG((reinterpret_cast<uintptr_t>(jb.src) | reinterpret_cast<uintptr_t>(jb.dst)) % 16 == 0, "bsi_reduce_rows: job %d: pointers must be 16-byte aligned", i);
         J.job[i] = jb;
         J.cta_begin[i] = total;
-        total += jb.groups * ((jb.D + 255) / 256);
+        total += jb.groups * ((jb.D + 127) / 128);
     }
     for (int i = n_jobs; i <= kMaxReduceJobs; ++i) J.cta_begin[i] = total;
     k_reduce_rows<<<total, kTrThreads, 0, (cudaStream_t)stream>>>(J);

@@ -134,6 +134,7 @@ class _ReduceBatch:
 
     def flush(self) -> None:
         if self.jobs:
+            self.jobs.sort(key=lambda j: -j.rows)  # the long (bias-gradient) reductions first: their CTAs are the kernel's critical path
             arr = (L.ReduceJob * len(self.jobs))(*self.jobs)
             L.check(L.load().bsi_reduce_rows(arr, len(self.jobs), _st(self.dev)), "bsi_reduce_rows")
         self.jobs, self.keep = [], []

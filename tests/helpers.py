@@ -185,8 +185,9 @@ def _mix32(x: torch.Tensor) -> torch.Tensor:
 
 def dropout_keep(seed: int, idx: torch.Tensor, p: float) -> torch.Tensor:
     """Keep mask of the native kernels' stateless dropout (csrc/common.cuh dropout_keep) for element indices `idx` (int64)."""
-    thresh = int(float(np.float32(p)) * 4294967296.0)
-    return _mix32((idx * 0x9E3779B9 + seed) & 0xFFFFFFFF) >= thresh
+    thresh = int(float(np.float32(p)) * 65536.0)
+    h = _mix32(((idx >> 1) * 0x9E3779B9 + seed) & 0xFFFFFFFF)  # 16 bits per element: elements 2i, 2i + 1 share the hash of pair i
+    return torch.where((idx & 1) == 1, h >> 16, h & 0xFFFF) >= thresh
 
 
 def attention_dropout_mask(seed: int, B: int, heads: int, T: int, p: float) -> torch.Tensor:
@@ -194,8 +195,9 @@ def attention_dropout_mask(seed: int, B: int, heads: int, T: int, p: float) -> t
     bh = torch.arange(B * heads, dtype=torch.int64)
     sd = _mix32((seed ^ ((bh * 0x9E3779B9) & 0xFFFFFFFF)) & 0xFFFFFFFF)
     idx = torch.arange(T * T, dtype=torch.int64)
-    thresh = int(float(np.float32(p)) * 4294967296.0)
-    keep = _mix32((idx[None, :] * 0x9E3779B9 + sd[:, None]) & 0xFFFFFFFF) >= thresh
+    thresh = int(float(np.float32(p)) * 65536.0)
+    h = _mix32(((idx[None, :] >> 1) * 0x9E3779B9 + sd[:, None]) & 0xFFFFFFFF)
+    keep = torch.where((idx[None, :] & 1) == 1, h >> 16, h & 0xFFFF) >= thresh
     return keep.reshape(B, heads, T, T)
 
 
