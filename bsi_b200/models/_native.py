@@ -33,6 +33,7 @@ class NativeDenoiser(nn.Module):
         state = self.__dict__.copy()
         state.update(_engine=None, _arena=None, _packed_sig=None, _scratch={}, _epoch=0)
         state.pop("_grad_sink", None)
+        state.pop("_train_wcache", None)  # bf16 weight copies of the training path: rebuilt on first use
         return state
 
     def __del__(self):

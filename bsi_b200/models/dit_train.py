@@ -158,14 +158,28 @@ class DiTTrainFunction(torch.autograd.Function):
         ln_g, ln_b, w_dec, b_dec = next(it), next(it), next(it), next(it)
         wts: list[Tensor] = []  # transposed bf16 weights, in parameter order, for the data-gradient GEMMs of the backward
 
+        # bf16 / transposed bf16 copies of the weights are kept between calls while the weights do not change (micro-batches of one
+        # optimisation step): keyed like NativeDenoiser._signature -- address, torch version counter, generation of the optimizer arena
+        cache = model.__dict__.setdefault("_train_wcache", {})
+
+        def stamp(w: Tensor):
+            arena = getattr(w, "_bsi_arena", None)
+            return (w.data_ptr(), w._version, arena[0].generation if arena is not None else 0)
+
         def bf(w: Tensor, pad_rows: int = 0, pad_cols: int = 0) -> Tensor:
             """bf16 copy [N'][K'] (zero padded) for the forward GEMM; its transpose [K'][N'] is produced in the same pass."""
+            key, st_w = (id(w), pad_rows, pad_cols), stamp(w)
+            hit = cache.get(key)
+            if hit is not None and hit[0] == st_w:
+                wts.append(hit[2])
+                return hit[1]
             n, k = w.shape
             n_p, k_p = max(n, pad_rows), max(k, pad_cols)
             alloc = torch.zeros if (n_p != n or k_p != k) else torch.empty
             w16, wt16 = alloc((n_p, k_p), dtype=torch.bfloat16, device=dev), alloc((k_p, n_p), dtype=torch.bfloat16, device=dev)
             L.check(lib.bsi_cast_transpose_bf16(w16.data_ptr(), wt16.data_ptr(), w.detach().float().contiguous().data_ptr(), n, k, k_p, n_p, _st(dev)),
                     "bsi_cast_transpose_bf16")
+            cache[key] = (st_w, w16, wt16)
             wts.append(wt16)
             return w16
 
