@@ -254,11 +254,14 @@ class AdamW(torch.optim.Optimizer):
         self._grad_scale = 1.0 / dist.get_world_size(group)
 
     # --- direct gradient sink for the native training path (bsi_b200/models/dit_train.py)
-    def attach_model(self, model, overlap: bool = True, group=None) -> None:
+    def attach_model(self, model, overlap: bool = False, group=None) -> None:
         """Let the native ``DenoisingDiT`` backward write weight gradients straight into this optimizer's gradient arena (the
-        weight-gradient GEMM accumulates in place: no temporaries, no autograd ``+=`` pass) and, under ``torch.distributed``,
-        start the all-reduce of each transformer block's gradient range as soon as the block's backward is done, so that the
-        exchange overlaps the rest of the backward pass (what DDP's bucketed hooks do, bsi/tasks/bsi.py:163-166)."""
+        weight-gradient GEMM accumulates in place: no temporaries, no autograd ``+=`` pass).  ``overlap=True`` additionally starts,
+        under ``torch.distributed``, the all-reduce of each transformer block's gradient range as soon as the block's backward is
+        done (what DDP's bucketed hooks do, bsi/tasks/bsi.py:163-166).  It is off by default because it does not pay on B200: the
+        persistent GEMM kernels of the backward occupy every SM, NCCL's CTAs squeeze in between them and slow both down -- 8 GPUs,
+        global batch 1024: 87.2 ms per step with per-block collectives against 84.6 ms with one all-reduce after the backward
+        (profiles/train_8gpu_r02.jsonl)."""
         model._grad_sink = self
         self._overlap, self._group = overlap, group
         self._index = {id(p): i for i, p in enumerate(self._params)}

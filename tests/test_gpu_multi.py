@@ -102,7 +102,7 @@ def _train_worker(rank, world, port, q, mode="allreduce"):
     bsi.noise_source = "torch"
     opt = NO.AdamW(model.parameters(), lr=1e-3, weight_decay=0.01, max_grad_norm=1.0)
     if mode == "sink":
-        opt.attach_model(model)  # gradients straight into the arena, per-block all-reduce started during the backward
+        opt.attach_model(model, overlap=True)  # gradients straight into the arena, per-block all-reduce started during the backward
     net = model
     if mode == "ddp" and world > 1:  # the reference's own arrangement (BSITraining.configure_ddp, bsi/tasks/bsi.py:163-166)
         from torch.nn.parallel import DistributedDataParallel

@@ -27,6 +27,7 @@ ap.add_argument("--depth", type=int, default=24)
 ap.add_argument("--steps", type=int, default=3)
 ap.add_argument("--profile", action="store_true")
 ap.add_argument("--no-sink", action="store_true", help="gradients through autograd, one all-reduce after backward")
+ap.add_argument("--overlap", action="store_true", help="start each block's all-reduce during the backward (default: one all-reduce after it)")
 ap.add_argument("--dropout", type=float, default=0.0, help="0.05 in config/experiment/imagenet64.yaml")
 a = ap.parse_args()
 
@@ -51,7 +52,7 @@ ema = NO.create_ema(model, beta=0.9999, update_after_step=1000, update_every=1)
 opt = NO.AdamW(model.parameters(), lr=1e-3, weight_decay=0.01, max_grad_norm=1.0)
 opt.attach_ema(ema)
 if not a.no_sink:
-    opt.attach_model(model)  # weight gradients straight into the arena; per-block all-reduce overlapped with the backward
+    opt.attach_model(model, overlap=a.overlap)  # weight gradients straight into the arena; --overlap: per-block all-reduce during the backward
 gen = torch.Generator(device=dev).manual_seed(2 + rank)
 x = torch.randint(0, 256, (local, 3, 64, 64), device=dev, generator=gen).float() * (2 / 255) - 1
 
@@ -93,7 +94,7 @@ if world > 1:
 ms = float(ms)
 flops = a.global_batch * 3 * (161.26e9 * a.depth / 24 + 0.352e9)  # forward + dgrad + wgrad per sample
 if rank == 0:
-    print(json.dumps(dict(what="imagenet64-dit train step (native path)", n_gpus=world, global_batch=a.global_batch, per_gpu_batch=local, micro_batch=micro,
+    print(json.dumps(dict(what="imagenet64-dit train step (native path)", no_sink=a.no_sink, overlap=a.overlap, n_gpus=world, global_batch=a.global_batch, per_gpu_batch=local, micro_batch=micro,
                           depth=a.depth, dropout=a.dropout, ms_per_step=ms, samples_per_s=a.global_batch / ms * 1e3, tflops_total=flops / ms / 1e9,
                           tflops_per_gpu=flops / ms / 1e9 / world, peak_mem_gb=torch.cuda.max_memory_allocated() / 2**30, loss=float(loss),
                           grad_norm=float(opt.total_grad_norm()), params=sum(p.numel() for p in model.parameters()))), flush=True)
