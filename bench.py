@@ -277,8 +277,8 @@ def elbo_rate(a, bsi, dev, world: int, rank: int):
 def train_step_rate(a, dev, world: int, rank: int, global_batch: int = 1024, micro: int = 256):
     """BASELINE.json configs[4]: imagenet64-dit train_loss forward/backward, bf16 tensor-core operands, data parallel with the global
     batch FIXED at 1024 (strong scaling -- the reference's loader divides the batch by the world size, bsi/data/h5image.py:309-312);
-    a rank accumulates its share over micro-batches.  One step = train_loss(x).mean().backward() [per-block NCCL all-reduces started
-    during the backward + one for the rest] + clip/AdamW/EMA, dropout 0.05 as in config/experiment/imagenet64.yaml."""
+    a rank accumulates its share over micro-batches.  One step = train_loss(x).mean().backward() + one NCCL all-reduce over
+    the flat gradient arena + clip/AdamW/EMA, dropout 0.05 as in config/experiment/imagenet64.yaml."""
     import torch.distributed as dist
 
     from bsi_b200 import BSI, Discretization
@@ -559,7 +559,7 @@ def run_native(a):
                 "workload": f"{a.config} train_loss fwd/bwd + gradient all-reduce + clip/AdamW/EMA, global batch {side['gb']} over {world} GPU(s) "
                             f"({side['tr_local']} per GPU in micro-batches of {side['tr_micro']}), dropout 0.05" + ("" if full_size else " [REDUCED development run]"),
                 "ms_per_step": tr_ms, "samples_per_s": side["gb"] / tr_ms * 1e3, "tflops_per_gpu": tr_flops / tr_ms / 1e9 / world, "scaling": "strong",
-                "all_reduce": "per-block NCCL all-reduces started during the backward + one for the remainder" if world > 1 else "none (1 GPU)",
+                "all_reduce": "one NCCL all-reduce over the flat gradient arena after the backward (per-block collectives during the backward are 2.6 ms slower on 8 GPUs)" if world > 1 else "none (1 GPU)",
                 "finite": side["tr_ok"],
             }
         if world == 1 and not a.no_cpu_baseline:
