@@ -67,11 +67,15 @@ cases = [
     ("k_gate_residual_backward_pipe", gate_bwd_rows, M * D * (4 + 2 + 2)),
     ("k_layernorm_mod (inference kernel, same rows)", ln_fwd, M * D * (4 + 2)),
 ]
+only = os.environ.get("CASES")  # comma-separated substrings: run only the matching cases (ncu captures)
+n_iter = int(os.environ.get("ITERS", 12))
 for name, fn, nbytes in cases:
-    for i in range(3):
+    if only and not any(o in name for o in only.split(",")):
+        continue
+    for i in range(1 if only else 3):
         fn(sets[i % len(sets)])
     torch.cuda.synchronize()
-    tot, n = 0.0, 12
+    tot, n = 0.0, n_iter
     for i in range(n):
         flush.add_(1.0) if ap_dirty else flush.sum()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
