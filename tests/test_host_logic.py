@@ -466,3 +466,38 @@ def test_adaln_chain_backward_matches_autograd():
         assert g.shape == w.shape
         rel = float((g.float() - w.float()).norm() / w.float().norm().clamp_min(1e-6))
         assert rel < 3e-2, rel
+
+
+def test_dropout_mask_restatement_matches_the_header(tmp_path):
+    """tests/helpers.py restates csrc/common.cuh's stateless dropout decision (16 random bits per element, elements 2i and 2i + 1 share
+    one hash) for the GPU parity tests; here the header's own __host__ functions are compiled with nvcc and compared on the CPU."""
+    import ctypes
+    import shutil
+    import subprocess
+
+    import helpers as H
+
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not available")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "drop.cu"
+    src.write_text('#include "common.cuh"\n'
+                   'extern "C" int keep_host(unsigned seed, unsigned idx, float p) { return bsi::dropout_keep(seed, idx, bsi::dropout_thresh(p)) ? 1 : 0; }\n'
+                   'extern "C" unsigned mix_host(unsigned x) { return bsi::mix32(x); }\n')
+    so = tmp_path / "drop.so"
+    subprocess.run([nvcc, "-shared", "-Xcompiler", "-fPIC", "-std=c++17", "-I", os.path.join(root, "bsi_b200", "csrc"), "-I", os.path.join(root, "include"),
+                    "-o", str(so), str(src)], check=True, capture_output=True, timeout=300)
+    lib = ctypes.CDLL(str(so))
+    lib.keep_host.argtypes = [ctypes.c_uint32, ctypes.c_uint32, ctypes.c_float]
+    lib.mix_host.argtypes = [ctypes.c_uint32]
+    lib.mix_host.restype = ctypes.c_uint32
+    xs = torch.tensor([0, 1, 2, 12345, 0xFFFFFFFF, 0x9E3779B9], dtype=torch.int64)
+    assert H._mix32(xs).tolist() == [lib.mix_host(int(v)) for v in xs.tolist()]
+    idx = torch.cat([torch.arange(0, 4096, dtype=torch.int64), torch.tensor([2**31 - 1, 2**31, 2**32 - 2, 2**32 - 1], dtype=torch.int64)])
+    for seed, p in ((77, 0.2), (0xDEADBEEF, 0.05), (5, 0.999)):
+        want = [lib.keep_host(seed, int(i), p) for i in idx.tolist()]
+        got = H.dropout_keep(seed, idx, p).to(torch.int64).tolist()
+        assert got == want, (seed, p)
+    frac = 1.0 - sum(lib.keep_host(123, i, 0.05) for i in range(200000)) / 200000.0
+    assert abs(frac - 0.05) < 2e-3, frac  # the drop rate is what was asked for
