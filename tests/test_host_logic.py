@@ -501,3 +501,58 @@ def test_dropout_mask_restatement_matches_the_header(tmp_path):
         assert got == want, (seed, p)
     frac = 1.0 - sum(lib.keep_host(123, i, 0.05) for i in range(200000)) / 200000.0
     assert abs(frac - 0.05) < 2e-3, frac  # the drop rate is what was asked for
+
+
+def _wgrad_schedule(n_tiles, k_tiles, total_kb, pairs):
+    """Python restatement of the weight-gradient GEMM's work distribution (csrc/wgrad_sm100.cu, splits == 0): per CTA pair the list of
+    segments (tile, kb0, kb1).  Host side: workers = min(pairs, steps / 8), H = steps / workers; device side: heads + tails."""
+    tiles = n_tiles * k_tiles
+    all_steps = tiles * total_kb
+    workers = int(min(max(all_steps // 8, 1), pairs))
+    H_ = all_steps // workers
+    f = workers // tiles
+    heads, left = tiles * f, workers - tiles * f
+    tail0 = total_kb if left == 0 else f * H_
+    tail_len = total_kb - tail0
+    tail_total = tiles * tail_len
+    out = []
+    for w in range(workers):
+        segs = []
+        if w < heads:
+            seg, t = divmod(w, tiles)
+            if left == 0:
+                kb0, kb1 = total_kb * seg // f, total_kb * (seg + 1) // f
+            else:
+                kb0, kb1 = seg * H_, seg * H_ + H_
+            if kb1 > kb0:
+                segs.append((t, kb0, kb1))
+        else:
+            tw = w - heads
+            pos, hi = tail_total * tw // left, tail_total * (tw + 1) // left
+            while pos < hi:
+                t, off = divmod(pos, tail_len)
+                ln = min(hi - pos, tail_len - off)
+                segs.append((t, tail0 + off, tail0 + off + ln))
+                pos += ln
+        out.append(segs)
+    return out
+
+
+def test_wgrad_equal_work_schedule_covers_every_block_step_exactly_once():
+    """Every (output tile, k-block) of dW += dY^T X is computed by exactly one CTA pair, for the DiT-L shapes and for awkward ones;
+    the busiest pair carries at most 6 % more than the mean on the big shapes (H is rounded down, so the tail pairs get the remainder:
+    +4.8 % on the out-projection shape, under 1.5 % on the others) -- whole (tile, split) items on 74 pairs were 16-39 % off."""
+    cases = [(12, 4, 512, 74), (4, 4, 512, 74), (16, 4, 512, 74), (4, 16, 512, 74), (12, 4, 1024, 74),  # DiT-L at batch 128 / 256
+             (24, 4, 2, 74), (4, 4, 2, 74), (1, 1, 5, 74), (1, 1, 16, 74), (37, 2, 9, 74), (74, 1, 64, 74), (75, 1, 64, 74), (5, 3, 1000, 74),
+             (2, 2, 7, 3), (3, 5, 11, 8), (148, 1, 33, 74)]
+    for n_tiles, k_tiles, total_kb, pairs in cases:
+        sched = _wgrad_schedule(n_tiles, k_tiles, total_kb, pairs)
+        seen = np.zeros((n_tiles * k_tiles, total_kb), dtype=np.int32)
+        for segs in sched:
+            for t, kb0, kb1 in segs:
+                assert 0 <= t < n_tiles * k_tiles and 0 <= kb0 < kb1 <= total_kb, (n_tiles, k_tiles, total_kb, pairs, t, kb0, kb1)
+                seen[t, kb0:kb1] += 1
+        assert (seen == 1).all(), (n_tiles, k_tiles, total_kb, pairs)
+        loads = [sum(b - a for _, a, b in segs) for segs in sched]
+        if n_tiles * k_tiles * total_kb >= 8192:
+            assert max(loads) <= 1.06 * (sum(loads) / len(loads)) + 1, (n_tiles, k_tiles, total_kb, loads)
